@@ -1,0 +1,220 @@
+"""squava_b200 -- B200 (sm_100a) implementation of squava's data-parallel hot path.
+
+This package is a thin ctypes binding over ``libsquava_b200.so`` (C ABI in
+``include/squava_b200.h``): random playouts + the terminal-position test, and
+the fixed-depth alpha-beta batch.  It is what the tests and ``bench.py`` call;
+the reference-facing host programs (``squavam``, ``squavathr``, ``opening3`` ...)
+are the C++ sources under ``squava_b200/host`` and bind the same ABI.
+
+There is no CPU fallback: importing works anywhere (so that the symbol table
+can be checked on a CPU box), but every compute call needs ``init()`` to have
+found an sm_100 device, and raises ``SquavaError`` otherwise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+__all__ = [
+    "SquavaError", "BOARD", "SUBTREE", "NO_MOVE", "lib", "lib_path", "init", "shutdown",
+    "is_initialised", "classify", "playouts", "playouts_dev", "classify_dev",
+    "alphabeta_root", "alphabeta_subtrees", "int32_peak", "launch_count",
+    "last_playout_kernel_ms", "debug_philox", "device_count", "sm_count", "EXPORTS",
+]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+lib_path = os.path.join(_HERE, "libsquava_b200.so")
+
+BOARD = np.dtype([("x", "<u4"), ("o", "<u4")])
+SUBTREE = np.dtype([("x", "<u4"), ("o", "<u4"), ("last_cell", "i1"), ("ply", "i1"),
+                    ("side_to_move", "i1"), ("reserved", "i1"), ("carried", "<i4")])
+NO_MOVE = -(2 ** 31)
+
+AB_ALPHABETA, AB_SQUAVATHR, AB_OPENING3, AB_OPENING2 = 1, 2, 3, 4
+
+# every symbol include/squava_b200.h declares
+EXPORTS = [
+    "sq_init", "sq_shutdown", "sq_strerror", "sq_last_error", "sq_abi_version", "sq_device_count",
+    "sq_sm_count", "sq_classify", "sq_playouts", "sq_alphabeta_root", "sq_alphabeta_subtrees",
+    "sq_classify_dev", "sq_playouts_dev", "sq_int32_peak", "sq_launch_count",
+    "sq_last_playout_kernel_ms", "sq_debug_philox",
+]
+
+
+class SquavaError(RuntimeError):
+    def __init__(self, status, where):
+        self.status = status
+        detail = ""
+        try:
+            detail = lib().sq_last_error().decode()
+            name = lib().sq_strerror(status).decode()
+        except Exception:  # pragma: no cover
+            name = str(status)
+        super().__init__("%s: %s (%d)%s" % (where, name, status, (": " + detail) if detail else ""))
+
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library.  Fails loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(lib_path):
+            raise ImportError(
+                "libsquava_b200.so is missing: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` or `make -C squava_b200/csrc` (there is no CPU fallback)")
+        L = C.CDLL(lib_path)
+        vp, i64, u64, i32 = C.c_void_p, C.c_int64, C.c_uint64, C.c_int
+        L.sq_init.argtypes = [C.POINTER(C.c_int), i32, u64]
+        L.sq_shutdown.restype = None
+        L.sq_strerror.argtypes = [i32]; L.sq_strerror.restype = C.c_char_p
+        L.sq_last_error.restype = C.c_char_p
+        L.sq_sm_count.argtypes = [i32]
+        L.sq_classify.argtypes = [vp, i64, vp, vp, vp]
+        L.sq_playouts.argtypes = [vp, vp, i64, u64, u64, vp]
+        L.sq_alphabeta_root.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, vp]
+        L.sq_alphabeta_subtrees.argtypes = [vp, i64, i32, i32, vp, vp, vp]
+        L.sq_classify_dev.argtypes = [i32, vp, i64, vp, vp, vp, vp]
+        L.sq_playouts_dev.argtypes = [i32, vp, vp, i64, u64, u64, u64, vp, vp]
+        L.sq_int32_peak.argtypes = [i32, i32, i32, C.POINTER(C.c_double)]
+        L.sq_launch_count.restype = u64
+        L.sq_last_playout_kernel_ms.argtypes = [i32, C.POINTER(C.c_float)]
+        L.sq_debug_philox.argtypes = [vp, vp, vp]
+        _lib = L
+    return _lib
+
+
+def _ck(status, where):
+    if status != 0:
+        raise SquavaError(status, where)
+
+
+def init(devices=None, seed=0x5155415641):
+    """sq_init.  devices: list of CUDA device ordinals (default [0])."""
+    L = lib()
+    if devices is None:
+        _ck(L.sq_init(None, 0, seed), "sq_init")
+    else:
+        arr = (C.c_int * len(devices))(*devices)
+        _ck(L.sq_init(arr, len(devices), seed), "sq_init")
+
+
+def shutdown():
+    lib().sq_shutdown()
+
+
+def is_initialised():
+    return lib().sq_device_count() > 0
+
+
+def device_count():
+    return lib().sq_device_count()
+
+
+def sm_count(slot=0):
+    return lib().sq_sm_count(slot)
+
+
+def as_boards(boards):
+    """Accepts a BOARD array or an (n, 2) integer array of (x, o) masks."""
+    b = np.asarray(boards)
+    if b.dtype != BOARD:
+        b = np.ascontiguousarray(b, dtype=np.uint32).reshape(-1, 2).view(BOARD).reshape(-1)
+    return np.ascontiguousarray(b)
+
+
+def classify(boards):
+    """-> (flags u8[n], winner_mcts_order i8[n], winner_ab_order i8[n])"""
+    b = as_boards(boards)
+    n = b.shape[0]
+    f = np.empty(n, np.uint8); wm = np.empty(n, np.int8); wa = np.empty(n, np.int8)
+    _ck(lib().sq_classify(b.ctypes.data, n, f.ctypes.data, wm.ctypes.data, wa.ctypes.data), "sq_classify")
+    return f, wm, wa
+
+
+def playouts(boards, to_move, playouts_per_leaf, stream_id=0, out=None):
+    """-> u64[n, 4] = {MAX wins, MIN wins, draws, plies} per leaf (host buffers)."""
+    b = as_boards(boards)
+    tm = np.ascontiguousarray(to_move, dtype=np.int8)
+    n = b.shape[0]
+    if tm.shape[0] != n:
+        raise ValueError("to_move length")
+    if out is None:
+        out = np.empty((n, 4), np.uint64)
+    _ck(lib().sq_playouts(b.ctypes.data, tm.ctypes.data, n, int(playouts_per_leaf), int(stream_id),
+                          out.ctypes.data), "sq_playouts")
+    return out
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        return None
+    return int(getattr(stream, "cuda_stream", stream))
+
+
+def classify_dev(boards_ptr, n, flags_ptr, wm_ptr, wa_ptr, slot=0, stream=None):
+    _ck(lib().sq_classify_dev(slot, boards_ptr, n, flags_ptr, wm_ptr, wa_ptr, _stream_ptr(stream)),
+        "sq_classify_dev")
+
+
+def playouts_dev(leaves_ptr, to_move_ptr, n_leaves, playouts_per_leaf, out_ptr, leaf_index_base=0,
+                 stream_id=0, slot=0, stream=None):
+    """Device-resident form: raw device pointers (e.g. torch ``tensor.data_ptr()``); asynchronous."""
+    _ck(lib().sq_playouts_dev(slot, leaves_ptr, to_move_ptr, n_leaves, leaf_index_base,
+                              int(playouts_per_leaf), int(stream_id), out_ptr, _stream_ptr(stream)),
+        "sq_playouts_dev")
+
+
+def _scores(scores):
+    s = np.ascontiguousarray(scores, dtype=np.int8).reshape(-1)
+    if s.shape[0] != 25:
+        raise ValueError("scores must have 25 entries")
+    return s
+
+
+def alphabeta_root(positions, dialect, max_depth, scores):
+    """-> (values i32[n,25], best_value i32[n], best_mask u32[n], nodes u64[n])"""
+    b = as_boards(positions)
+    n = b.shape[0]
+    s = _scores(scores)
+    values = np.empty((n, 25), np.int32); bv = np.empty(n, np.int32)
+    bm = np.empty(n, np.uint32); nodes = np.empty(n, np.uint64)
+    _ck(lib().sq_alphabeta_root(b.ctypes.data, n, dialect, max_depth, s.ctypes.data, values.ctypes.data,
+                                bv.ctypes.data, bm.ctypes.data, nodes.ctypes.data), "sq_alphabeta_root")
+    return values, bv, bm, nodes
+
+
+def alphabeta_subtrees(subtrees, dialect, max_depth, scores):
+    """subtrees: SUBTREE array -> (value i32[n], nodes u64[n])"""
+    t = np.ascontiguousarray(subtrees, dtype=SUBTREE)
+    n = t.shape[0]
+    s = _scores(scores)
+    value = np.empty(n, np.int32); nodes = np.empty(n, np.uint64)
+    _ck(lib().sq_alphabeta_subtrees(t.ctypes.data, n, dialect, max_depth, s.ctypes.data,
+                                    value.ctypes.data, nodes.ctypes.data), "sq_alphabeta_subtrees")
+    return value, nodes
+
+
+def int32_peak(kind=2, reps=5, slot=0):
+    """Measured INT32 thread-ops/s: kind 0 LOP3, 1 IMAD, 2 both pipes interleaved."""
+    v = C.c_double()
+    _ck(lib().sq_int32_peak(slot, kind, reps, C.byref(v)), "sq_int32_peak")
+    return v.value
+
+
+def launch_count():
+    return int(lib().sq_launch_count())
+
+
+def last_playout_kernel_ms(slot=0):
+    v = C.c_float()
+    _ck(lib().sq_last_playout_kernel_ms(slot, C.byref(v)), "sq_last_playout_kernel_ms")
+    return v.value
+
+
+def debug_philox(counter, key):
+    c = np.ascontiguousarray(counter, dtype=np.uint32); k = np.ascontiguousarray(key, dtype=np.uint32)
+    out = np.empty(4, np.uint32)
+    _ck(lib().sq_debug_philox(c.ctypes.data, k.ctypes.data, out.ctypes.data), "sq_debug_philox")
+    return out

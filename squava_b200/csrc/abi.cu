@@ -1,0 +1,474 @@
+// abi.cu -- the extern "C" surface of libsquava_b200.so (see include/squava_b200.h).
+//
+// Host side only does plumbing: device contexts, staging buffers for the
+// host-pointer entry points, sharding over the devices named in sq_init(), and
+// launch accounting.  All arithmetic of the hot path lives in kernels.cuh /
+// alphabeta.cuh.  There is no CPU fallback anywhere in this file.
+#include "../../include/squava_b200.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+#include "alphabeta.cuh"
+#include "sq_tables.h"
+
+namespace {
+
+struct Device {
+    int id = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the most recent playout kernel
+    bool timed = false;
+    unsigned long long* counters = nullptr;     // [0] playout round counter
+    // staging for host-pointer calls (grown on demand)
+    void* buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t cap[6] = {0, 0, 0, 0, 0, 0};
+    int playout_blocks_per_sm = 0;
+    int ab_blocks_per_sm = 0;
+};
+
+std::mutex g_mu;
+std::vector<Device> g_dev;
+bool g_init = false;
+uint64_t g_seed = 0;
+std::atomic<uint64_t> g_launches{0};
+thread_local char t_err[512] = "";
+
+int fail_cuda(cudaError_t e, const char* what) {
+    snprintf(t_err, sizeof t_err, "%s: %s", what, cudaGetErrorString(e));
+    return SQ_ERR_CUDA;
+}
+#define CK(call)                                             \
+    do {                                                     \
+        cudaError_t e_ = (call);                             \
+        if (e_ != cudaSuccess) return fail_cuda(e_, #call);  \
+    } while (0)
+
+int reserve(Device& d, int which, size_t bytes) {
+    if (d.cap[which] >= bytes) return SQ_OK;
+    if (d.buf[which]) CK(cudaFree(d.buf[which]));
+    d.buf[which] = nullptr; d.cap[which] = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    CK(cudaMalloc(&d.buf[which], want));
+    d.cap[which] = want;
+    return SQ_OK;
+}
+
+// contiguous share of n units for slot k of m
+void share(int64_t n, int m, int k, int64_t& lo, int64_t& hi) {
+    lo = n * k / m; hi = n * (k + 1) / m;
+}
+
+int launch_classify(Device& d, const sq_board* boards, int64_t n, uint8_t* flags, int8_t* wm,
+                    int8_t* wa, cudaStream_t st) {
+    if (n <= 0) return SQ_OK;
+    int64_t blocks = (n + 255) / 256;
+    int64_t cap = (int64_t)d.sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    sq::classify_kernel<<<(unsigned)blocks, 256, 0, st>>>(boards, n, flags, wm, wa);
+    g_launches++;
+    CK(cudaGetLastError());
+    return SQ_OK;
+}
+
+int launch_playouts(Device& d, const sq_board* leaves, const int8_t* to_move, int64_t n_leaves,
+                    uint64_t leaf_index_base, uint64_t per_leaf, uint64_t stream_id,
+                    uint64_t* out, cudaStream_t st) {
+    if (n_leaves <= 0) return SQ_OK;
+    CK(cudaMemsetAsync(out, 0, (size_t)n_leaves * 4 * sizeof(uint64_t), st));
+    if (per_leaf == 0) return SQ_OK;
+    sq::PlayoutParams P;
+    P.leaves = leaves; P.to_move = to_move; P.n_leaves = n_leaves;
+    P.leaf_index_base = leaf_index_base; P.per_leaf = per_leaf;
+    uint64_t S = (per_leaf + sq::kItemQuota - 1) / sq::kItemQuota;
+    if (S > 0xffffffffull) { snprintf(t_err, sizeof t_err, "playouts_per_leaf too large"); return SQ_ERR_INVALID; }
+    P.items_per_leaf = (uint32_t)S;
+    P.quota_lo = (uint32_t)(per_leaf / S);
+    P.quota_extra = (uint32_t)(per_leaf % S);
+    P.key0 = (uint32_t)g_seed ^ (uint32_t)(stream_id >> 32);
+    P.key1 = (uint32_t)(g_seed >> 32);
+    P.ctr3 = (uint32_t)stream_id;
+    unsigned long long items = (unsigned long long)n_leaves * S;
+    P.n_rounds = (int64_t)((items + 31) / 32);
+    P.round_counter = d.counters;
+    P.out = reinterpret_cast<unsigned long long*>(out);
+    CK(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long), st));
+    const int warps_per_block = sq::kPlayoutThreads / 32;
+    int64_t blocks = (int64_t)d.sm_count * d.playout_blocks_per_sm;
+    int64_t need = (P.n_rounds + warps_per_block - 1) / warps_per_block;
+    if (blocks > need) blocks = need;
+    size_t smem = (size_t)sq::kMaxEmpty * sq::kPlayoutThreads * sizeof(uint32_t);
+    CK(cudaEventRecord(d.ev0, st));
+    sq::playout_kernel<<<(unsigned)blocks, sq::kPlayoutThreads, smem, st>>>(P);
+    g_launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(d.ev1, st));
+    d.timed = true;
+    return SQ_OK;
+}
+
+int check_ready() {
+    if (!g_init) { snprintf(t_err, sizeof t_err, "sq_init() has not succeeded"); return SQ_ERR_NOT_INIT; }
+    return SQ_OK;
+}
+int check_slot(int slot) {
+    int rc = check_ready();
+    if (rc) return rc;
+    if (slot < 0 || slot >= (int)g_dev.size()) { snprintf(t_err, sizeof t_err, "bad device slot %d", slot); return SQ_ERR_INVALID; }
+    return SQ_OK;
+}
+
+void destroy_all() {
+    for (auto& d : g_dev) {
+        if (d.id < 0) continue;
+        cudaSetDevice(d.id);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        for (int i = 0; i < 6; i++) if (d.buf[i]) cudaFree(d.buf[i]);
+        if (d.counters) cudaFree(d.counters);
+        if (d.ev0) cudaEventDestroy(d.ev0);
+        if (d.ev1) cudaEventDestroy(d.ev1);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    g_dev.clear();
+    g_init = false;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sq_abi_version(void) { return SQ_ABI_VERSION; }
+
+const char* sq_strerror(int status) {
+    switch (status) {
+    case SQ_OK: return "ok";
+    case SQ_ERR_INVALID: return "invalid argument";
+    case SQ_ERR_NOT_INIT: return "library not initialised (sq_init)";
+    case SQ_ERR_CUDA: return "CUDA runtime error";
+    case SQ_ERR_NO_DEVICE: return "no usable sm_100 CUDA device";
+    case SQ_ERR_UNSUPPORTED: return "unsupported combination";
+    case SQ_ERR_NOMEM: return "out of memory";
+    default: return "unknown status";
+    }
+}
+const char* sq_last_error(void) { return t_err; }
+
+int sq_init(const int* device_ids, int n_devices, uint64_t seed) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    destroy_all();
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        snprintf(t_err, sizeof t_err, "cudaGetDeviceCount: %s (count %d)", cudaGetErrorString(e), count);
+        cudaGetLastError();
+        return SQ_ERR_NO_DEVICE;
+    }
+    int one = 0;
+    if (!device_ids || n_devices <= 0) { device_ids = &one; n_devices = 1; }
+    sq::ScanTables tables;
+    sq::build_scan_tables(tables);
+    sq::AbTables ab_tables;
+    sq::build_ab_tables(ab_tables);
+    for (int k = 0; k < n_devices; k++) {
+        Device d;
+        d.id = device_ids[k];
+        if (d.id < 0 || d.id >= count) { destroy_all(); snprintf(t_err, sizeof t_err, "device id %d out of range", d.id); return SQ_ERR_INVALID; }
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, d.id));
+        if (prop.major != 10) {
+            destroy_all();
+            snprintf(t_err, sizeof t_err, "device %d is sm_%d%d; this library carries sm_100a code only", d.id, prop.major, prop.minor);
+            return SQ_ERR_NO_DEVICE;
+        }
+        d.sm_count = prop.multiProcessorCount;
+        CK(cudaSetDevice(d.id));
+        CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&d.ev0));
+        CK(cudaEventCreate(&d.ev1));
+        CK(cudaMalloc(&d.counters, 8 * sizeof(unsigned long long)));
+        CK(cudaMemset(d.counters, 0, 8 * sizeof(unsigned long long)));
+        CK(cudaMemcpyToSymbol(sq::c_scan, &tables, sizeof tables));
+        CK(cudaMemcpyToSymbol(sq::c_ab, &ab_tables, sizeof ab_tables));
+        size_t smem = (size_t)sq::kMaxEmpty * sq::kPlayoutThreads * sizeof(uint32_t);
+        CK(cudaFuncSetAttribute(sq::playout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.playout_blocks_per_sm, sq::playout_kernel,
+                                                         sq::kPlayoutThreads, smem));
+        if (d.playout_blocks_per_sm < 1) d.playout_blocks_per_sm = 1;
+        CK(sq::ab_configure(&d.ab_blocks_per_sm));
+        g_dev.push_back(d);
+    }
+    g_seed = seed;
+    g_init = true;
+    return SQ_OK;
+}
+
+void sq_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    destroy_all();
+}
+
+int sq_device_count(void) { return g_init ? (int)g_dev.size() : 0; }
+int sq_sm_count(int slot) {
+    if (check_slot(slot)) return 0;
+    return g_dev[slot].sm_count;
+}
+uint64_t sq_launch_count(void) { return g_launches.load(); }
+
+// ---- device-resident forms -------------------------------------------------
+int sq_classify_dev(int slot, const sq_board* boards, int64_t n, uint8_t* flags, int8_t* wm,
+                    int8_t* wa, void* stream) {
+    int rc = check_slot(slot);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && !boards)) { snprintf(t_err, sizeof t_err, "sq_classify_dev: null boards"); return SQ_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    Device& d = g_dev[slot];
+    CK(cudaSetDevice(d.id));
+    return launch_classify(d, boards, n, flags, wm, wa, (cudaStream_t)stream);
+}
+
+int sq_playouts_dev(int slot, const sq_board* leaves, const int8_t* to_move, int64_t n_leaves,
+                    uint64_t leaf_index_base, uint64_t per_leaf, uint64_t stream_id, uint64_t* out,
+                    void* stream) {
+    int rc = check_slot(slot);
+    if (rc) return rc;
+    if (n_leaves < 0 || (n_leaves > 0 && (!leaves || !to_move || !out))) {
+        snprintf(t_err, sizeof t_err, "sq_playouts_dev: null pointer"); return SQ_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    Device& d = g_dev[slot];
+    CK(cudaSetDevice(d.id));
+    return launch_playouts(d, leaves, to_move, n_leaves, leaf_index_base, per_leaf, stream_id, out,
+                           (cudaStream_t)stream);
+}
+
+// ---- host-buffer forms -------------------------------------------------------
+int sq_classify(const sq_board* boards, int64_t n, uint8_t* flags, int8_t* wm, int8_t* wa) {
+    int rc = check_ready();
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && !boards)) { snprintf(t_err, sizeof t_err, "sq_classify: null boards"); return SQ_ERR_INVALID; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    int m = (int)g_dev.size();
+    for (int k = 0; k < m; k++) {
+        Device& d = g_dev[k];
+        int64_t lo, hi; share(n, m, k, lo, hi);
+        int64_t cnt = hi - lo;
+        if (cnt <= 0) continue;
+        CK(cudaSetDevice(d.id));
+        if ((rc = reserve(d, 0, cnt * sizeof(sq_board)))) return rc;
+        if ((rc = reserve(d, 1, cnt * 3))) return rc;
+        uint8_t* dout = (uint8_t*)d.buf[1];
+        CK(cudaMemcpyAsync(d.buf[0], boards + lo, cnt * sizeof(sq_board), cudaMemcpyHostToDevice, d.stream));
+        rc = launch_classify(d, (const sq_board*)d.buf[0], cnt, dout, (int8_t*)dout + cnt, (int8_t*)dout + 2 * cnt, d.stream);
+        if (rc) return rc;
+        if (flags) CK(cudaMemcpyAsync(flags + lo, dout, cnt, cudaMemcpyDeviceToHost, d.stream));
+        if (wm) CK(cudaMemcpyAsync(wm + lo, dout + cnt, cnt, cudaMemcpyDeviceToHost, d.stream));
+        if (wa) CK(cudaMemcpyAsync(wa + lo, dout + 2 * cnt, cnt, cudaMemcpyDeviceToHost, d.stream));
+    }
+    for (int k = 0; k < m; k++) { CK(cudaSetDevice(g_dev[k].id)); CK(cudaStreamSynchronize(g_dev[k].stream)); }
+    return SQ_OK;
+}
+
+int sq_playouts(const sq_board* leaves, const int8_t* to_move, int64_t n_leaves,
+                uint64_t per_leaf, uint64_t stream_id, uint64_t (*out)[4]) {
+    int rc = check_ready();
+    if (rc) return rc;
+    if (n_leaves < 0 || (n_leaves > 0 && (!leaves || !to_move || !out))) {
+        snprintf(t_err, sizeof t_err, "sq_playouts: null pointer"); return SQ_ERR_INVALID;
+    }
+    for (int64_t i = 0; i < n_leaves; i++) {
+        if ((leaves[i].x & leaves[i].o) || ((leaves[i].x | leaves[i].o) >> 25) ||
+            (to_move[i] != 1 && to_move[i] != -1)) {
+            snprintf(t_err, sizeof t_err, "sq_playouts: leaf %lld is not a board / to_move not +-1", (long long)i);
+            return SQ_ERR_INVALID;
+        }
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    int m = (int)g_dev.size();
+    for (int k = 0; k < m; k++) {
+        Device& d = g_dev[k];
+        int64_t lo, hi; share(n_leaves, m, k, lo, hi);
+        int64_t cnt = hi - lo;
+        if (cnt <= 0) continue;
+        CK(cudaSetDevice(d.id));
+        if ((rc = reserve(d, 0, cnt * sizeof(sq_board)))) return rc;
+        if ((rc = reserve(d, 1, cnt))) return rc;
+        if ((rc = reserve(d, 2, cnt * 4 * sizeof(uint64_t)))) return rc;
+        CK(cudaMemcpyAsync(d.buf[0], leaves + lo, cnt * sizeof(sq_board), cudaMemcpyHostToDevice, d.stream));
+        CK(cudaMemcpyAsync(d.buf[1], to_move + lo, cnt, cudaMemcpyHostToDevice, d.stream));
+        rc = launch_playouts(d, (const sq_board*)d.buf[0], (const int8_t*)d.buf[1], cnt, (uint64_t)lo,
+                             per_leaf, stream_id, (uint64_t*)d.buf[2], d.stream);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(out + lo, d.buf[2], cnt * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.stream));
+    }
+    for (int k = 0; k < m; k++) { CK(cudaSetDevice(g_dev[k].id)); CK(cudaStreamSynchronize(g_dev[k].stream)); }
+    return SQ_OK;
+}
+
+int sq_alphabeta_root(const sq_board* positions, int64_t n, int dialect, int max_depth,
+                      const int8_t scores[25], int32_t (*values)[25], int32_t* best_value,
+                      uint32_t* best_mask, uint64_t* nodes) {
+    int rc = check_ready();
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!positions || !values)) || !scores) {
+        snprintf(t_err, sizeof t_err, "sq_alphabeta_root: null pointer"); return SQ_ERR_INVALID;
+    }
+    if (dialect != SQ_AB_ALPHABETA && dialect != SQ_AB_SQUAVATHR) {
+        snprintf(t_err, sizeof t_err, "sq_alphabeta_root: dialect %d has no root-move search in the reference", dialect);
+        return SQ_ERR_UNSUPPORTED;
+    }
+    if (max_depth < 0 || max_depth > sq::kAbMaxDepth) { snprintf(t_err, sizeof t_err, "max_depth out of range [0,%d]", sq::kAbMaxDepth); return SQ_ERR_INVALID; }
+    for (int64_t i = 0; i < n; i++)
+        if ((positions[i].x & positions[i].o) || ((positions[i].x | positions[i].o) >> 25)) {
+            snprintf(t_err, sizeof t_err, "sq_alphabeta_root: position %lld is not a board", (long long)i);
+            return SQ_ERR_INVALID;
+        }
+    std::lock_guard<std::mutex> lk(g_mu);
+    int m = (int)g_dev.size();
+    for (int k = 0; k < m; k++) {
+        Device& d = g_dev[k];
+        int64_t lo, hi; share(n, m, k, lo, hi);
+        int64_t cnt = hi - lo;
+        if (cnt <= 0) continue;
+        CK(cudaSetDevice(d.id));
+        if ((rc = reserve(d, 0, cnt * sizeof(sq_board)))) return rc;
+        if ((rc = reserve(d, 2, cnt * 25 * sizeof(int32_t)))) return rc;
+        if ((rc = reserve(d, 3, cnt * sizeof(unsigned long long)))) return rc;
+        CK(cudaMemcpyAsync(d.buf[0], positions + lo, cnt * sizeof(sq_board), cudaMemcpyHostToDevice, d.stream));
+        uint64_t launches = 0;
+        cudaError_t e = sq::ab_root_search(positions + lo, (const sq_board*)d.buf[0], cnt, dialect, max_depth, scores,
+                                           (int32_t*)d.buf[2], (unsigned long long*)d.buf[3],
+                                           d.sm_count * d.ab_blocks_per_sm, d.stream, &launches);
+        g_launches += launches;
+        if (e != cudaSuccess) return fail_cuda(e, "ab_root_search");
+        CK(cudaMemcpyAsync(values + lo, d.buf[2], cnt * 25 * sizeof(int32_t), cudaMemcpyDeviceToHost, d.stream));
+        if (nodes) CK(cudaMemcpyAsync(nodes + lo, d.buf[3], cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.stream));
+    }
+    for (int k = 0; k < m; k++) { CK(cudaSetDevice(g_dev[k].id)); CK(cudaStreamSynchronize(g_dev[k].stream)); }
+    // movekeeper.go:26-52 over each finished row (a 25-entry host reduction)
+    for (int64_t i = 0; i < n; i++) {
+        int mx = -20000; uint32_t mask = 0;
+        for (int c = 0; c < 25; c++) {
+            int32_t v = values[i][c];
+            if (v == SQ_NO_MOVE) continue;
+            if (v >= mx) { if (v > mx) { mx = v; mask = 0; } mask |= 1u << c; }
+        }
+        if (best_mask) best_mask[i] = mask;
+        if (best_value) best_value[i] = mask ? mx : 0;
+    }
+    return SQ_OK;
+}
+
+int sq_alphabeta_subtrees(const sq_subtree* subtrees, int64_t n, int dialect, int max_depth,
+                          const int8_t scores[25], int32_t* value, uint64_t* nodes) {
+    int rc = check_ready();
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!subtrees || !value)) || !scores) {
+        snprintf(t_err, sizeof t_err, "sq_alphabeta_subtrees: null pointer"); return SQ_ERR_INVALID;
+    }
+    if (dialect < 1 || dialect > 4) { snprintf(t_err, sizeof t_err, "unknown dialect %d", dialect); return SQ_ERR_INVALID; }
+    if (max_depth < 0 || max_depth > sq::kAbMaxDepth) { snprintf(t_err, sizeof t_err, "max_depth out of range [0,%d]", sq::kAbMaxDepth); return SQ_ERR_INVALID; }
+    for (int64_t i = 0; i < n; i++) {
+        const sq_subtree& s = subtrees[i];
+        bool ok = !(s.b.x & s.b.o) && !((s.b.x | s.b.o) >> 25) && s.last_cell >= 0 && s.last_cell < 25 &&
+                  (((s.b.x | s.b.o) >> s.last_cell) & 1u) && (s.side_to_move == 1 || s.side_to_move == -1) &&
+                  s.ply >= 0 && s.ply <= max_depth;
+        if (!ok) { snprintf(t_err, sizeof t_err, "sq_alphabeta_subtrees: subtree %lld malformed", (long long)i); return SQ_ERR_INVALID; }
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    int m = (int)g_dev.size();
+    for (int k = 0; k < m; k++) {
+        Device& d = g_dev[k];
+        int64_t lo, hi; share(n, m, k, lo, hi);
+        int64_t cnt = hi - lo;
+        if (cnt <= 0) continue;
+        CK(cudaSetDevice(d.id));
+        if ((rc = reserve(d, 0, cnt * sizeof(sq_subtree)))) return rc;
+        if ((rc = reserve(d, 2, cnt * sizeof(int32_t)))) return rc;
+        if ((rc = reserve(d, 3, cnt * sizeof(unsigned long long)))) return rc;
+        CK(cudaMemcpyAsync(d.buf[0], subtrees + lo, cnt * sizeof(sq_subtree), cudaMemcpyHostToDevice, d.stream));
+        uint64_t launches = 0;
+        cudaError_t e = sq::ab_subtree_search(subtrees + lo, (const sq_subtree*)d.buf[0], cnt, dialect, max_depth, scores,
+                                              (int32_t*)d.buf[2], (unsigned long long*)d.buf[3],
+                                              d.sm_count * d.ab_blocks_per_sm, d.stream, &launches);
+        g_launches += launches;
+        if (e != cudaSuccess) return fail_cuda(e, "ab_subtree_search");
+        CK(cudaMemcpyAsync(value + lo, d.buf[2], cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, d.stream));
+        if (nodes) CK(cudaMemcpyAsync(nodes + lo, d.buf[3], cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.stream));
+    }
+    for (int k = 0; k < m; k++) { CK(cudaSetDevice(g_dev[k].id)); CK(cudaStreamSynchronize(g_dev[k].stream)); }
+    return SQ_OK;
+}
+
+// ---- measurement helpers -------------------------------------------------------
+int sq_int32_peak(int slot, int kind, int reps, double* ops_per_s) {
+    int rc = check_slot(slot);
+    if (rc) return rc;
+    if (!ops_per_s || kind < 0 || kind > 2) return SQ_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(g_mu);
+    Device& d = g_dev[slot];
+    CK(cudaSetDevice(d.id));
+    if ((rc = reserve(d, 4, 256))) return rc;
+    const int iters = 4096, threads = 1024;
+    const int blocks = d.sm_count * 2;
+    double best = 0;
+    if (reps < 1) reps = 1;
+    for (int r = 0; r < reps + 1; r++) {
+        CK(cudaEventRecord(d.ev0, d.stream));
+        uint32_t* o = (uint32_t*)d.buf[4];
+        if (kind == 0) sq::int32_peak_kernel<0><<<blocks, threads, 0, d.stream>>>(o, 12345u + r, iters);
+        else if (kind == 1) sq::int32_peak_kernel<1><<<blocks, threads, 0, d.stream>>>(o, 12345u + r, iters);
+        else sq::int32_peak_kernel<2><<<blocks, threads, 0, d.stream>>>(o, 12345u + r, iters);
+        g_launches++;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(d.ev1, d.stream));
+        CK(cudaEventSynchronize(d.ev1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+        double ops = (double)blocks * threads * (double)iters * 16.0 * 8.0;
+        if (r > 0 && ms > 0 && ops / (ms * 1e-3) > best) best = ops / (ms * 1e-3);
+    }
+    d.timed = false;
+    *ops_per_s = best;
+    return SQ_OK;
+}
+
+int sq_last_playout_kernel_ms(int slot, float* ms) {
+    int rc = check_slot(slot);
+    if (rc) return rc;
+    if (!ms) return SQ_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(g_mu);
+    Device& d = g_dev[slot];
+    if (!d.timed) { snprintf(t_err, sizeof t_err, "no playout kernel has run on slot %d", slot); return SQ_ERR_INVALID; }
+    CK(cudaSetDevice(d.id));
+    CK(cudaEventSynchronize(d.ev1));
+    CK(cudaEventElapsedTime(ms, d.ev0, d.ev1));
+    return SQ_OK;
+}
+
+int sq_debug_philox(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]) {
+    int rc = check_ready();
+    if (rc) return rc;
+    if (!counter || !key || !out) return SQ_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(g_mu);
+    Device& d = g_dev[0];
+    CK(cudaSetDevice(d.id));
+    if ((rc = reserve(d, 4, 256))) return rc;
+    uint32_t* b = (uint32_t*)d.buf[4];
+    CK(cudaMemcpyAsync(b, counter, 16, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(b + 4, key, 8, cudaMemcpyHostToDevice, d.stream));
+    sq::philox_debug_kernel<<<1, 1, 0, d.stream>>>(b, b + 4, b + 8);
+    g_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, b + 8, 16, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    return SQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,635 @@
+// alphabeta.cuh -- fixed-depth alpha-beta as a GPU batch of independent subtrees.
+//
+// What is computed: for every root move (or explicit subtree) the value the
+// reference's sequential search returns.  Every reference entry point searches
+// with a window that contains all reachable values, so
+// that value is the plain minimax value of the dialect's tree and does not
+// depend on visiting order or on how bounds are shared.  That freedom is what
+// the GPU uses:
+//   1. the top 1-3 plies under each root move are EXPANDED breadth-first into
+//      nodes (kernels ab_roots / ab_expand); every node has a value slot and a
+//      count of unfinished children;
+//   2. the deepest nodes are UNITS: one thread runs a sequential, explicit-stack
+//      alpha-beta over each (kernel ab_dfs, lanes pull units from a queue);
+//   3. a finished node folds its value into its parent's slot (atomicMin/Max)
+//      and the last child to finish carries the parent's value further up;
+//   4. a unit's window is tightened by the current slot values of its ancestors
+//      (alpha from MAX ancestors, beta from MIN ancestors), re-read whenever the
+//      unit's own root frame gets a child back.
+//
+// Dialects (SQ_AB_*): 1 src/alphabeta (delayed evaluation, carried value is the
+// previous delta only), 2 squavathr (evaluate at entry, cumulative, no2 /
+// noMiddle2 penalties), 3/4 opening3 / opening2 (evaluate at entry, cumulative,
+// orderedCells child order).
+#pragma once
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../include/squava_b200.h"
+#include "sq_device.cuh"
+#include "sq_tables.h"
+
+namespace sq {
+
+constexpr int kAbMaxDepth = 24;
+constexpr int kAbThreads = 128;
+constexpr int kWin = 10000;
+
+struct AbTables {
+    uint32_t quads[25][8];     // quads through each cell (API layout), 0-terminated
+    uint32_t triplets[25][12]; // triplets through each cell
+    uint8_t n_quads[25], n_triplets[25];
+    uint32_t no2[25][2];        // squavathr.go:305-311 triplets containing the cell (0 = none)
+    uint32_t nomid_quad[25];    // squavathr.go:297-302: quad in which the cell is a middle cell
+    uint32_t nomid_other[25];   // ... and the bit of the other middle cell
+    uint8_t order[25];          // opening3.go:328-361: k-th child cell
+    uint8_t rank[25];           // inverse
+};
+__constant__ AbTables c_ab;  // copied to shared memory by each kernel: lanes index it by different cells
+
+inline void build_ab_tables(AbTables& t) {
+    memset(&t, 0, sizeof t);
+    ScanTables s;
+    build_scan_tables(s);
+    for (int c = 0; c < 25; c++) {
+        for (int i = 0; i < 28; i++)
+            if (s.ab_quads[i] >> c & 1u) t.quads[c][t.n_quads[c]++] = s.ab_quads[i];
+        for (int i = 0; i < 48; i++)
+            if (s.ab_triplets[i] >> c & 1u) t.triplets[c][t.n_triplets[c]++] = s.ab_triplets[i];
+    }
+    // squavathr.go:305-311 -- the four corner-cutting diagonals of length 3
+    const int no2[4][3] = {{10, 6, 2}, {2, 8, 14}, {22, 18, 14}, {22, 16, 10}};
+    for (auto& tr : no2) {
+        uint32_t m = (1u << tr[0]) | (1u << tr[1]) | (1u << tr[2]);
+        for (int c : tr) { if (!t.no2[c][0]) t.no2[c][0] = m; else t.no2[c][1] = m; }
+    }
+    // squavathr.go:297-302 -- the four diagonals of length 4; [1] and [2] are the middles
+    const int nm[4][4] = {{15, 11, 7, 3}, {5, 11, 17, 23}, {1, 7, 13, 19}, {9, 13, 17, 21}};
+    for (auto& q : nm) {
+        uint32_t m = (1u << q[0]) | (1u << q[1]) | (1u << q[2]) | (1u << q[3]);
+        t.nomid_quad[q[1]] = m; t.nomid_other[q[1]] = 1u << q[2];
+        t.nomid_quad[q[2]] = m; t.nomid_other[q[2]] = 1u << q[1];
+    }
+    // opening3.go:328-361: inner-ring corners, centre, inner-ring edges, then the outer
+    // ring's edge triples (top, left, right, bottom), corners last
+    const uint8_t ord[25] = {6, 8, 16, 18, 12, 7, 11, 13, 17, 1, 2, 3, 5, 10, 15, 9, 14, 19, 21, 22, 23, 0, 4, 20, 24};
+    for (int k = 0; k < 25; k++) { t.order[k] = ord[k]; t.rank[ord[k]] = (uint8_t)k; }
+}
+
+struct AbNode {
+    uint32_t x, o;       // API-layout masks, the pending move already on the board
+    int32_t carried;     // boardValue argument
+    int8_t cell;         // pending (last) move
+    int8_t ply;
+    int8_t side;         // side to move at this node
+    int8_t split;        // further plies to expand breadth-first; 0 = DFS unit
+    int32_t parent;      // node index, or -1 - output index
+    int32_t group;       // position / subtree index the evaluator count is charged to
+};
+
+struct AbRun {
+    AbNode* nodes;
+    int* value;                      // slot values
+    int* pending;                    // unfinished children
+    int* units;                      // indices of DFS units
+    unsigned int* counters;          // [0] n_nodes [1] n_units [2] queue head
+    int* out;                        // final values
+    unsigned long long* node_count;  // evaluator calls per group
+    int node_capacity;
+    int max_depth;
+    int sentinel;        // |value| of a node with no legal move: 20000, or 10000 (opening2)
+    int win_lo, win_hi;  // the dialect's root window
+    int8_t scores[25];
+};
+
+// ---- evaluators -----------------------------------------------------------------
+struct Eval { bool terminal; int value; };
+
+// The lines-through-(cell) part common to every dialect (alphabeta.go:123-147,
+// squavathr.go:317-341, opening3.go:138-164): own = mask of the colour standing
+// on `cell`, opp = the other colour, sign = +1 if own is X.  A sum of +-3 over a
+// quad through `cell` can only be three of `own` and one empty cell.
+__device__ __forceinline__ Eval eval_lines(const AbTables& T, uint32_t own, uint32_t opp, int cell,
+                                           int sign, int ply) {
+    Eval e; e.terminal = false; e.value = 0;
+    int threes = 0; bool four = false, three = false;
+    const int nq = T.n_quads[cell];
+    for (int k = 0; k < nq; k++) {
+        uint32_t q = T.quads[cell][k];
+        uint32_t mine = own & q;
+        four |= (mine == q);
+        threes += (__popc(mine) == 3 && (opp & q) == 0) ? 1 : 0;
+    }
+    const int nt = T.n_triplets[cell];
+    for (int k = 0; k < nt; k++) {
+        uint32_t t = T.triplets[cell][k];
+        three |= ((own & t) == t);
+    }
+    if (four) { e.terminal = true; e.value = sign * (kWin - ply); }        // four beats three
+    else if (three) { e.terminal = true; e.value = -sign * (kWin - ply); }
+    else e.value = sign * 30 * threes;
+    return e;
+}
+
+// squavathr.go:343-371: extra terms for the mark on `cell`
+__device__ __forceinline__ int eval_penalties(const AbTables& T, uint32_t own, uint32_t opp, int cell, int sign) {
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        uint32_t t = T.no2[cell][k];
+        if (t && __popc(own & t) == 2 && (opp & t) == 0) v -= sign * 100;
+    }
+    uint32_t q = T.nomid_quad[cell];
+    if (q && (own & T.nomid_other[cell])) {
+        if (__popc(own & q) - __popc(opp & q) == 2) v -= sign * 100;
+    }
+    return v;
+}
+
+// squavathr.go:244: deltaValue on the board BEFORE the root mark is placed -- only
+// the three-of-four sums of the other cells can contribute.
+__device__ __forceinline__ int eval_unmarked(const AbTables& T, uint32_t x, uint32_t o, int cell) {
+    int v = 0;
+    const int nq = T.n_quads[cell];
+    for (int k = 0; k < nq; k++) {
+        uint32_t q = T.quads[cell][k];
+        int sum = __popc(x & q) - __popc(o & q);
+        if (sum == 3 || sum == -3) v += sum * 10;
+    }
+    return v;
+}
+
+__device__ __forceinline__ void load_tables(AbTables& dst) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_ab);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&dst);
+    for (int i = threadIdx.x; i < (int)(sizeof(AbTables) / 4); i += blockDim.x) d[i] = src[i];
+    __syncthreads();
+}
+
+// ---- node bookkeeping ---------------------------------------------------------------
+__device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+// A finished node hands its value to its parent; the last child to finish carries on upward.
+__device__ void ab_complete(const AbRun& R, int node, int value) {
+    for (;;) {
+        int parent = R.nodes[node].parent;
+        if (parent < 0) { R.out[-1 - parent] = value; return; }
+        if (R.nodes[parent].side > 0) atomicMax(&R.value[parent], value);
+        else atomicMin(&R.value[parent], value);
+        __threadfence();
+        int old = atomicSub(&R.pending[parent], 1);
+        if (old != 1) return;
+        __threadfence();
+        value = ld_volatile(&R.value[parent]);
+        node = parent;
+    }
+}
+
+// alpha from the MAX ancestors' slots, beta from the MIN ancestors' slots
+__device__ __forceinline__ void ab_bounds(const AbRun& R, int node, int& alpha, int& beta) {
+    int p = R.nodes[node].parent;
+    while (p >= 0) {
+        int v = ld_volatile(&R.value[p]);
+        if (R.nodes[p].side > 0) alpha = max(alpha, v); else beta = min(beta, v);
+        p = R.nodes[p].parent;
+    }
+}
+
+__device__ __forceinline__ int ab_new_node(const AbRun& R, const AbNode& n) {
+    unsigned int idx = atomicAdd(&R.counters[0], 1u);
+    if (idx >= (unsigned)R.node_capacity) return -1;  // cannot happen: capacity is an exact bound
+    R.nodes[idx] = n;
+    R.value[idx] = n.side > 0 ? -R.sentinel : R.sentinel;
+    R.pending[idx] = 0;
+    if (n.split == 0) { unsigned int u = atomicAdd(&R.counters[1], 1u); R.units[u] = (int)idx; }
+    return (int)idx;
+}
+
+// Resolve a node on entry, or report that it has children.  Returns true if `value`
+// is final.  DIALECT 1 (alphabeta.go:165-223): the pending move is evaluated with the
+// FIRST child's mark already on the board and a stop returns from there; DIALECTS 2-4
+// evaluate it once at entry (squavathr.go:393-398, opening3.go:138-175).
+template <int DIALECT>
+__device__ __forceinline__ bool ab_enter(const AbTables& T, const AbRun& R, const AbNode& n, int& value,
+                                         int& carried_down) {
+    const uint32_t empties = kFull25 & ~(n.x | n.o);
+    const bool pend_is_x = (n.x >> n.cell) & 1u;
+    const int sign = pend_is_x ? 1 : -1;
+    if (DIALECT == 1) {
+        carried_down = n.carried;
+        if (!empties) { value = n.side > 0 ? -R.sentinel : R.sentinel; return true; }
+        uint32_t first = empties & (0u - empties);
+        uint32_t x = n.x | (n.side > 0 ? first : 0u), o = n.o | (n.side > 0 ? 0u : first);
+        Eval e = eval_lines(T, pend_is_x ? x : o, pend_is_x ? o : x, n.cell, sign, n.ply);
+        if (e.terminal) { value = e.value; return true; }
+        if (n.ply >= R.max_depth) { value = e.value + sign * R.scores[n.cell] + n.carried; return true; }
+        return false;
+    } else {
+        Eval e = eval_lines(T, pend_is_x ? n.x : n.o, pend_is_x ? n.o : n.x, n.cell, sign, n.ply);
+        if (e.terminal) { value = e.value; return true; }
+        int d = e.value + sign * R.scores[n.cell];
+        if (DIALECT == 2) d += eval_penalties(T, pend_is_x ? n.x : n.o, pend_is_x ? n.o : n.x, n.cell, sign);
+        if (n.ply == R.max_depth) { value = d + n.carried; return true; }
+        carried_down = n.carried + d;
+        if (!empties) { value = n.side > 0 ? -R.sentinel : R.sentinel; return true; }
+        return false;
+    }
+}
+
+// ---- kernels ------------------------------------------------------------------------
+// Root moves: ChooseMove's loop body, alphabeta.go:98-110 / squavathr.go:241-253.
+// One thread per (position, cell).  split[i] = breadth-first plies below the root move.
+template <int DIALECT>
+__global__ void __launch_bounds__(kAbThreads)
+ab_roots_kernel(AbRun R, const sq_board* __restrict__ pos, const int8_t* __restrict__ split, int n) {
+    __shared__ AbTables T;
+    load_tables(T);
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * 25) return;
+    int i = t / 25, c = t % 25;
+    uint32_t x = pos[i].x & kFull25, o = pos[i].o & kFull25, bit = 1u << c;
+    if ((x | o) & bit) { R.out[t] = INT32_MIN; return; }
+    atomicAdd(&R.node_count[i], 1ull);
+    AbNode nd;
+    nd.x = x | bit; nd.o = o; nd.cell = (int8_t)c; nd.ply = 1; nd.side = -1;
+    nd.split = split[i]; nd.parent = -1 - t; nd.group = i;
+    if (DIALECT == 1) {
+        Eval e = eval_lines(T, x | bit, o, c, 1, 0);                 // alphabeta.go:101-102
+        if (e.terminal) { R.out[t] = e.value; return; }
+        int v = e.value + R.scores[c];
+        if (0 >= R.max_depth) { R.out[t] = v; return; }
+        nd.carried = v;
+    } else {
+        int v = eval_unmarked(T, x, o, c);                             // squavathr.go:244
+        if (0 == R.max_depth) { R.out[t] = v; return; }             // :245-247
+        nd.carried = v;
+    }
+    ab_new_node(R, nd);
+}
+
+// Explicit subtrees: the caller's node is the level-0 node.
+__global__ void __launch_bounds__(kAbThreads)
+ab_subtree_nodes_kernel(AbRun R, const sq_subtree* __restrict__ st, const int8_t* __restrict__ split, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    AbNode nd;
+    nd.x = st[i].b.x & kFull25; nd.o = st[i].b.o & kFull25;
+    nd.carried = st[i].carried; nd.cell = st[i].last_cell; nd.ply = st[i].ply;
+    nd.side = st[i].side_to_move; nd.split = split[i]; nd.parent = -1 - i; nd.group = i;
+    ab_new_node(R, nd);
+}
+
+// Breadth-first expansion of nodes [lo, hi) that still have split > 0.
+template <int DIALECT>
+__global__ void __launch_bounds__(kAbThreads)
+ab_expand_kernel(AbRun R, int lo, int hi) {
+    __shared__ AbTables T;
+    load_tables(T);
+    int idx = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= hi) return;
+    const AbNode n = R.nodes[idx];
+    if (n.split <= 0) return;
+    int value = 0, carried_down = 0;
+    unsigned long long evals = 1;
+    if (ab_enter<DIALECT>(T, R, n, value, carried_down)) {
+        atomicAdd(&R.node_count[n.group], evals);
+        ab_complete(R, idx, value);
+        return;
+    }
+    uint32_t empties = kFull25 & ~(n.x | n.o);
+    R.pending[idx] = __popc(empties);
+    __threadfence();
+    const bool pend_is_x = (n.x >> n.cell) & 1u;
+    const int sign = pend_is_x ? 1 : -1;
+    while (empties) {
+        uint32_t bit = empties & (0u - empties);
+        empties ^= bit;
+        AbNode c;
+        c.x = n.x | (n.side > 0 ? bit : 0u);
+        c.o = n.o | (n.side > 0 ? 0u : bit);
+        c.cell = (int8_t)(__ffs(bit) - 1);
+        c.ply = n.ply + 1;
+        c.side = -n.side;
+        c.split = n.split - 1;
+        c.parent = idx;
+        c.group = n.group;
+        if (DIALECT == 1) {   // the parent's move re-evaluated with this child's mark on
+            Eval e = eval_lines(T, pend_is_x ? c.x : c.o, pend_is_x ? c.o : c.x, n.cell, sign, n.ply);
+            c.carried = e.value + sign * R.scores[n.cell];
+            evals++;
+        } else {
+            c.carried = carried_down;
+        }
+        ab_new_node(R, c);
+    }
+    atomicAdd(&R.node_count[n.group], evals);
+}
+
+// Sequential alpha-beta per lane over the queued units.
+template <int DIALECT>
+__global__ void __launch_bounds__(kAbThreads)
+ab_dfs_kernel(AbRun R, int n_units) {
+    __shared__ AbTables T;
+    load_tables(T);
+    constexpr bool kOrdered = DIALECT >= 3;   // children in orderedCells order
+    constexpr int kFrames = kAbMaxDepth + 2;
+    uint32_t f_moves[kFrames], f_cur[kFrames];
+    short f_value[kFrames], f_alpha[kFrames], f_beta[kFrames];
+    int f_carried[kFrames];
+    signed char f_cell[kFrames];
+
+    int sp = -1, unit = -1, base_ply = 0, base_side = 1, group = 0;
+    uint32_t x = 0, o = 0, emp = 0;       // emp: empty cells in child-order space
+    unsigned long long evals = 0;
+
+    auto order_mask = [&](uint32_t cells) -> uint32_t {  // API layout -> child-order space
+        if (!kOrdered) return cells;
+        uint32_t m = 0;
+        while (cells) { int c = __ffs(cells) - 1; cells &= cells - 1; m |= 1u << T.rank[c]; }
+        return m;
+    };
+
+    for (;;) {
+        if (sp < 0) {
+            unsigned int u = atomicAdd(&R.counters[2], 1u);
+            if (u >= (unsigned)n_units) break;
+            unit = R.units[u];
+            const AbNode n = R.nodes[unit];
+            int alpha = R.win_lo, beta = R.win_hi;
+            ab_bounds(R, unit, alpha, beta);
+            if (alpha >= beta) {   // already cut off: hand up a value that changes nothing
+                ab_complete(R, unit, n.side > 0 ? -30000 : 30000);
+                continue;
+            }
+            int value = 0, carried_down = 0;
+            evals = 1; group = n.group;
+            if (ab_enter<DIALECT>(T, R, n, value, carried_down)) {
+                atomicAdd(&R.node_count[group], evals);
+                ab_complete(R, unit, value);
+                continue;
+            }
+            x = n.x; o = n.o; base_ply = n.ply; base_side = n.side;
+            emp = order_mask(kFull25 & ~(x | o));
+            sp = 0;
+            f_moves[0] = emp; f_cur[0] = 0;
+            f_value[0] = (short)(n.side > 0 ? -R.sentinel : R.sentinel);
+            f_alpha[0] = (short)alpha; f_beta[0] = (short)beta;
+            f_carried[0] = carried_down; f_cell[0] = n.cell;
+            continue;
+        }
+
+        const int ply = base_ply + sp;
+        const int side = (sp & 1) ? -base_side : base_side;
+        int ret;
+        bool returning;     // a child of frame sp has produced `ret`
+        if (f_moves[sp] == 0) {
+            ret = f_value[sp]; sp--; returning = true;    // this node is done: back to its parent
+        } else {
+            uint32_t kbit = f_moves[sp] & (0u - f_moves[sp]);
+            f_moves[sp] ^= kbit;
+            int cell = kOrdered ? T.order[__ffs(kbit) - 1] : (__ffs(kbit) - 1);
+            uint32_t bit = 1u << cell;
+            if (side > 0) x |= bit; else o |= bit;
+            emp &= ~kbit;
+            f_cur[sp] = kbit | ((uint32_t)cell << 25);
+            evals++;
+            if (DIALECT == 1) {
+                // evaluate the move that led here, the child's mark being on the board
+                const int sign = -side, pc = f_cell[sp];
+                Eval e = eval_lines(T, sign > 0 ? x : o, sign > 0 ? o : x, pc, sign, ply);
+                int d = e.value + sign * R.scores[pc];
+                if (e.terminal || ply >= R.max_depth) {
+                    ret = e.terminal ? e.value : d + f_carried[sp];
+                    if (side > 0) x &= ~bit; else o &= ~bit;      // the node itself returns
+                    emp |= kbit;
+                    sp--; returning = true;
+                } else {
+                    sp++;
+                    f_moves[sp] = emp; f_cur[sp] = 0;
+                    f_value[sp] = (short)(side > 0 ? R.sentinel : -R.sentinel);   // child is the other side
+                    f_alpha[sp] = f_alpha[sp - 1]; f_beta[sp] = f_beta[sp - 1];
+                    f_carried[sp] = d; f_cell[sp] = (signed char)cell;
+                    returning = false;
+                }
+            } else {
+                // evaluate the child at its entry
+                Eval e = eval_lines(T, side > 0 ? x : o, side > 0 ? o : x, cell, side, ply + 1);
+                int d = e.value + side * R.scores[cell];
+                if (DIALECT == 2 && !e.terminal) d += eval_penalties(T, side > 0 ? x : o, side > 0 ? o : x, cell, side);
+                if (e.terminal || ply + 1 == R.max_depth) {
+                    ret = e.terminal ? e.value : d + f_carried[sp];
+                    returning = true;                               // the child returned at once
+                } else {
+                    sp++;
+                    f_moves[sp] = emp; f_cur[sp] = 0;
+                    f_value[sp] = (short)(side > 0 ? R.sentinel : -R.sentinel);
+                    f_alpha[sp] = f_alpha[sp - 1]; f_beta[sp] = f_beta[sp - 1];
+                    f_carried[sp] = f_carried[sp - 1] + d; f_cell[sp] = (signed char)cell;
+                    returning = false;
+                }
+            }
+        }
+        // hand `ret` to frame sp; a cutoff there hands that frame's value further up
+        while (returning) {
+            if (sp < 0) {
+                atomicAdd(&R.node_count[group], evals);
+                ab_complete(R, unit, ret);
+                break;
+            }
+            const int s = (sp & 1) ? -base_side : base_side;
+            const uint32_t cur = f_cur[sp];
+            const uint32_t bit = 1u << (cur >> 25), kbit = cur & kFull25;
+            if (s > 0) x &= ~bit; else o &= ~bit;
+            emp |= kbit;
+            int v = f_value[sp], a = f_alpha[sp], b = f_beta[sp];
+            if (s > 0) { v = max(v, ret); a = max(a, v); } else { v = min(v, ret); b = min(b, v); }
+            if (sp == 0) ab_bounds(R, unit, a, b);      // siblings may have tightened the window
+            f_value[sp] = (short)v; f_alpha[sp] = (short)a; f_beta[sp] = (short)b;
+            if (b <= a) { ret = v; sp--; } else returning = false;
+        }
+    }
+}
+
+// ---- host orchestration ---------------------------------------------------------------
+inline cudaError_t ab_configure(int* blocks_per_sm) {
+    int b1 = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, ab_dfs_kernel<1>, kAbThreads, 0);
+    if (e != cudaSuccess) return e;
+    *blocks_per_sm = b1 < 1 ? 1 : b1;
+    return cudaSuccess;
+}
+
+// Breadth-first plies to expand under a node with `empties` empty cells and `rem`
+// plies of search left, so that a DFS unit stays small enough for the tail of the
+// launch to be short.  Override with SQ_AB_SPLIT=<0..3>.
+inline int ab_choose_split(int empties, int rem) {
+    const char* env = getenv("SQ_AB_SPLIT");
+    const int forced = (env && *env) ? atoi(env) : -1;
+    int split;
+    if (forced >= 0) split = forced;
+    else {
+        // rough size of the subtree: product of the branching factors, damped
+        double est = 1.0;
+        for (int k = 0; k < rem && empties - k > 0; k++) est *= 0.55 * (empties - k) + 0.45;
+        split = est > 3e7 ? 3 : est > 3e5 ? 2 : est > 3e3 ? 1 : 0;
+    }
+    if (split > rem - 1) split = rem - 1 < 0 ? 0 : rem - 1;
+    if (split > empties - 1) split = empties - 1 < 0 ? 0 : empties - 1;
+    if (split > 3) split = 3;
+    return split;
+}
+
+struct AbWork {   // device allocations of one chunk
+    AbNode* nodes = nullptr; int* value = nullptr; int* pending = nullptr; int* units = nullptr;
+    unsigned int* counters = nullptr; int8_t* split = nullptr;
+};
+
+inline void ab_free(AbWork& w, cudaStream_t st) {
+    if (w.nodes) cudaFreeAsync(w.nodes, st);
+    if (w.value) cudaFreeAsync(w.value, st);
+    if (w.pending) cudaFreeAsync(w.pending, st);
+    if (w.units) cudaFreeAsync(w.units, st);
+    if (w.counters) cudaFreeAsync(w.counters, st);
+    if (w.split) cudaFreeAsync(w.split, st);
+    w = AbWork();
+}
+
+#define SQ_AB_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ab_free(w, st); return e_; } } while (0)
+
+template <int DIALECT>
+cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n, const int8_t* h_split,
+                         long long capacity, int grid_cap, cudaStream_t st, uint64_t* launches) {
+    SQ_AB_CK(cudaMallocAsync(&w.nodes, sizeof(AbNode) * capacity, st));
+    SQ_AB_CK(cudaMallocAsync(&w.value, sizeof(int) * capacity, st));
+    SQ_AB_CK(cudaMallocAsync(&w.pending, sizeof(int) * capacity, st));
+    SQ_AB_CK(cudaMallocAsync(&w.units, sizeof(int) * capacity, st));
+    SQ_AB_CK(cudaMallocAsync(&w.counters, sizeof(unsigned int) * 8, st));
+    SQ_AB_CK(cudaMallocAsync(&w.split, n, st));
+    SQ_AB_CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned int) * 8, st));
+    SQ_AB_CK(cudaMemcpyAsync(w.split, h_split, n, cudaMemcpyHostToDevice, st));
+    R.nodes = w.nodes; R.value = w.value; R.pending = w.pending; R.units = w.units;
+    R.counters = w.counters; R.node_capacity = (int)capacity;
+    if (roots) {
+        int threads = n * 25;
+        ab_roots_kernel<DIALECT><<<(threads + kAbThreads - 1) / kAbThreads, kAbThreads, 0, st>>>(
+            R, (const sq_board*)d_in, w.split, n);
+    } else {
+        ab_subtree_nodes_kernel<<<(n + kAbThreads - 1) / kAbThreads, kAbThreads, 0, st>>>(
+            R, (const sq_subtree*)d_in, w.split, n);
+    }
+    (*launches)++;
+    SQ_AB_CK(cudaGetLastError());
+    unsigned int h_counters[3] = {0, 0, 0};
+    int lo = 0;
+    for (int level = 0; level < 3; level++) {
+        SQ_AB_CK(cudaMemcpyAsync(h_counters, w.counters, sizeof h_counters, cudaMemcpyDeviceToHost, st));
+        SQ_AB_CK(cudaStreamSynchronize(st));
+        int hi = (int)h_counters[0];
+        if (hi <= lo) break;
+        ab_expand_kernel<DIALECT><<<(hi - lo + kAbThreads - 1) / kAbThreads, kAbThreads, 0, st>>>(R, lo, hi);
+        (*launches)++;
+        SQ_AB_CK(cudaGetLastError());
+        lo = hi;
+    }
+    SQ_AB_CK(cudaMemcpyAsync(h_counters, w.counters, sizeof h_counters, cudaMemcpyDeviceToHost, st));
+    SQ_AB_CK(cudaStreamSynchronize(st));
+    int n_units = (int)h_counters[1];
+    if (n_units > 0) {
+        long long blocks = ((long long)n_units + kAbThreads - 1) / kAbThreads;
+        if (blocks > grid_cap) blocks = grid_cap;
+        ab_dfs_kernel<DIALECT><<<(unsigned)blocks, kAbThreads, 0, st>>>(R, n_units);
+        (*launches)++;
+        SQ_AB_CK(cudaGetLastError());
+    }
+    ab_free(w, st);
+    return cudaSuccess;
+}
+
+inline cudaError_t ab_dispatch(int dialect, AbRun R, AbWork& w, const void* d_in, bool roots, int n,
+                               const int8_t* h_split, long long capacity, int grid_cap, cudaStream_t st,
+                               uint64_t* launches) {
+    switch (dialect) {
+    case 1: return ab_run_chunk<1>(R, w, d_in, roots, n, h_split, capacity, grid_cap, st, launches);
+    case 2: return ab_run_chunk<2>(R, w, d_in, roots, n, h_split, capacity, grid_cap, st, launches);
+    default: return ab_run_chunk<3>(R, w, d_in, roots, n, h_split, capacity, grid_cap, st, launches);
+    }
+}
+
+inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t scores[25]) {
+    memset(&R, 0, sizeof R);
+    R.max_depth = dialect == 2 ? max_depth : max_depth;
+    R.sentinel = dialect == 4 ? kWin : 2 * kWin;
+    R.win_lo = dialect >= 3 ? -kWin : -2 * kWin;
+    R.win_hi = dialect >= 3 ? kWin : 2 * kWin;
+    memcpy(R.scores, scores, 25);
+}
+
+constexpr long long kAbChunkNodes = 24ll << 20;   // node slots per chunk (about 1 GB of workspace)
+
+// worst-case node count below one level-0 node with e empties and `split` expanded plies
+inline long long ab_node_bound(int e, int split) {
+    long long total = 1, layer = 1;
+    for (int k = 0; k < split; k++) { layer *= (e - k > 0 ? e - k : 0); total += layer; }
+    return total;
+}
+
+// positions: h_pos (host copy, for sizing) and d_pos (device).  d_values [n][25], d_nodes [n].
+inline cudaError_t ab_root_search(const sq_board* h_pos, const sq_board* d_pos, long long n, int dialect,
+                                  int max_depth, const int8_t scores[25], int32_t* d_values,
+                                  unsigned long long* d_nodes, int grid_cap, cudaStream_t st,
+                                  uint64_t* launches) {
+    AbRun R; AbWork w;
+    ab_fill_run(R, dialect, dialect == 2 ? max_depth - 1 : max_depth, scores);   // squavathr.go:239
+    cudaError_t e = cudaMemsetAsync(d_nodes, 0, sizeof(unsigned long long) * n, st);
+    if (e != cudaSuccess) return e;
+    std::vector<int8_t> split((size_t)n);
+    long long lo = 0;
+    while (lo < n) {
+        long long cap = 0, hi = lo;
+        while (hi < n) {
+            int empt = 25 - __builtin_popcount((h_pos[hi].x | h_pos[hi].o) & kFull25);
+            int sp = ab_choose_split(empt - 1, R.max_depth - 1);
+            long long need = (long long)empt * ab_node_bound(empt - 1, sp);
+            if (hi > lo && cap + need > kAbChunkNodes) break;
+            split[hi] = (int8_t)sp; cap += need; hi++;
+        }
+        AbRun Rc = R;
+        Rc.out = d_values + lo * 25;
+        Rc.node_count = d_nodes + lo;
+        e = ab_dispatch(dialect, Rc, w, d_pos + lo, true, (int)(hi - lo), split.data() + lo, cap + 16, grid_cap, st, launches);
+        if (e != cudaSuccess) return e;
+        lo = hi;
+    }
+    return cudaSuccess;
+}
+
+inline cudaError_t ab_subtree_search(const sq_subtree* h_st, const sq_subtree* d_st, long long n, int dialect,
+                                     int max_depth, const int8_t scores[25], int32_t* d_value,
+                                     unsigned long long* d_nodes, int grid_cap, cudaStream_t st,
+                                     uint64_t* launches) {
+    AbRun R; AbWork w;
+    ab_fill_run(R, dialect, max_depth, scores);
+    cudaError_t e = cudaMemsetAsync(d_nodes, 0, sizeof(unsigned long long) * n, st);
+    if (e != cudaSuccess) return e;
+    std::vector<int8_t> split((size_t)n);
+    long long lo = 0;
+    while (lo < n) {
+        long long cap = 0, hi = lo;
+        while (hi < n) {
+            int empt = 25 - __builtin_popcount((h_st[hi].b.x | h_st[hi].b.o) & kFull25);
+            int sp = ab_choose_split(empt, R.max_depth - h_st[hi].ply);
+            long long need = ab_node_bound(empt, sp);
+            if (hi > lo && cap + need > kAbChunkNodes) break;
+            split[hi] = (int8_t)sp; cap += need; hi++;
+        }
+        AbRun Rc = R;
+        Rc.out = d_value + lo;
+        Rc.node_count = d_nodes + lo;
+        e = ab_dispatch(dialect, Rc, w, d_st + lo, false, (int)(hi - lo), split.data() + lo, cap + 16, grid_cap, st, launches);
+        if (e != cudaSuccess) return e;
+        lo = hi;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace sq

@@ -1,0 +1,266 @@
+// kernels.cuh -- classification and random-playout kernels (sm_100a).
+//
+// Roofline: INT32 issue throughput (LOP3/IADD3 on the ALU pipe + IMAD on the FMA
+// pipe); HBM traffic is 9 B in + 32 B out per LEAF, i.e. nothing.  No tensor
+// cores: nothing here is a contraction.
+#pragma once
+#include "../../include/squava_b200.h"
+#include "sq_device.cuh"
+
+namespace sq {
+
+__constant__ ScanTables c_scan;
+
+// ---------------------------------------------------------------------------
+// Terminal-position test
+// ---------------------------------------------------------------------------
+
+// First owned line in a reference scan order (slow path: both colours own one).
+__device__ __noinline__ int ordered_winner(uint32_t x, uint32_t o, const uint32_t* quads,
+                                           const uint32_t* trips) {
+    for (int i = 0; i < 28; i++) {
+        uint32_t q = quads[i];
+        if ((x & q) == q) return 1;
+        if ((o & q) == q) return -1;
+    }
+    for (int i = 0; i < 48; i++) {
+        uint32_t t = trips[i];
+        if ((x & t) == t) return -1;  // three in a row loses
+        if ((o & t) == t) return 1;
+    }
+    return 0;
+}
+
+struct Classified { uint32_t flags; int winner_mcts, winner_ab; };
+
+// x, o in API layout.  Restates FindWinner (src/mcts/mcts.go:92-121 and
+// src/alphabeta/alphabeta.go:355-378): quads first, so four beats three.
+__device__ __forceinline__ Classified classify_board(uint32_t x, uint32_t o) {
+    Pairs px = pairs(pad(x)), po = pairs(pad(o));
+    uint32_t x3 = any3(px), o3 = any3(po);
+    uint32_t x4 = any4(px), o4 = any4(po);
+    Classified c;
+    c.flags = (x4 ? 1u : 0u) | (o4 ? 2u : 0u) | (x3 ? 4u : 0u) | (o3 ? 8u : 0u) |
+              (((x | o) & kFull25) == kFull25 ? 16u : 0u);
+    bool need_scan = (x4 && o4) || (!x4 && !o4 && x3 && o3);
+    if (need_scan) {
+        c.winner_mcts = ordered_winner(x, o, c_scan.mcts_quads, c_scan.mcts_triplets);
+        c.winner_ab = ordered_winner(x, o, c_scan.ab_quads, c_scan.ab_triplets);
+    } else {
+        int w = x4 ? 1 : o4 ? -1 : x3 ? -1 : o3 ? 1 : 0;
+        c.winner_mcts = c.winner_ab = w;
+    }
+    return c;
+}
+
+__global__ void __launch_bounds__(256)
+classify_kernel(const sq_board* __restrict__ boards, int64_t n, uint8_t* __restrict__ flags,
+                int8_t* __restrict__ wm, int8_t* __restrict__ wa) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint2 b = *reinterpret_cast<const uint2*>(boards + i);
+        Classified c = classify_board(b.x & kFull25, b.y & kFull25);
+        if (flags) flags[i] = (uint8_t)c.flags;
+        if (wm) wm[i] = (int8_t)c.winner_mcts;
+        if (wa) wa[i] = (int8_t)c.winner_ab;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Random playouts
+// ---------------------------------------------------------------------------
+//
+// Work decomposition.  The playouts_per_leaf playouts of a leaf are cut into
+// S = ceil(N / kItemQuota) ITEMS of (almost) equal quota; item t = leaf*S + j.
+// A warp ROUND is 32 consecutive items, one per lane; warps pull rounds from a
+// global counter.  Within a round every lane runs the same branch-free ply
+// loop: a lane whose playout ends re-arms itself from its leaf in the same
+// iteration (lane refill), so the warp stays converged at ply granularity.
+//
+// Per ply (mover's mask a, other's mask b, n empty cells):
+//   draw   idx = hi32(r*n), r = lo32(r*n)   one IMAD.WIDE; 3 draws per 32-bit
+//          Philox word (bias <= n(n-1)(n-2)/2^32 < 3.3e-6 relative)
+//   pick   the idx-th empty cell: per-lane Fisher-Yates array of cell BITS in
+//          shared memory (word k of lane t at [k*blockDim + t]: bank = lane,
+//          conflict-free).  Swap-with-last keeps it a permutation of the leaf's
+//          empty cells, so a new playout needs no re-initialisation.
+//   test   the mover's new mask only (only the mover can have made a line):
+//          any3 != 0 or board full -> terminal; any4 decides win vs loss.
+//
+// Random stream of item (leaf, j): Philox4x32-10, key (seed_lo ^ stream_hi,
+// seed_hi), counter (block, j, leaf_index, stream_lo); block b feeds plies
+// 12b .. 12b+11 of the item, counted over ALL its playouts back to back.
+
+constexpr int kItemQuota = 1024;       // playouts per item (max); < 65536 (packed counters)
+constexpr int kPlayoutThreads = 256;   // CTA size
+constexpr int kMaxEmpty = 25;
+
+struct PlayoutParams {
+    const sq_board* leaves;
+    const int8_t* to_move;
+    int64_t n_leaves;
+    uint64_t leaf_index_base;
+    uint64_t per_leaf;         // N
+    uint32_t items_per_leaf;   // S
+    uint32_t quota_lo;         // N / S
+    uint32_t quota_extra;      // N % S: items j < quota_extra run quota_lo + 1
+    uint32_t key0, key1, ctr3;
+    int64_t n_rounds;
+    unsigned long long* round_counter;
+    unsigned long long* out;   // [n_leaves][4]
+};
+
+__global__ void __launch_bounds__(kPlayoutThreads, 4)
+playout_kernel(PlayoutParams P) {
+    extern __shared__ uint32_t s_arr[];  // [kMaxEmpty][blockDim.x]
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    uint32_t* arr = s_arr + tid;         // element k at arr[k * kPlayoutThreads]
+
+    for (;;) {
+        unsigned long long round = 0;
+        if (lane == 0) round = atomicAdd(P.round_counter, 1ull);
+        round = __shfl_sync(0xffffffffu, round, 0);
+        if ((int64_t)round >= P.n_rounds) break;
+
+        // ---- per-lane item setup -------------------------------------------
+        const uint64_t item = round * 32ull + lane;
+        const uint64_t leaf64 = item / P.items_per_leaf;
+        const uint32_t j = (uint32_t)(item - leaf64 * P.items_per_leaf);
+        const bool have = leaf64 < (uint64_t)P.n_leaves;
+        const uint32_t quota = have ? P.quota_lo + (j < P.quota_extra ? 1u : 0u) : 0u;
+
+        uint32_t leaf_a = 0, leaf_b = 0, n0 = 1, rem = 0, played = 0;
+        uint32_t first_is_x = 1;
+        uint32_t direct_x = 0, direct_o = 0, direct_d = 0;  // outcomes decided without playing
+        arr[0] = 0;
+        if (have) {
+            uint2 bd = *reinterpret_cast<const uint2*>(P.leaves + leaf64);
+            int tm = P.to_move[leaf64];
+            uint32_t x = bd.x & kFull25, o = bd.y & kFull25;
+            first_is_x = tm > 0;
+            Classified c = classify_board(x, o);
+            if (c.flags) {
+                // GetMoves says terminal (mcts.go:316-330,336-345): zero plies, result
+                // straight from GetResult's scan order (mcts.go:348-388).
+                int w = c.winner_mcts;
+                direct_x = w > 0 ? quota : 0u;
+                direct_o = w < 0 ? quota : 0u;
+                direct_d = w == 0 ? quota : 0u;
+            } else {
+                uint32_t xp = pad(x), op = pad(o);
+                leaf_a = first_is_x ? xp : op;
+                leaf_b = first_is_x ? op : xp;
+                uint32_t e = kFullPadded & ~(xp | op);
+                n0 = __popc(e);
+                for (uint32_t k = 0; k < n0; k++) {
+                    uint32_t bit = e & (0u - e);
+                    e ^= bit;
+                    arr[k * kPlayoutThreads] = bit;
+                }
+                rem = quota;
+                played = quota;
+            }
+        }
+
+        // ---- ply loop --------------------------------------------------------
+        uint32_t a = leaf_a, b = leaf_b, n = n0;
+        uint32_t inc_w = 1u;       // what the mover's win adds: 1 = first player, 0x10000 = second
+        uint32_t acc = 0, plies = 0;
+        uint32_t blk = 0;
+        const uint32_t c1 = j, c2 = (uint32_t)(P.leaf_index_base + leaf64);
+        while (__any_sync(0xffffffffu, rem != 0)) {
+            uint32_t w[4];
+            philox4x32_10(blk, c1, c2, P.ctr3, P.key0, P.key1, w);
+            blk++;
+#pragma unroll
+            for (int wi = 0; wi < 4; wi++) {
+                uint32_t r = w[wi];
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    unsigned long long prod = (unsigned long long)r * n;
+                    uint32_t idx = (uint32_t)(prod >> 32);
+                    r = (uint32_t)prod;
+                    uint32_t bit = arr[idx * kPlayoutThreads];
+                    uint32_t last = arr[(n - 1) * kPlayoutThreads];
+                    arr[idx * kPlayoutThreads] = last;
+                    arr[(n - 1) * kPlayoutThreads] = bit;
+                    uint32_t m = a | bit;
+                    Pairs p = pairs(m);
+                    uint32_t t3 = any3(p), t4 = any4(p);
+                    uint32_t n1 = n - 1;
+                    bool term = (t3 != 0) | (n1 == 0);
+                    bool active = rem != 0;
+                    uint32_t inc = t4 ? inc_w : (t3 ? (inc_w ^ 0x10001u) : 0u);
+                    plies += active ? 1u : 0u;
+                    if (term && active) { acc += inc; rem--; }
+                    a = term ? leaf_a : b;
+                    b = term ? leaf_b : m;
+                    n = term ? n0 : n1;
+                    inc_w = term ? 1u : (inc_w ^ 0x10001u);
+                }
+            }
+        }
+
+        // ---- fold into per-leaf counts ------------------------------------------
+        uint32_t first_wins = acc & 0xffffu, second_wins = acc >> 16;
+        uint32_t xw = first_is_x ? first_wins : second_wins;
+        uint32_t ow = first_is_x ? second_wins : first_wins;
+        uint32_t dr = played - first_wins - second_wins;   // playouts that filled the board lineless
+        xw += direct_x; ow += direct_o; dr += direct_d;
+        uint32_t key = have ? (uint32_t)leaf64 : 0xffffffffu;
+        uint32_t peers = __match_any_sync(0xffffffffu, key);
+        uint32_t sx = __reduce_add_sync(peers, xw);
+        uint32_t so = __reduce_add_sync(peers, ow);
+        uint32_t sd = __reduce_add_sync(peers, dr);
+        uint32_t sp = __reduce_add_sync(peers, plies);
+        if (have && lane == (__ffs(peers) - 1)) {
+            unsigned long long* o4 = P.out + leaf64 * 4;
+            if (sx) atomicAdd(o4 + 0, (unsigned long long)sx);
+            if (so) atomicAdd(o4 + 1, (unsigned long long)so);
+            if (sd) atomicAdd(o4 + 2, (unsigned long long)sd);
+            if (sp) atomicAdd(o4 + 3, (unsigned long long)sp);
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// INT32 issue-rate probe: the measured roofline denominator
+// ---------------------------------------------------------------------------
+// kind 0: 8 independent LOP3 chains (ALU pipe); kind 1: 8 IMAD chains (FMA pipe);
+// kind 2: 4 + 4 interleaved.  Every op is one warp instruction = 32 thread-ops.
+template <int KIND>
+__global__ void __launch_bounds__(1024, 2)
+int32_peak_kernel(uint32_t* out, uint32_t seed, int iters) {
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = seed + threadIdx.x * 0x9E3779B9u + k * 0x85EBCA6Bu;
+    uint32_t c0 = seed | 1u, c1 = seed * 3u + 7u;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                bool alu = KIND == 0 || (KIND == 2 && (k & 1) == 0);
+                if (alu) {
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[k]) : "r"(c0), "r"(c1));
+                } else {
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(v[k]) : "r"(c0), "r"(c1));
+                }
+            }
+        }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= v[k];
+    if (s == 0x12345678u) out[0] = s;  // keeps the chains alive
+}
+
+__global__ void philox_debug_kernel(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+    uint32_t w[4];
+    philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], w);
+    for (int i = 0; i < 4; i++) out[i] = w[i];
+}
+
+}  // namespace sq

@@ -1,0 +1,142 @@
+"""Fixed-depth alpha-beta on the GPU: values and tie sets bit-exact against the CPU oracle
+(live) and the committed golden vectors."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = json.load(open(os.path.join(HERE, "golden", "oracle_vectors.json")))
+
+
+@pytest.fixture(scope="module")
+def dev(sq):
+    sq.init()
+    yield sq
+    sq.shutdown()
+
+
+def boards_of(pairs, sq):
+    return np.array(pairs, dtype=np.uint32).view(sq.BOARD).reshape(-1)
+
+
+def test_ab1_root_golden(dev, oracle):
+    sc = oracle.tables()["scores_ab"]
+    by_depth = {}
+    for c in G["ab1_root"]:
+        by_depth.setdefault(c["depth"], []).append(c)
+    for depth, cases in by_depth.items():
+        b = boards_of([(c["x"], c["o"]) for c in cases], dev)
+        values, bv, bm, nodes = dev.alphabeta_root(b, 1, depth, sc)
+        for i, c in enumerate(cases):
+            assert values[i].tolist() == c["values"], (depth, i)
+            assert int(bm[i]) == c["best_mask"] and int(bv[i]) == c["best_value"]
+            assert nodes[i] > 0
+
+
+def test_ab2_root_golden(dev, oracle):
+    sc = oracle.tables()["scores_ab"]
+    for c in G["ab2_root"]:
+        values, bv, bm, _ = dev.alphabeta_root(boards_of([(c["x"], c["o"])], dev), 2, c["depth"], sc)
+        assert values[0].tolist() == c["values"]
+        assert int(bm[0]) == c["best_mask"] and int(bv[0]) == c["best_value"]
+
+
+def subtree_array(dev, rows):
+    t = np.zeros(len(rows), dev.SUBTREE)
+    for i, (x, o, last, ply, side, carried) in enumerate(rows):
+        t[i] = (x, o, last, ply, side, 0, carried)
+    return t
+
+
+def test_opening3_and_opening2_golden(dev, oracle):
+    sc = oracle.tables()["scores_opening"]
+    for depth in (6, 7):
+        cases = [c for c in G["opening3"] if c["depth"] == depth]
+        t = subtree_array(dev, [(1 << c["first"], 1 << c["reply"], c["reply"], 2, 1, sc[c["first"]]) for c in cases])
+        v, _ = dev.alphabeta_subtrees(t, 3, depth, sc)
+        assert v.tolist() == [c["value"] for c in cases]
+    for depth in (6, 8):
+        cases = [c for c in G["opening2"] if c["depth"] == depth]
+        t = subtree_array(dev, [(1 << c["first"], 0, c["first"], 1, -1, 0) for c in cases])
+        v, _ = dev.alphabeta_subtrees(t, 4, depth, sc)
+        assert v.tolist() == [c["value"] for c in cases]
+
+
+@pytest.mark.parametrize("split", ["0", "1", "2", "3", ""])
+def test_ab1_root_live_oracle_all_split_depths(dev, oracle, split, monkeypatch):
+    """the breadth-first split depth must not change any value"""
+    from squava_b200 import positions
+    sc = oracle.tables()["scores_ab"]
+    boards, _ = positions.midgame_batch(48, marks=(10, 12, 14, 16, 18, 20), seed=77)
+    if split:
+        os.environ["SQ_AB_SPLIT"] = split
+    else:
+        os.environ.pop("SQ_AB_SPLIT", None)
+    try:
+        values, bv, bm, _ = dev.alphabeta_root(boards, 1, 10, sc)
+    finally:
+        os.environ.pop("SQ_AB_SPLIT", None)
+    for i in range(boards.shape[0]):
+        ov, obm, obv, _ = oracle.ab1_root(int(boards[i]["x"]), int(boards[i]["o"]), 10, sc)
+        assert values[i].tolist() == ov, i
+        assert (int(bm[i]), int(bv[i])) == (obm, obv)
+
+
+def test_ab2_root_live_oracle(dev, oracle):
+    from squava_b200 import positions
+    sc = oracle.tables()["scores_ab"]
+    boards, _ = positions.midgame_batch(32, marks=(10, 12, 14, 16), seed=78)
+    for depth in (1, 2, 7, 11):
+        values, bv, bm, _ = dev.alphabeta_root(boards, 2, depth, sc)
+        for i in range(boards.shape[0]):
+            ov, obm, obv, _ = oracle.ab2_root(int(boards[i]["x"]), int(boards[i]["o"]), depth, sc)
+            assert values[i].tolist() == ov, (depth, i)
+            assert (int(bm[i]), int(bv[i])) == (obm, obv)
+
+
+@pytest.mark.parametrize("dialect", [1, 2, 3, 4])
+def test_subtrees_live_oracle(dev, oracle, dialect):
+    from squava_b200 import positions
+    rng = np.random.Generator(np.random.PCG64(dialect))
+    sc = oracle.tables()["scores_opening" if dialect >= 3 else "scores_ab"]
+    rows = []
+    for marks in (9, 12, 15, 18, 21, 23, 24):
+        for _ in range(6):
+            x, o = positions.random_position(rng, marks)
+            occ = [c for c in range(25) if (x | o) >> c & 1]
+            last = int(rng.choice(occ))
+            side = -1 if (x >> last) & 1 else 1
+            rows.append((x, o, last, int(rng.integers(1, 4)), side, int(rng.integers(-50, 50))))
+    # positions that already hold a line elsewhere, and full boards
+    rows.append((0x1364d93, 0x1ffffff & ~0x1364d93, 0, 3, -1, 5))
+    depth = 8
+    t = subtree_array(dev, rows)
+    v, _ = dev.alphabeta_subtrees(t, dialect, depth, sc)
+    for i, (x, o, last, ply, side, carried) in enumerate(rows):
+        ov, _ = oracle.ab_subtree(dialect, x, o, last, ply, side, carried, depth, sc)
+        assert int(v[i]) == ov, (dialect, i, rows[i])
+
+
+def test_edge_cases(dev, oracle):
+    sc = oracle.tables()["scores_ab"]
+    v, bv, bm, nodes = dev.alphabeta_root(np.zeros(0, dev.BOARD), 1, 6, sc)
+    assert v.shape == (0, 25)
+    # full board: no move
+    x = 0x1364d93
+    v, bv, bm, _ = dev.alphabeta_root(boards_of([(x, 0x1ffffff & ~x)], dev), 1, 6, sc)
+    assert (v == dev.NO_MOVE).all() and bm[0] == 0 and bv[0] == 0
+    # depth 0: every root move is a leaf
+    from squava_b200 import positions
+    boards, _ = positions.midgame_batch(8, marks=(8, 10), seed=5)
+    for dialect in (1, 2):
+        v, bv, bm, _ = dev.alphabeta_root(boards, dialect, 1 if dialect == 2 else 0, sc)
+        for i in range(8):
+            f = oracle.ab1_root if dialect == 1 else oracle.ab2_root
+            assert v[i].tolist() == f(int(boards[i]["x"]), int(boards[i]["o"]), 1 if dialect == 2 else 0, sc)[0]
+    with pytest.raises(dev.SquavaError):
+        dev.alphabeta_root(boards, 3, 6, sc)          # no root search in opening2/3
+    with pytest.raises(dev.SquavaError):
+        dev.alphabeta_root(boards, 1, 99, sc)
