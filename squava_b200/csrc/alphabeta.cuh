@@ -40,8 +40,8 @@ struct AbTables {
     uint32_t triplets[25][12]; // triplets through each cell
     uint8_t n_quads[25], n_triplets[25];
     uint32_t no2[25][2];        // squavathr.go:305-311 triplets containing the cell (0 = none)
-    uint32_t nomid_quad[25];    // squavathr.go:297-302: quad in which the cell is a middle cell
-    uint32_t nomid_other[25];   // ... and the bit of the other middle cell
+    uint32_t nomid_quad[25][2];   // squavathr.go:297-302: quads in which the cell is a middle cell
+    uint32_t nomid_other[25][2];  // ... and the bit of the other middle cell of that quad
     uint8_t order[25];          // opening3.go:328-361: k-th child cell
     uint8_t rank[25];           // inverse
 };
@@ -67,8 +67,10 @@ inline void build_ab_tables(AbTables& t) {
     const int nm[4][4] = {{15, 11, 7, 3}, {5, 11, 17, 23}, {1, 7, 13, 19}, {9, 13, 17, 21}};
     for (auto& q : nm) {
         uint32_t m = (1u << q[0]) | (1u << q[1]) | (1u << q[2]) | (1u << q[3]);
-        t.nomid_quad[q[1]] = m; t.nomid_other[q[1]] = 1u << q[2];
-        t.nomid_quad[q[2]] = m; t.nomid_other[q[2]] = 1u << q[1];
+        for (int a = 1; a <= 2; a++) {     // each inner-ring corner is a middle of two of them
+            int c = q[a], other = q[3 - a], k = t.nomid_quad[c][0] ? 1 : 0;
+            t.nomid_quad[c][k] = m; t.nomid_other[c][k] = 1u << other;
+        }
     }
     // opening3.go:328-361: inner-ring corners, centre, inner-ring edges, then the outer
     // ring's edge triples (top, left, right, bottom), corners last
@@ -139,9 +141,10 @@ __device__ __forceinline__ int eval_penalties(const AbTables& T, uint32_t own, u
         uint32_t t = T.no2[cell][k];
         if (t && __popc(own & t) == 2 && (opp & t) == 0) v -= sign * 100;
     }
-    uint32_t q = T.nomid_quad[cell];
-    if (q && (own & T.nomid_other[cell])) {
-        if (__popc(own & q) - __popc(opp & q) == 2) v -= sign * 100;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        uint32_t q = T.nomid_quad[cell][k];
+        if (q && (own & T.nomid_other[cell][k]) && __popc(own & q) - __popc(opp & q) == 2) v -= sign * 100;
     }
     return v;
 }

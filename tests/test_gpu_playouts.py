@@ -60,7 +60,7 @@ def test_empty_board_matches_cpu_oracle_sampling(dev, oracle):
     n = 400_000
     out = dev.playouts(np.zeros(1, dev.BOARD), np.ones(1, np.int8), n, 5)[0]
     ref = oracle.playouts(0, 0, 1, n, 1234)
-    assert int(out[2]) == 0 and ref[2] == 0
+    assert int(out[2]) <= 3 and ref[2] <= 3       # P(draw) = 4/C(25,13) = 7.7e-7 per playout
     p = ref[0] / n
     assert abs(int(out[0]) / n - p) <= 3.0 * (2 * p * (1 - p) / n) ** 0.5
     assert abs(int(out[3]) / n - ref[3] / n) < 0.05
