@@ -1,0 +1,172 @@
+// squava_host.hpp -- host-side mirror of the reference's engine surface, in C++
+// (the reference is Go; this image has no Go toolchain).
+//
+// Same names, argument meaning and failure behaviour as the reference:
+//   Player            playoff5.go:21-29 (identical copy sqv.go:23-31)
+//   mcts::MCTS        src/mcts/mcts.go:32-90  (New, SetUCTK, SetIterations, ...)
+//   alphabeta::AlphaBeta  src/alphabeta/alphabeta.go:20-117
+//   MoveKeeper        src/movekeeper/movekeeper.go:10-52
+// Everything that is hot in the reference (rollouts + terminal test, the
+// alpha-beta recursion) is a call into libsquava_b200.so (include/squava_b200.h);
+// what stays here is what the north star leaves on the host: the MCTS tree
+// (select / expand / backprop, UCB1, tree reuse) and move bookkeeping.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/squava_b200.h"
+
+namespace squava {
+
+constexpr int MAXIMIZER = 1, MINIMIZER = -1, UNSET = 0;
+constexpr int WIN = 10000, LOSS = -10000;
+
+// The reference never returns errors: failure is panic or os.Exit.  Same here.
+inline void must(int status, const char* what) {
+    if (status != SQ_OK) {
+        std::fprintf(stderr, "%s: %s (%s)\n", what, sq_strerror(status), sq_last_error());
+        std::exit(2);
+    }
+}
+
+struct Board {            // [25]int / [5][5]int of the reference as two masks
+    uint32_t x = 0, o = 0;
+    int at(int c) const { return (x >> c) & 1u ? MAXIMIZER : (o >> c) & 1u ? MINIMIZER : UNSET; }
+    void set(int c, int player) {
+        x &= ~(1u << c); o &= ~(1u << c);
+        if (player == MAXIMIZER) x |= 1u << c; else if (player == MINIMIZER) o |= 1u << c;
+    }
+    uint32_t empty() const { return 0x1FFFFFFu & ~(x | o); }
+    sq_board raw() const { return sq_board{x, o}; }
+    std::string str() const;        // GameState.String(), squavam.go:327-339
+    std::string str_grid() const;   // PrintBoard(), alphabeta.go:226-247
+};
+
+struct Move { int x, y, value, leafCount; };
+
+class Player {             // playoff5.go:21-29
+public:
+    virtual ~Player() {}
+    virtual std::string Name() = 0;
+    virtual void MakeMove(int x, int y, int player) = 0;
+    virtual void SetDepth(int moveCounter) = 0;
+    virtual Move ChooseMove() = 0;   // x,y coords of move, value, leaf node count
+    virtual void PrintBoard() = 0;
+    virtual void SetScores(bool randomize) = 0;
+    virtual int FindWinner() = 0;
+};
+
+// src/movekeeper/movekeeper.go
+class MoveKeeper {
+public:
+    MoveKeeper(int max, bool deterministic, std::mt19937_64* rng) : max_(max), det_(deterministic), rng_(rng) {}
+    void SetMove(int a, int b, int value);
+    void ChooseMove(int& x, int& y, int& value);
+    int count() const { return next_; }
+private:
+    int moves_[25][2]; int next_ = 0; int max_; bool det_; std::mt19937_64* rng_;
+};
+
+std::mt19937_64& host_rng();           // rand.Seed(time.Now()...) unless SQUAVA_SEED is set
+void seed_host_rng(uint64_t seed);
+std::string go_duration(double seconds);  // time.Duration.String()
+
+// ---- MCTS ------------------------------------------------------------------------
+namespace mcts {
+
+struct GameState {         // mcts.go:9-13 (cachedResults is only a memo there)
+    int playerJustMoved = MINIMIZER;
+    Board board;
+    void DoMove(int move) { playerJustMoved = -playerJustMoved; board.set(move, playerJustMoved); }  // :292-295
+};
+
+struct Node {              // mcts.go:15-23
+    int move = -1;
+    Node* parentNode = nullptr;
+    std::vector<std::unique_ptr<Node>> childNodes;
+    double wins = 0, visits = 0;
+    std::vector<int> untriedMoves;
+    int playerJustMoved = 0;
+};
+
+struct Options {
+    int batch = 256;                 // leaves per GPU call (leaf-parallel); 1 = the reference's sequence
+    int playouts_per_leaf = 1;       // rollouts per expanded leaf
+    bool ucb_factor2 = true;         // src/mcts (mcts.go:248-250) has 2*ln; squavam.go:197-199 does not
+};
+
+// UCT(rootstate, itermax, UCTK, rootnode), squavam.go:98 / mcts.go:123.  Returns the chosen
+// child (owned by *root); leaves = rollouts performed; value = int(1000*UCB1) as mcts.go:198.
+Node* UCT(const GameState& rootstate, int itermax, double UCTK, std::unique_ptr<Node>& root,
+          const Options& opt, int* leaves, int* value);
+
+class MCTS : public Player {           // mcts.go:32-90
+public:
+    MCTS(bool deterministic, int maxdepth);
+    std::string Name() override { return "MCTS"; }
+    void SetUCTK(double k) { UCTK_ = k; }
+    void SetIterations(int n) { iterations_ = n; }
+    void SetBatch(int leaves, int playouts_per_leaf) { opt_.batch = leaves; opt_.playouts_per_leaf = playouts_per_leaf; }
+    void MakeMove(int x, int y, int player) override;
+    void SetDepth(int) override {}
+    Move ChooseMove() override;
+    void PrintBoard() override;
+    void SetScores(bool) override {}
+    int FindWinner() override;
+private:
+    GameState game_;
+    int iterations_ = 500000;
+    std::unique_ptr<Node> movesNode_;
+    double UCTK_ = 1.0;
+    Options opt_;
+};
+
+}  // namespace mcts
+
+// ---- alpha-beta ---------------------------------------------------------------------
+namespace alphabeta {
+
+class AlphaBeta : public Player {      // alphabeta.go:20-117
+public:
+    AlphaBeta(bool deterministic, int maxdepth) : maxDepth_(maxdepth), deterministic_(deterministic) {}
+    std::string Name() override { return name_; }
+    void MakeMove(int x, int y, int player) override { bd_.set(5 * x + y, player); }
+    void SetDepth(int moveCounter) override;
+    Move ChooseMove() override;
+    void PrintBoard() override;
+    void SetScores(bool randomize) override;
+    int FindWinner() override;
+    const Board& board() const { return bd_; }
+protected:
+    Board bd_;
+    std::string name_ = "AlphaBeta";
+    int maxDepth_;
+    bool deterministic_;
+};
+extern int8_t scores[25];    // package-level, shared by all instances (alphabeta.go:330)
+
+}  // namespace alphabeta
+
+// ---- tiny Go-style flag parser ("-i 100", "-i=100", "-C", "-C=false") ----------------
+class Flags {
+public:
+    void Int(const char* name, int* v, const char* help);
+    void Float(const char* name, double* v, const char* help);
+    void Bool(const char* name, bool* v, const char* help);
+    void String(const char* name, std::string* v, const char* help);
+    void Parse(int argc, char** argv);
+private:
+    struct F { std::string name, help; int kind; void* ptr; };
+    std::vector<F> flags_;
+    void usage(const char* prog);
+};
+
+// common start-up: sq_init on the devices named by -gpus / SQUAVA_GPUS (default device 0)
+void init_devices(int n_gpus, uint64_t seed);
+
+}  // namespace squava

@@ -1,0 +1,86 @@
+// squavam -- drop-in for the reference's stand-alone MCTS program (squavam.go): same
+// flags (-i, -u, -C), same stdin protocol ("x y" per move, EOF exits 0), same output lines.
+// The UCT loop's rollout block (squavam.go:128-147) runs on the GPU in leaf-parallel
+// batches; extra flags: -batch, -ppl, -gpus, -seed.
+#include <chrono>
+#include <cstdio>
+
+#include "squava_host.hpp"
+
+using namespace squava;
+using namespace squava::mcts;
+
+static bool end_of_game(const GameState& s) {      // GetMoves' second result, squavam.go:246-284
+    sq_board b = s.board.raw(); uint8_t f = 0;
+    must(sq_classify(&b, 1, &f, nullptr, nullptr), "sq_classify");
+    return f != 0;
+}
+
+static int readMove(const Board& bd) {             // squavam.go:345-372
+    for (;;) {
+        std::printf("Enter move (N M): ");
+        std::fflush(stdout);
+        int x, y;
+        int n = std::scanf("%d %d", &x, &y);
+        if (n == EOF) std::exit(0);
+        if (n != 2) { std::printf("Failed to read: unexpected input\n"); std::exit(1); }
+        if (x < 0 || x > 4 || y < 0 || y > 4) { std::printf("Choose two numbers between 0 and 4, try again\n"); continue; }
+        if (bd.at(5 * x + y) == UNSET) return 5 * x + y;
+        std::printf("Cell (%d, %d) already occupied, try again\n", x, y);
+    }
+}
+
+int main(int argc, char** argv) {
+    int iterMax = 10000, batch = 256, ppl = 1, gpus = 0, seed = -1;
+    double uctk = 1.00;
+    bool computerFirst = false;
+    Flags fl;
+    fl.Int("i", &iterMax, "maximum iterations");
+    fl.Float("u", &uctk, "UCTK explore/exploit coefficient");
+    fl.Bool("C", &computerFirst, "Computer takes first move");
+    fl.Int("batch", &batch, "leaves per GPU batch (1 = the reference's strictly sequential UCT)");
+    fl.Int("ppl", &ppl, "playouts per leaf");
+    fl.Int("gpus", &gpus, "number of GPUs (default 1)");
+    fl.Int("seed", &seed, "seed for reproducible play (default: clock, as the reference)");
+    fl.Parse(argc, argv);
+    if (seed >= 0) seed_host_rng((uint64_t)seed);
+    init_devices(gpus, (uint64_t)host_rng()());
+
+    GameState state;
+    state.playerJustMoved = MINIMIZER;
+    if (computerFirst) state.playerJustMoved = MAXIMIZER;
+    Options opt; opt.batch = batch; opt.playouts_per_leaf = ppl; opt.ucb_factor2 = false;   // squavam.go:197-199
+    std::unique_ptr<Node> movesNode;
+    while (!end_of_game(state)) {
+        int m;
+        std::printf("%s\n", state.board.str().c_str());
+        if (state.playerJustMoved == MAXIMIZER) {
+            auto start = std::chrono::steady_clock::now();
+            Node* best = UCT(state, iterMax, uctk, movesNode, opt, nullptr, nullptr);
+            m = best->move;
+            std::unique_ptr<Node> keep;
+            for (auto& c : movesNode->childNodes) if (c.get() == best) keep = std::move(c);
+            keep->parentNode = nullptr;
+            movesNode = std::move(keep);
+            double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+            std::printf("My move: %d %d %s\n", m / 5, m % 5, go_duration(el).c_str());
+        } else {
+            m = readMove(state.board);
+            if (movesNode) {     // pick out the child of movesNode corresponding to m (squavam.go:70-78)
+                std::unique_ptr<Node> keep;
+                for (auto& c : movesNode->childNodes) if (c->move == m) { keep = std::move(c); break; }
+                if (keep) { keep->parentNode = nullptr; movesNode = std::move(keep); }
+                else movesNode.reset();
+            }
+        }
+        state.DoMove(m);
+    }
+    std::printf("%s\n", state.board.str().c_str());
+    sq_board b = state.board.raw(); int8_t w = 0;
+    must(sq_classify(&b, 1, nullptr, &w, nullptr), "sq_classify");
+    char last = "O_X"[state.playerJustMoved + 1];
+    if (w == state.playerJustMoved) std::printf("Player %c wins!\n", last);       // GetResult == 1.0
+    else std::printf("Player %c loses!\n", last);                                // 0.0, draws included (squavam.go:88-93)
+    sq_shutdown();
+    return 0;
+}

@@ -1,0 +1,135 @@
+// squavathr -- drop-in for the reference's alpha-beta program with a root-move worker pool
+// (squavathr.go).  chooseMove's toDo/finished round trip (squavathr.go:236-269,448-466)
+// becomes ONE sq_alphabeta_root call (dialect 2); flags keep their names.  -N (goroutine
+// count) is accepted and ignored; -B (opening book) is not part of the hot path.
+#include <chrono>
+#include <cstdio>
+
+#include "squava_host.hpp"
+
+using namespace squava;
+
+static int8_t scores[25];
+
+static void setScores(bool randomize) {          // squavathr.go:612-630
+    if (randomize) {
+        static const int vals[11] = {-5, -4, -3 - 2, -1, 0, 1, 2, 3, 4, 5, 0};
+        for (int i = 0; i < 25; i++) scores[i] = (int8_t)vals[std::uniform_int_distribution<int>(0, 10)(host_rng())];
+    } else {
+        static const int8_t d[25] = {3, 3, 0, 3, 3, 3, 4, 1, 4, 3, 0, 1, 0, 1, 0, 3, 4, 1, 4, 3, 3, 3, 0, 3, 3};
+        for (int i = 0; i < 25; i++) scores[i] = d[i];
+    }
+}
+
+static int setDepth(int moveCounter, int endGameDepth) {   // squavathr.go:183-198
+    int maxDepth = 0;
+    if (moveCounter < 4) maxDepth = 10;
+    if (moveCounter > 3) maxDepth = 12;
+    if (moveCounter > 10) maxDepth = endGameDepth;
+    return maxDepth;
+}
+
+static int findWinner(const Board& bd) {                   // squavathr.go:271-294
+    sq_board b = bd.raw(); int8_t w = 0;
+    must(sq_classify(&b, 1, nullptr, nullptr, &w), "sq_classify");
+    return w;
+}
+
+// deltaValue(100, &bd, 0, l, m, 0)'s stopRecursing for a move just made (squavathr.go:133,158):
+// true exactly when the mover owns a line, which after a legal move means the board has one.
+static bool game_over_after_move(const Board& bd) {
+    sq_board b = bd.raw(); uint8_t f = 0;
+    must(sq_classify(&b, 1, &f, nullptr, nullptr), "sq_classify");
+    return (f & (SQ_X4 | SQ_O4 | SQ_X3 | SQ_O3)) != 0;
+}
+
+static void readMove(const Board& bd, bool printit, int& x, int& y) {     // squavathr.go:559-610
+    for (;;) {
+        if (printit) { std::printf("Your move: "); std::fflush(stdout); }
+        int n = std::scanf("%d %d", &x, &y);
+        if (n == EOF) std::exit(0);
+        if (n != 2) { std::printf("Give two numbers\n"); int c; while ((c = std::getchar()) != '\n' && c != EOF) {} continue; }
+        if (x < 0 || x > 4 || y < 0 || y > 4) { if (printit) std::printf("Choose two numbers between 0 and 4, try again\n"); continue; }
+        if (bd.at(5 * x + y) == UNSET) return;
+        if (printit) std::printf("Cell (%d, %d) already occupied, try again\n", x, y);
+    }
+}
+
+int main(int argc, char** argv) {
+    bool humanFirst = true, computerFirst = false, deterministic = false, noPrint = false, randomize = false, useBook = false;
+    int maxDepthFlag = 15, threads = 0, gpus = 0, seed = -1;
+    std::string firstMove;
+    Flags fl;
+    fl.Bool("H", &humanFirst, "Human takes first move");
+    fl.Bool("C", &computerFirst, "Computer takes first move");
+    fl.Int("d", &maxDepthFlag, "maximum lookahead depth");
+    fl.Bool("D", &deterministic, "Play deterministically");
+    fl.Bool("n", &noPrint, "Don't print board, just emit moves");
+    fl.String("M", &firstMove, "Tell computer to make this first move (x,y)");
+    fl.Int("N", &threads, "Use this many threads (ignored: the root moves are one GPU batch)");
+    fl.Bool("r", &randomize, "Randomize bias scores");
+    fl.Bool("B", &useBook, "Use book start or defense (not supported by this build)");
+    fl.Int("gpus", &gpus, "number of GPUs (default 1)");
+    fl.Int("seed", &seed, "seed for reproducible play");
+    fl.Parse(argc, argv);
+    if (seed >= 0) seed_host_rng((uint64_t)seed);
+    bool printBoard = !noPrint;
+    if (useBook) { std::fprintf(stderr, "-B: the opening book is outside the accelerated path; playing without it\n"); }
+    init_devices(gpus, 0);
+    setScores(randomize);
+    if (computerFirst) humanFirst = false;
+    int moveCounter = 0;
+    Board bd;
+    if (!firstMove.empty()) {
+        int x1, y1;
+        if (std::sscanf(firstMove.c_str(), "%d,%d", &x1, &y1) != 2)
+            std::printf("Wrong move input. Format N,M, where N and M numbers 0 - 4 \n");
+        else {
+            std::printf("My move: %d %d\n", x1, y1);
+            humanFirst = true;
+            bd.set(5 * x1 + y1, MAXIMIZER);
+            std::printf("%s", bd.str_grid().c_str());
+        }
+    }
+    bool endOfGame = false;
+    while (!endOfGame) {
+        int maxDepth = setDepth(moveCounter, maxDepthFlag);
+        if (humanFirst) {
+            int l, m;
+            readMove(bd, printBoard, l, m);
+            bd.set(5 * l + m, MINIMIZER);
+            endOfGame = game_over_after_move(bd);
+            moveCounter++;
+        }
+        if (endOfGame) break;
+        humanFirst = true;
+        auto start = std::chrono::steady_clock::now();
+        // chooseMove(&bd, deterministic, maxDepth), squavathr.go:236-269
+        sq_board b = bd.raw();
+        int32_t values[1][25]; int32_t bv = 0; uint32_t bm = 0; uint64_t nodes = 0;
+        must(sq_alphabeta_root(&b, 1, SQ_AB_SQUAVATHR, maxDepth, scores, values, &bv, &bm, &nodes), "sq_alphabeta_root");
+        MoveKeeper moves(2 * LOSS, deterministic, &host_rng());
+        for (int c = 0; c < 25; c++) if (values[0][c] != SQ_NO_MOVE) moves.SetMove(c / 5, c % 5, values[0][c]);
+        int a, bb, score;
+        moves.ChooseMove(a, bb, score);
+        double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+        if (a < 0) break;    // cat gets the game
+        bd.set(5 * a + bb, MAXIMIZER);
+        moveCounter++;
+        if (printBoard) {
+            std::printf("My move: %d %d (%d) [%llu] %s\n", a, bb, score, (unsigned long long)nodes, go_duration(el).c_str());
+            std::printf("%s", bd.str_grid().c_str());
+        } else {
+            std::printf("%d %d\n", a, bb);
+        }
+        std::fflush(stdout);
+        endOfGame = game_over_after_move(bd);
+    }
+    if (printBoard) {
+        int w = findWinner(bd);
+        std::printf("%s", w == MAXIMIZER ? "\nX wins\n" : w == MINIMIZER ? "\nO wins\n" : "\nCat wins\n");
+        std::printf("%s", bd.str_grid().c_str());
+    }
+    sq_shutdown();
+    return 0;
+}
