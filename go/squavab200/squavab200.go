@@ -1,0 +1,166 @@
+// Package squavab200 is the cgo binding of libsquava_b200.so (include/squava_b200.h): what a
+// maintainer of bediger4000/squava adds to call the B200 hot path from the unmodified Go
+// programs.  NOT COMPILED IN THIS REPO'S CI: the build image has no Go toolchain (see
+// DESIGN.md); the same ABI is exercised by the C++ host programs and the ctypes tests.
+//
+// Build (on a box with Go >= 1.16 and the library installed):
+//   CGO_CFLAGS="-I/path/to/repo/include" CGO_LDFLAGS="-L/path/to/repo/squava_b200 -lsquava_b200" go build ./...
+package squavab200
+
+/*
+#include <stdlib.h>
+#include "squava_b200.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"runtime"
+	"unsafe"
+)
+
+// Board is the [25]int / [5][5]int board of the reference as two masks: bit 5*x+y.
+type Board struct{ X, O uint32 }
+
+// FromCells converts the reference's [25]int board (src/mcts/mcts.go:11).
+func FromCells(cells *[25]int) Board {
+	var b Board
+	for i, v := range cells {
+		switch v {
+		case 1:
+			b.X |= 1 << uint(i)
+		case -1:
+			b.O |= 1 << uint(i)
+		}
+	}
+	return b
+}
+
+// FromGrid converts the reference's [5][5]int board (src/alphabeta/alphabeta.go:9).
+func FromGrid(bd *[5][5]int) Board {
+	var flat [25]int
+	for i, row := range bd {
+		for j, v := range row {
+			flat[5*i+j] = v
+		}
+	}
+	return FromCells(&flat)
+}
+
+func check(rc C.int, what string) {
+	if rc != C.SQ_OK {
+		// the reference has no error returns: failure is panic or os.Exit
+		panic(fmt.Sprintf("%s: %s (%s)", what, C.GoString(C.sq_strerror(rc)), C.GoString(C.sq_last_error())))
+	}
+}
+
+// Init selects the GPUs (nil = device 0) and the seed of every random stream.
+func Init(devices []int, seed uint64) {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	if len(devices) == 0 {
+		check(C.sq_init(nil, 0, C.uint64_t(seed)), "sq_init")
+		return
+	}
+	ids := make([]C.int, len(devices))
+	for i, d := range devices {
+		ids[i] = C.int(d)
+	}
+	check(C.sq_init(&ids[0], C.int(len(ids)), C.uint64_t(seed)), "sq_init")
+}
+
+// Shutdown releases the devices.
+func Shutdown() { C.sq_shutdown() }
+
+// Classify: flags, FindWinner in mcts.go order, FindWinner in alphabeta.go order.
+func Classify(boards []Board) (flags []uint8, winnerMCTS, winnerAB []int8) {
+	n := len(boards)
+	flags, winnerMCTS, winnerAB = make([]uint8, n), make([]int8, n), make([]int8, n)
+	if n == 0 {
+		return
+	}
+	check(C.sq_classify((*C.sq_board)(unsafe.Pointer(&boards[0])), C.int64_t(n),
+		(*C.uint8_t)(unsafe.Pointer(&flags[0])), (*C.int8_t)(unsafe.Pointer(&winnerMCTS[0])),
+		(*C.int8_t)(unsafe.Pointer(&winnerAB[0]))), "sq_classify")
+	return
+}
+
+// Counts of playouts from one leaf: {MAXIMIZER wins, MINIMIZER wins, draws, plies}.
+type Counts [4]uint64
+
+// Playouts runs perLeaf random playouts from every leaf (replaces squavam.go:128-147).
+func Playouts(leaves []Board, toMove []int8, perLeaf, streamID uint64) []Counts {
+	n := len(leaves)
+	out := make([]Counts, n)
+	if n == 0 {
+		return out
+	}
+	check(C.sq_playouts((*C.sq_board)(unsafe.Pointer(&leaves[0])), (*C.int8_t)(unsafe.Pointer(&toMove[0])),
+		C.int64_t(n), C.uint64_t(perLeaf), C.uint64_t(streamID),
+		(*[4]C.uint64_t)(unsafe.Pointer(&out[0]))), "sq_playouts")
+	return out
+}
+
+// RootValues is one row of AlphaBetaRoot.
+type RootValues struct {
+	Values    [25]int32 // NoMove where occupied
+	BestValue int32
+	BestMask  uint32 // cells tied at BestValue: movekeeper's set
+	Nodes     uint64
+}
+
+// NoMove marks an occupied cell in RootValues.Values.
+const NoMove = int32(-1 << 31)
+
+// Dialects of the reference's alpha-beta programs.
+const (
+	AlphaBeta = 1 // src/alphabeta
+	Squavathr = 2 // squavathr.go
+	Opening3  = 3 // opening3.go
+	Opening2  = 4 // opening2.go
+)
+
+// AlphaBetaRoot replaces ChooseMove's loop (alphabeta.go:98-110) / chooseMove + the worker
+// pool (squavathr.go:236-269,448-466) for a batch of positions, MAXIMIZER to move.
+func AlphaBetaRoot(positions []Board, dialect, maxDepth int, scores *[25]int8) []RootValues {
+	n := len(positions)
+	out := make([]RootValues, n)
+	if n == 0 {
+		return out
+	}
+	values := make([][25]int32, n)
+	bv := make([]int32, n)
+	bm := make([]uint32, n)
+	nodes := make([]uint64, n)
+	check(C.sq_alphabeta_root((*C.sq_board)(unsafe.Pointer(&positions[0])), C.int64_t(n), C.int(dialect),
+		C.int(maxDepth), (*C.int8_t)(unsafe.Pointer(&scores[0])), (*[25]C.int32_t)(unsafe.Pointer(&values[0])),
+		(*C.int32_t)(unsafe.Pointer(&bv[0])), (*C.uint32_t)(unsafe.Pointer(&bm[0])),
+		(*C.uint64_t)(unsafe.Pointer(&nodes[0]))), "sq_alphabeta_root")
+	for i := range out {
+		out[i] = RootValues{values[i], bv[i], bm[i], nodes[i]}
+	}
+	return out
+}
+
+// Subtree is one unit of squavathr's toDo channel / one top-level call of opening2/3.
+type Subtree struct {
+	B          Board
+	LastCell   int8
+	Ply        int8
+	SideToMove int8
+	_          int8
+	Carried    int32
+}
+
+// AlphaBetaSubtrees evaluates explicit subtrees; value[i] is what the reference's alphaBeta returns.
+func AlphaBetaSubtrees(st []Subtree, dialect, maxDepth int, scores *[25]int8) (value []int32, nodes []uint64) {
+	n := len(st)
+	value, nodes = make([]int32, n), make([]uint64, n)
+	if n == 0 {
+		return
+	}
+	check(C.sq_alphabeta_subtrees((*C.sq_subtree)(unsafe.Pointer(&st[0])), C.int64_t(n), C.int(dialect),
+		C.int(maxDepth), (*C.int8_t)(unsafe.Pointer(&scores[0])), (*C.int32_t)(unsafe.Pointer(&value[0])),
+		(*C.uint64_t)(unsafe.Pointer(&nodes[0]))), "sq_alphabeta_subtrees")
+	return
+}
