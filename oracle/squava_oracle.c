@@ -442,11 +442,17 @@ typedef struct {
     int sentinel; /* AB-3: value of a node with no empty cell is -+sentinel */
 } ab_t;
 
+/* evaluator calls (deltaValue / the inlined evaluation of opening2-3) of the calling thread's
+ * most recent search: the unit SURVEY.md 8(d) counts alpha-beta throughput in */
+static __thread int64_t g_evals;
+int64_t sqo_last_evals(void) { return g_evals; }
+
 /* lines-through-(x,y) part shared by every dialect's evaluator:
  * alphabeta.go:123-147 == squavathr.go:317-341 == opening3.go:138-164.
  * Returns 1 and *value = the terminal score if (x,y) completes a line.      */
 static int lines_value(const ab_t *a, int ply, int c, int *value) {
     const int *bd = a->bd; int v = 0;
+    g_evals++;
     for (int k = 0; k < g_iq_n[c]; k++) {
         const int *q = g_aq[g_iq[c][k]];
         int sum = bd[q[0]] + bd[q[1]] + bd[q[2]] + bd[q[3]];
@@ -510,7 +516,7 @@ static void keep_moves(const int32_t values[25], uint32_t *best_mask, int32_t *b
 
 void sqo_ab1_root(sqo_board b, int max_depth, const int scores[25], int32_t values[25],
                   uint32_t *best_mask, int32_t *best_value, int64_t *leaves) {
-    ab_t a; tables(); unpack(b, a.bd);
+    ab_t a; tables(); unpack(b, a.bd); g_evals = 0;
     a.max_depth = max_depth; a.scores = scores; a.leaves = 0; a.sentinel = 2 * WIN;
     for (int c = 0; c < 25; c++) {            /* ChooseMove, alphabeta.go:98-110 */
         values[c] = SQO_NO_MOVE;
@@ -574,7 +580,7 @@ static int ab2(ab_t *a, int ply, int player, int alpha, int beta, int c, int boa
 
 void sqo_ab2_root(sqo_board b, int max_depth, const int scores[25], int32_t values[25],
                   uint32_t *best_mask, int32_t *best_value, int64_t *leaves) {
-    ab_t a; tables(); unpack(b, a.bd);
+    ab_t a; tables(); unpack(b, a.bd); g_evals = 0;
     a.max_depth = max_depth - 1;              /* squavathr.go:239 */
     a.scores = scores; a.leaves = 0; a.sentinel = 2 * WIN;
     for (int c = 0; c < 25; c++) {            /* chooseMove, squavathr.go:241-253 */
@@ -625,7 +631,7 @@ static int ab3(ab_t *a, int ply, int next_player, int alpha, int beta, int c, in
 
 int32_t sqo_ab_subtree(int dialect, sqo_board b, int last_cell, int ply, int side,
                        int32_t carried, int max_depth, const int scores[25], int64_t *leaves) {
-    ab_t a; tables(); unpack(b, a.bd);
+    ab_t a; tables(); unpack(b, a.bd); g_evals = 0;
     a.max_depth = max_depth; a.scores = scores; a.leaves = 0;
     a.sentinel = dialect == 4 ? WIN : 2 * WIN;
     int v = 0;

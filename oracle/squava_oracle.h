@@ -112,6 +112,9 @@ int32_t sqo_ab_subtree(int dialect, sqo_board b, int last_cell, int ply, int sid
                        int32_t carried, int max_depth, const int scores[25],
                        int64_t *leaves);
 
+/* evaluator calls made by the calling thread's most recent sqo_ab* search */
+int64_t sqo_last_evals(void);
+
 /* opening3's symmetry de-duplication (opening3.go:66-128): writes the
  * (first, reply) cell pairs it would search, in its order; returns count.   */
 int sqo_opening3_subtrees(int first[150], int reply[150]);

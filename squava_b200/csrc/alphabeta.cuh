@@ -94,7 +94,8 @@ struct AbRun {
     int* value;                      // slot values
     int* pending;                    // unfinished children
     int* units;                      // indices of DFS units
-    unsigned int* counters;          // [0] n_nodes [1] n_units [2] queue head
+    int* aborted;                    // units that ran out of budget in this pass: split one ply deeper
+    unsigned int* counters;          // [0] n_nodes [1] n_units [2] queue head [3] n_aborted
     int* out;                        // final values
     unsigned long long* node_count;  // evaluator calls per group
     int node_capacity;
@@ -200,11 +201,14 @@ __device__ __forceinline__ void ab_bounds(const AbRun& R, int node, int& alpha, 
 
 __device__ __forceinline__ int ab_new_node(const AbRun& R, const AbNode& n) {
     unsigned int idx = atomicAdd(&R.counters[0], 1u);
-    if (idx >= (unsigned)R.node_capacity) return -1;  // cannot happen: capacity is an exact bound
+    if (idx >= (unsigned)R.node_capacity) return -1;  // cannot happen: the host checks the room before every expansion
     R.nodes[idx] = n;
     R.value[idx] = n.side > 0 ? -R.sentinel : R.sentinel;
     R.pending[idx] = 0;
-    if (n.split == 0) { unsigned int u = atomicAdd(&R.counters[1], 1u); R.units[u] = (int)idx; }
+    if (n.split == 0) {
+        unsigned int u = atomicAdd(&R.counters[1], 1u);
+        R.units[u] = (int)idx;
+    }
     return (int)idx;
 }
 
@@ -282,16 +286,20 @@ ab_subtree_nodes_kernel(AbRun R, const sq_subtree* __restrict__ st, const int8_t
     ab_new_node(R, nd);
 }
 
-// Breadth-first expansion of nodes [lo, hi) that still have split > 0.
+// One ply of breadth-first expansion.  list == nullptr: the nodes [lo, lo+count) that still
+// have split > 0 (static pre-split); otherwise the nodes list[0..count) -- units that ran out
+// of budget in the last pass -- whose children become the next pass's units.
 template <int DIALECT>
 __global__ void __launch_bounds__(kAbThreads)
-ab_expand_kernel(AbRun R, int lo, int hi) {
+ab_expand_kernel(AbRun R, const int* __restrict__ list, int lo, int count) {
     __shared__ AbTables T;
     load_tables(T);
-    int idx = lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= hi) return;
-    const AbNode n = R.nodes[idx];
-    if (n.split <= 0) return;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const int idx = list ? list[t] : lo + t;
+    AbNode n = R.nodes[idx];
+    if (list) n.split = 1;
+    else if (n.split <= 0) return;
     int value = 0, carried_down = 0;
     unsigned long long evals = 1;
     if (ab_enter<DIALECT>(T, R, n, value, carried_down)) {
@@ -304,13 +312,14 @@ ab_expand_kernel(AbRun R, int lo, int hi) {
     __threadfence();
     const bool pend_is_x = (n.x >> n.cell) & 1u;
     const int sign = pend_is_x ? 1 : -1;
-    while (empties) {
-        uint32_t bit = empties & (0u - empties);
-        empties ^= bit;
+    for (int k = 0; k < 25; k++) {               // children in the dialect's visiting order
+        const int cell = DIALECT >= 3 ? T.order[k] : k;
+        const uint32_t bit = 1u << cell;
+        if (!(empties & bit)) continue;
         AbNode c;
         c.x = n.x | (n.side > 0 ? bit : 0u);
         c.o = n.o | (n.side > 0 ? 0u : bit);
-        c.cell = (int8_t)(__ffs(bit) - 1);
+        c.cell = (int8_t)cell;
         c.ply = n.ply + 1;
         c.side = -n.side;
         c.split = n.split - 1;
@@ -331,7 +340,7 @@ ab_expand_kernel(AbRun R, int lo, int hi) {
 // Sequential alpha-beta per lane over the queued units.
 template <int DIALECT>
 __global__ void __launch_bounds__(kAbThreads)
-ab_dfs_kernel(AbRun R, int n_units) {
+ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget) {
     __shared__ AbTables T;
     load_tables(T);
     constexpr bool kOrdered = DIALECT >= 3;   // children in orderedCells order
@@ -381,6 +390,12 @@ ab_dfs_kernel(AbRun R, int n_units) {
             continue;
         }
 
+        if (evals > budget) {      // too big for one lane: hand the unit back to be split one ply deeper
+            atomicAdd(&R.node_count[group], evals);
+            R.aborted[atomicAdd(&R.counters[3], 1u)] = unit;
+            sp = -1;
+            continue;
+        }
         const int ply = base_ply + sp;
         const int side = (sp & 1) ? -base_side : base_side;
         int ret;
@@ -462,9 +477,15 @@ inline cudaError_t ab_configure(int* blocks_per_sm) {
     return cudaSuccess;
 }
 
-// Breadth-first plies to expand under a node with `empties` empty cells and `rem`
-// plies of search left, so that a DFS unit stays small enough for the tail of the
-// launch to be short.  Override with SQ_AB_SPLIT=<0..3>.
+// Evaluator calls a unit may spend in one pass before it is split (SQ_AB_BUDGET overrides).
+inline unsigned long long ab_budget() {
+    const char* env = getenv("SQ_AB_BUDGET");
+    if (env && *env) return strtoull(env, nullptr, 10);
+    return 4096;
+}
+
+// Static pre-split: plies to expand breadth-first under a level-0 node before the first pass
+// (skips passes that would certainly abort).  Override with SQ_AB_SPLIT=<0..3>.
 inline int ab_choose_split(int empties, int rem) {
     const char* env = getenv("SQ_AB_SPLIT");
     const int forced = (env && *env) ? atoi(env) : -1;
@@ -474,7 +495,7 @@ inline int ab_choose_split(int empties, int rem) {
         // rough size of the subtree: product of the branching factors, damped
         double est = 1.0;
         for (int k = 0; k < rem && empties - k > 0; k++) est *= 0.55 * (empties - k) + 0.45;
-        split = est > 3e7 ? 3 : est > 3e5 ? 2 : est > 3e3 ? 1 : 0;
+        split = est > 3e7 ? 1 : 0;
     }
     if (split > rem - 1) split = rem - 1 < 0 ? 0 : rem - 1;
     if (split > empties - 1) split = empties - 1 < 0 ? 0 : empties - 1;
@@ -485,6 +506,7 @@ inline int ab_choose_split(int empties, int rem) {
 struct AbWork {   // device allocations of one chunk
     AbNode* nodes = nullptr; int* value = nullptr; int* pending = nullptr; int* units = nullptr;
     unsigned int* counters = nullptr; int8_t* split = nullptr;
+    int* aborted = nullptr;
 };
 
 inline void ab_free(AbWork& w, cudaStream_t st) {
@@ -494,6 +516,7 @@ inline void ab_free(AbWork& w, cudaStream_t st) {
     if (w.units) cudaFreeAsync(w.units, st);
     if (w.counters) cudaFreeAsync(w.counters, st);
     if (w.split) cudaFreeAsync(w.split, st);
+    if (w.aborted) cudaFreeAsync(w.aborted, st);
     w = AbWork();
 }
 
@@ -506,11 +529,12 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
     SQ_AB_CK(cudaMallocAsync(&w.value, sizeof(int) * capacity, st));
     SQ_AB_CK(cudaMallocAsync(&w.pending, sizeof(int) * capacity, st));
     SQ_AB_CK(cudaMallocAsync(&w.units, sizeof(int) * capacity, st));
+    SQ_AB_CK(cudaMallocAsync(&w.aborted, sizeof(int) * capacity, st));
     SQ_AB_CK(cudaMallocAsync(&w.counters, sizeof(unsigned int) * 8, st));
     SQ_AB_CK(cudaMallocAsync(&w.split, n, st));
     SQ_AB_CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned int) * 8, st));
     SQ_AB_CK(cudaMemcpyAsync(w.split, h_split, n, cudaMemcpyHostToDevice, st));
-    R.nodes = w.nodes; R.value = w.value; R.pending = w.pending; R.units = w.units;
+    R.nodes = w.nodes; R.value = w.value; R.pending = w.pending; R.units = w.units; R.aborted = w.aborted;
     R.counters = w.counters; R.node_capacity = (int)capacity;
     if (roots) {
         int threads = n * 25;
@@ -522,25 +546,47 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
     }
     (*launches)++;
     SQ_AB_CK(cudaGetLastError());
-    unsigned int h_counters[3] = {0, 0, 0};
+    unsigned int h_counters[4] = {0, 0, 0, 0};
     int lo = 0;
-    for (int level = 0; level < 3; level++) {
+    for (int level = 0; level < 3; level++) {        // static pre-split (usually none)
         SQ_AB_CK(cudaMemcpyAsync(h_counters, w.counters, sizeof h_counters, cudaMemcpyDeviceToHost, st));
         SQ_AB_CK(cudaStreamSynchronize(st));
         int hi = (int)h_counters[0];
         if (hi <= lo) break;
-        ab_expand_kernel<DIALECT><<<(hi - lo + kAbThreads - 1) / kAbThreads, kAbThreads, 0, st>>>(R, lo, hi);
+        ab_expand_kernel<DIALECT><<<(hi - lo + kAbThreads - 1) / kAbThreads, kAbThreads, 0, st>>>(R, nullptr, lo, hi - lo);
         (*launches)++;
         SQ_AB_CK(cudaGetLastError());
         lo = hi;
     }
-    SQ_AB_CK(cudaMemcpyAsync(h_counters, w.counters, sizeof h_counters, cudaMemcpyDeviceToHost, st));
-    SQ_AB_CK(cudaStreamSynchronize(st));
-    int n_units = (int)h_counters[1];
-    if (n_units > 0) {
+    // Adaptive passes: every unit gets `budget` evaluator calls; the ones that need more are
+    // split one ply deeper and their children (now with their siblings' bounds in the parent
+    // slots) form the next pass.  Small subtrees keep sequential pruning, big ones get spread.
+    unsigned long long budget = ab_budget();
+    for (int pass = 0;; pass++) {
+        SQ_AB_CK(cudaMemcpyAsync(h_counters, w.counters, sizeof h_counters, cudaMemcpyDeviceToHost, st));
+        SQ_AB_CK(cudaStreamSynchronize(st));
+        const int n_units = (int)h_counters[1];
+        if (n_units == 0) break;
         long long blocks = ((long long)n_units + kAbThreads - 1) / kAbThreads;
         if (blocks > grid_cap) blocks = grid_cap;
-        ab_dfs_kernel<DIALECT><<<(unsigned)blocks, kAbThreads, 0, st>>>(R, n_units);
+        ab_dfs_kernel<DIALECT><<<(unsigned)blocks, kAbThreads, 0, st>>>(R, n_units, budget);
+        (*launches)++;
+        SQ_AB_CK(cudaGetLastError());
+        SQ_AB_CK(cudaMemcpyAsync(h_counters, w.counters, sizeof h_counters, cudaMemcpyDeviceToHost, st));
+        SQ_AB_CK(cudaStreamSynchronize(st));
+        const int n_aborted = (int)h_counters[3];
+        if (n_aborted == 0) break;
+        const unsigned int zero3[3] = {0, 0, 0};
+        SQ_AB_CK(cudaMemcpyAsync(w.counters + 1, zero3, sizeof zero3, cudaMemcpyHostToDevice, st));
+        if ((long long)h_counters[0] + 25ll * n_aborted > capacity) {
+            // no room to split further: finish the stragglers without a budget
+            SQ_AB_CK(cudaMemcpyAsync(w.units, w.aborted, sizeof(int) * n_aborted, cudaMemcpyDeviceToDevice, st));
+            const unsigned int nu = (unsigned)n_aborted;
+            SQ_AB_CK(cudaMemcpyAsync(w.counters + 1, &nu, sizeof nu, cudaMemcpyHostToDevice, st));
+            budget = ~0ull;
+            continue;
+        }
+        ab_expand_kernel<DIALECT><<<(n_aborted + kAbThreads - 1) / kAbThreads, kAbThreads, 0, st>>>(R, w.aborted, 0, n_aborted);
         (*launches)++;
         SQ_AB_CK(cudaGetLastError());
     }
@@ -567,7 +613,7 @@ inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t score
     memcpy(R.scores, scores, 25);
 }
 
-constexpr long long kAbChunkNodes = 24ll << 20;   // node slots per chunk (about 1 GB of workspace)
+constexpr long long kAbChunkNodes = 16ll << 20;   // node slots per chunk: pre-split nodes + the pool adaptive splitting draws on (~640 MB)
 
 // worst-case node count below one level-0 node with e empties and `split` expanded plies
 inline long long ab_node_bound(int e, int split) {
@@ -593,13 +639,13 @@ inline cudaError_t ab_root_search(const sq_board* h_pos, const sq_board* d_pos, 
             int empt = 25 - __builtin_popcount((h_pos[hi].x | h_pos[hi].o) & kFull25);
             int sp = ab_choose_split(empt - 1, R.max_depth - 1);
             long long need = (long long)empt * ab_node_bound(empt - 1, sp);
-            if (hi > lo && cap + need > kAbChunkNodes) break;
+            if (hi > lo && cap + need > kAbChunkNodes / 4) break;
             split[hi] = (int8_t)sp; cap += need; hi++;
         }
         AbRun Rc = R;
         Rc.out = d_values + lo * 25;
         Rc.node_count = d_nodes + lo;
-        e = ab_dispatch(dialect, Rc, w, d_pos + lo, true, (int)(hi - lo), split.data() + lo, cap + 16, grid_cap, st, launches);
+        e = ab_dispatch(dialect, Rc, w, d_pos + lo, true, (int)(hi - lo), split.data() + lo, cap + 16 > kAbChunkNodes ? cap + 16 : kAbChunkNodes, grid_cap, st, launches);
         if (e != cudaSuccess) return e;
         lo = hi;
     }
@@ -622,13 +668,13 @@ inline cudaError_t ab_subtree_search(const sq_subtree* h_st, const sq_subtree* d
             int empt = 25 - __builtin_popcount((h_st[hi].b.x | h_st[hi].b.o) & kFull25);
             int sp = ab_choose_split(empt, R.max_depth - h_st[hi].ply);
             long long need = ab_node_bound(empt, sp);
-            if (hi > lo && cap + need > kAbChunkNodes) break;
+            if (hi > lo && cap + need > kAbChunkNodes / 4) break;
             split[hi] = (int8_t)sp; cap += need; hi++;
         }
         AbRun Rc = R;
         Rc.out = d_value + lo;
         Rc.node_count = d_nodes + lo;
-        e = ab_dispatch(dialect, Rc, w, d_st + lo, false, (int)(hi - lo), split.data() + lo, cap + 16, grid_cap, st, launches);
+        e = ab_dispatch(dialect, Rc, w, d_st + lo, false, (int)(hi - lo), split.data() + lo, cap + 16 > kAbChunkNodes ? cap + 16 : kAbChunkNodes, grid_cap, st, launches);
         if (e != cudaSuccess) return e;
         lo = hi;
     }

@@ -60,6 +60,7 @@ def load():
                                  i32p, C.POINTER(C.c_int64)]
     L.sqo_ab_subtree.restype = C.c_int32
     L.sqo_opening3_subtrees.argtypes = [i32p, i32p]
+    L.sqo_last_evals.restype = C.c_int64
     _lib = L
     return _Oracle(L)
 
@@ -156,6 +157,9 @@ class _Oracle:
         v = self.L.sqo_ab_subtree(dialect, Board(x, o), last_cell, ply, side, carried, max_depth,
                                   sc, C.byref(lv))
         return v, lv.value
+
+    def last_evals(self):
+        return int(self.L.sqo_last_evals())
 
     def opening3_subtrees(self):
         f = (C.c_int32 * 150)(); r = (C.c_int32 * 150)()

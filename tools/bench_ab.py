@@ -49,13 +49,15 @@ def main():
             k = min(args.check, args.count)
             t0 = time.perf_counter()
             leaves = 0
+            oevals = 0
             for i in range(k):
                 f = o.ab1_root if args.dialect == 1 else o.ab2_root
                 ov, obm, obv, lv = f(int(boards[i]["x"]), int(boards[i]["o"]), args.depth, sc)
                 assert values[i].tolist() == ov and int(bm[i]) == obm and int(bv[i]) == obv, (m, i)
                 leaves += lv
+                oevals += o.last_evals()
             cdt = time.perf_counter() - t0
-            rec.update({"checked": k, "oracle_leaves_checked": leaves, "oracle_seconds_1core": cdt,
+            rec.update({"checked": k, "oracle_leaves_checked": leaves, "oracle_evals_checked": oevals, "oracle_seconds_1core": cdt,
                         "oracle_leaves_per_s_1core": leaves / max(cdt, 1e-9),
                         "gpu_evals_checked": int(nodes[:k].sum())})
         print(json.dumps(rec), flush=True)
