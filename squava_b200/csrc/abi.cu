@@ -95,6 +95,7 @@ int launch_playouts(Device& d, const sq_board* leaves, const int8_t* to_move, in
     P.key0 = (uint32_t)g_seed ^ (uint32_t)(stream_id >> 32);
     P.key1 = (uint32_t)(g_seed >> 32);
     P.ctr3 = (uint32_t)stream_id;
+    P.one = 1u;
     unsigned long long items = (unsigned long long)n_leaves * S;
     P.n_rounds = (int64_t)((items + 31) / 32);
     P.round_counter = d.counters;

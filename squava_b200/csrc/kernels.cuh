@@ -105,12 +105,17 @@ struct PlayoutParams {
     uint32_t quota_lo;         // N / S
     uint32_t quota_extra;      // N % S: items j < quota_extra run quota_lo + 1
     uint32_t key0, key1, ctr3;
+    uint32_t one;              // == 1, but opaque to ptxas: x*one+y is issued as IMAD on the FMA pipe,
+                               // which balances it against the ALU pipe (LOP3/SEL/ISETP) -- see DESIGN.md
     int64_t n_rounds;
     unsigned long long* round_counter;
     unsigned long long* out;   // [n_leaves][4]
 };
 
-__global__ void __launch_bounds__(kPlayoutThreads, 4)
+#ifndef SQ_PLAYOUT_CTAS_PER_SM
+#define SQ_PLAYOUT_CTAS_PER_SM 4
+#endif
+__global__ void __launch_bounds__(kPlayoutThreads, SQ_PLAYOUT_CTAS_PER_SM)
 playout_kernel(PlayoutParams P) {
     extern __shared__ uint32_t s_arr[];  // [kMaxEmpty][blockDim.x]
     const int tid = threadIdx.x;
@@ -164,12 +169,19 @@ playout_kernel(PlayoutParams P) {
         }
 
         // ---- ply loop --------------------------------------------------------
+        // No per-ply gating of finished lanes: a lane keeps playing after its quota, and the
+        // counters are SNAPSHOT at the ply its last playout ends (a rare, real branch).
         uint32_t a = leaf_a, b = leaf_b, n = n0;
-        uint32_t inc_w = 1u;       // what the mover's win adds: 1 = first player, 0x10000 = second
-        uint32_t acc = 0, plies = 0;
+        uint32_t inc_w = 1u;          // what the mover's win adds: 1 = first player, 0x10000 = second
+        uint32_t acc = 0;
+        uint32_t acc_fin = 0, plies = 0;   // snapshots: every iteration of an unfinished lane is one ply
+        int remi = (int)rem;          // playouts still to finish; <= 0: done
         uint32_t blk = 0;
         const uint32_t c1 = j, c2 = (uint32_t)(P.leaf_index_base + leaf64);
-        while (__any_sync(0xffffffffu, rem != 0)) {
+        const uint32_t one = P.one;
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(arr);   // element k at sbase + k*kStride
+        constexpr uint32_t kStride = kPlayoutThreads * 4;
+        while (__any_sync(0xffffffffu, remi > 0)) {
             uint32_t w[4];
             philox4x32_10(blk, c1, c2, P.ctr3, P.key0, P.key1, w);
             blk++;
@@ -178,29 +190,40 @@ playout_kernel(PlayoutParams P) {
                 uint32_t r = w[wi];
 #pragma unroll
                 for (int d = 0; d < 3; d++) {
-                    unsigned long long prod = (unsigned long long)r * n;
-                    uint32_t idx = (uint32_t)(prod >> 32);
-                    r = (uint32_t)prod;
-                    uint32_t bit = arr[idx * kPlayoutThreads];
-                    uint32_t last = arr[(n - 1) * kPlayoutThreads];
-                    arr[idx * kPlayoutThreads] = last;
-                    arr[(n - 1) * kPlayoutThreads] = bit;
-                    uint32_t m = a | bit;
-                    Pairs p = pairs(m);
-                    uint32_t t3 = any3(p), t4 = any4(p);
-                    uint32_t n1 = n - 1;
-                    bool term = (t3 != 0) | (n1 == 0);
-                    bool active = rem != 0;
-                    uint32_t inc = t4 ? inc_w : (t3 ? (inc_w ^ 0x10001u) : 0u);
-                    plies += active ? 1u : 0u;
-                    if (term && active) { acc += inc; rem--; }
+                    // draw: idx = floor(r*n / 2^32), r <- r*n mod 2^32
+                    const uint32_t idx = __umulhi(r, n);
+                    r = r * n;
+                    const uint32_t ai = idx * kStride + sbase;
+                    const uint32_t al = n * kStride + (sbase - kStride);
+                    uint32_t bit, last;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(bit) : "r"(ai));
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(last) : "r"(al));
+                    asm volatile("st.shared.u32 [%0], %1;" :: "r"(ai), "r"(last));
+                    asm volatile("st.shared.u32 [%0], %1;" :: "r"(al), "r"(bit));
+                    const uint32_t m = a + bit;          // bit is an empty cell: + is |
+                    const Pairs p = pairs(m);
+                    const uint32_t t3 = any3(p), t4 = any4(p);
+                    const uint32_t n1 = n * one - 1u;
+                    const bool line = t3 != 0;
+                    const bool term = line | (n1 == 0);
+                    const uint32_t inc_l = inc_w ^ 0x10001u;
+                    const uint32_t inc = t4 ? inc_w : inc_l;
+                    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q mad.lo.u32 %0, %2, %3, %0;\n\t}"
+                        : "+r"(acc) : "r"(t3), "r"(inc), "r"(one));
+                    const bool fin = term & (remi == 1);
+                    const uint32_t plies_now = blk * 12u - 11u + (uint32_t)(wi * 3 + d);   // blk already advanced
+                    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %4, 0;\n\t@q mov.u32 %0, %2;\n\t@q mov.u32 %1, %3;\n\t}"
+                        : "+r"(acc_fin), "+r"(plies) : "r"(acc), "r"(plies_now), "r"((uint32_t)fin));
+                    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q add.s32 %0, %0, -1;\n\t}"
+                        : "+r"(remi) : "r"((uint32_t)term));
                     a = term ? leaf_a : b;
                     b = term ? leaf_b : m;
                     n = term ? n0 : n1;
-                    inc_w = term ? 1u : (inc_w ^ 0x10001u);
+                    inc_w = term ? 1u : inc_l;
                 }
             }
         }
+        acc = acc_fin;
 
         // ---- fold into per-leaf counts ------------------------------------------
         uint32_t first_wins = acc & 0xffffu, second_wins = acc >> 16;
