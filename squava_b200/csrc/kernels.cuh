@@ -203,7 +203,7 @@ playout_kernel(PlayoutParams P) {
                     const uint32_t m = a + bit;          // bit is an empty cell: + is |
                     const Pairs p = pairs(m);
                     const uint32_t t3 = any3(p), t4 = any4(p);
-                    const uint32_t n1 = n * one - 1u;
+                    const uint32_t n1 = n - 1u;
                     const bool line = t3 != 0;
                     const bool term = line | (n1 == 0);
                     const uint32_t inc_l = inc_w ^ 0x10001u;

@@ -129,8 +129,10 @@ static double UCB1(const Node* p, double UCTK, bool factor2) {          // mcts.
 static Node* bestMove(Node* p, double UCTK, bool factor2) {             // mcts.go:218-238
     double bestscore = kEps;
     Node* best = nullptr;
+    // same expression as UCB1() per child; ln(parent visits) is the same for all of them
+    const double lg = (factor2 ? 2. : 1.) * std::log(p->visits);
     for (auto& c : p->childNodes) {
-        double u = UCB1(c.get(), UCTK, factor2);
+        double u = c->wins / (c->visits + kEps) + UCTK * std::sqrt(lg / (c->visits + kEps));
         if (u > bestscore) { bestscore = u; best = c.get(); }
     }
     return best;
