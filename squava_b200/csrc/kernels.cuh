@@ -91,7 +91,10 @@ classify_kernel(const sq_board* __restrict__ boards, int64_t n, uint8_t* __restr
 // seed_hi), counter (block, j, leaf_index, stream_lo); block b feeds plies
 // 12b .. 12b+11 of the item, counted over ALL its playouts back to back.
 
-constexpr int kItemQuota = 1024;       // playouts per item (max); < 65536 (packed counters)
+#ifndef SQ_ITEM_QUOTA
+#define SQ_ITEM_QUOTA 1024
+#endif
+constexpr int kItemQuota = SQ_ITEM_QUOTA;       // playouts per item (max); < 65536 (packed counters)
 constexpr int kPlayoutThreads = 256;   // CTA size
 constexpr int kMaxEmpty = 25;
 
