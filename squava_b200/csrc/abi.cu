@@ -191,6 +191,12 @@ int sq_init(const int* device_ids, int n_devices, uint64_t seed) {
         d.sm_count = prop.multiProcessorCount;
         CK(cudaSetDevice(d.id));
         CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+        {   // keep the alpha-beta workspace in the stream-ordered pool between calls
+            cudaMemPool_t pool;
+            CK(cudaDeviceGetDefaultMemPool(&pool, d.id));
+            uint64_t keep = ~0ull;
+            CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
         CK(cudaEventCreate(&d.ev0));
         CK(cudaEventCreate(&d.ev1));
         CK(cudaMalloc(&d.counters, 8 * sizeof(unsigned long long)));

@@ -22,6 +22,8 @@
 // noMiddle2 penalties), 3/4 opening3 / opening2 (evaluate at entry, cumulative,
 // orderedCells child order).
 #pragma once
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -338,23 +340,84 @@ ab_expand_kernel(AbRun R, const int* __restrict__ list, int lo, int count) {
 }
 
 // Sequential alpha-beta per lane over the queued units.
+//
+// The frame being searched lives in registers; the frames below it in shared memory
+// ([frame][word][thread]: a warp's accesses are conflict-free).  A child that cannot have
+// children of its own (depth stop, terminal, full board) is resolved in place and never
+// pushed, so most evaluator calls touch no stack memory at all.
+//
+// One LINE WALK per child: the lines through the child's cell are walked once, with a fixed
+// trip count over transposed, padded tables (conflict-free, no divergence), giving
+//   four / three   the mover completed a 4-line / 3-line through the cell
+//   e1, e2         the empty cells that complete one / two three-of-four quads through it
+// DIALECT 1 evaluates a move once per CHILD of the node it leads to, the boards differing by
+// the child's mark only: a mark on an e1 (e2) cell removes one (two) of the counted quads, so
+// the per-child evaluation of the pending move is two bit tests on the walk done when the
+// node was entered.  The same identity handles the mark a leaf places before it evaluates.
+struct AbWalkTables {
+    uint32_t quads[8][32];      // [k][cell]; unused slots hold kDummyLine
+    uint32_t triplets[12][32];
+};
+constexpr uint32_t kDummyLine = 0xC0000000u;   // two bits no board has: never owned, never three-of-four
+
+__device__ __forceinline__ void ab_load_walk_tables(AbWalkTables& W) {
+    for (int i = threadIdx.x; i < 8 * 32; i += blockDim.x) {
+        int k = i >> 5, c = i & 31;
+        W.quads[k][c] = (c < 25 && k < c_ab.n_quads[c]) ? c_ab.quads[c][k] : kDummyLine;
+    }
+    for (int i = threadIdx.x; i < 12 * 32; i += blockDim.x) {
+        int k = i >> 5, c = i & 31;
+        W.triplets[k][c] = (c < 25 && k < c_ab.n_triplets[c]) ? c_ab.triplets[c][k] : kDummyLine;
+    }
+    __syncthreads();
+}
+
+struct AbWalk { bool four, three; uint32_t e1, e2; };
+
+__device__ __forceinline__ AbWalk ab_walk(const AbWalkTables& W, uint32_t own, uint32_t opp, int cell) {
+    uint32_t e1 = 0, e2 = 0, min_q = 0xffffffffu, min_t = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t hole = W.quads[k][cell] & ~own;          // cells of the quad the mover lacks
+        min_q = min(min_q, hole);                                // 0 <=> the quad is complete
+        const uint32_t bad = hole & ((hole - 1u) | opp);         // more than one hole, or the hole is taken
+        const uint32_t h = bad ? 0u : hole;
+        e2 |= e1 & h;
+        e1 |= h;
+    }
+#pragma unroll
+    for (int k = 0; k < 12; k++) min_t = min(min_t, W.triplets[k][cell] & ~own);
+    AbWalk r;
+    r.four = min_q == 0; r.three = min_t == 0; r.e1 = e1; r.e2 = e2;
+    return r;
+}
+
+template <int DIALECT> struct AbFrameWords { static constexpr int n = DIALECT == 1 ? 5 : 3; };
+
 template <int DIALECT>
 __global__ void __launch_bounds__(kAbThreads)
-ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget) {
+ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
     __shared__ AbTables T;
+    __shared__ AbWalkTables W;
+    extern __shared__ uint32_t s_stack[];      // [n_frames][words][kAbThreads]
     load_tables(T);
-    constexpr bool kOrdered = DIALECT >= 3;   // children in orderedCells order
-    constexpr int kFrames = kAbMaxDepth + 2;
-    uint32_t f_moves[kFrames], f_cur[kFrames];
-    short f_value[kFrames], f_alpha[kFrames], f_beta[kFrames];
-    int f_carried[kFrames];
-    signed char f_cell[kFrames];
+    ab_load_walk_tables(W);
+    constexpr bool kOrdered = DIALECT >= 3;    // children in orderedCells order
+    constexpr int kWords = AbFrameWords<DIALECT>::n;
+    uint32_t* const my = s_stack + threadIdx.x;
+#define SQ_FR(f, w) my[((f) * kWords + (w)) * kAbThreads]
 
     int sp = -1, unit = -1, base_ply = 0, base_side = 1, group = 0;
-    uint32_t x = 0, o = 0, emp = 0;       // emp: empty cells in child-order space
+    uint32_t x = 0, o = 0, emp = 0;            // emp: empty cells in child-order space
+    // the frame in registers
+    uint32_t moves = 0;                        // children still to try (child-order space)
+    int value = 0, alpha = 0, beta = 0, carried = 0;
+    uint32_t fe1 = 0, fe2 = 0;                 // DIALECT 1: walk of the pending move ...
+    int fpc = 0;                               // ... which stands on this cell
     unsigned long long evals = 0;
+    (void)n_frames;
 
-    auto order_mask = [&](uint32_t cells) -> uint32_t {  // API layout -> child-order space
+    auto order_mask = [&](uint32_t cells) -> uint32_t {   // API layout -> child-order space
         if (!kOrdered) return cells;
         uint32_t m = 0;
         while (cells) { int c = __ffs(cells) - 1; cells &= cells - 1; m |= 1u << T.rank[c]; }
@@ -362,88 +425,103 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget) {
     };
 
     for (;;) {
+        int ret = 0;
+        bool returning = false;   // `ret` is to be handed to frame sp ...
+        bool restore = false;     // ... which is in shared memory (a pushed child came back)
         if (sp < 0) {
             unsigned int u = atomicAdd(&R.counters[2], 1u);
             if (u >= (unsigned)n_units) break;
             unit = R.units[u];
             const AbNode n = R.nodes[unit];
-            int alpha = R.win_lo, beta = R.win_hi;
-            ab_bounds(R, unit, alpha, beta);
-            if (alpha >= beta) {   // already cut off: hand up a value that changes nothing
+            int a0 = R.win_lo, b0 = R.win_hi;
+            ab_bounds(R, unit, a0, b0);
+            if (a0 >= b0) {           // already cut off: hand up a value that changes nothing
                 ab_complete(R, unit, n.side > 0 ? -30000 : 30000);
                 continue;
             }
-            int value = 0, carried_down = 0;
+            int v0 = 0, carried_down = 0;
             evals = 1; group = n.group;
-            if (ab_enter<DIALECT>(T, R, n, value, carried_down)) {
+            if (ab_enter<DIALECT>(T, R, n, v0, carried_down)) {
                 atomicAdd(&R.node_count[group], evals);
-                ab_complete(R, unit, value);
+                ab_complete(R, unit, v0);
                 continue;
             }
             x = n.x; o = n.o; base_ply = n.ply; base_side = n.side;
             emp = order_mask(kFull25 & ~(x | o));
             sp = 0;
-            f_moves[0] = emp; f_cur[0] = 0;
-            f_value[0] = (short)(n.side > 0 ? -R.sentinel : R.sentinel);
-            f_alpha[0] = (short)alpha; f_beta[0] = (short)beta;
-            f_carried[0] = carried_down; f_cell[0] = n.cell;
+            moves = emp;
+            value = n.side > 0 ? -R.sentinel : R.sentinel;
+            alpha = a0; beta = b0; carried = carried_down;
+            if (DIALECT == 1) {       // the pending move is not terminal (ab_enter said so): keep its walk
+                const bool px = (x >> n.cell) & 1u;
+                AbWalk w = ab_walk(W, px ? x : o, px ? o : x, n.cell);
+                fe1 = w.e1; fe2 = w.e2; fpc = n.cell;
+            }
             continue;
         }
-
-        if (evals > budget) {      // too big for one lane: hand the unit back to be split one ply deeper
+        if (evals > budget) {          // too big for one lane: hand the unit back to be split one ply deeper
             atomicAdd(&R.node_count[group], evals);
             R.aborted[atomicAdd(&R.counters[3], 1u)] = unit;
             sp = -1;
             continue;
         }
+
         const int ply = base_ply + sp;
         const int side = (sp & 1) ? -base_side : base_side;
-        int ret;
-        bool returning;     // a child of frame sp has produced `ret`
-        if (f_moves[sp] == 0) {
-            ret = f_value[sp]; sp--; returning = true;    // this node is done: back to its parent
+        if (moves == 0) {
+            ret = value; returning = true;            // node done (also: a node with no legal move)
+            sp--; restore = true;
         } else {
-            uint32_t kbit = f_moves[sp] & (0u - f_moves[sp]);
-            f_moves[sp] ^= kbit;
-            int cell = kOrdered ? T.order[__ffs(kbit) - 1] : (__ffs(kbit) - 1);
-            uint32_t bit = 1u << cell;
-            if (side > 0) x |= bit; else o |= bit;
-            emp &= ~kbit;
-            f_cur[sp] = kbit | ((uint32_t)cell << 25);
+            const uint32_t kbit = moves & (0u - moves);
+            moves ^= kbit;
+            const int kidx = __ffs(kbit) - 1;
+            const int cell = kOrdered ? T.order[kidx] : kidx;
+            const uint32_t bit = 1u << cell;
+            const uint32_t emp_after = emp & ~kbit;
+            const uint32_t xs = x | (side > 0 ? bit : 0u), os = o | (side > 0 ? 0u : bit);
+            const int cply = ply + 1;
             evals++;
+            int d = 0;
             if (DIALECT == 1) {
-                // evaluate the move that led here, the child's mark being on the board
-                const int sign = -side, pc = f_cell[sp];
-                Eval e = eval_lines(T, sign > 0 ? x : o, sign > 0 ? o : x, pc, sign, ply);
-                int d = e.value + sign * R.scores[pc];
-                if (e.terminal || ply >= R.max_depth) {
-                    ret = e.terminal ? e.value : d + f_carried[sp];
-                    if (side > 0) x &= ~bit; else o &= ~bit;      // the node itself returns
-                    emp |= kbit;
-                    sp--; returning = true;
-                } else {
-                    sp++;
-                    f_moves[sp] = emp; f_cur[sp] = 0;
-                    f_value[sp] = (short)(side > 0 ? R.sentinel : -R.sentinel);   // child is the other side
-                    f_alpha[sp] = f_alpha[sp - 1]; f_beta[sp] = f_beta[sp - 1];
-                    f_carried[sp] = d; f_cell[sp] = (signed char)cell;
-                    returning = false;
-                }
+                // the pending move, evaluated with this child's mark on the board
+                const int cnt = __popc(fe1 & ~bit) + __popc(fe2 & ~bit);
+                d = -side * (30 * cnt + R.scores[fpc]);
+            }
+            if (DIALECT == 1 && emp_after == 0) {
+                ret = side > 0 ? R.sentinel : -R.sentinel;            // the child (other side) has no move
+                returning = true;
             } else {
-                // evaluate the child at its entry
-                Eval e = eval_lines(T, side > 0 ? x : o, side > 0 ? o : x, cell, side, ply + 1);
-                int d = e.value + side * R.scores[cell];
-                if (DIALECT == 2 && !e.terminal) d += eval_penalties(T, side > 0 ? x : o, side > 0 ? o : x, cell, side);
-                if (e.terminal || ply + 1 == R.max_depth) {
-                    ret = e.terminal ? e.value : d + f_carried[sp];
-                    returning = true;                               // the child returned at once
+                const AbWalk w = ab_walk(W, side > 0 ? xs : os, side > 0 ? os : xs, cell);
+                if (w.four) { ret = side * (kWin - cply); returning = true; }
+                else if (w.three) { ret = -side * (kWin - cply); returning = true; }
+                else if (DIALECT == 1) {
+                    if (cply >= R.max_depth) {
+                        // the child stops at its first empty cell, which it marks before evaluating
+                        const uint32_t j0 = emp_after & (0u - emp_after);          // order space == cell space
+                        const int cnt = __popc(w.e1 & ~j0) + __popc(w.e2 & ~j0);
+                        ret = side * (30 * cnt + R.scores[cell]) + d;
+                        evals++;
+                        returning = true;
+                    }
                 } else {
+                    int dv = side * (30 * (__popc(w.e1) + __popc(w.e2)) + R.scores[cell]);
+                    if (DIALECT == 2) dv += eval_penalties(T, side > 0 ? xs : os, side > 0 ? os : xs, cell, side);
+                    if (cply == R.max_depth) { ret = dv + carried; returning = true; }
+                    else if (emp_after == 0) { ret = side > 0 ? R.sentinel : -R.sentinel; returning = true; }
+                    else d = dv + carried;
+                }
+                if (!returning) {
+                    // push: the register frame goes to shared memory, the child becomes the register frame
+                    SQ_FR(sp, 0) = moves | ((uint32_t)kidx << 25);
+                    SQ_FR(sp, 1) = ((uint32_t)value & 0xffffu) | ((uint32_t)alpha << 16);
+                    SQ_FR(sp, 2) = ((uint32_t)beta & 0xffffu) | ((uint32_t)carried << 16);
+                    if (DIALECT == 1) { SQ_FR(sp, 3) = fe1 | ((uint32_t)fpc << 25); SQ_FR(sp, 4) = fe2; }
+                    x = xs; o = os; emp = emp_after;
                     sp++;
-                    f_moves[sp] = emp; f_cur[sp] = 0;
-                    f_value[sp] = (short)(side > 0 ? R.sentinel : -R.sentinel);
-                    f_alpha[sp] = f_alpha[sp - 1]; f_beta[sp] = f_beta[sp - 1];
-                    f_carried[sp] = f_carried[sp - 1] + d; f_cell[sp] = (signed char)cell;
-                    returning = false;
+                    moves = emp;
+                    value = side > 0 ? R.sentinel : -R.sentinel;      // the child is the other side
+                    carried = d;
+                    if (DIALECT == 1) { fe1 = w.e1; fe2 = w.e2; fpc = cell; }
                 }
             }
         }
@@ -455,23 +533,39 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget) {
                 break;
             }
             const int s = (sp & 1) ? -base_side : base_side;
-            const uint32_t cur = f_cur[sp];
-            const uint32_t bit = 1u << (cur >> 25), kbit = cur & kFull25;
-            if (s > 0) x &= ~bit; else o &= ~bit;
-            emp |= kbit;
-            int v = f_value[sp], a = f_alpha[sp], b = f_beta[sp];
-            if (s > 0) { v = max(v, ret); a = max(a, v); } else { v = min(v, ret); b = min(b, v); }
-            if (sp == 0) ab_bounds(R, unit, a, b);      // siblings may have tightened the window
-            f_value[sp] = (short)v; f_alpha[sp] = (short)a; f_beta[sp] = (short)b;
-            if (b <= a) { ret = v; sp--; } else returning = false;
+            if (restore) {
+                // a pushed child came back: restore the frame and take its move off the board
+                const uint32_t w0 = SQ_FR(sp, 0), w1 = SQ_FR(sp, 1), w2 = SQ_FR(sp, 2);
+                moves = w0 & kFull25;
+                value = (int)(short)(w1 & 0xffffu); alpha = (int)(short)(w1 >> 16);
+                beta = (int)(short)(w2 & 0xffffu); carried = (int)(short)(w2 >> 16);
+                if (DIALECT == 1) {
+                    const uint32_t w3 = SQ_FR(sp, 3);
+                    fe1 = w3 & kFull25; fpc = (int)(w3 >> 25); fe2 = SQ_FR(sp, 4);
+                }
+                const int kidx = (int)(w0 >> 25);
+                const uint32_t bit = 1u << (kOrdered ? T.order[kidx] : kidx);
+                if (s > 0) x &= ~bit; else o &= ~bit;
+                emp |= 1u << kidx;
+            }
+            if (s > 0) { value = max(value, ret); alpha = max(alpha, value); }
+            else { value = min(value, ret); beta = min(beta, value); }
+            if (sp == 0) ab_bounds(R, unit, alpha, beta);        // siblings may have tightened the window
+            if (beta <= alpha) { ret = value; sp--; restore = true; } else returning = false;
         }
     }
+#undef SQ_FR
 }
 
 // ---- host orchestration ---------------------------------------------------------------
 inline cudaError_t ab_configure(int* blocks_per_sm) {
     int b1 = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, ab_dfs_kernel<1>, kAbThreads, 0);
+    const int max_smem = (kAbMaxDepth + 2) * 5 * kAbThreads * 4;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(ab_dfs_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ab_dfs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ab_dfs_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, ab_dfs_kernel<1>, kAbThreads, 10 * 5 * kAbThreads * 4);
     if (e != cudaSuccess) return e;
     *blocks_per_sm = b1 < 1 ? 1 : b1;
     return cudaSuccess;
@@ -481,7 +575,7 @@ inline cudaError_t ab_configure(int* blocks_per_sm) {
 inline unsigned long long ab_budget() {
     const char* env = getenv("SQ_AB_BUDGET");
     if (env && *env) return strtoull(env, nullptr, 10);
-    return 4096;
+    return 0;   // 0: chosen per pass from the number of units
 }
 
 // Static pre-split: plies to expand breadth-first under a level-0 node before the first pass
@@ -495,7 +589,8 @@ inline int ab_choose_split(int empties, int rem) {
         // rough size of the subtree: product of the branching factors, damped
         double est = 1.0;
         for (int k = 0; k < rem && empties - k > 0; k++) est *= 0.55 * (empties - k) + 0.45;
-        split = est > 3e7 ? 1 : 0;
+        (void)est;
+        split = 0;   // adaptive passes do the splitting
     }
     if (split > rem - 1) split = rem - 1 < 0 ? 0 : rem - 1;
     if (split > empties - 1) split = empties - 1 < 0 ? 0 : empties - 1;
@@ -524,7 +619,7 @@ inline void ab_free(AbWork& w, cudaStream_t st) {
 
 template <int DIALECT>
 cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n, const int8_t* h_split,
-                         long long capacity, int grid_cap, cudaStream_t st, uint64_t* launches) {
+                         long long capacity, int grid_cap, int min_ply, cudaStream_t st, uint64_t* launches) {
     SQ_AB_CK(cudaMallocAsync(&w.nodes, sizeof(AbNode) * capacity, st));
     SQ_AB_CK(cudaMallocAsync(&w.value, sizeof(int) * capacity, st));
     SQ_AB_CK(cudaMallocAsync(&w.pending, sizeof(int) * capacity, st));
@@ -561,20 +656,40 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
     // Adaptive passes: every unit gets `budget` evaluator calls; the ones that need more are
     // split one ply deeper and their children (now with their siblings' bounds in the parent
     // slots) form the next pass.  Small subtrees keep sequential pruning, big ones get spread.
-    unsigned long long budget = ab_budget();
+    const bool trace = getenv("SQ_AB_TRACE") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what, int a, int b) {
+        if (!trace) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ab] %-8s %9d %9d  %8.3f ms\n", what, a, b, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
+    lap("setup", n, (int)capacity);
+    const unsigned long long fixed_budget = ab_budget();
+    bool unlimited = false;
+    int plies_split = 0;      // how many plies below the level-0 nodes this pass's units sit (at least)
     for (int pass = 0;; pass++) {
         SQ_AB_CK(cudaMemcpyAsync(h_counters, w.counters, sizeof h_counters, cudaMemcpyDeviceToHost, st));
         SQ_AB_CK(cudaStreamSynchronize(st));
         const int n_units = (int)h_counters[1];
         if (n_units == 0) break;
+        // few units: split early (most lanes are idle anyway); many: let lanes run longer
+        unsigned long long budget = fixed_budget ? fixed_budget : n_units < (1 << 15) ? 256 : n_units < (1 << 18) ? 1024 : 4096;
+        if (unlimited) budget = ~0ull;
+        // frames a unit can push: one per ply from its own down to max_depth - 1
+        int n_frames = R.max_depth - (min_ply + plies_split) + 1;
+        if (n_frames > kAbMaxDepth + 2) n_frames = kAbMaxDepth + 2;
+        if (n_frames < 2) n_frames = 2;
         long long blocks = ((long long)n_units + kAbThreads - 1) / kAbThreads;
         if (blocks > grid_cap) blocks = grid_cap;
-        ab_dfs_kernel<DIALECT><<<(unsigned)blocks, kAbThreads, 0, st>>>(R, n_units, budget);
+        ab_dfs_kernel<DIALECT><<<(unsigned)blocks, kAbThreads, (size_t)n_frames * AbFrameWords<DIALECT>::n * kAbThreads * 4, st>>>(
+            R, n_units, budget, n_frames);
         (*launches)++;
         SQ_AB_CK(cudaGetLastError());
         SQ_AB_CK(cudaMemcpyAsync(h_counters, w.counters, sizeof h_counters, cudaMemcpyDeviceToHost, st));
         SQ_AB_CK(cudaStreamSynchronize(st));
         const int n_aborted = (int)h_counters[3];
+        lap("dfs", n_units, n_aborted);
         if (n_aborted == 0) break;
         const unsigned int zero3[3] = {0, 0, 0};
         SQ_AB_CK(cudaMemcpyAsync(w.counters + 1, zero3, sizeof zero3, cudaMemcpyHostToDevice, st));
@@ -583,10 +698,11 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
             SQ_AB_CK(cudaMemcpyAsync(w.units, w.aborted, sizeof(int) * n_aborted, cudaMemcpyDeviceToDevice, st));
             const unsigned int nu = (unsigned)n_aborted;
             SQ_AB_CK(cudaMemcpyAsync(w.counters + 1, &nu, sizeof nu, cudaMemcpyHostToDevice, st));
-            budget = ~0ull;
+            unlimited = true;
             continue;
         }
         ab_expand_kernel<DIALECT><<<(n_aborted + kAbThreads - 1) / kAbThreads, kAbThreads, 0, st>>>(R, w.aborted, 0, n_aborted);
+        plies_split++;
         (*launches)++;
         SQ_AB_CK(cudaGetLastError());
     }
@@ -595,12 +711,12 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
 }
 
 inline cudaError_t ab_dispatch(int dialect, AbRun R, AbWork& w, const void* d_in, bool roots, int n,
-                               const int8_t* h_split, long long capacity, int grid_cap, cudaStream_t st,
-                               uint64_t* launches) {
+                               const int8_t* h_split, long long capacity, int grid_cap, int min_ply,
+                               cudaStream_t st, uint64_t* launches) {
     switch (dialect) {
-    case 1: return ab_run_chunk<1>(R, w, d_in, roots, n, h_split, capacity, grid_cap, st, launches);
-    case 2: return ab_run_chunk<2>(R, w, d_in, roots, n, h_split, capacity, grid_cap, st, launches);
-    default: return ab_run_chunk<3>(R, w, d_in, roots, n, h_split, capacity, grid_cap, st, launches);
+    case 1: return ab_run_chunk<1>(R, w, d_in, roots, n, h_split, capacity, grid_cap, min_ply, st, launches);
+    case 2: return ab_run_chunk<2>(R, w, d_in, roots, n, h_split, capacity, grid_cap, min_ply, st, launches);
+    default: return ab_run_chunk<3>(R, w, d_in, roots, n, h_split, capacity, grid_cap, min_ply, st, launches);
     }
 }
 
@@ -613,7 +729,7 @@ inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t score
     memcpy(R.scores, scores, 25);
 }
 
-constexpr long long kAbChunkNodes = 16ll << 20;   // node slots per chunk: pre-split nodes + the pool adaptive splitting draws on (~640 MB)
+constexpr long long kAbChunkNodes = 64ll << 20;   // node slots per chunk: level-0 nodes + the pool adaptive splitting draws on (~2.5 GB)
 
 // worst-case node count below one level-0 node with e empties and `split` expanded plies
 inline long long ab_node_bound(int e, int split) {
@@ -639,13 +755,13 @@ inline cudaError_t ab_root_search(const sq_board* h_pos, const sq_board* d_pos, 
             int empt = 25 - __builtin_popcount((h_pos[hi].x | h_pos[hi].o) & kFull25);
             int sp = ab_choose_split(empt - 1, R.max_depth - 1);
             long long need = (long long)empt * ab_node_bound(empt - 1, sp);
-            if (hi > lo && cap + need > kAbChunkNodes / 4) break;
+            if (hi > lo && cap + need > kAbChunkNodes / 16) break;
             split[hi] = (int8_t)sp; cap += need; hi++;
         }
         AbRun Rc = R;
         Rc.out = d_values + lo * 25;
         Rc.node_count = d_nodes + lo;
-        e = ab_dispatch(dialect, Rc, w, d_pos + lo, true, (int)(hi - lo), split.data() + lo, cap + 16 > kAbChunkNodes ? cap + 16 : kAbChunkNodes, grid_cap, st, launches);
+        e = ab_dispatch(dialect, Rc, w, d_pos + lo, true, (int)(hi - lo), split.data() + lo, cap + 16 > kAbChunkNodes ? cap + 16 : kAbChunkNodes, grid_cap, 1, st, launches);
         if (e != cudaSuccess) return e;
         lo = hi;
     }
@@ -668,13 +784,15 @@ inline cudaError_t ab_subtree_search(const sq_subtree* h_st, const sq_subtree* d
             int empt = 25 - __builtin_popcount((h_st[hi].b.x | h_st[hi].b.o) & kFull25);
             int sp = ab_choose_split(empt, R.max_depth - h_st[hi].ply);
             long long need = ab_node_bound(empt, sp);
-            if (hi > lo && cap + need > kAbChunkNodes / 4) break;
+            if (hi > lo && cap + need > kAbChunkNodes / 16) break;
             split[hi] = (int8_t)sp; cap += need; hi++;
         }
         AbRun Rc = R;
         Rc.out = d_value + lo;
         Rc.node_count = d_nodes + lo;
-        e = ab_dispatch(dialect, Rc, w, d_st + lo, false, (int)(hi - lo), split.data() + lo, cap + 16 > kAbChunkNodes ? cap + 16 : kAbChunkNodes, grid_cap, st, launches);
+        int min_ply = 127;
+        for (long long q = lo; q < hi; q++) if (h_st[q].ply < min_ply) min_ply = h_st[q].ply;
+        e = ab_dispatch(dialect, Rc, w, d_st + lo, false, (int)(hi - lo), split.data() + lo, cap + 16 > kAbChunkNodes ? cap + 16 : kAbChunkNodes, grid_cap, min_ply, st, launches);
         if (e != cudaSuccess) return e;
         lo = hi;
     }
