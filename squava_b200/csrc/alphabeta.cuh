@@ -729,7 +729,13 @@ inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t score
     memcpy(R.scores, scores, 25);
 }
 
-constexpr long long kAbChunkNodes = 64ll << 20;   // node slots per chunk: level-0 nodes + the pool adaptive splitting draws on (~2.5 GB)
+constexpr long long kAbChunkNodesDefault = 64ll << 20;   // node slots per chunk: level-0 nodes + the pool adaptive splitting draws on (~2.5 GB)
+
+inline long long ab_pool_nodes() {      // SQ_AB_POOL_NODES shrinks the pool (tests of the no-room path)
+    const char* env = getenv("SQ_AB_POOL_NODES");
+    long long v = (env && *env) ? atoll(env) : kAbChunkNodesDefault;
+    return v < 4096 ? 4096 : v;
+}
 
 // worst-case node count below one level-0 node with e empties and `split` expanded plies
 inline long long ab_node_bound(int e, int split) {
@@ -748,6 +754,7 @@ inline cudaError_t ab_root_search(const sq_board* h_pos, const sq_board* d_pos, 
     cudaError_t e = cudaMemsetAsync(d_nodes, 0, sizeof(unsigned long long) * n, st);
     if (e != cudaSuccess) return e;
     std::vector<int8_t> split((size_t)n);
+    const long long kAbChunkNodes = ab_pool_nodes();
     long long lo = 0;
     while (lo < n) {
         long long cap = 0, hi = lo;
@@ -777,6 +784,7 @@ inline cudaError_t ab_subtree_search(const sq_subtree* h_st, const sq_subtree* d
     cudaError_t e = cudaMemsetAsync(d_nodes, 0, sizeof(unsigned long long) * n, st);
     if (e != cudaSuccess) return e;
     std::vector<int8_t> split((size_t)n);
+    const long long kAbChunkNodes = ab_pool_nodes();
     long long lo = 0;
     while (lo < n) {
         long long cap = 0, hi = lo;

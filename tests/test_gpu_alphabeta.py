@@ -85,6 +85,30 @@ def test_ab1_root_live_oracle_all_split_depths(dev, oracle, split, monkeypatch):
         assert (int(bm[i]), int(bv[i])) == (obm, obv)
 
 
+@pytest.mark.parametrize("budget,pool", [("1", ""), ("7", ""), ("100000000", ""), ("16", "6000"), ("", "5000")])
+def test_schedule_does_not_change_values(dev, oracle, budget, pool):
+    """per-pass budgets, the number of passes and running out of node pool (units then finish
+    without a budget) are scheduling only: values must not move"""
+    from squava_b200 import positions
+    sc = oracle.tables()["scores_ab"]
+    boards, _ = positions.midgame_batch(24, marks=(10, 12, 14), seed=79)
+    for k, v in (("SQ_AB_BUDGET", budget), ("SQ_AB_POOL_NODES", pool)):
+        if v:
+            os.environ[k] = v
+        else:
+            os.environ.pop(k, None)
+    try:
+        values, bv, bm, _ = dev.alphabeta_root(boards, 1, 10, sc)
+        v3, _ = dev.alphabeta_subtrees(subtree_array(dev, [(1 << 12, 1 << 6, 6, 2, 1, 0)]), 3, 6, oracle.tables()["scores_opening"])
+    finally:
+        os.environ.pop("SQ_AB_BUDGET", None)
+        os.environ.pop("SQ_AB_POOL_NODES", None)
+    for i in range(boards.shape[0]):
+        ov, obm, obv, _ = oracle.ab1_root(int(boards[i]["x"]), int(boards[i]["o"]), 10, sc)
+        assert values[i].tolist() == ov and (int(bm[i]), int(bv[i])) == (obm, obv), i
+    assert int(v3[0]) == oracle.ab_subtree(3, 1 << 12, 1 << 6, 6, 2, 1, 0, 6, oracle.tables()["scores_opening"])[0]
+
+
 def test_ab2_root_live_oracle(dev, oracle):
     from squava_b200 import positions
     sc = oracle.tables()["scores_ab"]
