@@ -170,6 +170,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...") goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     import squava_b200 as sq
