@@ -118,6 +118,7 @@ const (
 	Squavathr = 2 // squavathr.go
 	Opening3  = 3 // opening3.go
 	Opening2  = 4 // opening2.go
+	Avoid     = 5 // src/alphabeta after SetAvoid(): deltaValue2
 )
 
 // AlphaBetaRoot replaces ChooseMove's loop (alphabeta.go:98-110) / chooseMove + the worker

@@ -59,6 +59,7 @@ typedef struct sq_board { uint32_t x, o; } sq_board;
 #define SQ_AB_SQUAVATHR 2 /* squavathr.go:236-269,315-446 */
 #define SQ_AB_OPENING3 3  /* opening3.go:136-225 */
 #define SQ_AB_OPENING2 4  /* opening2.go:91-180 (full-board node value -+10000) */
+#define SQ_AB_ALPHABETA_AVOID 5 /* src/alphabeta after SetAvoid(): deltaValue2, alphabeta.go:382-454,473-475 */
 
 /* ---- lifecycle -------------------------------------------------------- */
 /* device_ids == NULL / n_devices <= 0: use device 0.  seed keys every random
@@ -99,7 +100,8 @@ int sq_playouts(const sq_board *leaves, const int8_t *to_move, int64_t n_leaves,
 
 /* ---- fixed-depth alpha-beta -------------------------------------------- */
 /* Replaces ChooseMove's per-root-move loop: src/alphabeta/alphabeta.go:92-117
- * (dialect 1, max_depth = p.maxDepth as SetDepth leaves it, :79-89) or
+ * (dialect 1, or 5 = the same engine after SetAvoid(); max_depth = p.maxDepth as SetDepth
+ * leaves it, :79-89) or
  * squavathr chooseMove + its worker pool, squavathr.go:236-269,448-466 (dialect
  * 2, max_depth = chooseMove's argument).  MAXIMIZER is to move in every
  * position.  scores = the 25-entry bias table (alphabeta.go:330,343-349).

@@ -165,29 +165,45 @@ def _lines(bd, ply, c):
     return False, v
 
 
-def delta1(bd, ply, c, current, max_depth, scores):
-    """alphabeta.go:121-163"""
+def avoid_terms(bd, c):
+    """alphabeta.go:412-439 (deltaValue2) == squavathr.go:343-371"""
+    v = 0
+    for t in NO2:
+        if c in t and abs(sum(bd[j] for j in t)) == 2:
+            v += bd[c] * -100
+    for q in NOMID2:
+        p = bd[c]
+        if (c == q[1] and p == bd[q[2]]) or (c == q[2] and p == bd[q[1]]):
+            if abs(sum(bd[j] for j in q)) == 2:
+                v += p * -100
+    return v
+
+
+def delta1(bd, ply, c, current, max_depth, scores, avoid=False):
+    """alphabeta.go:121-163; avoid=True: deltaValue2, alphabeta.go:382-454"""
     term, v = _lines(bd, ply, c)
     if term:
         return True, v
+    if avoid:
+        v += avoid_terms(bd, c)
     v += bd[c] * scores[c]
     if ply >= max_depth:
         return True, v + current
     return False, v
 
 
-def ab1(bd, ply, player, alpha, beta, c, bv, max_depth, scores):
+def ab1(bd, ply, player, alpha, beta, c, bv, max_depth, scores, avoid=False):
     """alphabeta.go:165-223"""
     value = 2 * LOSS if player == MAX else 2 * WIN
     for i in range(25):
         if bd[i] != UNSET:
             continue
         bd[i] = player
-        stop, delta = delta1(bd, ply, c, bv, max_depth, scores)
+        stop, delta = delta1(bd, ply, c, bv, max_depth, scores, avoid)
         if stop:
             bd[i] = UNSET
             return delta
-        n = ab1(bd, ply + 1, -player, alpha, beta, i, delta, max_depth, scores)
+        n = ab1(bd, ply + 1, -player, alpha, beta, i, delta, max_depth, scores, avoid)
         bd[i] = UNSET
         if player == MAX:
             value = max(value, n)
@@ -200,7 +216,7 @@ def ab1(bd, ply, player, alpha, beta, c, bv, max_depth, scores):
     return value
 
 
-def ab1_root(bd, max_depth, scores):
+def ab1_root(bd, max_depth, scores, avoid=False):
     """alphabeta.go:92-117 -> values[25]"""
     bd = list(bd)
     out = [NO_MOVE] * 25
@@ -208,9 +224,9 @@ def ab1_root(bd, max_depth, scores):
         if bd[c] != UNSET:
             continue
         bd[c] = MAX
-        stop, v = delta1(bd, 0, c, 0, max_depth, scores)
+        stop, v = delta1(bd, 0, c, 0, max_depth, scores, avoid)
         if not stop:
-            v = ab1(bd, 1, MIN, 2 * LOSS, 2 * WIN, c, v, max_depth, scores)
+            v = ab1(bd, 1, MIN, 2 * LOSS, 2 * WIN, c, v, max_depth, scores, avoid)
         bd[c] = UNSET
         out[c] = v
     return out

@@ -440,6 +440,7 @@ typedef struct {
     const int *scores;
     int64_t leaves;
     int sentinel; /* AB-3: value of a node with no empty cell is -+sentinel */
+    int avoid;    /* AB-1 with SetAvoid(): boardValue = deltaValue2, alphabeta.go:382-454,474 */
 } ab_t;
 
 /* evaluator calls (deltaValue / the inlined evaluation of opening2-3) of the calling thread's
@@ -467,11 +468,32 @@ static int lines_value(const ab_t *a, int ply, int c, int *value) {
     *value = v; return 0;
 }
 
+/* the no2 / noMiddle2 terms: squavathr.go:343-371 == alphabeta.go:412-439 (deltaValue2) */
+static int avoid_terms(const ab_t *a, int c) {
+    const int *bd = a->bd; int v = 0;
+    for (int t = 0; t < 4; t++)
+        for (int i = 0; i < 3; i++)
+            if (k_no2[t][i] == c) {
+                int sum = bd[k_no2[t][0]] + bd[k_no2[t][1]] + bd[k_no2[t][2]];
+                if (sum == 2 || sum == -2) v += bd[c] * -100;
+                break;
+            }
+    for (int q = 0; q < 4; q++) {
+        const int *m = k_no_middle2[q]; int player = bd[c];
+        if ((c == m[1] && player == bd[m[2]]) || (c == m[2] && player == bd[m[1]])) {
+            int sum = bd[m[0]] + bd[m[1]] + bd[m[2]] + bd[m[3]];
+            if (sum == 2 || sum == -2) v += player * -100;
+        }
+    }
+    return v;
+}
+
 /* ---- AB-1: src/alphabeta ---- */
-/* deltaValue, alphabeta.go:121-163 */
+/* deltaValue, alphabeta.go:121-163; with a->avoid: deltaValue2, alphabeta.go:382-454 */
 static int delta1(const ab_t *a, int ply, int c, int current, int *value) {
     int v;
     if (lines_value(a, ply, c, &v)) { *value = v; return 1; }
+    if (a->avoid) v += avoid_terms(a, c);
     v += a->bd[c] * a->scores[c];
     int stop = 0;
     if (ply >= a->max_depth) { stop = 1; v += current; }
@@ -514,10 +536,20 @@ static void keep_moves(const int32_t values[25], uint32_t *best_mask, int32_t *b
     if (best_value) *best_value = mask ? max : 0; /* movekeeper.go:40-44 */
 }
 
+static void ab1_root(sqo_board b, int max_depth, const int scores[25], int32_t values[25],
+                     uint32_t *best_mask, int32_t *best_value, int64_t *leaves, int avoid);
 void sqo_ab1_root(sqo_board b, int max_depth, const int scores[25], int32_t values[25],
                   uint32_t *best_mask, int32_t *best_value, int64_t *leaves) {
+    ab1_root(b, max_depth, scores, values, best_mask, best_value, leaves, 0);
+}
+void sqo_ab5_root(sqo_board b, int max_depth, const int scores[25], int32_t values[25],
+                  uint32_t *best_mask, int32_t *best_value, int64_t *leaves) {
+    ab1_root(b, max_depth, scores, values, best_mask, best_value, leaves, 1);
+}
+static void ab1_root(sqo_board b, int max_depth, const int scores[25], int32_t values[25],
+                     uint32_t *best_mask, int32_t *best_value, int64_t *leaves, int avoid) {
     ab_t a; tables(); unpack(b, a.bd); g_evals = 0;
-    a.max_depth = max_depth; a.scores = scores; a.leaves = 0; a.sentinel = 2 * WIN;
+    a.max_depth = max_depth; a.scores = scores; a.leaves = 0; a.sentinel = 2 * WIN; a.avoid = avoid;
     for (int c = 0; c < 25; c++) {            /* ChooseMove, alphabeta.go:98-110 */
         values[c] = SQO_NO_MOVE;
         if (a.bd[c] != UNSET) continue;
@@ -536,20 +568,7 @@ void sqo_ab1_root(sqo_board b, int max_depth, const int scores[25], int32_t valu
 static int delta2(const ab_t *a, int ply, int c, int current, int *value) {
     const int *bd = a->bd; int v;
     if (lines_value(a, ply, c, &v)) { *value = v; return 1; }
-    for (int t = 0; t < 4; t++)            /* :343-354 */
-        for (int i = 0; i < 3; i++)
-            if (k_no2[t][i] == c) {
-                int sum = bd[k_no2[t][0]] + bd[k_no2[t][1]] + bd[k_no2[t][2]];
-                if (sum == 2 || sum == -2) v += bd[c] * -100;
-                break;
-            }
-    for (int q = 0; q < 4; q++) {          /* :356-371 */
-        const int *m = k_no_middle2[q]; int player = bd[c];
-        if ((c == m[1] && player == bd[m[2]]) || (c == m[2] && player == bd[m[1]])) {
-            int sum = bd[m[0]] + bd[m[1]] + bd[m[2]] + bd[m[3]];
-            if (sum == 2 || sum == -2) v += player * -100;
-        }
-    }
+    v += avoid_terms(a, c);                /* :343-371 */
     v += bd[c] * a->scores[c];
     int stop = 0;
     if (ply == a->max_depth) { stop = 1; v += current; }
@@ -582,7 +601,7 @@ void sqo_ab2_root(sqo_board b, int max_depth, const int scores[25], int32_t valu
                   uint32_t *best_mask, int32_t *best_value, int64_t *leaves) {
     ab_t a; tables(); unpack(b, a.bd); g_evals = 0;
     a.max_depth = max_depth - 1;              /* squavathr.go:239 */
-    a.scores = scores; a.leaves = 0; a.sentinel = 2 * WIN;
+    a.scores = scores; a.leaves = 0; a.sentinel = 2 * WIN; a.avoid = 0;
     for (int c = 0; c < 25; c++) {            /* chooseMove, squavathr.go:241-253 */
         values[c] = SQO_NO_MOVE;
         if (a.bd[c] != UNSET) continue;
@@ -634,9 +653,10 @@ int32_t sqo_ab_subtree(int dialect, sqo_board b, int last_cell, int ply, int sid
     ab_t a; tables(); unpack(b, a.bd); g_evals = 0;
     a.max_depth = max_depth; a.scores = scores; a.leaves = 0;
     a.sentinel = dialect == 4 ? WIN : 2 * WIN;
+    a.avoid = dialect == 5;
     int v = 0;
     switch (dialect) {
-    case 1: v = ab1(&a, ply, side, 2 * LOSS, 2 * WIN, last_cell, carried); break;
+    case 1: case 5: v = ab1(&a, ply, side, 2 * LOSS, 2 * WIN, last_cell, carried); break;
     case 2: v = ab2(&a, ply, side, 2 * LOSS, 2 * WIN, last_cell, carried); break;
     case 3: case 4: v = ab3(&a, ply, side, LOSS, WIN, last_cell, carried); break;
     }

@@ -96,6 +96,11 @@ int64_t sqo_playout_exact(sqo_board b, int to_move, double p[3], double *mean_pl
 void sqo_ab1_root(sqo_board b, int max_depth, const int scores[25],
                   int32_t values[25], uint32_t *best_mask, int32_t *best_value,
                   int64_t *leaves);
+/* AB-1 after SetAvoid() (alphabeta.go:473-475): the evaluator is deltaValue2 (:382-454),
+ * i.e. deltaValue plus the no2 / noMiddle2 -100 terms; playoff5's "G" player.   */
+void sqo_ab5_root(sqo_board b, int max_depth, const int scores[25],
+                  int32_t values[25], uint32_t *best_mask, int32_t *best_value,
+                  int64_t *leaves);
 /* AB-2 squavathr chooseMove (squavathr.go:236-269) + worker (:448-466).
  * max_depth is chooseMove's argument (it decrements it itself, :239).       */
 void sqo_ab2_root(sqo_board b, int max_depth, const int scores[25],
@@ -107,7 +112,8 @@ void sqo_ab2_root(sqo_board b, int max_depth, const int scores[25],
  *  dialect 2: squavathr alphaBeta(max_depth, bd, ply, side, -20000, +20000, x, y, carried) :389
  *             (max_depth here is the worker's, i.e. already decremented)
  *  dialect 3: opening3 alphaBeta(bd, ply, side, -10000, +10000, x, y, carried)  opening3.go:136
- *  dialect 4: opening2 alphaBeta(...)  opening2.go:91 (full-board value -+10000) */
+ *  dialect 4: opening2 alphaBeta(...)  opening2.go:91 (full-board value -+10000)
+ *  dialect 5: dialect 1 with the deltaValue2 evaluator (SetAvoid)                */
 int32_t sqo_ab_subtree(int dialect, sqo_board b, int last_cell, int ply, int side,
                        int32_t carried, int max_depth, const int scores[25],
                        int64_t *leaves);

@@ -326,7 +326,7 @@ int sq_alphabeta_root(const sq_board* positions, int64_t n, int dialect, int max
     if (n < 0 || (n > 0 && (!positions || !values)) || !scores) {
         snprintf(t_err, sizeof t_err, "sq_alphabeta_root: null pointer"); return SQ_ERR_INVALID;
     }
-    if (dialect != SQ_AB_ALPHABETA && dialect != SQ_AB_SQUAVATHR) {
+    if (dialect != SQ_AB_ALPHABETA && dialect != SQ_AB_SQUAVATHR && dialect != SQ_AB_ALPHABETA_AVOID) {
         snprintf(t_err, sizeof t_err, "sq_alphabeta_root: dialect %d has no root-move search in the reference", dialect);
         return SQ_ERR_UNSUPPORTED;
     }
@@ -379,7 +379,7 @@ int sq_alphabeta_subtrees(const sq_subtree* subtrees, int64_t n, int dialect, in
     if (n < 0 || (n > 0 && (!subtrees || !value)) || !scores) {
         snprintf(t_err, sizeof t_err, "sq_alphabeta_subtrees: null pointer"); return SQ_ERR_INVALID;
     }
-    if (dialect < 1 || dialect > 4) { snprintf(t_err, sizeof t_err, "unknown dialect %d", dialect); return SQ_ERR_INVALID; }
+    if (dialect < 1 || dialect > 5) { snprintf(t_err, sizeof t_err, "unknown dialect %d", dialect); return SQ_ERR_INVALID; }
     if (max_depth < 0 || max_depth > sq::kAbMaxDepth) { snprintf(t_err, sizeof t_err, "max_depth out of range [0,%d]", sq::kAbMaxDepth); return SQ_ERR_INVALID; }
     for (int64_t i = 0; i < n; i++) {
         const sq_subtree& s = subtrees[i];

@@ -80,6 +80,14 @@ inline void build_ab_tables(AbTables& t) {
     for (int k = 0; k < 25; k++) { t.order[k] = ord[k]; t.rank[ord[k]] = (uint8_t)k; }
 }
 
+// dialect traits: 1 and 5 share the delayed-evaluation search of src/alphabeta; 5 adds the
+// deltaValue2 ("avoid") terms, which are squavathr's no2 / noMiddle2 penalties
+template <int D> struct AbTraits {
+    static constexpr bool delayed = D == 1 || D == 5;
+    static constexpr bool penalties = D == 2 || D == 5;
+    static constexpr bool ordered = D == 3;           // dialect 4 runs as 3 with another sentinel
+};
+
 struct AbNode {
     uint32_t x, o;       // API-layout masks, the pending move already on the board
     int32_t carried;     // boardValue argument
@@ -224,20 +232,24 @@ __device__ __forceinline__ bool ab_enter(const AbTables& T, const AbRun& R, cons
     const uint32_t empties = kFull25 & ~(n.x | n.o);
     const bool pend_is_x = (n.x >> n.cell) & 1u;
     const int sign = pend_is_x ? 1 : -1;
-    if (DIALECT == 1) {
+    if (AbTraits<DIALECT>::delayed) {
         carried_down = n.carried;
         if (!empties) { value = n.side > 0 ? -R.sentinel : R.sentinel; return true; }
         uint32_t first = empties & (0u - empties);
         uint32_t x = n.x | (n.side > 0 ? first : 0u), o = n.o | (n.side > 0 ? 0u : first);
         Eval e = eval_lines(T, pend_is_x ? x : o, pend_is_x ? o : x, n.cell, sign, n.ply);
         if (e.terminal) { value = e.value; return true; }
-        if (n.ply >= R.max_depth) { value = e.value + sign * R.scores[n.cell] + n.carried; return true; }
+        if (n.ply >= R.max_depth) {
+            value = e.value + sign * R.scores[n.cell] + n.carried;
+            if (AbTraits<DIALECT>::penalties) value += eval_penalties(T, pend_is_x ? x : o, pend_is_x ? o : x, n.cell, sign);
+            return true;
+        }
         return false;
     } else {
         Eval e = eval_lines(T, pend_is_x ? n.x : n.o, pend_is_x ? n.o : n.x, n.cell, sign, n.ply);
         if (e.terminal) { value = e.value; return true; }
         int d = e.value + sign * R.scores[n.cell];
-        if (DIALECT == 2) d += eval_penalties(T, pend_is_x ? n.x : n.o, pend_is_x ? n.o : n.x, n.cell, sign);
+        if (AbTraits<DIALECT>::penalties) d += eval_penalties(T, pend_is_x ? n.x : n.o, pend_is_x ? n.o : n.x, n.cell, sign);
         if (n.ply == R.max_depth) { value = d + n.carried; return true; }
         carried_down = n.carried + d;
         if (!empties) { value = n.side > 0 ? -R.sentinel : R.sentinel; return true; }
@@ -262,10 +274,11 @@ ab_roots_kernel(AbRun R, const sq_board* __restrict__ pos, const int8_t* __restr
     AbNode nd;
     nd.x = x | bit; nd.o = o; nd.cell = (int8_t)c; nd.ply = 1; nd.side = -1;
     nd.split = split[i]; nd.parent = -1 - t; nd.group = i;
-    if (DIALECT == 1) {
+    if (AbTraits<DIALECT>::delayed) {
         Eval e = eval_lines(T, x | bit, o, c, 1, 0);                 // alphabeta.go:101-102
         if (e.terminal) { R.out[t] = e.value; return; }
         int v = e.value + R.scores[c];
+        if (AbTraits<DIALECT>::penalties) v += eval_penalties(T, x | bit, o, c, 1);
         if (0 >= R.max_depth) { R.out[t] = v; return; }
         nd.carried = v;
     } else {
@@ -315,7 +328,7 @@ ab_expand_kernel(AbRun R, const int* __restrict__ list, int lo, int count) {
     const bool pend_is_x = (n.x >> n.cell) & 1u;
     const int sign = pend_is_x ? 1 : -1;
     for (int k = 0; k < 25; k++) {               // children in the dialect's visiting order
-        const int cell = DIALECT >= 3 ? T.order[k] : k;
+        const int cell = AbTraits<DIALECT>::ordered ? T.order[k] : k;
         const uint32_t bit = 1u << cell;
         if (!(empties & bit)) continue;
         AbNode c;
@@ -327,9 +340,10 @@ ab_expand_kernel(AbRun R, const int* __restrict__ list, int lo, int count) {
         c.split = n.split - 1;
         c.parent = idx;
         c.group = n.group;
-        if (DIALECT == 1) {   // the parent's move re-evaluated with this child's mark on
+        if (AbTraits<DIALECT>::delayed) {   // the parent's move re-evaluated with this child's mark on
             Eval e = eval_lines(T, pend_is_x ? c.x : c.o, pend_is_x ? c.o : c.x, n.cell, sign, n.ply);
             c.carried = e.value + sign * R.scores[n.cell];
+            if (AbTraits<DIALECT>::penalties) c.carried += eval_penalties(T, pend_is_x ? c.x : c.o, pend_is_x ? c.o : c.x, n.cell, sign);
             evals++;
         } else {
             c.carried = carried_down;
@@ -392,7 +406,7 @@ __device__ __forceinline__ AbWalk ab_walk(const AbWalkTables& W, uint32_t own, u
     return r;
 }
 
-template <int DIALECT> struct AbFrameWords { static constexpr int n = DIALECT == 1 ? 5 : 3; };
+template <int DIALECT> struct AbFrameWords { static constexpr int n = AbTraits<DIALECT>::delayed ? 5 : 3; };
 
 template <int DIALECT>
 __global__ void __launch_bounds__(kAbThreads)
@@ -402,7 +416,9 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
     extern __shared__ uint32_t s_stack[];      // [n_frames][words][kAbThreads]
     load_tables(T);
     ab_load_walk_tables(W);
-    constexpr bool kOrdered = DIALECT >= 3;    // children in orderedCells order
+    constexpr bool kOrdered = AbTraits<DIALECT>::ordered;    // children in orderedCells order
+    constexpr bool kDelayed = AbTraits<DIALECT>::delayed;
+    constexpr bool kPenalties = AbTraits<DIALECT>::penalties;
     constexpr int kWords = AbFrameWords<DIALECT>::n;
     uint32_t* const my = s_stack + threadIdx.x;
 #define SQ_FR(f, w) my[((f) * kWords + (w)) * kAbThreads]
@@ -452,7 +468,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
             moves = emp;
             value = n.side > 0 ? -R.sentinel : R.sentinel;
             alpha = a0; beta = b0; carried = carried_down;
-            if (DIALECT == 1) {       // the pending move is not terminal (ab_enter said so): keep its walk
+            if (kDelayed) {       // the pending move is not terminal (ab_enter said so): keep its walk
                 const bool px = (x >> n.cell) & 1u;
                 AbWalk w = ab_walk(W, px ? x : o, px ? o : x, n.cell);
                 fe1 = w.e1; fe2 = w.e2; fpc = n.cell;
@@ -482,30 +498,32 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
             const int cply = ply + 1;
             evals++;
             int d = 0;
-            if (DIALECT == 1) {
+            if (kDelayed) {
                 // the pending move, evaluated with this child's mark on the board
                 const int cnt = __popc(fe1 & ~bit) + __popc(fe2 & ~bit);
                 d = -side * (30 * cnt + R.scores[fpc]);
+                if (kPenalties) d += eval_penalties(T, side > 0 ? os : xs, side > 0 ? xs : os, fpc, -side);
             }
-            if (DIALECT == 1 && emp_after == 0) {
+            if (kDelayed && emp_after == 0) {
                 ret = side > 0 ? R.sentinel : -R.sentinel;            // the child (other side) has no move
                 returning = true;
             } else {
                 const AbWalk w = ab_walk(W, side > 0 ? xs : os, side > 0 ? os : xs, cell);
                 if (w.four) { ret = side * (kWin - cply); returning = true; }
                 else if (w.three) { ret = -side * (kWin - cply); returning = true; }
-                else if (DIALECT == 1) {
+                else if (kDelayed) {
                     if (cply >= R.max_depth) {
                         // the child stops at its first empty cell, which it marks before evaluating
                         const uint32_t j0 = emp_after & (0u - emp_after);          // order space == cell space
                         const int cnt = __popc(w.e1 & ~j0) + __popc(w.e2 & ~j0);
                         ret = side * (30 * cnt + R.scores[cell]) + d;
+                        if (kPenalties) ret += eval_penalties(T, side > 0 ? xs : os, (side > 0 ? os : xs) | j0, cell, side);
                         evals++;
                         returning = true;
                     }
                 } else {
                     int dv = side * (30 * (__popc(w.e1) + __popc(w.e2)) + R.scores[cell]);
-                    if (DIALECT == 2) dv += eval_penalties(T, side > 0 ? xs : os, side > 0 ? os : xs, cell, side);
+                    if (kPenalties) dv += eval_penalties(T, side > 0 ? xs : os, side > 0 ? os : xs, cell, side);
                     if (cply == R.max_depth) { ret = dv + carried; returning = true; }
                     else if (emp_after == 0) { ret = side > 0 ? R.sentinel : -R.sentinel; returning = true; }
                     else d = dv + carried;
@@ -515,13 +533,13 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                     SQ_FR(sp, 0) = moves | ((uint32_t)kidx << 25);
                     SQ_FR(sp, 1) = ((uint32_t)value & 0xffffu) | ((uint32_t)alpha << 16);
                     SQ_FR(sp, 2) = ((uint32_t)beta & 0xffffu) | ((uint32_t)carried << 16);
-                    if (DIALECT == 1) { SQ_FR(sp, 3) = fe1 | ((uint32_t)fpc << 25); SQ_FR(sp, 4) = fe2; }
+                    if (kDelayed) { SQ_FR(sp, 3) = fe1 | ((uint32_t)fpc << 25); SQ_FR(sp, 4) = fe2; }
                     x = xs; o = os; emp = emp_after;
                     sp++;
                     moves = emp;
                     value = side > 0 ? R.sentinel : -R.sentinel;      // the child is the other side
                     carried = d;
-                    if (DIALECT == 1) { fe1 = w.e1; fe2 = w.e2; fpc = cell; }
+                    if (kDelayed) { fe1 = w.e1; fe2 = w.e2; fpc = cell; }
                 }
             }
         }
@@ -539,7 +557,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                 moves = w0 & kFull25;
                 value = (int)(short)(w1 & 0xffffu); alpha = (int)(short)(w1 >> 16);
                 beta = (int)(short)(w2 & 0xffffu); carried = (int)(short)(w2 >> 16);
-                if (DIALECT == 1) {
+                if (kDelayed) {
                     const uint32_t w3 = SQ_FR(sp, 3);
                     fe1 = w3 & kFull25; fpc = (int)(w3 >> 25); fe2 = SQ_FR(sp, 4);
                 }
@@ -565,6 +583,7 @@ inline cudaError_t ab_configure(int* blocks_per_sm) {
     if ((e = cudaFuncSetAttribute(ab_dfs_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ab_dfs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ab_dfs_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ab_dfs_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, ab_dfs_kernel<1>, kAbThreads, 10 * 5 * kAbThreads * 4);
     if (e != cudaSuccess) return e;
     *blocks_per_sm = b1 < 1 ? 1 : b1;
@@ -716,6 +735,7 @@ inline cudaError_t ab_dispatch(int dialect, AbRun R, AbWork& w, const void* d_in
     switch (dialect) {
     case 1: return ab_run_chunk<1>(R, w, d_in, roots, n, h_split, capacity, grid_cap, min_ply, st, launches);
     case 2: return ab_run_chunk<2>(R, w, d_in, roots, n, h_split, capacity, grid_cap, min_ply, st, launches);
+    case 5: return ab_run_chunk<5>(R, w, d_in, roots, n, h_split, capacity, grid_cap, min_ply, st, launches);
     default: return ab_run_chunk<3>(R, w, d_in, roots, n, h_split, capacity, grid_cap, min_ply, st, launches);
     }
 }
@@ -723,9 +743,10 @@ inline cudaError_t ab_dispatch(int dialect, AbRun R, AbWork& w, const void* d_in
 inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t scores[25]) {
     memset(&R, 0, sizeof R);
     R.max_depth = dialect == 2 ? max_depth : max_depth;
+    const bool opening = dialect == 3 || dialect == 4;
     R.sentinel = dialect == 4 ? kWin : 2 * kWin;
-    R.win_lo = dialect >= 3 ? -kWin : -2 * kWin;
-    R.win_hi = dialect >= 3 ? kWin : 2 * kWin;
+    R.win_lo = opening ? -kWin : -2 * kWin;
+    R.win_hi = opening ? kWin : 2 * kWin;
     memcpy(R.scores, scores, 25);
 }
 

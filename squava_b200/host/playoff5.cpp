@@ -1,5 +1,6 @@
 // playoff5 -- engine-vs-engine harness over the Player interface (playoff5.go:31-126),
-// restricted to the two engines on the accelerated path: A (alpha-beta) and M (MCTS).
+// restricted to the engines on the accelerated path: A (alpha-beta), G (alpha-beta + the
+// "avoid" evaluator) and M (MCTS).
 #include <chrono>
 #include <cstdio>
 
@@ -9,9 +10,53 @@ using namespace squava;
 
 static Player* create(const std::string& t, int maxDepth, bool det) {     // playoff5.go:185-221
     if (t == "A" || t == "a") return new alphabeta::AlphaBeta(det, maxDepth);
+    if (t == "G" || t == "g") { auto* p = new alphabeta::AlphaBeta(det, maxDepth); p->SetAvoid(); return p; }
     if (t == "M" || t == "m") return new mcts::MCTS(det, maxDepth);
-    std::fprintf(stderr, "player type %s is outside the accelerated path (A and M only)\n", t.c_str());
+    std::fprintf(stderr, "player type %s is outside the accelerated path (A, G and M only)\n", t.c_str());
     std::exit(2);
+}
+
+// nonInteractiveGames, playoff5.go:128-183 -- quirks kept: `randomize` is passed where
+// createPlayers expects `deterministic`, SetScores is never called (the bias table stays
+// zero), MCTS players keep their defaults, values[][] is indexed by the move counter.
+static void nonInteractiveGames(int gameCount, const std::string& firstType, const std::string& secondType,
+                                bool randomize, int maxDepth) {
+    for (int g = 0; g < gameCount; g++) {
+        int moveCounter = 0;
+        std::unique_ptr<Player> first(create(firstType, maxDepth, randomize)), second(create(secondType, maxDepth, randomize));
+        std::printf("%d %s %s %d %s ", g, first->Name().c_str(), second->Name().c_str(), maxDepth, randomize ? "true" : "false");
+        int moves[25][2] = {{0}}, values[25][2] = {{0}};
+        int winner = 0;
+        while (moveCounter < 25) {
+            first->SetDepth(moveCounter);
+            Move mv = first->ChooseMove();
+            moves[moveCounter][0] = mv.x; moves[moveCounter][1] = mv.y;
+            values[moveCounter][0] = mv.value;
+            second->MakeMove(mv.x, mv.y, MINIMIZER);
+            moveCounter++;
+            winner = first->FindWinner();
+            if (winner != 0 || moveCounter >= 25) break;
+            second->SetDepth(moveCounter);
+            mv = second->ChooseMove();
+            moves[moveCounter][0] = mv.x; moves[moveCounter][1] = mv.y;
+            values[moveCounter][1] = mv.value;
+            first->MakeMove(mv.x, mv.y, MINIMIZER);
+            moveCounter++;
+            winner = -second->FindWinner();
+            if (winner != 0) break;
+        }
+        std::printf("%d %d", moveCounter, winner);
+        for (int i = 0; i < moveCounter; i++) {
+            const char* marker[2] = {"", ""};
+            for (int j = 0; j < 2; j++) {
+                if (values[i][j] > 9000) marker[j] = "+";
+                if (values[i][j] < -9000) marker[j] = "-";
+            }
+            std::printf(" %d%s,%d%s", moves[i][0], marker[0], moves[i][1], marker[1]);
+        }
+        std::printf("\n");
+        std::fflush(stdout);
+    }
 }
 
 int main(int argc, char** argv) {
@@ -23,9 +68,9 @@ int main(int argc, char** argv) {
     fl.Int("d", &maxDepth, "maximum lookahead depth (alpha/beta)");
     fl.Bool("D", &deterministic, "Play deterministically");
     fl.Bool("r", &randomize, "Randomize bias scores");
-    fl.String("1", &firstType, "first player type, A: alphabeta, M: MCTS");
-    fl.String("2", &secondType, "second player type, A: alphabeta, M: MCTS");
-    fl.Int("n", &games, "play <number> games non-interactively (only 1 supported)");
+    fl.String("1", &firstType, "first player type, A: alphabeta, G: A/B+avoid bad positions, M: MCTS");
+    fl.String("2", &secondType, "second player type, A: alphabeta, G: A/B+avoid bad positions, M: MCTS");
+    fl.Int("n", &games, "play <number> games non-interactively");
     fl.Float("u1", &u1, "UCTK coefficient, player 1 (MCTS)");
     fl.Float("u2", &u2, "UCTK coefficient, player 2 (MCTS)");
     fl.Int("i1", &i1, "MCTS iterations, player 1");
@@ -35,6 +80,11 @@ int main(int argc, char** argv) {
     fl.Parse(argc, argv);
     if (seed >= 0) seed_host_rng((uint64_t)seed);
     init_devices(gpus, (uint64_t)host_rng()());
+    if (games > 1) {                                  // playoff5.go:48-51
+        nonInteractiveGames(games, firstType, secondType, randomize, maxDepth);
+        sq_shutdown();
+        return 0;
+    }
     std::unique_ptr<Player> first(create(firstType, maxDepth, deterministic)), second(create(secondType, maxDepth, deterministic));
     if (auto* m = dynamic_cast<mcts::MCTS*>(first.get())) { m->SetUCTK(u1); m->SetIterations(i1); }
     if (auto* m = dynamic_cast<mcts::MCTS*>(second.get())) { m->SetUCTK(u2); m->SetIterations(i2); }

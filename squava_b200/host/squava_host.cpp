@@ -278,7 +278,7 @@ void AlphaBeta::SetDepth(int moveCounter) {       // alphabeta.go:79-89
 Move AlphaBeta::ChooseMove() {                    // alphabeta.go:92-117
     sq_board b = bd_.raw();
     int32_t values[1][25]; int32_t bv = 0; uint32_t bm = 0; uint64_t nodes = 0;
-    must(sq_alphabeta_root(&b, 1, SQ_AB_ALPHABETA, maxDepth_, scores, values, &bv, &bm, &nodes), "sq_alphabeta_root");
+    must(sq_alphabeta_root(&b, 1, dialect_, maxDepth_, scores, values, &bv, &bm, &nodes), "sq_alphabeta_root");
     MoveKeeper moves(2 * LOSS, deterministic_, &host_rng());
     for (int c = 0; c < 25; c++) if (values[0][c] != SQ_NO_MOVE) moves.SetMove(c / 5, c % 5, values[0][c]);
     int a, bb, v;

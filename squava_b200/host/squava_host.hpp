@@ -141,12 +141,14 @@ public:
     void PrintBoard() override;
     void SetScores(bool randomize) override;
     int FindWinner() override;
+    void SetAvoid() { name_ = "A/B+Avoid"; dialect_ = SQ_AB_ALPHABETA_AVOID; }   // alphabeta.go:473-475
     const Board& board() const { return bd_; }
 protected:
     Board bd_;
     std::string name_ = "AlphaBeta";
     int maxDepth_;
     bool deterministic_;
+    int dialect_ = SQ_AB_ALPHABETA;
 };
 extern int8_t scores[25];    // package-level, shared by all instances (alphabeta.go:330)
 

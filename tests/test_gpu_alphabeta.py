@@ -109,6 +109,25 @@ def test_schedule_does_not_change_values(dev, oracle, budget, pool):
     assert int(v3[0]) == oracle.ab_subtree(3, 1 << 12, 1 << 6, 6, 2, 1, 0, 6, oracle.tables()["scores_opening"])[0]
 
 
+def test_ab5_avoid_evaluator_live_oracle(dev, oracle):
+    """src/alphabeta after SetAvoid(): deltaValue2 (alphabeta.go:382-454)"""
+    from squava_b200 import positions
+    sc = oracle.tables()["scores_ab"]
+    boards, _ = positions.midgame_batch(40, marks=(6, 8, 10, 12, 14, 16), seed=80)
+    changed = 0
+    for depth in (0, 3, 6, 8):
+        values, bv, bm, _ = dev.alphabeta_root(boards, 5, depth, sc)
+        for i in range(boards.shape[0]):
+            x, o = int(boards[i]["x"]), int(boards[i]["o"])
+            if depth == 8 and bin(x | o).count("1") < 10:
+                continue
+            ov, obm, obv, _ = oracle.ab5_root(x, o, depth, sc)
+            assert values[i].tolist() == ov, (depth, i)
+            assert (int(bm[i]), int(bv[i])) == (obm, obv)
+            changed += ov != oracle.ab1_root(x, o, depth, sc)[0]
+    assert changed > 0          # the extra terms do matter on some of these positions
+
+
 def test_ab2_root_live_oracle(dev, oracle):
     from squava_b200 import positions
     sc = oracle.tables()["scores_ab"]
@@ -121,11 +140,11 @@ def test_ab2_root_live_oracle(dev, oracle):
             assert (int(bm[i]), int(bv[i])) == (obm, obv)
 
 
-@pytest.mark.parametrize("dialect", [1, 2, 3, 4])
+@pytest.mark.parametrize("dialect", [1, 2, 3, 4, 5])
 def test_subtrees_live_oracle(dev, oracle, dialect):
     from squava_b200 import positions
     rng = np.random.Generator(np.random.PCG64(dialect))
-    sc = oracle.tables()["scores_opening" if dialect >= 3 else "scores_ab"]
+    sc = oracle.tables()["scores_opening" if dialect in (3, 4) else "scores_ab"]
     rows = []
     for marks in (9, 12, 15, 18, 21, 23, 24):
         for _ in range(6):

@@ -74,3 +74,15 @@ def test_playoff5_game_ends_consistently(oracle):
     assert rc == 0, err
     assert re.search(r"(player 1 X \(MCTS\) wins|player 2 O \(MCTS\) wins|Cat wins)", out)
     assert "Winner disagreement" not in out
+
+
+def test_playoff5_batch_mode_line_format():
+    """playoff5 -n 2: one line per game, "<i> <first> <second> <depth> <randomize> <moves> <winner> x,y ..." (playoff5.go:135,166-181)"""
+    rc, out, err = run("playoff5", "-n", "2", "-1", "A", "-2", "A", "-seed", "9")
+    assert rc == 0, err
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 2
+    for i, l in enumerate(lines):
+        m = re.match(r"^%d AlphaBeta AlphaBeta 10 false (\d+) (-?[01])((?: \d[+-]?,\d[+-]?)+)$" % i, l)
+        assert m, l
+        assert len(m.group(3).split()) == int(m.group(1))

@@ -149,6 +149,16 @@ def test_ab2_c_vs_python(oracle, marks, depth):
         assert (bm, bv) == P.best_mask(pv)
 
 
+@pytest.mark.parametrize("marks,depth", [(16, 6), (14, 5), (18, 9), (10, 3)])
+def test_ab5_c_vs_python(oracle, marks, depth):
+    sc = P.SCORES_AB
+    for x, o in positions(marks, 3, marks * 100 + depth + 5):
+        vals, bm, bv, _ = oracle.ab5_root(x, o, depth, sc)
+        pv = P.ab1_root(P.from_masks(x, o), depth, sc, avoid=True)
+        assert vals == pv
+        assert (bm, bv) == P.best_mask(pv)
+
+
 def test_ab1_equals_plain_minimax(oracle):
     """SURVEY Appendix C's exactness note: the root value is the minimax value of the tree."""
     sc = P.SCORES_AB
@@ -166,10 +176,10 @@ def test_ab1_equals_plain_minimax(oracle):
             assert vals[c] == v
 
 
-@pytest.mark.parametrize("dialect", [1, 2, 3, 4])
+@pytest.mark.parametrize("dialect", [1, 2, 3, 4, 5])
 def test_subtrees_c_vs_python(oracle, dialect):
     rng = random.Random(dialect)
-    sc = P.SCORES_OPENING if dialect >= 3 else P.SCORES_AB
+    sc = P.SCORES_OPENING if dialect in (3, 4) else P.SCORES_AB
     for x, o in positions(15, 3, 300 + dialect) + positions(21, 3, 400 + dialect):
         bd = P.from_masks(x, o)
         occupied = [c for c in range(25) if bd[c] != 0]
@@ -177,8 +187,8 @@ def test_subtrees_c_vs_python(oracle, dialect):
         side = -bd[last]
         ply, md, carried = 2, 6, rng.randint(-40, 40)
         v, _ = oracle.ab_subtree(dialect, x, o, last, ply, side, carried, md, sc)
-        if dialect == 1:
-            pv = P.ab1(list(bd), ply, side, -20000, 20000, last, carried, md, sc)
+        if dialect in (1, 5):
+            pv = P.ab1(list(bd), ply, side, -20000, 20000, last, carried, md, sc, avoid=dialect == 5)
         elif dialect == 2:
             pv = P.ab2(list(bd), ply, side, -20000, 20000, last, carried, md, sc)
         else:
