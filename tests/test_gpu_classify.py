@@ -35,8 +35,25 @@ def alternating_boards(max_marks):
 
 
 def test_exhaustive_small(dev, oracle):
-    b = alternating_boards(5).view(dev.BOARD).reshape(-1)
-    assert b.shape[0] > 500000
+    """every reachable-shaped board (X-count - O-count in {0,1}) with at most 6 marks"""
+    b = alternating_boards(6).view(dev.BOARD).reshape(-1)
+    assert b.shape[0] == 4_156_726
+    f, wm, wa = check(dev, oracle, b)
+    assert (f != 0).sum() > 0 and (wm == wa).all()        # one colour can own a line by then, never both
+
+
+def test_random_alternating_dense_boards(dev, oracle):
+    """8..24 marks, X-count - O-count in {0,1}: the shapes play produces (lines allowed)"""
+    rng = np.random.Generator(np.random.PCG64(10))
+    n = 3_000_000
+    k = rng.integers(8, 25, size=n)
+    order = np.argsort(rng.random((n, 25)), axis=1)
+    rank = np.empty_like(order); np.put_along_axis(rank, order, np.arange(25)[None, :].repeat(n, 0), axis=1)
+    w = (1 << np.arange(25, dtype=np.uint32))
+    nx = (k + 1) // 2
+    b = np.empty(n, dev.BOARD)
+    b["x"] = ((rank < nx[:, None]) * w).sum(axis=1, dtype=np.uint32)
+    b["o"] = (((rank >= nx[:, None]) & (rank < k[:, None])) * w).sum(axis=1, dtype=np.uint32)
     check(dev, oracle, b)
 
 
