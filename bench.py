@@ -292,11 +292,13 @@ def main():
     peak_fma = sq.int32_peak(kind=1, reps=3)
     alg_ops = OPS_PER_PLY * plies_per_step + OPS_PER_PLAYOUT * N_LEAVES * per_leaf
     achieved = alg_ops / (kernel_ms * 1e-3)
-    traffic = None
+    traffic, warp_inst = None, None
     tp = os.path.join(ROOT, "profiles", "playout_kernel_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and per_leaf == PER_LEAF:
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            prof = json.load(open(tp))
+            traffic = prof.get("dram_bytes_per_launch")
+            warp_inst = prof.get("warp_instructions_per_launch")
         except Exception:
             traffic = None
     roofline = {
@@ -308,6 +310,11 @@ def main():
         "peak_alu_only_tops": peak_alu / 1e12, "peak_fma_only_tops": peak_fma / 1e12,
         "algorithmic_bytes_per_launch": N_LEAVES * (9 + 32),
     }
+    if warp_inst:
+        # what the kernel really issues (ncu smsp__inst_executed of the same launch) against the same peak
+        roofline["executed_thread_inst_per_launch"] = warp_inst * 32
+        roofline["executed_thread_inst_per_ply"] = warp_inst * 32 / plies_per_step
+        roofline["frac_executed"] = warp_inst * 32 / (kernel_ms * 1e-3) / peak_mixed
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
