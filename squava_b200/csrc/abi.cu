@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -112,6 +114,22 @@ int launch_playouts(Device& d, const sq_board* leaves, const int8_t* to_move, in
     CK(cudaGetLastError());
     CK(cudaEventRecord(d.ev1, st));
     d.timed = true;
+    return SQ_OK;
+}
+
+// The alpha-beta search is host-driven (one synchronisation per pass), so with several devices
+// each share runs on its own host thread.  fn(k) returns a status; its message is kept.
+template <typename F>
+int for_each_device(int m, F fn) {
+    if (m == 1) return fn(0);
+    std::vector<int> rcs(m, SQ_OK);
+    std::vector<std::string> msgs(m);
+    std::vector<std::thread> th;
+    for (int k = 0; k < m; k++)
+        th.emplace_back([&, k] { rcs[k] = fn(k); if (rcs[k]) msgs[k] = t_err; });
+    for (auto& t : th) t.join();
+    for (int k = 0; k < m; k++)
+        if (rcs[k]) { snprintf(t_err, sizeof t_err, "%s", msgs[k].c_str()); return rcs[k]; }
     return SQ_OK;
 }
 
@@ -274,6 +292,16 @@ int sq_classify(const sq_board* boards, int64_t n, uint8_t* flags, int8_t* wm, i
         CK(cudaMemcpyAsync(d.buf[0], boards + lo, cnt * sizeof(sq_board), cudaMemcpyHostToDevice, d.stream));
         rc = launch_classify(d, (const sq_board*)d.buf[0], cnt, dout, (int8_t*)dout + cnt, (int8_t*)dout + 2 * cnt, d.stream);
         if (rc) return rc;
+    }
+    // second sweep: a device-to-host copy into pageable memory waits for its stream, so all
+    // devices are launched before the first result is collected
+    for (int k = 0; k < m; k++) {
+        Device& d = g_dev[k];
+        int64_t lo, hi; share(n, m, k, lo, hi);
+        int64_t cnt = hi - lo;
+        if (cnt <= 0) continue;
+        CK(cudaSetDevice(d.id));
+        uint8_t* dout = (uint8_t*)d.buf[1];
         if (flags) CK(cudaMemcpyAsync(flags + lo, dout, cnt, cudaMemcpyDeviceToHost, d.stream));
         if (wm) CK(cudaMemcpyAsync(wm + lo, dout + cnt, cnt, cudaMemcpyDeviceToHost, d.stream));
         if (wa) CK(cudaMemcpyAsync(wa + lo, dout + 2 * cnt, cnt, cudaMemcpyDeviceToHost, d.stream));
@@ -312,6 +340,13 @@ int sq_playouts(const sq_board* leaves, const int8_t* to_move, int64_t n_leaves,
         rc = launch_playouts(d, (const sq_board*)d.buf[0], (const int8_t*)d.buf[1], cnt, (uint64_t)lo,
                              per_leaf, stream_id, (uint64_t*)d.buf[2], d.stream);
         if (rc) return rc;
+    }
+    for (int k = 0; k < m; k++) {      // collect after every device has been launched
+        Device& d = g_dev[k];
+        int64_t lo, hi; share(n_leaves, m, k, lo, hi);
+        int64_t cnt = hi - lo;
+        if (cnt <= 0) continue;
+        CK(cudaSetDevice(d.id));
         CK(cudaMemcpyAsync(out + lo, d.buf[2], cnt * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.stream));
     }
     for (int k = 0; k < m; k++) { CK(cudaSetDevice(g_dev[k].id)); CK(cudaStreamSynchronize(g_dev[k].stream)); }
@@ -337,16 +372,17 @@ int sq_alphabeta_root(const sq_board* positions, int64_t n, int dialect, int max
             return SQ_ERR_INVALID;
         }
     std::lock_guard<std::mutex> lk(g_mu);
-    int m = (int)g_dev.size();
-    for (int k = 0; k < m; k++) {
+    const int m = (int)g_dev.size();
+    rc = for_each_device(m, [&](int k) -> int {
         Device& d = g_dev[k];
         int64_t lo, hi; share(n, m, k, lo, hi);
         int64_t cnt = hi - lo;
-        if (cnt <= 0) continue;
+        if (cnt <= 0) return SQ_OK;
+        int r;
         CK(cudaSetDevice(d.id));
-        if ((rc = reserve(d, 0, cnt * sizeof(sq_board)))) return rc;
-        if ((rc = reserve(d, 2, cnt * 25 * sizeof(int32_t)))) return rc;
-        if ((rc = reserve(d, 3, cnt * sizeof(unsigned long long)))) return rc;
+        if ((r = reserve(d, 0, cnt * sizeof(sq_board)))) return r;
+        if ((r = reserve(d, 2, cnt * 25 * sizeof(int32_t)))) return r;
+        if ((r = reserve(d, 3, cnt * sizeof(unsigned long long)))) return r;
         CK(cudaMemcpyAsync(d.buf[0], positions + lo, cnt * sizeof(sq_board), cudaMemcpyHostToDevice, d.stream));
         uint64_t launches = 0;
         cudaError_t e = sq::ab_root_search(positions + lo, (const sq_board*)d.buf[0], cnt, dialect, max_depth, scores,
@@ -356,8 +392,10 @@ int sq_alphabeta_root(const sq_board* positions, int64_t n, int dialect, int max
         if (e != cudaSuccess) return fail_cuda(e, "ab_root_search");
         CK(cudaMemcpyAsync(values + lo, d.buf[2], cnt * 25 * sizeof(int32_t), cudaMemcpyDeviceToHost, d.stream));
         if (nodes) CK(cudaMemcpyAsync(nodes + lo, d.buf[3], cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.stream));
-    }
-    for (int k = 0; k < m; k++) { CK(cudaSetDevice(g_dev[k].id)); CK(cudaStreamSynchronize(g_dev[k].stream)); }
+        CK(cudaStreamSynchronize(d.stream));
+        return SQ_OK;
+    });
+    if (rc) return rc;
     // movekeeper.go:26-52 over each finished row (a 25-entry host reduction)
     for (int64_t i = 0; i < n; i++) {
         int mx = -20000; uint32_t mask = 0;
@@ -389,16 +427,17 @@ int sq_alphabeta_subtrees(const sq_subtree* subtrees, int64_t n, int dialect, in
         if (!ok) { snprintf(t_err, sizeof t_err, "sq_alphabeta_subtrees: subtree %lld malformed", (long long)i); return SQ_ERR_INVALID; }
     }
     std::lock_guard<std::mutex> lk(g_mu);
-    int m = (int)g_dev.size();
-    for (int k = 0; k < m; k++) {
+    const int m = (int)g_dev.size();
+    return for_each_device(m, [&](int k) -> int {
         Device& d = g_dev[k];
         int64_t lo, hi; share(n, m, k, lo, hi);
         int64_t cnt = hi - lo;
-        if (cnt <= 0) continue;
+        if (cnt <= 0) return SQ_OK;
+        int r;
         CK(cudaSetDevice(d.id));
-        if ((rc = reserve(d, 0, cnt * sizeof(sq_subtree)))) return rc;
-        if ((rc = reserve(d, 2, cnt * sizeof(int32_t)))) return rc;
-        if ((rc = reserve(d, 3, cnt * sizeof(unsigned long long)))) return rc;
+        if ((r = reserve(d, 0, cnt * sizeof(sq_subtree)))) return r;
+        if ((r = reserve(d, 2, cnt * sizeof(int32_t)))) return r;
+        if ((r = reserve(d, 3, cnt * sizeof(unsigned long long)))) return r;
         CK(cudaMemcpyAsync(d.buf[0], subtrees + lo, cnt * sizeof(sq_subtree), cudaMemcpyHostToDevice, d.stream));
         uint64_t launches = 0;
         cudaError_t e = sq::ab_subtree_search(subtrees + lo, (const sq_subtree*)d.buf[0], cnt, dialect, max_depth, scores,
@@ -408,9 +447,9 @@ int sq_alphabeta_subtrees(const sq_subtree* subtrees, int64_t n, int dialect, in
         if (e != cudaSuccess) return fail_cuda(e, "ab_subtree_search");
         CK(cudaMemcpyAsync(value + lo, d.buf[2], cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, d.stream));
         if (nodes) CK(cudaMemcpyAsync(nodes + lo, d.buf[3], cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.stream));
-    }
-    for (int k = 0; k < m; k++) { CK(cudaSetDevice(g_dev[k].id)); CK(cudaStreamSynchronize(g_dev[k].stream)); }
-    return SQ_OK;
+        CK(cudaStreamSynchronize(d.stream));
+        return SQ_OK;
+    });
 }
 
 // ---- measurement helpers -------------------------------------------------------
