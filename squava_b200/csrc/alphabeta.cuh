@@ -112,6 +112,7 @@ struct AbRun {
     int max_depth;
     int sentinel;        // |value| of a node with no legal move: 20000, or 10000 (opening2)
     int win_lo, win_hi;  // the dialect's root window
+    int shortcuts;       // exact shortcuts allowed (see ab_move_classes); off when |heuristic sums| could reach a win score
     int8_t scores[25];
 };
 
@@ -368,6 +369,35 @@ ab_expand_kernel(AbRun R, const int* __restrict__ list, int lo, int count) {
 // the child's mark only: a mark on an e1 (e2) cell removes one (two) of the counted quads, so
 // the per-child evaluation of the pending move is two bit tests on the walk done when the
 // node was entered.  The same identity handles the mark a leaf places before it evaluates.
+// Exact shortcuts at a node the mover `own` is about to move from (values of the dialects'
+// trees, not heuristics):
+//   win  = empty cells that complete a 4-line for the mover: that child is terminal with
+//          +-(10000 - child ply), the best value any descendant can have as long as no node
+//          below can run out of cells (a node without a legal move returns -+20000) -- so the
+//          node's value is known without searching anything;
+//   sui  = empty cells that complete a 3-line but no 4-line: that child is terminal with the
+//          worst value the mover can get at this ply -- it is folded into the node's value and
+//          the child is never visited.
+// The caller applies them only when the subtree cannot reach a full board.  Lines are found
+// with shifts in the padded layout; only lines THROUGH the candidate cell count, exactly like
+// the reference's evaluators, so lines already on the board elsewhere are ignored.
+__device__ __forceinline__ void ab_move_classes(uint32_t own, uint32_t empties, uint32_t& win, uint32_t& sui) {
+    const uint32_t m = pad(own), e = pad(empties);
+    uint32_t w = 0, l = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int d = k == 0 ? 1 : k == 1 ? 6 : k == 2 ? 7 : 5;
+        const uint32_t a1 = m << d, a2 = m << (2 * d), a3 = m << (3 * d);   // own stone 1/2/3 steps before
+        const uint32_t b1 = m >> d, b2 = m >> (2 * d), b3 = m >> (3 * d);   // ... after
+        l |= (a1 & (a2 | b1)) | (b1 & b2);
+        w |= (a1 & a2 & (a3 | b1)) | (b1 & b2 & (a1 | b3));
+    }
+    w &= e;
+    l &= e & ~w;
+    win = unpad(w);
+    sui = unpad(l);
+}
+
 struct AbWalkTables {
     uint32_t quads[8][32];      // [k][cell]; unused slots hold kDummyLine
     uint32_t triplets[12][32];
@@ -431,6 +461,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
     uint32_t fe1 = 0, fe2 = 0;                 // DIALECT 1: walk of the pending move ...
     int fpc = 0;                               // ... which stands on this cell
     unsigned long long evals = 0;
+    bool fresh = false;                        // the register frame was just entered
     (void)n_frames;
 
     auto order_mask = [&](uint32_t cells) -> uint32_t {   // API layout -> child-order space
@@ -473,6 +504,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                 AbWalk w = ab_walk(W, px ? x : o, px ? o : x, n.cell);
                 fe1 = w.e1; fe2 = w.e2; fpc = n.cell;
             }
+            fresh = true;
             continue;
         }
         if (evals > budget) {          // too big for one lane: hand the unit back to be split one ply deeper
@@ -484,7 +516,33 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
 
         const int ply = base_ply + sp;
         const int side = (sp & 1) ? -base_side : base_side;
-        if (moves == 0) {
+        if (fresh) {
+            fresh = false;
+            // exact shortcuts; need: no node below can be left without a legal move
+            if (R.shortcuts && __popc(emp) > R.max_depth - ply) {
+                uint32_t win, sui;
+                ab_move_classes(side > 0 ? x : o, kFull25 & ~(x | o), win, sui);
+                const int best = side * (kWin - (ply + 1));        // the mover completes a 4-line now
+                if (win) {
+                    ret = best; returning = true; sp--; restore = true;
+                } else {
+                    if (side > 0) beta = min(beta, best); else alpha = max(alpha, best);   // mate distance
+                    if (sui) {
+                        value = -best;                            // what a 3-line move is worth
+                        if (side > 0) alpha = max(alpha, value); else beta = min(beta, value);
+                        moves &= ~order_mask(sui);
+                    }
+                    if (beta <= alpha) {
+                        if (side > 0) ret = value >= beta ? value : beta;
+                        else ret = value <= alpha ? value : alpha;
+                        returning = true; sp--; restore = true;
+                    }
+                }
+            }
+        }
+        if (returning) {
+            // resolved by the shortcuts above
+        } else if (moves == 0) {
             ret = value; returning = true;            // node done (also: a node with no legal move)
             sp--; restore = true;
         } else {
@@ -540,6 +598,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                     value = side > 0 ? R.sentinel : -R.sentinel;      // the child is the other side
                     carried = d;
                     if (kDelayed) { fe1 = w.e1; fe2 = w.e2; fpc = cell; }
+                    fresh = true;
                 }
             }
         }
@@ -748,6 +807,9 @@ inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t score
     R.win_lo = opening ? -kWin : -2 * kWin;
     R.win_hi = opening ? kWin : 2 * kWin;
     memcpy(R.scores, scores, 25);
+    // the shortcuts assume a win outranks every heuristic sum; squavathr's cumulative value
+    // with its -100 terms stays below 9000 only for depths <= 16
+    R.shortcuts = !(dialect == 2 && max_depth > 16) && !getenv("SQ_AB_NO_SHORTCUTS");
 }
 
 constexpr long long kAbChunkNodesDefault = 64ll << 20;   // node slots per chunk: level-0 nodes + the pool adaptive splitting draws on (~2.5 GB)

@@ -85,6 +85,26 @@ def test_ab1_root_live_oracle_all_split_depths(dev, oracle, split, monkeypatch):
         assert (int(bm[i]), int(bv[i])) == (obm, obv)
 
 
+def test_shortcuts_do_not_change_values(dev, oracle):
+    """win / 3-line move classes and mate-distance bounds are exact: same values with them off,
+    and on boards that CAN fill up inside the horizon (where they must switch themselves off)"""
+    from squava_b200 import positions
+    sc = oracle.tables()["scores_ab"]
+    boards, _ = positions.midgame_batch(30, marks=(10, 12, 14, 16, 18, 20, 22), seed=81)
+    on = dev.alphabeta_root(boards, 1, 12, sc)
+    os.environ["SQ_AB_NO_SHORTCUTS"] = "1"
+    try:
+        off = dev.alphabeta_root(boards, 1, 12, sc)
+    finally:
+        os.environ.pop("SQ_AB_NO_SHORTCUTS", None)
+    assert (on[0] == off[0]).all() and (on[2] == off[2]).all()
+    assert on[3].sum() < off[3].sum()            # and they do save work
+    for i in range(boards.shape[0]):
+        x, o = int(boards[i]["x"]), int(boards[i]["o"])
+        if bin(x | o).count("1") >= 14:          # oracle at depth 12 is quick from here
+            assert on[0][i].tolist() == oracle.ab1_root(x, o, 12, sc)[0], i
+
+
 @pytest.mark.parametrize("budget,pool", [("1", ""), ("7", ""), ("100000000", ""), ("16", "6000"), ("", "5000")])
 def test_schedule_does_not_change_values(dev, oracle, budget, pool):
     """per-pass budgets, the number of passes and running out of node pool (units then finish
