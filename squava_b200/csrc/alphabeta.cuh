@@ -258,6 +258,35 @@ __device__ __forceinline__ bool ab_enter(const AbTables& T, const AbRun& R, cons
     }
 }
 
+// Exact shortcuts at a node the mover `own` is about to move from (values of the dialects'
+// trees, not heuristics):
+//   win  = empty cells that complete a 4-line for the mover: that child is terminal with
+//          +-(10000 - child ply), the best value any descendant can have as long as no node
+//          below can run out of cells (a node without a legal move returns -+20000) -- so the
+//          node's value is known without searching anything;
+//   sui  = empty cells that complete a 3-line but no 4-line: that child is terminal with the
+//          worst value the mover can get at this ply -- it is folded into the node's value and
+//          the child is never visited.
+// The caller applies them only when the subtree cannot reach a full board.  Lines are found
+// with shifts in the padded layout; only lines THROUGH the candidate cell count, exactly like
+// the reference's evaluators, so lines already on the board elsewhere are ignored.
+__device__ __forceinline__ void ab_move_classes(uint32_t own, uint32_t empties, uint32_t& win, uint32_t& sui) {
+    const uint32_t m = pad(own), e = pad(empties);
+    uint32_t w = 0, l = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int d = k == 0 ? 1 : k == 1 ? 6 : k == 2 ? 7 : 5;
+        const uint32_t a1 = m << d, a2 = m << (2 * d), a3 = m << (3 * d);   // own stone 1/2/3 steps before
+        const uint32_t b1 = m >> d, b2 = m >> (2 * d), b3 = m >> (3 * d);   // ... after
+        l |= (a1 & (a2 | b1)) | (b1 & b2);
+        w |= (a1 & a2 & (a3 | b1)) | (b1 & b2 & (a1 | b3));
+    }
+    w &= e;
+    l &= e & ~w;
+    win = unpad(w);
+    sui = unpad(l);
+}
+
 // ---- kernels ------------------------------------------------------------------------
 // Root moves: ChooseMove's loop body, alphabeta.go:98-110 / squavathr.go:241-253.
 // One thread per (position, cell).  split[i] = breadth-first plies below the root move.
@@ -324,6 +353,26 @@ ab_expand_kernel(AbRun R, const int* __restrict__ list, int lo, int count) {
         return;
     }
     uint32_t empties = kFull25 & ~(n.x | n.o);
+    // the same exact shortcuts as in the per-lane search (ab_move_classes)
+    if (R.shortcuts && __popc(empties) > R.max_depth - n.ply) {
+        uint32_t win, sui;
+        ab_move_classes(n.side > 0 ? n.x : n.o, empties, win, sui);
+        const int best = n.side * (kWin - (n.ply + 1));
+        if (win) {
+            atomicAdd(&R.node_count[n.group], evals);
+            ab_complete(R, idx, best);
+            return;
+        }
+        if (sui) {
+            empties &= ~sui;
+            if (!empties) {                       // every move completes a 3-line
+                atomicAdd(&R.node_count[n.group], evals);
+                ab_complete(R, idx, -best);
+                return;
+            }
+            R.value[idx] = -best;                 // children fold into this with atomicMin/Max
+        }
+    }
     R.pending[idx] = __popc(empties);
     __threadfence();
     const bool pend_is_x = (n.x >> n.cell) & 1u;
@@ -369,35 +418,6 @@ ab_expand_kernel(AbRun R, const int* __restrict__ list, int lo, int count) {
 // the child's mark only: a mark on an e1 (e2) cell removes one (two) of the counted quads, so
 // the per-child evaluation of the pending move is two bit tests on the walk done when the
 // node was entered.  The same identity handles the mark a leaf places before it evaluates.
-// Exact shortcuts at a node the mover `own` is about to move from (values of the dialects'
-// trees, not heuristics):
-//   win  = empty cells that complete a 4-line for the mover: that child is terminal with
-//          +-(10000 - child ply), the best value any descendant can have as long as no node
-//          below can run out of cells (a node without a legal move returns -+20000) -- so the
-//          node's value is known without searching anything;
-//   sui  = empty cells that complete a 3-line but no 4-line: that child is terminal with the
-//          worst value the mover can get at this ply -- it is folded into the node's value and
-//          the child is never visited.
-// The caller applies them only when the subtree cannot reach a full board.  Lines are found
-// with shifts in the padded layout; only lines THROUGH the candidate cell count, exactly like
-// the reference's evaluators, so lines already on the board elsewhere are ignored.
-__device__ __forceinline__ void ab_move_classes(uint32_t own, uint32_t empties, uint32_t& win, uint32_t& sui) {
-    const uint32_t m = pad(own), e = pad(empties);
-    uint32_t w = 0, l = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int d = k == 0 ? 1 : k == 1 ? 6 : k == 2 ? 7 : 5;
-        const uint32_t a1 = m << d, a2 = m << (2 * d), a3 = m << (3 * d);   // own stone 1/2/3 steps before
-        const uint32_t b1 = m >> d, b2 = m >> (2 * d), b3 = m >> (3 * d);   // ... after
-        l |= (a1 & (a2 | b1)) | (b1 & b2);
-        w |= (a1 & a2 & (a3 | b1)) | (b1 & b2 & (a1 | b3));
-    }
-    w &= e;
-    l &= e & ~w;
-    win = unpad(w);
-    sui = unpad(l);
-}
-
 struct AbWalkTables {
     uint32_t quads[8][32];      // [k][cell]; unused slots hold kDummyLine
     uint32_t triplets[12][32];
