@@ -6,7 +6,9 @@ oracle/tools/make_golden.py).  It exists so that the C oracle
 restatement: this one takes its line tables from tests/golden/ref_tables.json
 (parsed out of the reference's Go sources), the C one builds them by rule.
 
-PARITY UNPINNED against reference *output* -- see oracle/squava_oracle.h.
+PARITY PARTLY PINNED -- see oracle/squava_oracle.h: the MCTS-side functions here are checked
+against output of the reference's own squava2.py (tests/test_reference_vectors.py); the
+alpha-beta dialects are unpinned against reference output.
 
 Boards are lists of 25 ints in {-1, 0, +1}; cell c = 5*x + y.
 Reference lines cited per function (paths relative to the reference root).

@@ -1,7 +1,8 @@
 /*
  * squava_oracle.c -- see squava_oracle.h.  TEST INFRASTRUCTURE, NOT PRODUCT.
- * PARITY UNPINNED against reference output (no Go toolchain); tables pinned
- * against tests/golden/ref_tables.json, logic against oracle/pyoracle.py.
+ * PARITY PARTLY PINNED (see the header): terminal test / GetResult / rollouts against output of
+ * the reference's squava2.py, tables against the Go sources; the alpha-beta dialects are
+ * UNPINNED against reference output (Go only, no Go toolchain) and held by oracle/pyoracle.py.
  *
  * Every function names the reference lines it restates.  Array board + table
  * walks on purpose (see header).

@@ -5,13 +5,20 @@
  * bench.py's cpu_baseline / --impl reference legs may load this library; the
  * shipped path (squava_b200/ + libsquava_b200.so) never calls into it.
  *
- * PARITY UNPINNED: the reference (bediger4000/squava, 100 % Go, no tests, no
- * golden vectors, no Go toolchain in this image) cannot be executed here, so
- * nothing in this file has been compared with OUTPUT of the reference.  What is
- * pinned: every line/scan-order table against tests/golden/ref_tables.json
- * (parsed from the reference's Go sources by oracle/tools/extract_ref_tables.py),
- * and every function against an independent Python restatement
- * (oracle/pyoracle.py) plus SURVEY.md Appendix B's third-opinion vectors.
+ * PARITY: PARTLY PINNED.
+ *   Pinned against output of the reference's own code: the MCTS-side primitives
+ *   (GetMoves' terminal test and move list, GetResult for both players, the random
+ *   rollout's outcome frequencies and length) against squava2.py -- the Python
+ *   prototype in the reference tree that src/mcts and squavam.go were transliterated
+ *   from (same board, same tables, same scan order) -- executed in the build
+ *   container by oracle/tools/make_ref_golden.py; vectors in
+ *   tests/golden/ref_squava2_vectors.json (4349 boards, 9 rollout positions).
+ *   Pinned against the reference's sources: every line / scan-order table
+ *   (tests/golden/ref_tables.json, parsed from the Go files).
+ *   UNPINNED against reference output: the alpha-beta dialects and movekeeper -- they
+ *   exist in Go only, the reference has no tests or golden vectors, and this image has
+ *   no Go toolchain.  They are held by an independent Python restatement
+ *   (oracle/pyoracle.py) and SURVEY.md Appendix B's third-opinion vectors.
  *
  * Deliberately array-and-table-walk code (an int board[25] and lists of cell
  * indices walked in the reference's own order), NOT bit tricks: it stands in for

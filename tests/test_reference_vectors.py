@@ -1,0 +1,94 @@
+"""Vectors produced by the REFERENCE'S OWN CODE (squava2.py, the Python prototype in the reference
+tree that src/mcts and squavam.go were transliterated from), generated in the build container by
+oracle/tools/make_ref_golden.py and committed as tests/golden/ref_squava2_vectors.json.
+
+CPU part: the C oracle (and the Python restatement) must agree with the reference on every board
+(terminal flag, move list, GetResult for both players) and its exact playout distribution must sit
+within 3 sigma of the reference's own rollout frequencies.  GPU part: the same through the C ABI."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+V = json.load(open(os.path.join(HERE, "golden", "ref_squava2_vectors.json")))
+
+
+def test_oracle_matches_reference_on_every_board(oracle):
+    import pyoracle as P
+    n_term = n_draw = 0
+    for b in V["boards"]:
+        x, o = b["x"], b["o"]
+        term = b["moves"] == []
+        assert oracle.terminal(x, o) == int(term)
+        bd = P.from_masks(x, o)
+        moves, pterm = P.get_moves(bd)
+        assert pterm == term and moves == b["moves"]
+        if term:
+            n_term += 1
+            for player, key in ((1, "result_x"), (-1, "result_o")):
+                want = b[key]
+                if want is None:            # the reference asserts on a full board without a line;
+                    n_draw += 1             # the Go code returns 0.0 there (mcts.go:386-387)
+                    assert oracle.get_result(x, o, player) == 0.0 and oracle.flags(x, o) == 16
+                else:
+                    assert oracle.get_result(x, o, player) == want == P.get_result(bd, player)
+    assert n_term > 1000 and n_draw == 8
+
+
+def test_exact_distribution_within_3_sigma_of_reference_rollouts(oracle):
+    for r in V["rollouts"]:
+        marks = bin(r["x"] | r["o"]).count("1")
+        n = r["n"]
+        if marks >= 8:
+            p, plies = oracle.playout_exact(r["x"], r["o"], r["to_move"])
+            for got, pk in ((r["x_wins"], p[0]), (r["o_wins"], p[1]), (r["draws"], p[2])):
+                assert abs(got / n - pk) <= 3.0 * (pk * (1 - pk) / n) ** 0.5 + 1e-12, (r, p)
+            assert abs(r["plies"] / n - plies) < 0.03
+        else:                                # DP too large: the oracle's own sampling, two-sample 3 sigma
+            m = 200000
+            out = oracle.playouts(r["x"], r["o"], r["to_move"], m, 99)
+            pk = (out[0] + r["x_wins"]) / (m + n)
+            assert abs(out[0] / m - r["x_wins"] / n) <= 3.0 * (pk * (1 - pk) * (1 / m + 1 / n)) ** 0.5
+            assert abs(out[3] / m - r["plies"] / n) < 0.06
+
+
+@pytest.mark.gpu
+def test_gpu_classify_matches_reference(sq):
+    sq.init()
+    try:
+        boards = np.array([(b["x"], b["o"]) for b in V["boards"]], dtype=np.uint32).view(sq.BOARD).reshape(-1)
+        f, wm, _ = sq.classify(boards)
+        for i, b in enumerate(V["boards"]):
+            assert (f[i] != 0) == (b["moves"] == [])                   # GetMoves' terminal test
+            if b["moves"] == [] and b["result_x"] is not None:
+                assert (wm[i] == 1) == (b["result_x"] == 1.0) and (wm[i] == -1) == (b["result_o"] == 1.0)
+            elif b["moves"] == []:
+                assert wm[i] == 0 and f[i] == 16
+            else:
+                empties = [c for c in range(25) if not ((b["x"] | b["o"]) >> c) & 1]
+                assert b["moves"] == empties
+    finally:
+        sq.shutdown()
+
+
+@pytest.mark.gpu
+def test_gpu_playouts_within_3_sigma_of_reference_rollouts(sq):
+    sq.init(seed=0x5155415641)
+    try:
+        rs = V["rollouts"]
+        boards = np.array([(r["x"], r["o"]) for r in rs], dtype=np.uint32).view(sq.BOARD).reshape(-1)
+        tm = np.array([r["to_move"] for r in rs], dtype=np.int8)
+        m = 10_000_000
+        out = sq.playouts(boards, tm, m, 2026)
+        for i, r in enumerate(rs):
+            n = r["n"]
+            for k, key in ((0, "x_wins"), (1, "o_wins")):
+                pk = (int(out[i, k]) + r[key]) / (m + n)
+                tol = 3.0 * (pk * (1 - pk) * (1 / m + 1 / n)) ** 0.5          # two-sample 3 sigma
+                assert abs(int(out[i, k]) / m - r[key] / n) <= tol, (i, key)
+            assert int(out[i, 2]) <= 1e-5 * m and r["draws"] == 0       # draws need one of 4 full boards: ~1e-6
+            assert abs(int(out[i, 3]) / m - r["plies"] / n) < 0.03
+    finally:
+        sq.shutdown()
