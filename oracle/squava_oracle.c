@@ -1,8 +1,10 @@
 /*
  * squava_oracle.c -- see squava_oracle.h.  TEST INFRASTRUCTURE, NOT PRODUCT.
  * PARITY PARTLY PINNED (see the header): terminal test / GetResult / rollouts against output of
- * the reference's squava2.py, tables against the Go sources; the alpha-beta dialects are
- * UNPINNED against reference output (Go only, no Go toolchain) and held by oracle/pyoracle.py.
+ * the reference's squava2.py, the alpha-beta evaluator and dialect 2's search against its
+ * squava.html, tables against the Go sources; what exists in Go only (dialect 1's delayed
+ * evaluation, dialect 3/4's traversal, movekeeper) is UNPINNED against reference output and
+ * held by oracle/pyoracle.py.
  *
  * Every function names the reference lines it restates.  Array board + table
  * walks on purpose (see header).

@@ -15,10 +15,19 @@
  *   tests/golden/ref_squava2_vectors.json (4349 boards, 9 rollout positions).
  *   Pinned against the reference's sources: every line / scan-order table
  *   (tests/golden/ref_tables.json, parsed from the Go files).
- *   UNPINNED against reference output: the alpha-beta dialects and movekeeper -- they
- *   exist in Go only, the reference has no tests or golden vectors, and this image has
- *   no Go toolchain.  They are held by an independent Python restatement
- *   (oracle/pyoracle.py) and SURVEY.md Appendix B's third-opinion vectors.
+ *   Also pinned against output of reference code: the alpha-beta EVALUATOR (lines through
+ *   the move, three-of-four credit, no2 / noMiddle2 terms, bias, depth stop) and the
+ *   evaluate-at-entry cumulative SEARCH of dialect 2, against squava.html -- the
+ *   reference's browser transliteration of its alpha-beta program, whose <script> is
+ *   translated mechanically to Python in memory and executed by
+ *   oracle/tools/make_ref_golden_js.py (no JavaScript engine exists in this image);
+ *   vectors in tests/golden/ref_squava_html_vectors.json.
+ *   UNPINNED against reference output: what only the Go files contain -- dialect 1's
+ *   delayed evaluation order (src/alphabeta), dialect 3/4's orderedCells traversal and
+ *   root windows, squavathr's root evaluation on the unmarked board, movekeeper.  The
+ *   reference has no tests or golden vectors and this image has no Go toolchain.  These
+ *   are held by an independent Python restatement (oracle/pyoracle.py) and SURVEY.md
+ *   Appendix B's third-opinion vectors.
  *
  * Deliberately array-and-table-walk code (an int board[25] and lists of cell
  * indices walked in the reference's own order), NOT bit tricks: it stands in for

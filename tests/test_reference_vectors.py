@@ -92,3 +92,64 @@ def test_gpu_playouts_within_3_sigma_of_reference_rollouts(sq):
             assert abs(int(out[i, 3]) / m - r["plies"] / n) < 0.03
     finally:
         sq.shutdown()
+
+
+# ---- alpha-beta: vectors from the reference's squava.html (mechanically translated JavaScript) ----
+H = json.load(open(os.path.join(HERE, "golden", "ref_squava_html_vectors.json")))
+
+
+def _html_requests(case):
+    """squava.html mymove() (lines 83-106) as dialect-2 subtree calls: (ply-0 evaluation, search)"""
+    x, o, d = case["x"], case["o"], case["max_depth"]
+    rows = []
+    for cell, (stop, delta0, val) in sorted(case["cells"].items(), key=lambda kv: int(kv[0])):
+        c = int(cell)
+        rows.append((c, x | (1 << c), o, stop, delta0, val, d))
+    return rows
+
+
+def test_oracle_matches_squava_html(oracle):
+    import pyoracle as P
+    sc = H["scores"]
+    checked = searched = 0
+    for case in H["cases"]:
+        for c, xm, om, stop, delta0, val, d in _html_requests(case):
+            # deltavalue(0, i, j, 0): dialect 2 at ply 0 with max_depth 0 returns exactly that number
+            v0, _ = oracle.ab_subtree(2, xm, om, c, 0, -1, 0, 0, sc)
+            assert v0 == delta0, (case["x"], case["o"], c)
+            assert stop == (abs(delta0) > 9000)
+            if not stop:
+                v, _ = oracle.ab_subtree(2, xm, om, c, 1, -1, delta0, d, sc)
+                assert v == val, (case["x"], case["o"], c, d)
+                if checked % 7 == 0:       # the Python restatement too (slower)
+                    assert P.ab2(P.from_masks(xm, om), 1, -1, -20000, 20000, c, delta0, d, sc) == val
+                searched += 1
+            else:
+                assert val == delta0
+            checked += 1
+    assert checked > 500 and searched > 400
+
+
+@pytest.mark.gpu
+def test_gpu_matches_squava_html(sq):
+    sq.init()
+    try:
+        sc = np.array(H["scores"], np.int8)
+        by_depth = {}
+        for case in H["cases"]:
+            for row in _html_requests(case):
+                by_depth.setdefault(row[6], []).append(row)
+        for d, rows in by_depth.items():
+            t = np.zeros(len(rows), sq.SUBTREE)
+            for i, (c, xm, om, stop, delta0, val, _) in enumerate(rows):
+                t[i] = (xm, om, c, 0, -1, 0, 0)
+            v0, _ = sq.alphabeta_subtrees(t, 2, 0, sc)
+            assert v0.tolist() == [r[4] for r in rows]
+            live = [r for r in rows if not r[3]]
+            t = np.zeros(len(live), sq.SUBTREE)
+            for i, (c, xm, om, stop, delta0, val, _) in enumerate(live):
+                t[i] = (xm, om, c, 1, -1, 0, delta0)
+            v, _ = sq.alphabeta_subtrees(t, 2, d, sc)
+            assert v.tolist() == [r[5] for r in live], d
+    finally:
+        sq.shutdown()
