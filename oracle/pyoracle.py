@@ -6,9 +6,8 @@ oracle/tools/make_golden.py).  It exists so that the C oracle
 restatement: this one takes its line tables from tests/golden/ref_tables.json
 (parsed out of the reference's Go sources), the C one builds them by rule.
 
-PARITY PARTLY PINNED -- see oracle/squava_oracle.h: the MCTS-side functions here are checked
-against output of the reference's own squava2.py (tests/test_reference_vectors.py); the
-alpha-beta dialects are unpinned against reference output.
+PARITY: see oracle/squava_oracle.h -- this restatement is checked against the same vectors
+produced by the reference's own code (tests/test_reference_vectors.py).
 
 Boards are lists of 25 ints in {-1, 0, +1}; cell c = 5*x + y.
 Reference lines cited per function (paths relative to the reference root).

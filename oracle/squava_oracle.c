@@ -1,10 +1,7 @@
 /*
  * squava_oracle.c -- see squava_oracle.h.  TEST INFRASTRUCTURE, NOT PRODUCT.
- * PARITY PARTLY PINNED (see the header): terminal test / GetResult / rollouts against output of
- * the reference's squava2.py, the alpha-beta evaluator and dialect 2's search against its
- * squava.html, tables against the Go sources; what exists in Go only (dialect 1's delayed
- * evaluation, dialect 3/4's traversal, movekeeper) is UNPINNED against reference output and
- * held by oracle/pyoracle.py.
+ * PARITY PINNED (see the header): against output of the reference's squava2.py, of its Go
+ * files executed through a mechanical in-memory translation, and of its squava.html likewise.
  *
  * Every function names the reference lines it restates.  Array board + table
  * walks on purpose (see header).

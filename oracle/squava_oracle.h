@@ -5,29 +5,30 @@
  * bench.py's cpu_baseline / --impl reference legs may load this library; the
  * shipped path (squava_b200/ + libsquava_b200.so) never calls into it.
  *
- * PARITY: PARTLY PINNED.
- *   Pinned against output of the reference's own code: the MCTS-side primitives
- *   (GetMoves' terminal test and move list, GetResult for both players, the random
- *   rollout's outcome frequencies and length) against squava2.py -- the Python
- *   prototype in the reference tree that src/mcts and squavam.go were transliterated
- *   from (same board, same tables, same scan order) -- executed in the build
- *   container by oracle/tools/make_ref_golden.py; vectors in
- *   tests/golden/ref_squava2_vectors.json (4349 boards, 9 rollout positions).
- *   Pinned against the reference's sources: every line / scan-order table
- *   (tests/golden/ref_tables.json, parsed from the Go files).
- *   Also pinned against output of reference code: the alpha-beta EVALUATOR (lines through
- *   the move, three-of-four credit, no2 / noMiddle2 terms, bias, depth stop) and the
- *   evaluate-at-entry cumulative SEARCH of dialect 2, against squava.html -- the
- *   reference's browser transliteration of its alpha-beta program, whose <script> is
- *   translated mechanically to Python in memory and executed by
- *   oracle/tools/make_ref_golden_js.py (no JavaScript engine exists in this image);
- *   vectors in tests/golden/ref_squava_html_vectors.json.
- *   UNPINNED against reference output: what only the Go files contain -- dialect 1's
- *   delayed evaluation order (src/alphabeta), dialect 3/4's orderedCells traversal and
- *   root windows, squavathr's root evaluation on the unmarked board, movekeeper.  The
- *   reference has no tests or golden vectors and this image has no Go toolchain.  These
- *   are held by an independent Python restatement (oracle/pyoracle.py) and SURVEY.md
- *   Appendix B's third-opinion vectors.
+ * PARITY: PINNED against output of the reference's own code, obtained three ways (the
+ * reference has no tests or golden vectors of its own, and this image has no Go toolchain,
+ * no JavaScript engine and no Python 2):
+ *   1. squava2.py, the Python prototype in the reference tree that src/mcts and squavam.go
+ *      were transliterated from, loaded from /root/reference and driven directly
+ *      (oracle/tools/make_ref_golden.py): GetMoves / GetResult on 4349 boards and the
+ *      outcome counts of its own rollout loop -> tests/golden/ref_squava2_vectors.json
+ *   2. the Go files themselves -- src/alphabeta + src/movekeeper (ChooseMove with deltaValue
+ *      and deltaValue2), squavathr.go (deltaValue, alphaBeta), opening2.go / opening3.go
+ *      (alphaBeta, Matrices, orderedCells), src/mcts (FindWinner, GetMoves, GetResult) --
+ *      translated MECHANICALLY to Python in memory (oracle/tools/go2py.py: a statement-by-
+ *      statement translator for the small Go subset they use) and executed
+ *      (oracle/tools/make_ref_golden_go.py); what is not translatable (goroutines/channels
+ *      in chooseMove, flag/time in main) is re-driven line for line
+ *      -> tests/golden/ref_go_vectors.json.  Root values, chosen moves, maxima AND the
+ *      order-dependent leaf counters of this file equal the Go code's.
+ *   3. squava.html, the browser transliteration of the alpha-beta program, its <script>
+ *      translated the same way (oracle/tools/make_ref_golden_js.py)
+ *      -> tests/golden/ref_squava_html_vectors.json
+ * plus every line / scan-order table against tests/golden/ref_tables.json (parsed from the
+ * Go sources).  CAVEAT: 2 and 3 execute a mechanical translation, not a Go / JavaScript
+ * implementation; Go's math/rand is not reproduced (random choices are compared
+ * statistically).  An independent Python restatement (oracle/pyoracle.py) and SURVEY.md
+ * Appendix B's vectors are further opinions.
  *
  * Deliberately array-and-table-walk code (an int board[25] and lists of cell
  * indices walked in the reference's own order), NOT bit tricks: it stands in for

@@ -153,3 +153,107 @@ def test_gpu_matches_squava_html(sq):
             assert v.tolist() == [r[5] for r in live], d
     finally:
         sq.shutdown()
+
+
+# ---- the Go sources themselves, executed through a mechanical Go->Python translation ------------
+GO = json.load(open(os.path.join(HERE, "golden", "ref_go_vectors.json")))
+TABLES = json.load(open(os.path.join(HERE, "golden", "ref_tables.json")))
+
+
+def _row(values):
+    row = [-(2 ** 31)] * 25
+    for k, v in values.items():
+        row[int(k)] = v
+    return row
+
+
+def test_oracle_matches_go_alphabeta_and_movekeeper(oracle):
+    """src/alphabeta ChooseMove + src/movekeeper under -D: every root value, the chosen move, the
+    maximum and even the leaf counter (which depends on the visiting order)"""
+    sc = TABLES["ab"]["scores"]
+    n = 0
+    for c in GO["alphabeta"]:
+        f = oracle.ab5_root if c["avoid"] else oracle.ab1_root
+        vals, bm, bv, leaves = f(c["x"], c["o"], c["depth"], sc)
+        assert vals == _row(c["values"]), c
+        assert bv == c["max"] and leaves == c["leaves"]
+        assert c["move"] == min(k for k in range(25) if bm >> k & 1)       # deterministic: moves[0]
+        n += 1
+    assert n > 80
+
+
+def test_oracle_matches_go_squavathr(oracle):
+    sc = TABLES["thr"]["scores"]
+    for c in GO["squavathr"]:
+        vals, bm, bv, leaves = oracle.ab2_root(c["x"], c["o"], c["depth"], sc)
+        assert vals == _row(c["values"]), c
+        assert leaves == c["leaves"]
+
+
+def test_oracle_matches_go_openings(oracle):
+    sc = TABLES["op3"]["scores"]
+    for d, rows in GO["opening3"].items():
+        assert [(r["first"], r["reply"]) for r in rows] == oracle.opening3_subtrees()
+        for r in rows:
+            v, lv = oracle.ab_subtree(3, 1 << r["first"], 1 << r["reply"], r["reply"], 2, 1, r["delta"], int(d), sc)
+            assert (v, lv) == (r["value"], r["leaves"]) and r["delta"] == sc[r["first"]]
+    for d, rows in GO["opening2"].items():
+        for r in rows:
+            v, lv = oracle.ab_subtree(4, 1 << r["first"], 0, r["first"], 1, -1, 0, int(d), sc)
+            assert (v, lv) == (r["value"], r["leaves"])
+
+
+def test_oracle_matches_go_winner_checks(oracle):
+    disagree = 0
+    for b in GO["winners"]:
+        x, o = b["x"], b["o"]
+        assert oracle.terminal(x, o) == int(b["terminal"])
+        assert oracle.mcts_find_winner(x, o) == b["winner"]
+        assert oracle.ab_find_winner(x, o) == b["ab_winner"]
+        assert oracle.get_result(x, o, 1) == b["result_x"] and oracle.get_result(x, o, -1) == b["result_o"]
+        if not b["terminal"]:
+            assert b["moves"] == [c for c in range(25) if not ((x | o) >> c) & 1]
+        disagree += b["winner"] != b["ab_winner"]
+    assert disagree > 0                      # the two Go checkers do differ on boards where both colours own lines
+
+
+@pytest.mark.gpu
+def test_gpu_matches_go_vectors(sq):
+    sq.init()
+    try:
+        sc = np.array(TABLES["ab"]["scores"], np.int8)
+        for avoid, dialect in ((False, 1), (True, 5)):
+            by_depth = {}
+            for c in GO["alphabeta"]:
+                if c["avoid"] == avoid:
+                    by_depth.setdefault(c["depth"], []).append(c)
+            for d, cs in by_depth.items():
+                b = np.array([(c["x"], c["o"]) for c in cs], dtype=np.uint32).view(sq.BOARD).reshape(-1)
+                values, bv, bm, _ = sq.alphabeta_root(b, dialect, d, sc)
+                for i, c in enumerate(cs):
+                    assert values[i].tolist() == _row(c["values"]), (dialect, d, i)
+                    assert int(bv[i]) == c["max"] and c["move"] == min(k for k in range(25) if int(bm[i]) >> k & 1)
+        sct = np.array(TABLES["thr"]["scores"], np.int8)
+        for c in GO["squavathr"]:
+            b = np.array([(c["x"], c["o"])], dtype=np.uint32).view(sq.BOARD).reshape(-1)
+            values, _, _, _ = sq.alphabeta_root(b, 2, c["depth"], sct)
+            assert values[0].tolist() == _row(c["values"]), c
+        sco = np.array(TABLES["op3"]["scores"], np.int8)
+        for d, rows in GO["opening3"].items():
+            t = np.zeros(len(rows), sq.SUBTREE)
+            for i, r in enumerate(rows):
+                t[i] = (1 << r["first"], 1 << r["reply"], r["reply"], 2, 1, 0, r["delta"])
+            v, _ = sq.alphabeta_subtrees(t, 3, int(d), sco)
+            assert v.tolist() == [r["value"] for r in rows]
+        for d, rows in GO["opening2"].items():
+            t = np.zeros(len(rows), sq.SUBTREE)
+            for i, r in enumerate(rows):
+                t[i] = (1 << r["first"], 0, r["first"], 1, -1, 0, 0)
+            v, _ = sq.alphabeta_subtrees(t, 4, int(d), sco)
+            assert v.tolist() == [r["value"] for r in rows]
+        b = np.array([(w["x"], w["o"]) for w in GO["winners"]], dtype=np.uint32).view(sq.BOARD).reshape(-1)
+        f, wm, wa = sq.classify(b)
+        for i, w in enumerate(GO["winners"]):
+            assert (f[i] != 0) == w["terminal"] and wm[i] == w["winner"] and wa[i] == w["ab_winner"]
+    finally:
+        sq.shutdown()
