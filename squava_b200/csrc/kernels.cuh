@@ -78,8 +78,8 @@ classify_kernel(const sq_board* __restrict__ boards, int64_t n, uint8_t* __restr
 // iteration (lane refill), so the warp stays converged at ply granularity.
 //
 // Per ply (mover's mask a, other's mask b, n empty cells):
-//   draw   idx = hi32(r*n), r = lo32(r*n)   one IMAD.WIDE; 3 draws per 32-bit
-//          Philox word (bias <= n(n-1)(n-2)/2^32 < 3.3e-6 relative)
+//   draw   idx = hi32(r*n), r = lo32(r*n): mixed-radix extraction of 3 draws per
+//          32-bit Philox word (bias <= n(n-1)(n-2)/2^32 < 3.3e-6 relative)
 //   pick   the idx-th empty cell: per-lane Fisher-Yates array of cell BITS in
 //          shared memory (word k of lane t at [k*blockDim + t]: bank = lane,
 //          conflict-free).  Swap-with-last keeps it a permutation of the leaf's
@@ -172,8 +172,10 @@ playout_kernel(PlayoutParams P) {
         }
 
         // ---- ply loop --------------------------------------------------------
-        // No per-ply gating of finished lanes: a lane keeps playing after its quota, and the
-        // counters are SNAPSHOT at the ply its last playout ends (a rare, real branch).
+        // No per-ply gating of finished lanes: a lane keeps playing after its quota is done, and
+        // its counters are SNAPSHOT (two predicated moves) at the ply its last playout ends.
+        // Plies need no counter at all: every iteration of an unfinished lane is one ply, so
+        // the snapshot takes the (warp-uniform) iteration number.
         uint32_t a = leaf_a, b = leaf_b, n = n0;
         uint32_t inc_w = 1u;          // what the mover's win adds: 1 = first player, 0x10000 = second
         uint32_t acc = 0;
