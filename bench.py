@@ -170,8 +170,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...") goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly one JSON line.  Libraries write there too (NCCL prints its
+    # "NCCL version ..." banner on stdout): keep the real stdout aside and point fd 1 at stderr.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import squava_b200 as sq
@@ -340,7 +343,8 @@ def main():
     if world > 1:
         dist.barrier()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     sq.shutdown()
     if world > 1:
         dist.destroy_process_group()
