@@ -75,7 +75,8 @@ def expr(e):
     e = re.sub(r"\[\]\w+\{\}", "[]", e)                    # []int{}
     e = re.sub(r"&\(([^()]*)\)", r"\1", e)             # &(curr.bd) -> curr.bd
     e = re.sub(r"&(\w)", r"\1", e)                      # &bd -> bd
-    e = re.sub(r"\bappend\(\s*(.+),\s*([^,()]+)\)$", r"(\1) + [\2]", e)
+    e = re.sub(r"\bappend\(\s*(.+),\s*([^,()]+)\.\.\.\)$", r"list(\1) + list(\2)", e)   # append(a, b...)
+    e = re.sub(r"\bappend\(\s*(.+),\s*([^,()]+)\)$", r"list(\1) + [\2]", e)
     # Go integer division truncates toward zero
     e = re.sub(r"(-?\w+(?:\[[^\]]*\])*)\s*/\s*(\w+)", r"int(\1 / \2)", e)
     return e
@@ -110,6 +111,9 @@ def translate_var(text):
     return "# skipped: " + text.splitlines()[0]
 
 
+ARRAY_FIELDS = set()     # struct fields of array type seen so far
+
+
 def translate_type(text):
     """type T struct { a int; b [25][2]int; c bool } -> a class whose instances hold zero values"""
     m = re.match(r"type\s+(\w+)\s+struct\s*\{(.*)\}", text, flags=re.S)
@@ -124,11 +128,14 @@ def translate_type(text):
         names = [n.strip(",") for n in parts[:-1]]
         dims = [int(d) for d in re.findall(r"\[(\d+)\]", typ)]
         base = re.sub(r"(\[\d*\])+", "", typ)
-        zero = "0.0" if base == "float64" else "False" if base == "bool" else "None" if base.startswith(("*", "func")) or "[]" in typ else "0"
+        zero = ("[]" if typ.startswith("[]") else "0.0" if base == "float64" else "False" if base == "bool"
+                else "None" if base.startswith(("*", "func")) else "0")
         for d in reversed(dims):
             zero = "[%s for _ in range(%d)]" % (zero, d)
         for n in names:
             lines.append("        self.%s = %s" % (n, zero))
+            if dims:
+                ARRAY_FIELDS.add(n)
     return "\n".join(lines)
 
 
@@ -176,7 +183,9 @@ def translate_func(text, globals_written=()):
         while s.startswith("}"):
             if stack[-1] == "case":          # the brace closes the switch: its last case ends too
                 stack.pop()
-            stack.pop()
+            closed = stack.pop()
+            if closed.startswith("forpost:"):
+                py.append("    " * (len(stack) + 1) + closed.split(":", 1)[1])
             s = s[1:].strip()
         if stack and stack[-1] == "case" and (s.startswith("case ") or s.startswith("default:")):
             stack.pop()
@@ -200,6 +209,14 @@ def translate_func(text, globals_written=()):
         elif re.match(r"for\s+(\w+)\s*:=\s*range\s+(.+)$", s):
             a, c = re.match(r"for\s+(\w+)\s*:=\s*range\s+(.+)$", s).groups()
             py.append(ind + "for %s in range(len(%s)):" % (a, expr(c))); kind = "for"
+        elif re.match(r"for\s*(.*?);\s*(.+?);\s*(.+)$", s) and opens:
+            init, cond, post = re.match(r"for\s*(.*?);\s*(.+?);\s*(.+)$", s).groups()
+            if init.strip():
+                py.append(ind + expr(init.replace(":=", "=")))
+            py.append(ind + "while %s:" % expr(cond))
+            post = post.strip()
+            post = (post[:-2] + " += 1") if post.endswith("++") else expr(post)
+            kind = "forpost:" + post          # emitted when the block closes (no `continue` inside)
         elif s == "for":
             py.append(ind + "while True:"); kind = "for"
         elif re.match(r"for\s+(.+)$", s) and opens:
@@ -219,7 +236,7 @@ def translate_func(text, globals_written=()):
             stack.append("case")
             continue
         elif s in ("break", "continue"):
-            inner = [k for k in stack if k in ("for", "case")]
+            inner = [("for" if k.startswith("forpost:") else k) for k in stack if k in ("for", "case") or k.startswith("forpost:")]
             py.append(ind + ("pass" if (s == "break" and inner and inner[-1] == "case") else s))
         elif s == "return":
             py.append(ind + "return " + (", ".join(named) if named else ""))
@@ -229,6 +246,8 @@ def translate_func(text, globals_written=()):
             py.append(ind + "%s += 1" % s[:-2])
         elif re.match(r"([\w\.\[\]]+)\+\+$", s):
             py.append(ind + "%s += 1" % s[:-2])
+        elif re.match(r"var\s+(\w+)\s+\*\w+$", s):
+            py.append(ind + "%s = None" % re.match(r"var\s+(\w+)", s).group(1))
         elif re.match(r"var\s+(\w+)\s+\[\]\w+$", s):
             py.append(ind + "%s = []" % re.match(r"var\s+(\w+)", s).group(1))
         elif re.match(r"var\s+(\w+)\s+(int|bool|float64|string)$", s):
@@ -241,6 +260,9 @@ def translate_func(text, globals_written=()):
             if mm and not re.match(r".*[=!<>]$", mm.group(1)):
                 lhs, op, rhs = mm.groups()
                 op = "=" if op == ":=" else op
+                fm = re.match(r"^\w+\.(\w+)$", rhs.strip())
+                if op == "=" and fm and fm.group(1) in ARRAY_FIELDS:     # Go arrays are values: assignment copies
+                    rhs = "list(%s)" % rhs.strip()
                 lhs = ", ".join(x.strip() for x in lhs.split(","))
                 py.append(ind + "%s %s %s" % (lhs, op, expr(rhs)))
             else:
@@ -285,3 +307,12 @@ def translate(src, want, globals_written=None):
             elif kind == "func":
                 out.append(translate_func(text, globals_written.get(name, ())))
     return "\n\n".join(out)
+
+
+def attach_methods(ns):
+    """make `obj.Method(args)` work: every translated Type_method becomes a method of class Type"""
+    for name, fn in list(ns.items()):
+        if "_" in name and callable(fn):
+            t, m = name.split("_", 1)
+            if isinstance(ns.get(t), type):
+                setattr(ns[t], m, fn)

@@ -1,0 +1,45 @@
+// host_capi.cpp -- a C entry point onto the host-side UCT driver (squava_host.cpp) with
+// injectable callbacks, so the TREE logic (select / expand / backprop / UCB1, mcts.go:123-271)
+// can be compared with the reference's on a CPU box: the rollout, the terminal test and
+// rand.Intn come from the caller.  With null callbacks it runs on the GPU like squavam does.
+#include "squava_host.hpp"
+
+using namespace squava;
+using namespace squava::mcts;
+
+extern "C" {
+
+typedef int (*sqh_intn_fn)(int n, void* ud);
+typedef int (*sqh_terminal_fn)(uint32_t x, uint32_t o, void* ud);
+typedef void (*sqh_playouts_fn)(const sq_board* leaves, const int8_t* to_move, int64_t n, uint64_t per_leaf,
+                                uint64_t stream, uint64_t (*out)[4], void* ud);
+
+// Runs UCT(rootstate, itermax, UCTK, nil).  Root children are reported in creation order.
+int sqh_uct(uint32_t x, uint32_t o, int player_just_moved, int itermax, double uctk, int factor2, int batch,
+            int playouts_per_leaf, sqh_intn_fn intn, sqh_terminal_fn terminal, sqh_playouts_fn playouts, void* ud,
+            int* n_children, int moves[25], double visits[25], double wins[25], int* best_move, int* value,
+            int* leaves) {
+    GameState st;
+    st.board.x = x; st.board.o = o; st.playerJustMoved = player_just_moved;
+    Hooks hk;
+    if (intn) hk.intn = [=](int n) { return intn(n, ud); };
+    if (terminal) hk.terminal = [=](const Board& b) { return terminal(b.x, b.o, ud) != 0; };
+    if (playouts) hk.playouts = [=](const sq_board* l, const int8_t* t, int64_t n, uint64_t p, uint64_t s, uint64_t (*out)[4]) {
+        playouts(l, t, n, p, s, out, ud);
+    };
+    Options opt;
+    opt.batch = batch; opt.playouts_per_leaf = playouts_per_leaf; opt.ucb_factor2 = factor2 != 0;
+    opt.hooks = &hk;
+    std::unique_ptr<Node> root;
+    int lv = 0, val = 0;
+    Node* best = UCT(st, itermax, uctk, root, opt, &lv, &val);
+    int k = 0;
+    for (auto& c : root->childNodes) {
+        if (k < 25) { moves[k] = c->move; visits[k] = c->visits; wins[k] = c->wins; }
+        k++;
+    }
+    *n_children = k; *best_move = best->move; *value = val; *leaves = lv;
+    return 0;
+}
+
+}  // extern "C"

@@ -152,14 +152,20 @@ struct Pending { Node* node; Board board; int to_move; };
 Node* UCT(const GameState& rootstate, int itermax, double UCTK, std::unique_ptr<Node>& root,
           const Options& opt, int* leaves, int* value) {
     static uint64_t stream_id = 0;
-    auto& rng = host_rng();
+    const Hooks* hk = opt.hooks;
+    auto rand_intn = [&](int n) { return hk && hk->intn ? hk->intn(n) : intn(host_rng(), n); };
     if (!root) {
         root.reset(new Node());
         root->move = -1;
         root->playerJustMoved = rootstate.playerJustMoved;
-        uint8_t flags = 0; sq_board rb = rootstate.board.raw();
-        must(sq_classify(&rb, 1, &flags, nullptr, nullptr), "sq_classify");
-        if (!flags) root->untriedMoves = empties_of(rootstate.board);
+        bool terminal;
+        if (hk && hk->terminal) terminal = hk->terminal(rootstate.board);
+        else {
+            uint8_t flags = 0; sq_board rb = rootstate.board.raw();
+            must(sq_classify(&rb, 1, &flags, nullptr, nullptr), "sq_classify");
+            terminal = flags != 0;
+        }
+        if (!terminal) root->untriedMoves = empties_of(rootstate.board);
     } else {
         root->playerJustMoved = rootstate.playerJustMoved;     // mcts.go:149-151
     }
@@ -191,7 +197,7 @@ Node* UCT(const GameState& rootstate, int itermax, double UCTK, std::unique_ptr<
             }
             bool fresh = false;
             if (!node->untriedMoves.empty()) {                // expand (mcts.go:166-171)
-                int idx = intn(rng, (int)node->untriedMoves.size());
+                int idx = rand_intn((int)node->untriedMoves.size());
                 int m = node->untriedMoves[idx];
                 state.DoMove(m);
                 node->untriedMoves.erase(node->untriedMoves.begin() + idx);
@@ -207,7 +213,8 @@ Node* UCT(const GameState& rootstate, int itermax, double UCTK, std::unique_ptr<
         }
         boards.resize(B); to_move.resize(B); out.assign((size_t)B * 4, 0);
         for (int k = 0; k < B; k++) { boards[k] = batch[k].board.raw(); to_move[k] = (int8_t)batch[k].to_move; }
-        must(sq_playouts(boards.data(), to_move.data(), B, (uint64_t)P, stream_id++, (uint64_t(*)[4])out.data()), "sq_playouts");
+        if (hk && hk->playouts) hk->playouts(boards.data(), to_move.data(), B, (uint64_t)P, stream_id++, (uint64_t(*)[4])out.data());
+        else must(sq_playouts(boards.data(), to_move.data(), B, (uint64_t)P, stream_id++, (uint64_t(*)[4])out.data()), "sq_playouts");
         for (int k = 0; k < B; k++) {
             const uint64_t* r = &out[(size_t)k * 4];
             if (is_new[k] && r[3] != 0) batch[k].node->untriedMoves = empties_of(batch[k].board);  // non-terminal

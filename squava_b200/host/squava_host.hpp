@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <memory>
 #include <random>
 #include <string>
@@ -94,10 +95,19 @@ struct Node {              // mcts.go:15-23
     int playerJustMoved = 0;
 };
 
+// What UCT needs from outside the tree.  Default (null members): the GPU library and the host
+// RNG.  Tests substitute deterministic callbacks to compare the tree logic with the reference's.
+struct Hooks {
+    std::function<int(int)> intn;                                  // rand.Intn
+    std::function<bool(const Board&)> terminal;                    // GetMoves' second result
+    std::function<void(const sq_board*, const int8_t*, int64_t, uint64_t, uint64_t, uint64_t (*)[4])> playouts;
+};
+
 struct Options {
     int batch = 256;                 // leaves per GPU call (leaf-parallel); 1 = the reference's sequence
     int playouts_per_leaf = 1;       // rollouts per expanded leaf
     bool ucb_factor2 = true;         // src/mcts (mcts.go:248-250) has 2*ln; squavam.go:197-199 does not
+    const Hooks* hooks = nullptr;
 };
 
 // UCT(rootstate, itermax, UCTK, rootnode), squavam.go:98 / mcts.go:123.  Returns the chosen

@@ -1,0 +1,124 @@
+"""Host-side UCT (select / expand / backprop / UCB1) against the reference's own driver.
+
+tests/golden/ref_go_uct_vectors.json holds trees grown by src/mcts/mcts.go's and squavam.go's UCT
+(translated in memory by oracle/tools/go2py.py, executed by make_ref_golden_uct.py) under a
+deterministic rand.Intn.  Fed the same stream -- and a rollout that draws from it exactly like the
+reference's loop (mcts.go:173-181) -- the C++ host driver (squava_b200/host, through
+libsquava_host.so's callback entry point) and the Python mirror (squava_b200/mcts.py) must grow the
+SAME tree: every root child's move, visits and wins, the returned move and int(1000*UCB1).
+Sequential mode (batch 1, one playout per leaf).  No GPU needed: the rollout is the test's."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import playout_emulator as E
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+V = json.load(open(os.path.join(HERE, "golden", "ref_go_uct_vectors.json")))
+MASK = (1 << 64) - 1
+
+
+def splitmix(k):
+    z = (k * 0x9E3779B97F4A7C15) & MASK
+    z ^= z >> 30
+    z = (z * 0xBF58476D1CE4E5B9) & MASK
+    z ^= z >> 27
+    z = (z * 0x94D049BB133111EB) & MASK
+    return z ^ (z >> 31)
+
+
+class Stream:
+    def __init__(self):
+        self.k = 0
+
+    def intn(self, n):
+        self.k += 1
+        return splitmix(self.k) % n
+
+    integers = intn            # numpy-Generator-like face for squava_b200.mcts
+
+
+def terminal(x, o):
+    return E.owns(x, E.TRIPLETS) or E.owns(o, E.TRIPLETS) or (x | o) == 0x1ffffff
+
+
+def rollout(stream, x, o, to_move):
+    """mcts.go:173-181: m := moves[rand.Intn(len(moves))] until terminal.  -> [X wins, O wins, draws, plies]"""
+    plies, mover = 0, to_move
+    while not terminal(x, o):
+        moves = [c for c in range(25) if not ((x | o) >> c) & 1]
+        m = moves[stream.intn(len(moves))]
+        if mover > 0:
+            x |= 1 << m
+        else:
+            o |= 1 << m
+        mover, plies = -mover, plies + 1
+    w = 1 if E.owns(x, E.QUADS) else -1 if E.owns(o, E.QUADS) else -1 if E.owns(x, E.TRIPLETS) else 1 if E.owns(o, E.TRIPLETS) else 0
+    return [int(w == 1), int(w == -1), int(w == 0), plies]
+
+
+@pytest.fixture(scope="module")
+def host_lib():
+    so = os.path.join(ROOT, "squava_b200", "host", "libsquava_host.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.dirname(so), "-s"])
+    return C.CDLL(so)
+
+
+INTN = C.CFUNCTYPE(C.c_int, C.c_int, C.c_void_p)
+TERM = C.CFUNCTYPE(C.c_int, C.c_uint32, C.c_uint32, C.c_void_p)
+PLAY = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p)
+
+
+def run_cpp(lib, case):
+    st = Stream()
+
+    def playouts(leaves, to_move, n, per_leaf, stream_id, out, ud):
+        b = np.ctypeslib.as_array(C.cast(leaves, C.POINTER(C.c_uint32)), shape=(n, 2))
+        t = np.ctypeslib.as_array(C.cast(to_move, C.POINTER(C.c_int8)), shape=(n,))
+        o = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint64)), shape=(n, 4))
+        for i in range(n):
+            tot = [0, 0, 0, 0]
+            for _ in range(per_leaf):
+                r = rollout(st, int(b[i, 0]), int(b[i, 1]), int(t[i]))
+                tot = [a + c for a, c in zip(tot, r)]
+            o[i] = tot
+    cb = (INTN(lambda n, ud: st.intn(n)), TERM(lambda x, o, ud: int(terminal(x, o))), PLAY(playouts))
+    moves = (C.c_int * 25)(); visits = (C.c_double * 25)(); wins = (C.c_double * 25)()
+    nch, best, value, leaves = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    lib.sqh_uct.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, INTN, TERM,
+                            PLAY, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                            C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    rc = lib.sqh_uct(case["x"], case["o"], case["pjm"], case["itermax"], case["uctk"], int(case["which"] == "mcts"), 1, 1,
+                     cb[0], cb[1], cb[2], None, C.byref(nch), moves, visits, wins, C.byref(best), C.byref(value), C.byref(leaves))
+    assert rc == 0
+    kids = [[moves[i], visits[i], wins[i]] for i in range(nch.value)]
+    return kids, best.value, value.value, st.k
+
+
+def test_cpp_host_uct_grows_the_reference_tree(host_lib):
+    for case in V["cases"]:
+        kids, best, value, draws = run_cpp(host_lib, case)
+        assert kids == case["children"], (case["which"], hex(case["x"]), case["itermax"])
+        assert (best, value, draws) == (case["best"], case["value"], case["draws"])
+
+
+def test_python_mirror_grows_the_reference_tree():
+    from squava_b200 import mcts
+    for case in V["cases"]:
+        st = Stream()
+
+        def roll(boards, to_move, ppl, stream_id):
+            return [rollout(st, x, o, tm) for (x, o), tm in zip(boards, to_move)]
+        root = mcts.uct(case["x"], case["o"], case["pjm"], case["itermax"], case["uctk"], roll, st, batch=1, ppl=1,
+                        factor2=case["which"] == "mcts")
+        kids = [[c.move, c.visits, c.wins] for c in root.children]
+        assert kids == case["children"], (case["which"], hex(case["x"]), case["itermax"])
+        best = root.best_move(case["uctk"], case["which"] == "mcts")
+        assert best.move == case["best"] and st.k == case["draws"]
+        assert int(1000. * best.ucb1(case["uctk"], case["which"] == "mcts")) == case["value"]
