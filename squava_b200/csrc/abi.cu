@@ -28,13 +28,16 @@ struct Device {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the most recent playout kernel
     bool timed = false;
-    unsigned long long* counters = nullptr;     // [0] playout round counter
+    unsigned long long* counters = nullptr;     // ring of playout round counters, one per launch in flight
+    unsigned launch_seq = 0;
     // staging for host-pointer calls (grown on demand)
     void* buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t cap[6] = {0, 0, 0, 0, 0, 0};
     int playout_blocks_per_sm = 0;
     int ab_blocks_per_sm = 0;
 };
+
+constexpr unsigned kCounterRing = 256;
 
 std::mutex g_mu;
 std::vector<Device> g_dev;
@@ -100,9 +103,10 @@ int launch_playouts(Device& d, const sq_board* leaves, const int8_t* to_move, in
     P.one = 1u;
     unsigned long long items = (unsigned long long)n_leaves * S;
     P.n_rounds = (int64_t)((items + 31) / 32);
-    P.round_counter = d.counters;
+    // each launch gets its own counter: launches on different streams may overlap on the device
+    P.round_counter = d.counters + (d.launch_seq++ % kCounterRing);
     P.out = reinterpret_cast<unsigned long long*>(out);
-    CK(cudaMemsetAsync(d.counters, 0, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(P.round_counter, 0, sizeof(unsigned long long), st));
     const int warps_per_block = sq::kPlayoutThreads / 32;
     int64_t blocks = (int64_t)d.sm_count * d.playout_blocks_per_sm;
     int64_t need = (P.n_rounds + warps_per_block - 1) / warps_per_block;
@@ -217,8 +221,8 @@ int sq_init(const int* device_ids, int n_devices, uint64_t seed) {
         }
         CK(cudaEventCreate(&d.ev0));
         CK(cudaEventCreate(&d.ev1));
-        CK(cudaMalloc(&d.counters, 8 * sizeof(unsigned long long)));
-        CK(cudaMemset(d.counters, 0, 8 * sizeof(unsigned long long)));
+        CK(cudaMalloc(&d.counters, kCounterRing * sizeof(unsigned long long)));
+        CK(cudaMemset(d.counters, 0, kCounterRing * sizeof(unsigned long long)));
         CK(cudaMemcpyToSymbol(sq::c_scan, &tables, sizeof tables));
         CK(cudaMemcpyToSymbol(sq::c_ab, &ab_tables, sizeof ab_tables));
         size_t smem = (size_t)sq::kMaxEmpty * sq::kPlayoutThreads * sizeof(uint32_t);

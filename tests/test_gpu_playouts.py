@@ -148,3 +148,23 @@ def test_linearity_and_symmetry_at_scale(dev):
     p = out[:, 0] / n
     tol = 4.5 * np.sqrt(2 * p * (1 - p) / n) + 1e-9
     assert (np.abs(out3[:, 0] / n - p) <= tol).all()
+
+
+def test_overlapping_launches_on_two_streams(dev):
+    """two playout kernels in flight on the same device must not share scheduling state"""
+    import torch
+    from squava_b200 import positions
+    boards, tm = positions.midgame_batch(256, seed=41)
+    want = dev.playouts(boards, tm, 20000, 6)
+    tb = torch.from_numpy(boards.view(np.uint32).reshape(-1, 2).view(np.int32).copy()).cuda()
+    tt = torch.from_numpy(tm.copy()).cuda()
+    out = torch.zeros((256, 4), dtype=torch.int64, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for rep in range(3):
+        dev.playouts_dev(tb[:128].data_ptr(), tt[:128].data_ptr(), 128, 20000, out[:128].data_ptr(),
+                         leaf_index_base=0, stream_id=6, stream=s1)
+        dev.playouts_dev(tb[128:].data_ptr(), tt[128:].data_ptr(), 128, 20000, out[128:].data_ptr(),
+                         leaf_index_base=128, stream_id=6, stream=s2)
+        torch.cuda.synchronize()
+        assert (out.cpu().numpy().astype(np.uint64) == want).all()
