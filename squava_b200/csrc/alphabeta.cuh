@@ -22,6 +22,7 @@
 // noMiddle2 penalties), 3/4 opening3 / opening2 (evaluate at entry, cumulative,
 // orderedCells child order).
 #pragma once
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -819,7 +820,7 @@ inline cudaError_t ab_dispatch(int dialect, AbRun R, AbWork& w, const void* d_in
     }
 }
 
-inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t scores[25]) {
+inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t scores[25], long long max_abs_carried = 0) {
     memset(&R, 0, sizeof R);
     R.max_depth = dialect == 2 ? max_depth : max_depth;
     const bool opening = dialect == 3 || dialect == 4;
@@ -827,9 +828,16 @@ inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t score
     R.win_lo = opening ? -kWin : -2 * kWin;
     R.win_hi = opening ? kWin : 2 * kWin;
     memcpy(R.scores, scores, 25);
-    // the shortcuts assume a win outranks every heuristic sum; squavathr's cumulative value
-    // with its -100 terms stays below 9000 only for depths <= 16
-    R.shortcuts = !(dialect == 2 && max_depth > 16) && !getenv("SQ_AB_NO_SHORTCUTS");
+    // The shortcuts assume a win (>= 10000 - max_depth in magnitude) outranks every heuristic
+    // value a leaf can return.  One evaluation contributes at most 8 quads x 30, the bias and
+    // (dialects 2 and 5) three -100 terms; dialects 2-4 sum it over the plies, dialects 1 and
+    // 5 add two consecutive evaluations; a caller-supplied carried value comes on top.
+    int max_score = 0;
+    for (int c = 0; c < 25; c++) max_score = std::max(max_score, std::abs((int)scores[c]));
+    const long long per_eval = 240 + max_score + ((dialect == 2 || dialect == 5) ? 300 : 0);
+    const bool cumulative = dialect == 2 || dialect == 3 || dialect == 4;
+    const long long worst = (cumulative ? (long long)(max_depth + 1) * per_eval : 2 * per_eval) + max_abs_carried;
+    R.shortcuts = worst < kWin - max_depth - 1 && !getenv("SQ_AB_NO_SHORTCUTS");
 }
 
 constexpr long long kAbChunkNodesDefault = 64ll << 20;   // node slots per chunk: level-0 nodes + the pool adaptive splitting draws on (~2.5 GB)
@@ -883,7 +891,9 @@ inline cudaError_t ab_subtree_search(const sq_subtree* h_st, const sq_subtree* d
                                      unsigned long long* d_nodes, int grid_cap, cudaStream_t st,
                                      uint64_t* launches) {
     AbRun R; AbWork w;
-    ab_fill_run(R, dialect, max_depth, scores);
+    long long max_carried = 0;
+    for (long long q = 0; q < n; q++) max_carried = std::max(max_carried, std::llabs((long long)h_st[q].carried));
+    ab_fill_run(R, dialect, max_depth, scores, max_carried);
     cudaError_t e = cudaMemsetAsync(d_nodes, 0, sizeof(unsigned long long) * n, st);
     if (e != cudaSuccess) return e;
     std::vector<int8_t> split((size_t)n);

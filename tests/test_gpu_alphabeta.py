@@ -183,6 +183,33 @@ def test_subtrees_live_oracle(dev, oracle, dialect):
         assert int(v[i]) == ov, (dialect, i, rows[i])
 
 
+@pytest.mark.parametrize("dialect", [1, 2, 3, 4, 5])
+def test_extreme_bias_tables_and_carried_values(dev, oracle, dialect):
+    """bias entries up to +-120 and carried values in the thousands can outrank a win score: the
+    exact shortcuts must switch themselves off and the values must still match"""
+    from squava_b200 import positions
+    rng = np.random.Generator(np.random.PCG64(100 + dialect))
+    sc = [int(v) for v in rng.integers(-120, 121, size=25)]
+    rows = []
+    for marks in (12, 15, 18, 21):
+        for _ in range(5):
+            x, o = positions.random_position(rng, marks)
+            occ = [c for c in range(25) if (x | o) >> c & 1]
+            last = int(rng.choice(occ))
+            side = -1 if (x >> last) & 1 else 1
+            rows.append((x, o, last, int(rng.integers(1, 3)), side, int(rng.integers(-6000, 6000))))
+    t = subtree_array(dev, rows)
+    v, _ = dev.alphabeta_subtrees(t, dialect, 7, sc)
+    for i, (x, o, last, ply, side, carried) in enumerate(rows):
+        assert int(v[i]) == oracle.ab_subtree(dialect, x, o, last, ply, side, carried, 7, sc)[0], (dialect, i)
+    if dialect in (1, 2, 5):
+        boards, _ = positions.midgame_batch(12, marks=(12, 14, 16), seed=90 + dialect)
+        values, _, _, _ = dev.alphabeta_root(boards, dialect, 8, sc)
+        f = {1: oracle.ab1_root, 2: oracle.ab2_root, 5: oracle.ab5_root}[dialect]
+        for i in range(12):
+            assert values[i].tolist() == f(int(boards[i]["x"]), int(boards[i]["o"]), 8, sc)[0], i
+
+
 def test_edge_cases(dev, oracle):
     sc = oracle.tables()["scores_ab"]
     v, bv, bm, nodes = dev.alphabeta_root(np.zeros(0, dev.BOARD), 1, 6, sc)
