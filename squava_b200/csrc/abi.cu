@@ -35,7 +35,13 @@ struct Device {
     size_t cap[6] = {0, 0, 0, 0, 0, 0};
     int playout_blocks_per_sm = 0;
     int ab_blocks_per_sm = 0;
+    // small-call path: pinned host staging [boards | to_move | out] and one device block
+    // [counter | out | boards | to_move], so a call is memcpy-in, H2D, memset, kernel, D2H
+    uint8_t* pin = nullptr;
+    uint8_t* small = nullptr;
 };
+
+constexpr int64_t kSmallLeaves = 1 << 16;      // per device
 
 constexpr unsigned kCounterRing = 256;
 
@@ -83,11 +89,13 @@ int launch_classify(Device& d, const sq_board* boards, int64_t n, uint8_t* flags
     return SQ_OK;
 }
 
+// counter == nullptr: zero `out`, take a counter from the ring and zero it.  Otherwise the caller
+// has already zeroed both (they sit in one block: one memset).
 int launch_playouts(Device& d, const sq_board* leaves, const int8_t* to_move, int64_t n_leaves,
                     uint64_t leaf_index_base, uint64_t per_leaf, uint64_t stream_id,
-                    uint64_t* out, cudaStream_t st) {
+                    uint64_t* out, cudaStream_t st, unsigned long long* counter = nullptr) {
     if (n_leaves <= 0) return SQ_OK;
-    CK(cudaMemsetAsync(out, 0, (size_t)n_leaves * 4 * sizeof(uint64_t), st));
+    if (!counter) CK(cudaMemsetAsync(out, 0, (size_t)n_leaves * 4 * sizeof(uint64_t), st));
     if (per_leaf == 0) return SQ_OK;
     sq::PlayoutParams P;
     P.leaves = leaves; P.to_move = to_move; P.n_leaves = n_leaves;
@@ -103,10 +111,13 @@ int launch_playouts(Device& d, const sq_board* leaves, const int8_t* to_move, in
     P.one = 1u;
     unsigned long long items = (unsigned long long)n_leaves * S;
     P.n_rounds = (int64_t)((items + 31) / 32);
-    // each launch gets its own counter: launches on different streams may overlap on the device
-    P.round_counter = d.counters + (d.launch_seq++ % kCounterRing);
     P.out = reinterpret_cast<unsigned long long*>(out);
-    CK(cudaMemsetAsync(P.round_counter, 0, sizeof(unsigned long long), st));
+    if (counter) P.round_counter = counter;
+    else {
+        // each launch gets its own counter: launches on different streams may overlap on the device
+        P.round_counter = d.counters + (d.launch_seq++ % kCounterRing);
+        CK(cudaMemsetAsync(P.round_counter, 0, sizeof(unsigned long long), st));
+    }
     const int warps_per_block = sq::kPlayoutThreads / 32;
     int64_t blocks = (int64_t)d.sm_count * d.playout_blocks_per_sm;
     int64_t need = (P.n_rounds + warps_per_block - 1) / warps_per_block;
@@ -155,6 +166,8 @@ void destroy_all() {
         if (d.stream) cudaStreamSynchronize(d.stream);
         for (int i = 0; i < 6; i++) if (d.buf[i]) cudaFree(d.buf[i]);
         if (d.counters) cudaFree(d.counters);
+        if (d.small) cudaFree(d.small);
+        if (d.pin) cudaFreeHost(d.pin);
         if (d.ev0) cudaEventDestroy(d.ev0);
         if (d.ev1) cudaEventDestroy(d.ev1);
         if (d.stream) cudaStreamDestroy(d.stream);
@@ -223,6 +236,8 @@ int sq_init(const int* device_ids, int n_devices, uint64_t seed) {
         CK(cudaEventCreate(&d.ev1));
         CK(cudaMalloc(&d.counters, kCounterRing * sizeof(unsigned long long)));
         CK(cudaMemset(d.counters, 0, kCounterRing * sizeof(unsigned long long)));
+        CK(cudaHostAlloc((void**)&d.pin, (size_t)kSmallLeaves * (8 + 1 + 32), cudaHostAllocDefault));
+        CK(cudaMalloc((void**)&d.small, 16 + (size_t)kSmallLeaves * (32 + 8 + 1)));
         CK(cudaMemcpyToSymbol(sq::c_scan, &tables, sizeof tables));
         CK(cudaMemcpyToSymbol(sq::c_ab, &ab_tables, sizeof ab_tables));
         size_t smem = (size_t)sq::kMaxEmpty * sq::kPlayoutThreads * sizeof(uint32_t);
@@ -290,6 +305,16 @@ int sq_classify(const sq_board* boards, int64_t n, uint8_t* flags, int8_t* wm, i
         int64_t cnt = hi - lo;
         if (cnt <= 0) continue;
         CK(cudaSetDevice(d.id));
+        if (cnt <= kSmallLeaves) {          // small call: pinned staging, one copy each way
+            memcpy(d.pin, boards + lo, cnt * sizeof(sq_board));
+            uint8_t* din = d.small + 16 + (size_t)cnt * 32;
+            uint8_t* dres = d.small + 16;
+            CK(cudaMemcpyAsync(din, d.pin, cnt * sizeof(sq_board), cudaMemcpyHostToDevice, d.stream));
+            rc = launch_classify(d, (const sq_board*)din, cnt, dres, (int8_t*)dres + cnt, (int8_t*)dres + 2 * cnt, d.stream);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(d.pin + (size_t)kSmallLeaves * 9, dres, cnt * 3, cudaMemcpyDeviceToHost, d.stream));
+            continue;
+        }
         if ((rc = reserve(d, 0, cnt * sizeof(sq_board)))) return rc;
         if ((rc = reserve(d, 1, cnt * 3))) return rc;
         uint8_t* dout = (uint8_t*)d.buf[1];
@@ -305,6 +330,14 @@ int sq_classify(const sq_board* boards, int64_t n, uint8_t* flags, int8_t* wm, i
         int64_t cnt = hi - lo;
         if (cnt <= 0) continue;
         CK(cudaSetDevice(d.id));
+        if (cnt <= kSmallLeaves) {
+            CK(cudaStreamSynchronize(d.stream));
+            const uint8_t* h = d.pin + (size_t)kSmallLeaves * 9;
+            if (flags) memcpy(flags + lo, h, cnt);
+            if (wm) memcpy(wm + lo, h + cnt, cnt);
+            if (wa) memcpy(wa + lo, h + 2 * cnt, cnt);
+            continue;
+        }
         uint8_t* dout = (uint8_t*)d.buf[1];
         if (flags) CK(cudaMemcpyAsync(flags + lo, dout, cnt, cudaMemcpyDeviceToHost, d.stream));
         if (wm) CK(cudaMemcpyAsync(wm + lo, dout + cnt, cnt, cudaMemcpyDeviceToHost, d.stream));
@@ -336,6 +369,22 @@ int sq_playouts(const sq_board* leaves, const int8_t* to_move, int64_t n_leaves,
         int64_t cnt = hi - lo;
         if (cnt <= 0) continue;
         CK(cudaSetDevice(d.id));
+        if (cnt <= kSmallLeaves) {
+            // small call: pinned staging, one copy in, one memset, one copy out
+            uint8_t* hin = d.pin;                              // [boards | to_move]
+            memcpy(hin, leaves + lo, cnt * sizeof(sq_board));
+            memcpy(hin + cnt * sizeof(sq_board), to_move + lo, cnt);
+            unsigned long long* dcounter = (unsigned long long*)d.small;
+            uint64_t* dout = (uint64_t*)(d.small + 16);
+            uint8_t* din = d.small + 16 + (size_t)cnt * 32;
+            CK(cudaMemcpyAsync(din, hin, cnt * 9, cudaMemcpyHostToDevice, d.stream));
+            CK(cudaMemsetAsync(d.small, 0, 16 + (size_t)cnt * 32, d.stream));
+            rc = launch_playouts(d, (const sq_board*)din, (const int8_t*)(din + cnt * sizeof(sq_board)), cnt, (uint64_t)lo,
+                                 per_leaf, stream_id, dout, d.stream, dcounter);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(d.pin + (size_t)kSmallLeaves * 9, dout, cnt * 32, cudaMemcpyDeviceToHost, d.stream));
+            continue;
+        }
         if ((rc = reserve(d, 0, cnt * sizeof(sq_board)))) return rc;
         if ((rc = reserve(d, 1, cnt))) return rc;
         if ((rc = reserve(d, 2, cnt * 4 * sizeof(uint64_t)))) return rc;
@@ -351,6 +400,11 @@ int sq_playouts(const sq_board* leaves, const int8_t* to_move, int64_t n_leaves,
         int64_t cnt = hi - lo;
         if (cnt <= 0) continue;
         CK(cudaSetDevice(d.id));
+        if (cnt <= kSmallLeaves) {
+            CK(cudaStreamSynchronize(d.stream));
+            memcpy(out + lo, d.pin + (size_t)kSmallLeaves * 9, cnt * 32);
+            continue;
+        }
         CK(cudaMemcpyAsync(out + lo, d.buf[2], cnt * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.stream));
     }
     for (int k = 0; k < m; k++) { CK(cudaSetDevice(g_dev[k].id)); CK(cudaStreamSynchronize(g_dev[k].stream)); }
