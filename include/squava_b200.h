@@ -60,6 +60,7 @@ typedef struct sq_board { uint32_t x, o; } sq_board;
 #define SQ_AB_OPENING3 3  /* opening3.go:136-225 */
 #define SQ_AB_OPENING2 4  /* opening2.go:91-180 (full-board node value -+10000) */
 #define SQ_AB_ALPHABETA_AVOID 5 /* src/alphabeta after SetAvoid(): deltaValue2, alphabeta.go:382-454,473-475 */
+#define SQ_AB_ABBOOK 6    /* src/abbook/abbook.go:93-131,171-275: dialect 1 with boardValue+delta handed down */
 
 /* ---- lifecycle -------------------------------------------------------- */
 /* device_ids == NULL / n_devices <= 0: use device 0.  seed keys every random
@@ -101,7 +102,7 @@ int sq_playouts(const sq_board *leaves, const int8_t *to_move, int64_t n_leaves,
 /* ---- fixed-depth alpha-beta -------------------------------------------- */
 /* Replaces ChooseMove's per-root-move loop: src/alphabeta/alphabeta.go:92-117
  * (dialect 1, or 5 = the same engine after SetAvoid(); max_depth = p.maxDepth as SetDepth
- * leaves it, :79-89) or
+ * leaves it, :79-89), src/abbook/abbook.go:104-123 (dialect 6, SetDepth :80-90) or
  * squavathr chooseMove + its worker pool, squavathr.go:236-269,448-466 (dialect
  * 2, max_depth = chooseMove's argument).  MAXIMIZER is to move in every
  * position.  scores = the 25-entry bias table (alphabeta.go:330,343-349).
@@ -119,7 +120,8 @@ int sq_alphabeta_root(const sq_board *positions, int64_t n, int dialect, int max
  * the board already holds the move at last_cell, side_to_move moves at `ply`,
  * `carried` is the boardValue argument.  max_depth is the callee's (squavathr's
  * worker sees chooseMove's value minus one).  value[i] = what the reference's
- * alphaBeta returns for that call.                                          */
+ * alphaBeta returns for that call.  |carried| must not exceed 15000
+ * (SQ_ERR_UNSUPPORTED; the reference's callers pass 0 or one evaluation).   */
 typedef struct sq_subtree {
     sq_board b;
     int8_t last_cell;     /* 0..24 */

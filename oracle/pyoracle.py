@@ -193,8 +193,8 @@ def delta1(bd, ply, c, current, max_depth, scores, avoid=False):
     return False, v
 
 
-def ab1(bd, ply, player, alpha, beta, c, bv, max_depth, scores, avoid=False):
-    """alphabeta.go:165-223"""
+def ab1(bd, ply, player, alpha, beta, c, bv, max_depth, scores, avoid=False, cumulative=False):
+    """alphabeta.go:165-223; cumulative=True: abbook.go:215-275 (boardValue+delta handed down)"""
     value = 2 * LOSS if player == MAX else 2 * WIN
     for i in range(25):
         if bd[i] != UNSET:
@@ -204,7 +204,8 @@ def ab1(bd, ply, player, alpha, beta, c, bv, max_depth, scores, avoid=False):
         if stop:
             bd[i] = UNSET
             return delta
-        n = ab1(bd, ply + 1, -player, alpha, beta, i, delta, max_depth, scores, avoid)
+        n = ab1(bd, ply + 1, -player, alpha, beta, i, bv + delta if cumulative else delta, max_depth, scores,
+                avoid, cumulative)
         bd[i] = UNSET
         if player == MAX:
             value = max(value, n)
@@ -217,8 +218,8 @@ def ab1(bd, ply, player, alpha, beta, c, bv, max_depth, scores, avoid=False):
     return value
 
 
-def ab1_root(bd, max_depth, scores, avoid=False):
-    """alphabeta.go:92-117 -> values[25]"""
+def ab1_root(bd, max_depth, scores, avoid=False, cumulative=False):
+    """alphabeta.go:92-117 (cumulative=True: abbook.go:104-123) -> values[25]"""
     bd = list(bd)
     out = [NO_MOVE] * 25
     for c in range(25):
@@ -227,7 +228,7 @@ def ab1_root(bd, max_depth, scores, avoid=False):
         bd[c] = MAX
         stop, v = delta1(bd, 0, c, 0, max_depth, scores, avoid)
         if not stop:
-            v = ab1(bd, 1, MIN, 2 * LOSS, 2 * WIN, c, v, max_depth, scores, avoid)
+            v = ab1(bd, 1, MIN, 2 * LOSS, 2 * WIN, c, v, max_depth, scores, avoid, cumulative)
         bd[c] = UNSET
         out[c] = v
     return out

@@ -291,6 +291,47 @@ void sqo_classify(const sqo_board *b, int64_t n, uint8_t *flags, int8_t *wm, int
     }
 }
 
+/* Enumeration of every board with k marks, X-count = ceil(k/2): rank r in
+ * [0, C(25,k)*C(k,nx)) -> (which k cells, which nx of them are X), combinatorial number system. */
+static uint64_t binom_tab[26][26];
+static void binom_init(void) {
+    if (binom_tab[0][0]) return;
+    for (int n = 0; n < 26; n++) {
+        binom_tab[n][0] = 1;
+        for (int r = 1; r <= n; r++) binom_tab[n][r] = binom_tab[n - 1][r - 1] + (r <= n - 1 ? binom_tab[n - 1][r] : 0);
+    }
+}
+static void unrank_comb(uint64_t r, int n, int k, int *out) {   /* k-subset of 0..n-1, ascending */
+    int c = 0;
+    for (int i = 0; i < k; i++) {
+        for (;; c++) {
+            uint64_t with = binom_tab[n - c - 1][k - i - 1];   /* subsets that take c next */
+            if (r < with) { out[i] = c++; break; }
+            r -= with;
+        }
+    }
+}
+int64_t sqo_count_alternating(int k) {
+    binom_init();
+    if (k < 0 || k > 25) return 0;
+    return (int64_t)(binom_tab[25][k] * binom_tab[k][(k + 1) / 2]);
+}
+void sqo_enumerate_alternating(int k, int64_t start, int64_t count, sqo_board *out) {
+    binom_init();
+    int nx = (k + 1) / 2;
+    uint64_t per = binom_tab[k][nx];
+    for (int64_t i = 0; i < count; i++) {
+        uint64_t r = (uint64_t)(start + i);
+        int cells[25], xs[25];
+        unrank_comb(r / per, 25, k, cells);
+        unrank_comb(r % per, k, nx, xs);
+        uint32_t all = 0, x = 0;
+        for (int j = 0; j < k; j++) all |= 1u << cells[j];
+        for (int j = 0; j < nx; j++) x |= 1u << cells[xs[j]];
+        out[i].x = x; out[i].o = all & ~x;
+    }
+}
+
 /* ------------------------------------------------------------------------ */
 /* Random playouts                                                           */
 /* ------------------------------------------------------------------------ */
@@ -441,6 +482,7 @@ typedef struct {
     int64_t leaves;
     int sentinel; /* AB-3: value of a node with no empty cell is -+sentinel */
     int avoid;    /* AB-1 with SetAvoid(): boardValue = deltaValue2, alphabeta.go:382-454,474 */
+    int cumulative; /* src/abbook: the recursion passes boardValue+delta down, abbook.go:228-229,255-256 */
 } ab_t;
 
 /* evaluator calls (deltaValue / the inlined evaluation of opening2-3) of the calling thread's
@@ -508,7 +550,7 @@ static int ab1(ab_t *a, int ply, int player, int alpha, int beta, int c, int boa
         a->bd[i] = player;
         int delta, stop = delta1(a, ply, c, board_value, &delta);
         if (stop) { a->bd[i] = UNSET; a->leaves++; return delta; }
-        int n = ab1(a, ply + 1, -player, alpha, beta, i, delta);
+        int n = ab1(a, ply + 1, -player, alpha, beta, i, a->cumulative ? board_value + delta : delta);
         a->bd[i] = UNSET;
         if (player == MAXIMIZER) {
             if (n > value) value = n;
@@ -546,10 +588,15 @@ void sqo_ab5_root(sqo_board b, int max_depth, const int scores[25], int32_t valu
                   uint32_t *best_mask, int32_t *best_value, int64_t *leaves) {
     ab1_root(b, max_depth, scores, values, best_mask, best_value, leaves, 1);
 }
+void sqo_ab6_root(sqo_board b, int max_depth, const int scores[25], int32_t values[25],
+                  uint32_t *best_mask, int32_t *best_value, int64_t *leaves) {
+    ab1_root(b, max_depth, scores, values, best_mask, best_value, leaves, 2);
+}
 static void ab1_root(sqo_board b, int max_depth, const int scores[25], int32_t values[25],
                      uint32_t *best_mask, int32_t *best_value, int64_t *leaves, int avoid) {
     ab_t a; tables(); unpack(b, a.bd); g_evals = 0;
-    a.max_depth = max_depth; a.scores = scores; a.leaves = 0; a.sentinel = 2 * WIN; a.avoid = avoid;
+    a.max_depth = max_depth; a.scores = scores; a.leaves = 0; a.sentinel = 2 * WIN;
+    a.avoid = avoid == 1; a.cumulative = avoid == 2;
     for (int c = 0; c < 25; c++) {            /* ChooseMove, alphabeta.go:98-110 */
         values[c] = SQO_NO_MOVE;
         if (a.bd[c] != UNSET) continue;
@@ -601,7 +648,7 @@ void sqo_ab2_root(sqo_board b, int max_depth, const int scores[25], int32_t valu
                   uint32_t *best_mask, int32_t *best_value, int64_t *leaves) {
     ab_t a; tables(); unpack(b, a.bd); g_evals = 0;
     a.max_depth = max_depth - 1;              /* squavathr.go:239 */
-    a.scores = scores; a.leaves = 0; a.sentinel = 2 * WIN; a.avoid = 0;
+    a.scores = scores; a.leaves = 0; a.sentinel = 2 * WIN; a.avoid = 0; a.cumulative = 0;
     for (int c = 0; c < 25; c++) {            /* chooseMove, squavathr.go:241-253 */
         values[c] = SQO_NO_MOVE;
         if (a.bd[c] != UNSET) continue;
@@ -653,10 +700,10 @@ int32_t sqo_ab_subtree(int dialect, sqo_board b, int last_cell, int ply, int sid
     ab_t a; tables(); unpack(b, a.bd); g_evals = 0;
     a.max_depth = max_depth; a.scores = scores; a.leaves = 0;
     a.sentinel = dialect == 4 ? WIN : 2 * WIN;
-    a.avoid = dialect == 5;
+    a.avoid = dialect == 5; a.cumulative = dialect == 6;
     int v = 0;
     switch (dialect) {
-    case 1: case 5: v = ab1(&a, ply, side, 2 * LOSS, 2 * WIN, last_cell, carried); break;
+    case 1: case 5: case 6: v = ab1(&a, ply, side, 2 * LOSS, 2 * WIN, last_cell, carried); break;
     case 2: v = ab2(&a, ply, side, 2 * LOSS, 2 * WIN, last_cell, carried); break;
     case 3: case 4: v = ab3(&a, ply, side, LOSS, WIN, last_cell, carried); break;
     }

@@ -89,6 +89,10 @@ unsigned sqo_flags(sqo_board b);
 void sqo_classify(const sqo_board *b, int64_t n, uint8_t *flags,
                   int8_t *winner_mcts, int8_t *winner_ab);
 
+/* every board with k marks and X-count = ceil(k/2), by rank (test enumeration) */
+int64_t sqo_count_alternating(int k);
+void sqo_enumerate_alternating(int k, int64_t start, int64_t count, sqo_board *out);
+
 /* ---- random playouts (mcts.go:173-181 + GetResult) ---------------------- */
 /* n_playouts uniformly random playouts from (b, to_move); out = {max_wins,
  * min_wins, draws, total_plies}.  RNG: xoshiro256** seeded by splitmix64(seed),
@@ -118,6 +122,11 @@ void sqo_ab1_root(sqo_board b, int max_depth, const int scores[25],
 void sqo_ab5_root(sqo_board b, int max_depth, const int scores[25],
                   int32_t values[25], uint32_t *best_mask, int32_t *best_value,
                   int64_t *leaves);
+/* src/abbook's search (abbook.go:93-131,171-275; playoff5's "B" player once its book is done):
+ * AB-1's delayed evaluation, but the recursion hands boardValue+delta down (:228-229,255-256). */
+void sqo_ab6_root(sqo_board b, int max_depth, const int scores[25],
+                  int32_t values[25], uint32_t *best_mask, int32_t *best_value,
+                  int64_t *leaves);
 /* AB-2 squavathr chooseMove (squavathr.go:236-269) + worker (:448-466).
  * max_depth is chooseMove's argument (it decrements it itself, :239).       */
 void sqo_ab2_root(sqo_board b, int max_depth, const int scores[25],
@@ -130,7 +139,8 @@ void sqo_ab2_root(sqo_board b, int max_depth, const int scores[25],
  *             (max_depth here is the worker's, i.e. already decremented)
  *  dialect 3: opening3 alphaBeta(bd, ply, side, -10000, +10000, x, y, carried)  opening3.go:136
  *  dialect 4: opening2 alphaBeta(...)  opening2.go:91 (full-board value -+10000)
- *  dialect 5: dialect 1 with the deltaValue2 evaluator (SetAvoid)                */
+ *  dialect 5: dialect 1 with the deltaValue2 evaluator (SetAvoid)
+ *  dialect 6: (*AlphaBetaBook).alphaBeta(...)  abbook.go:215 (dialect 1, boardValue+delta handed down) */
 int32_t sqo_ab_subtree(int dialect, sqo_board b, int last_cell, int ply, int side,
                        int32_t carried, int max_depth, const int scores[25],
                        int64_t *leaves);

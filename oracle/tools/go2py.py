@@ -141,10 +141,21 @@ def translate_type(text):
 
 def translate_const_block(text):
     out = []
-    for line in text.splitlines():
-        m = re.match(r"\s*(?:const\s+)?(\w+)\s*=\s*(-?\d+)\s*$", line)      # plain integer constants only
+    iota = None
+    for pos, line in enumerate(l for l in text.splitlines() if l.strip() and l.strip() not in ("const (", ")")):
+        m = re.match(r"\s*(?:const\s+)?(\w+)\s*=\s*(-?\d+)\s*$", line)      # plain integer constants
         if m:
             out.append("%s = %s" % (m.group(1), m.group(2)))
+            iota = None
+            continue
+        m = re.match(r"\s*(\w+)\s*=\s*iota\s*$", line)                       # NAME = iota, then bare names
+        if m:
+            iota = pos
+            out.append("%s = %d" % (m.group(1), pos))
+            continue
+        m = re.match(r"\s*(\w+)\s*$", line)
+        if m and iota is not None:
+            out.append("%s = %d" % (m.group(1), pos))
     return "\n".join(out)
 
 
@@ -166,6 +177,8 @@ def translate_func(text, globals_written=()):
     for r in named:
         py.append("    %s = 0" % r)
     stack = ["def"]
+    labels = []          # (label, depth of the labelled loop) for `break LABEL`
+    pending_label = None
     lines = []
     buf = ""
     for raw in body.splitlines():                         # join continuation lines (open parens)
@@ -186,15 +199,32 @@ def translate_func(text, globals_written=()):
             closed = stack.pop()
             if closed.startswith("forpost:"):
                 py.append("    " * (len(stack) + 1) + closed.split(":", 1)[1])
+            if closed == "for" or closed.startswith("forpost:"):
+                if labels and labels[-1][1] == len(stack):
+                    labels.pop()                              # the labelled loop itself ended
+                for lab, depth in labels:                     # a loop nested in a labelled one ended
+                    if depth < len(stack):
+                        py.append("    " * len(stack) + "if _brk_%s: break" % lab)
             s = s[1:].strip()
         if stack and stack[-1] == "case" and (s.startswith("case ") or s.startswith("default:")):
             stack.pop()
         if not s:
             continue
         ind = "    " * len(stack)
+        if re.match(r"^[A-Z]\w*:$", s):                    # a label: belongs to the loop that follows
+            pending_label = s[:-1]
+            continue
         opens = s.endswith("{")
         if opens:
             s = s[:-1].strip()
+        if pending_label and s.startswith("for"):
+            py.append(ind + "_brk_%s = False" % pending_label)
+            labels.append((pending_label, len(stack)))
+            pending_label = None
+        if re.match(r"^break\s+\w+$", s):
+            py.append(ind + "_brk_%s = True" % s.split()[1])
+            py.append(ind + "break")
+            continue
         kind = "if"
         mm = re.match(r"for\s+(\w+)\s*:=\s*(.+?);\s*\1\s*<\s*(.+?);\s*\1\+\+$", s)
         if mm:
@@ -228,8 +258,10 @@ def translate_func(text, globals_written=()):
         elif re.match(r"if\s+(.+)$", s) and opens:
             py.append(ind + "if %s:" % expr(re.match(r"if\s+(.+)$", s).group(1)))
         elif re.match(r"switch\s+(.+)$", s):
-            py.append(ind + "if True:")
-            kind = "switch:" + expr(re.match(r"switch\s+(.+)$", s).group(1))
+            tmp = "_sw%d" % len(py)                       # Go evaluates the tag once
+            py.append(ind + "%s = %s" % (tmp, expr(re.match(r"switch\s+(.+)$", s).group(1))))
+            py.append(ind + "for _once in (0,):")          # one pass; a `break` in a case leaves the switch
+            kind = "switch:" + tmp
         elif re.match(r"case\s+(.+):$", s):
             var = [k for k in stack if k.startswith("switch:")][-1].split(":", 1)[1]
             py.append(ind + "if %s == %s:" % (var, expr(re.match(r"case\s+(.+):$", s).group(1))))
@@ -237,7 +269,9 @@ def translate_func(text, globals_written=()):
             continue
         elif s in ("break", "continue"):
             inner = [("for" if k.startswith("forpost:") else k) for k in stack if k in ("for", "case") or k.startswith("forpost:")]
-            py.append(ind + ("pass" if (s == "break" and inner and inner[-1] == "case") else s))
+            if s == "continue" and inner and inner[-1] == "case":
+                raise NotImplementedError("continue inside a switch case")
+            py.append(ind + s)                             # in a case: leaves the one-pass loop of the switch
         elif s == "return":
             py.append(ind + "return " + (", ".join(named) if named else ""))
         elif s.startswith("return "):
@@ -250,6 +284,9 @@ def translate_func(text, globals_written=()):
             py.append(ind + "%s = None" % re.match(r"var\s+(\w+)", s).group(1))
         elif re.match(r"var\s+(\w+)\s+\[\]\w+$", s):
             py.append(ind + "%s = []" % re.match(r"var\s+(\w+)", s).group(1))
+        elif re.match(r"var\s+(\w+(?:\s*,\s*\w+)+)\s+(int|float64)$", s):
+            for nm in re.match(r"var\s+(.+?)\s+(?:int|float64)$", s).group(1).split(","):
+                py.append(ind + "%s = 0" % nm.strip())
         elif re.match(r"var\s+(\w+)\s+(int|bool|float64|string)$", s):
             py.append(ind + "%s = 0" % re.match(r"var\s+(\w+)", s).group(1))
         elif re.match(r"var\s+(\w+)\s+(\w+)$", s):

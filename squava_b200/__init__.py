@@ -30,7 +30,7 @@ SUBTREE = np.dtype([("x", "<u4"), ("o", "<u4"), ("last_cell", "i1"), ("ply", "i1
                     ("side_to_move", "i1"), ("reserved", "i1"), ("carried", "<i4")])
 NO_MOVE = -(2 ** 31)
 
-AB_ALPHABETA, AB_SQUAVATHR, AB_OPENING3, AB_OPENING2, AB_ALPHABETA_AVOID = 1, 2, 3, 4, 5
+AB_ALPHABETA, AB_SQUAVATHR, AB_OPENING3, AB_OPENING2, AB_ALPHABETA_AVOID, AB_ABBOOK = 1, 2, 3, 4, 5, 6
 
 # every symbol include/squava_b200.h declares
 EXPORTS = [

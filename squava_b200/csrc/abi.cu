@@ -419,7 +419,8 @@ int sq_alphabeta_root(const sq_board* positions, int64_t n, int dialect, int max
     if (n < 0 || (n > 0 && (!positions || !values)) || !scores) {
         snprintf(t_err, sizeof t_err, "sq_alphabeta_root: null pointer"); return SQ_ERR_INVALID;
     }
-    if (dialect != SQ_AB_ALPHABETA && dialect != SQ_AB_SQUAVATHR && dialect != SQ_AB_ALPHABETA_AVOID) {
+    if (dialect != SQ_AB_ALPHABETA && dialect != SQ_AB_SQUAVATHR && dialect != SQ_AB_ALPHABETA_AVOID &&
+        dialect != SQ_AB_ABBOOK) {
         snprintf(t_err, sizeof t_err, "sq_alphabeta_root: dialect %d has no root-move search in the reference", dialect);
         return SQ_ERR_UNSUPPORTED;
     }
@@ -475,10 +476,15 @@ int sq_alphabeta_subtrees(const sq_subtree* subtrees, int64_t n, int dialect, in
     if (n < 0 || (n > 0 && (!subtrees || !value)) || !scores) {
         snprintf(t_err, sizeof t_err, "sq_alphabeta_subtrees: null pointer"); return SQ_ERR_INVALID;
     }
-    if (dialect < 1 || dialect > 5) { snprintf(t_err, sizeof t_err, "unknown dialect %d", dialect); return SQ_ERR_INVALID; }
+    if (dialect < 1 || dialect > 6) { snprintf(t_err, sizeof t_err, "unknown dialect %d", dialect); return SQ_ERR_INVALID; }
     if (max_depth < 0 || max_depth > sq::kAbMaxDepth) { snprintf(t_err, sizeof t_err, "max_depth out of range [0,%d]", sq::kAbMaxDepth); return SQ_ERR_INVALID; }
     for (int64_t i = 0; i < n; i++) {
         const sq_subtree& s = subtrees[i];
+        // the search keeps running sums in 16 bits: 26 evaluations of at most 240 + 127 + 300 leave this much
+        if (s.carried > 15000 || s.carried < -15000) {
+            snprintf(t_err, sizeof t_err, "sq_alphabeta_subtrees: subtree %lld: |carried| > 15000", (long long)i);
+            return SQ_ERR_UNSUPPORTED;
+        }
         bool ok = !(s.b.x & s.b.o) && !((s.b.x | s.b.o) >> 25) && s.last_cell >= 0 && s.last_cell < 25 &&
                   (((s.b.x | s.b.o) >> s.last_cell) & 1u) && (s.side_to_move == 1 || s.side_to_move == -1) &&
                   s.ply >= 0 && s.ply <= max_depth;

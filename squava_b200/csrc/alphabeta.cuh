@@ -81,10 +81,12 @@ inline void build_ab_tables(AbTables& t) {
     for (int k = 0; k < 25; k++) { t.order[k] = ord[k]; t.rank[ord[k]] = (uint8_t)k; }
 }
 
-// dialect traits: 1 and 5 share the delayed-evaluation search of src/alphabeta; 5 adds the
+// dialect traits: 1, 5 and 6 share the delayed-evaluation search of src/alphabeta; 6 (src/abbook)
+// sums the evaluations along the path; 5 adds the
 // deltaValue2 ("avoid") terms, which are squavathr's no2 / noMiddle2 penalties
 template <int D> struct AbTraits {
-    static constexpr bool delayed = D == 1 || D == 5;
+    static constexpr bool delayed = D == 1 || D == 5 || D == 6;
+    static constexpr bool delayed_sum = D == 6;        // src/abbook hands boardValue+delta down (abbook.go:228,255)
     static constexpr bool penalties = D == 2 || D == 5;
     static constexpr bool ordered = D == 3;           // dialect 4 runs as 3 with another sentinel
 };
@@ -393,7 +395,7 @@ ab_expand_kernel(AbRun R, const int* __restrict__ list, int lo, int count) {
         c.group = n.group;
         if (AbTraits<DIALECT>::delayed) {   // the parent's move re-evaluated with this child's mark on
             Eval e = eval_lines(T, pend_is_x ? c.x : c.o, pend_is_x ? c.o : c.x, n.cell, sign, n.ply);
-            c.carried = e.value + sign * R.scores[n.cell];
+            c.carried = e.value + sign * R.scores[n.cell] + (AbTraits<DIALECT>::delayed_sum ? n.carried : 0);
             if (AbTraits<DIALECT>::penalties) c.carried += eval_penalties(T, pend_is_x ? c.x : c.o, pend_is_x ? c.o : c.x, n.cell, sign);
             evals++;
         } else {
@@ -582,6 +584,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                 const int cnt = __popc(fe1 & ~bit) + __popc(fe2 & ~bit);
                 d = -side * (30 * cnt + R.scores[fpc]);
                 if (kPenalties) d += eval_penalties(T, side > 0 ? os : xs, side > 0 ? xs : os, fpc, -side);
+                if (AbTraits<DIALECT>::delayed_sum) d += carried;
             }
             if (kDelayed && emp_after == 0) {
                 ret = side > 0 ? R.sentinel : -R.sentinel;            // the child (other side) has no move
@@ -664,6 +667,7 @@ inline cudaError_t ab_configure(int* blocks_per_sm) {
     if ((e = cudaFuncSetAttribute(ab_dfs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ab_dfs_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(ab_dfs_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(ab_dfs_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, ab_dfs_kernel<1>, kAbThreads, 10 * 5 * kAbThreads * 4);
     if (e != cudaSuccess) return e;
     *blocks_per_sm = b1 < 1 ? 1 : b1;
@@ -816,6 +820,7 @@ inline cudaError_t ab_dispatch(int dialect, AbRun R, AbWork& w, const void* d_in
     case 1: return ab_run_chunk<1>(R, w, d_in, roots, n, h_split, capacity, grid_cap, min_ply, st, launches);
     case 2: return ab_run_chunk<2>(R, w, d_in, roots, n, h_split, capacity, grid_cap, min_ply, st, launches);
     case 5: return ab_run_chunk<5>(R, w, d_in, roots, n, h_split, capacity, grid_cap, min_ply, st, launches);
+    case 6: return ab_run_chunk<6>(R, w, d_in, roots, n, h_split, capacity, grid_cap, min_ply, st, launches);
     default: return ab_run_chunk<3>(R, w, d_in, roots, n, h_split, capacity, grid_cap, min_ply, st, launches);
     }
 }
@@ -835,7 +840,7 @@ inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t score
     int max_score = 0;
     for (int c = 0; c < 25; c++) max_score = std::max(max_score, std::abs((int)scores[c]));
     const long long per_eval = 240 + max_score + ((dialect == 2 || dialect == 5) ? 300 : 0);
-    const bool cumulative = dialect == 2 || dialect == 3 || dialect == 4;
+    const bool cumulative = dialect == 2 || dialect == 3 || dialect == 4 || dialect == 6;
     const long long worst = (cumulative ? (long long)(max_depth + 1) * per_eval : 2 * per_eval) + max_abs_carried;
     R.shortcuts = worst < kWin - max_depth - 1 && !getenv("SQ_AB_NO_SHORTCUTS");
 }

@@ -42,4 +42,42 @@ int sqh_uct(uint32_t x, uint32_t o, int player_just_moved, int itermax, double u
     return 0;
 }
 
+// Drives src/abbook's player (abbook.go:93-131) against a scripted opponent, the way the golden
+// vectors were made.  role 0: the engine moves first; role 1: the opponent does.  With
+// book_only != 0 the run stops before the first move that needs the search (no GPU needed).
+// Returns the number of engine moves written; -99 if the book hit its os.Exit(99) path.
+int sqh_abbook_script(int role, int pick, int max_depth, const int* script, int n_script, int book_only,
+                      int moves[], int values[], int from_book[], int max_out, int board[25], int* still_in_book) {
+    abbook::AlphaBetaBook p(true, max_depth);
+    p.SetScores(false);
+    p.SetBookPick(pick);
+    int k = 0;
+    auto engine = [&]() -> bool {
+        const bool in_book = p.bookInProgress();
+        if (book_only && !in_book) return false;
+        Move mv = p.ChooseMove();
+        if (book_only && mv.leafCount != 0) return false;
+        if (k < max_out) { moves[k] = 5 * mv.x + mv.y; values[k] = mv.value; from_book[k] = in_book; }
+        k++;
+        return true;
+    };
+    bool go = true;
+    if (role == 0) {
+        for (int i = 0; i <= n_script && go; i++) {
+            go = engine();
+            if (!go || i == n_script || p.board().at(script[i]) != UNSET) break;
+            p.MakeMove(script[i] / 5, script[i] % 5, MINIMIZER);
+        }
+    } else {
+        for (int i = 0; i < n_script && go; i++) {
+            if (p.board().at(script[i]) != UNSET) break;
+            p.MakeMove(script[i] / 5, script[i] % 5, MINIMIZER);
+            go = engine();
+        }
+    }
+    for (int c = 0; c < 25; c++) board[c] = p.board().at(c);
+    *still_in_book = p.bookInProgress();
+    return k;
+}
+
 }  // extern "C"

@@ -276,6 +276,9 @@ namespace alphabeta {
 
 int8_t scores[25] = {0};
 
+AlphaBeta::AlphaBeta(bool deterministic, int maxdepth)
+    : maxDepth_(maxdepth), deterministic_(deterministic), scores_(scores) {}
+
 void AlphaBeta::SetDepth(int moveCounter) {       // alphabeta.go:79-89
     if (moveCounter < 4) maxDepth_ = 8;
     if (moveCounter > 3) maxDepth_ = 10;
@@ -285,7 +288,7 @@ void AlphaBeta::SetDepth(int moveCounter) {       // alphabeta.go:79-89
 Move AlphaBeta::ChooseMove() {                    // alphabeta.go:92-117
     sq_board b = bd_.raw();
     int32_t values[1][25]; int32_t bv = 0; uint32_t bm = 0; uint64_t nodes = 0;
-    must(sq_alphabeta_root(&b, 1, dialect_, maxDepth_, scores, values, &bv, &bm, &nodes), "sq_alphabeta_root");
+    must(sq_alphabeta_root(&b, 1, dialect_, maxDepth_, scores_, values, &bv, &bm, &nodes), "sq_alphabeta_root");
     MoveKeeper moves(2 * LOSS, deterministic_, &host_rng());
     for (int c = 0; c < 25; c++) if (values[0][c] != SQ_NO_MOVE) moves.SetMove(c / 5, c % 5, values[0][c]);
     int a, bb, v;
@@ -300,10 +303,10 @@ void AlphaBeta::PrintBoard() { std::printf("%s", bd_.str_grid().c_str()); }
 void AlphaBeta::SetScores(bool randomize) {        // alphabeta.go:334-351
     if (randomize) {
         static const int vals[11] = {-5, -4, -3 - 2, -1, 0, 1, 2, 3, 4, 5, 0};
-        for (int i = 0; i < 25; i++) scores[i] = (int8_t)vals[intn(host_rng(), 11)];
+        for (int i = 0; i < 25; i++) scores_[i] = (int8_t)vals[intn(host_rng(), 11)];
     } else {
         static const int8_t d[25] = {3, 3, 0, 3, 3, 3, 4, 1, 4, 3, 0, 1, 0, 1, 0, 3, 4, 1, 4, 3, 3, 3, 0, 3, 3};
-        std::memcpy(scores, d, 25);
+        std::memcpy(scores_, d, 25);
     }
 }
 
@@ -314,4 +317,102 @@ int AlphaBeta::FindWinner() {                      // alphabeta.go:355-378
 }
 
 }  // namespace alphabeta
+
+// ---- src/abbook ------------------------------------------------------------------------
+namespace abbook {
+
+int8_t scores[25];
+
+AlphaBetaBook::AlphaBetaBook(bool deterministic, int maxdepth) : AlphaBeta(deterministic, maxdepth) {
+    name_ = "A/B+Book";
+    dialect_ = SQ_AB_ABBOOK;
+    scores_ = abbook::scores;
+}
+
+void AlphaBetaBook::SetDepth(int moveCounter) {    // abbook.go:80-90
+    if (moveCounter < 4) maxDepth_ = 6;
+    if (moveCounter > 3) maxDepth_ = 8;
+    if (moveCounter > 10) maxDepth_ = 10;
+}
+
+Move AlphaBetaBook::ChooseMove() {                 // abbook.go:93-131
+    if (bookInProgress_) {
+        if (moveCount_ % 2 == 0) bookStart(); else bookDefend();
+        if (c_x_ != -1 && c_y_ != -1) {
+            MakeMove(c_x_, c_y_, MAXIMIZER);
+            return Move{c_x_, c_y_, 0, 0};
+        }
+    }
+    return AlphaBeta::ChooseMove();                // the same loop with dialect 6; MakeMove is virtual
+}
+
+// Answer the opponent's first two moves on the cell a "3 away on both axes" from
+// them (abbook.go:455-516).  Quirk kept: when no such cell exists, c_x/c_y keep their previous
+// value (0,0 at first) and that stale cell is played.
+void AlphaBetaBook::bookDefend() {
+    int lastx = -1, lasty = -1;
+    if (state_ == FIRST) {
+        state_ = BLOCKDIAG1;
+        for (int c = 0; c < 25 && lastx < 0; c++) if (bd_.at(c) != UNSET) { lastx = c / 5; lasty = c % 5; }
+        firstX_ = lastx; firstY_ = lasty;
+        for (int i = -3; i < 4; i += 6) for (int j = -3; j < 4; j += 6) {
+            int a = lastx + i, b = lasty + j;
+            if (a >= 0 && a <= 4 && b >= 0 && b <= 4) { c_x_ = a; c_y_ = b; return; }
+        }
+    } else if (state_ == BLOCKDIAG1) {
+        state_ = LAST;
+        bookInProgress_ = false;
+        for (int c = 0; c < 25 && lastx < 0; c++)
+            if (!(c / 5 == firstX_ && c % 5 == firstY_) && bd_.at(c) == MINIMIZER) { lastx = c / 5; lasty = c % 5; }
+        for (int i = -3; i < 4; i += 6) for (int j = -3; j < 4; j += 6) {
+            int a = lastx + i, b = lasty + j;
+            if (a >= 0 && a <= 4 && b >= 0 && b <= 4 && bd_.at(5 * a + b) == UNSET) { c_x_ = a; c_y_ = b; return; }
+        }
+    }
+}
+
+// The "triangle" opening (abbook.go:518-575).
+void AlphaBetaBook::bookStart() {
+    static const int firstMoves[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}};
+    bool looping = true;
+    while (looping) {
+        looping = false;
+        switch (state_) {
+        case FIRST: {
+            const int* c = firstMoves[pick_ >= 0 ? pick_ % 4 : intn(host_rng(), 4)];
+            c_x_ = c[0]; c_y_ = c[1];
+            state_ = DIAGONAL;
+            break;
+        }
+        case DIAGONAL:
+            if (bd_.at(5 * (c_x_ + 3) + c_y_ + 3) == UNSET) { c_x_ += 3; c_y_ += 3; state_ = CORNER; }
+            else { state_ = OTHERCORNER; looping = true; }
+            break;
+        case CORNER:
+            if (bd_.at(5 * (c_x_ - 3) + c_y_) == UNSET) c_x_ -= 3;
+            else if (bd_.at(5 * c_x_ + c_y_ - 3) == UNSET) c_y_ -= 3;
+            state_ = LAST;
+            bookInProgress_ = false;
+            break;
+        case OTHERCORNER:
+            if (bd_.at(5 * c_x_ + c_y_ + 3) == UNSET) { c_y_ += 3; state_ = OTHERDIAGONAL; }
+            else {
+                std::printf("Unreachable state in OTHERCORNER\n");
+                PrintBoard();
+                std::exit(99);
+            }
+            break;
+        case OTHERDIAGONAL:
+            if (bd_.at(5 * (c_x_ + 3) + c_y_ - 3) == UNSET) { c_x_ += 3; c_y_ -= 3; }
+            else { c_x_ = -1; c_y_ = -1; }
+            state_ = LAST;
+            bookInProgress_ = false;
+            break;
+        default:
+            break;
+        }
+    }
+}
+
+}  // namespace abbook
 }  // namespace squava

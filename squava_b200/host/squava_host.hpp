@@ -143,7 +143,7 @@ namespace alphabeta {
 
 class AlphaBeta : public Player {      // alphabeta.go:20-117
 public:
-    AlphaBeta(bool deterministic, int maxdepth) : maxDepth_(maxdepth), deterministic_(deterministic) {}
+    AlphaBeta(bool deterministic, int maxdepth);
     std::string Name() override { return name_; }
     void MakeMove(int x, int y, int player) override { bd_.set(5 * x + y, player); }
     void SetDepth(int moveCounter) override;
@@ -159,10 +159,37 @@ protected:
     int maxDepth_;
     bool deterministic_;
     int dialect_ = SQ_AB_ALPHABETA;
+    int8_t* scores_;         // the package-level bias table this engine reads and SetScores writes
 };
 extern int8_t scores[25];    // package-level, shared by all instances (alphabeta.go:330)
 
 }  // namespace alphabeta
+
+// ---- alpha-beta with the "triangle" opening book ---------------------------------------
+namespace abbook {
+
+// src/abbook/abbook.go:21-131,448-575.  The book is a small state machine on the host; once it
+// is exhausted the engine is src/alphabeta's search with boardValue+delta handed down
+// (dialect SQ_AB_ABBOOK) and its own SetDepth table and bias table.
+class AlphaBetaBook : public alphabeta::AlphaBeta {
+public:
+    AlphaBetaBook(bool deterministic, int maxdepth);
+    void MakeMove(int x, int y, int player) override { moveCount_++; bd_.set(5 * x + y, player); }   // :75-78
+    void SetDepth(int moveCounter) override;
+    Move ChooseMove() override;
+    bool bookInProgress() const { return bookInProgress_; }
+    void SetBookPick(int k) { pick_ = k; }      // tests: stands in for rand.Intn(4) (abbook.go:526); -1 = random
+private:
+    enum State { FIRST, DIAGONAL, CORNER, OTHERCORNER, OTHERDIAGONAL, BLOCKDIAG1, BLOCKDIAG2, LAST };
+    void bookDefend();
+    void bookStart();
+    int moveCount_ = 0, state_ = FIRST, c_x_ = 0, c_y_ = 0, firstX_ = 0, firstY_ = 0;
+    bool bookInProgress_ = true;
+    int pick_ = -1;
+};
+extern int8_t scores[25];    // abbook.go:379
+
+}  // namespace abbook
 
 // ---- tiny Go-style flag parser ("-i 100", "-i=100", "-C", "-C=false") ----------------
 class Flags {

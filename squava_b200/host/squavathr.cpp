@@ -1,7 +1,8 @@
 // squavathr -- drop-in for the reference's alpha-beta program with a root-move worker pool
 // (squavathr.go).  chooseMove's toDo/finished round trip (squavathr.go:236-269,448-466)
 // becomes ONE sq_alphabeta_root call (dialect 2); flags keep their names.  -N (goroutine
-// count) is accepted and ignored; -B (opening book) is not part of the hot path.
+// count) is accepted and ignored; -B plays the reference's hard-coded "triangle" book on the
+// host (squavathr.go:93-106,655-810) before the search takes over.
 #include <chrono>
 #include <cstdio>
 
@@ -55,6 +56,87 @@ static void readMove(const Board& bd, bool printit, int& x, int& y) {     // squ
     }
 }
 
+// ---- -B: the opening book, squavathr.go:647-810 -------------------------------------------
+enum BookState { FIRST, DIAGONAL, CORNER, OTHERCORNER, OTHERDIAGONAL, LAST };
+
+static void bookReply(Board& bd, int cX, int cY, int& moveCount) {   // the "My move / Your move" step
+    std::printf("My move: %d %d\n", cX, cY);
+    std::printf("%s", bd.str_grid().c_str());
+    int l, m;
+    readMove(bd, true, l, m);
+    bd.set(5 * l + m, MINIMIZER);
+    moveCount++;
+}
+
+// Defend against the triangle: answer the human's first two moves three cells away on both
+// axes (squavathr.go:662-733).  Returns the number of moves made by both sides.
+static int bookDefend(Board& bd, int firstX, int firstY) {
+    int moveCount = 0, cX = 0, cY = 0;
+    // FIRST
+    bool found = false;
+    for (int i = -3; i < 4 && !found; i += 6) for (int j = -3; j < 4 && !found; j += 6) {
+        int a = firstX + i, b = firstY + j;
+        if (a >= 0 && a <= 4 && b >= 0 && b <= 4) { cX = a; cY = b; bd.set(5 * a + b, MAXIMIZER); moveCount++; found = true; }
+    }
+    bookReply(bd, cX, cY, moveCount);     // printed even when no cell was found (cX,cY = 0,0), as the reference does
+    // DIAGONAL
+    int lastx = 0, lasty = 0;
+    for (int c = 0; c < 25; c++)
+        if (!(c / 5 == firstX && c % 5 == firstY) && bd.at(c) == MINIMIZER) { lastx = c / 5; lasty = c % 5; break; }
+    cX = -1; cY = -1;
+    for (int i = -3; i < 4 && cX < 0; i += 6) for (int j = -3; j < 4 && cX < 0; j += 6) {
+        int a = lastx + i, b = lasty + j;
+        if (a >= 0 && a <= 4 && b >= 0 && b <= 4 && bd.at(5 * a + b) == UNSET) { bd.set(5 * a + b, MAXIMIZER); moveCount++; cX = a; cY = b; }
+    }
+    if (cX != -1 && cY != -1) {           // else: the human is not playing the triangle
+        std::printf("My move: %d %d\n", cX, cY);
+        std::printf("%s", bd.str_grid().c_str());
+    }
+    return moveCount;
+}
+
+// Play the triangle (squavathr.go:735-810).
+static int bookStart(Board& bd) {
+    static const int firstMoves[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}};
+    int state = FIRST, moveCount = 0, cX = 0, cY = 0;
+    auto empty = [&](int x, int y) { return bd.at(5 * x + y) == UNSET; };
+    auto mark = [&]() { bd.set(5 * cX + cY, MAXIMIZER); moveCount++; };
+    while (state != LAST) {
+        switch (state) {
+        case FIRST: {
+            const char* pin = std::getenv("SQUAVA_BOOK_PICK");     // tests: stands in for rand.Intn(4), :746
+            const int* c = firstMoves[pin && *pin ? std::atoi(pin) & 3 : std::uniform_int_distribution<int>(0, 3)(host_rng())];
+            cX = c[0]; cY = c[1]; mark();
+            state = DIAGONAL;
+            break;
+        }
+        case DIAGONAL:
+            if (empty(cX + 3, cY + 3)) { cX += 3; cY += 3; mark(); state = CORNER; }
+            else state = OTHERCORNER;
+            break;
+        case CORNER:
+            if (empty(cX - 3, cY)) { cX -= 3; mark(); }
+            else if (empty(cX, cY - 3)) { cY -= 3; mark(); }
+            state = LAST;
+            break;
+        case OTHERCORNER:
+            if (empty(cX, cY + 3)) { cY += 3; mark(); state = OTHERDIAGONAL; }
+            else {
+                std::printf("Unreachable state in OTHERCORNER\n");
+                std::printf("%s", bd.str_grid().c_str());
+                std::exit(99);
+            }
+            break;
+        case OTHERDIAGONAL:
+            if (empty(cX + 3, cY - 3)) { cX += 3; cY -= 3; mark(); }
+            state = LAST;
+            break;
+        }
+        if (moveCount % 2 == 1) bookReply(bd, cX, cY, moveCount);
+    }
+    return moveCount;
+}
+
 int main(int argc, char** argv) {
     bool humanFirst = true, computerFirst = false, deterministic = false, noPrint = false, randomize = false, useBook = false;
     int maxDepthFlag = 15, threads = 0, gpus = 0, seed = -1;
@@ -68,18 +150,30 @@ int main(int argc, char** argv) {
     fl.String("M", &firstMove, "Tell computer to make this first move (x,y)");
     fl.Int("N", &threads, "Use this many threads (ignored: the root moves are one GPU batch)");
     fl.Bool("r", &randomize, "Randomize bias scores");
-    fl.Bool("B", &useBook, "Use book start or defense (not supported by this build)");
+    fl.Bool("B", &useBook, "Use book start or defense");
     fl.Int("gpus", &gpus, "number of GPUs (default 1)");
     fl.Int("seed", &seed, "seed for reproducible play");
     fl.Parse(argc, argv);
     if (seed >= 0) seed_host_rng((uint64_t)seed);
     bool printBoard = !noPrint;
-    if (useBook) { std::fprintf(stderr, "-B: the opening book is outside the accelerated path; playing without it\n"); }
     init_devices(gpus, 0);
     setScores(randomize);
     if (computerFirst) humanFirst = false;
     int moveCounter = 0;
     Board bd;
+    if (useBook) {                                  // squavathr.go:93-106
+        std::printf("Using opening book\n");
+        firstMove.clear();
+        if (humanFirst) {
+            int l, m;
+            readMove(bd, printBoard, l, m);
+            bd.set(5 * l + m, MINIMIZER);
+            moveCounter = 1 + bookDefend(bd, l, m);
+            if (moveCounter % 2 == 1) humanFirst = false;
+        } else {
+            moveCounter += bookStart(bd);
+        }
+    }
     if (!firstMove.empty()) {
         int x1, y1;
         if (std::sscanf(firstMove.c_str(), "%d,%d", &x1, &y1) != 2)

@@ -52,7 +52,7 @@ def load():
     L.sqo_playouts_batch.restype = None
     L.sqo_playout_exact.argtypes = [Board, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.sqo_playout_exact.restype = C.c_int64
-    for name in ("sqo_ab1_root", "sqo_ab2_root", "sqo_ab5_root"):
+    for name in ("sqo_ab1_root", "sqo_ab2_root", "sqo_ab5_root", "sqo_ab6_root"):
         f = getattr(L, name)
         f.argtypes = [Board, C.c_int, i32p, i32p, C.POINTER(C.c_uint32), i32p, C.POINTER(C.c_int64)]
         f.restype = None
@@ -151,6 +151,9 @@ class _Oracle:
 
     def ab5_root(self, x, o, max_depth, scores):
         return self._root("sqo_ab5_root", x, o, max_depth, scores)
+
+    def ab6_root(self, x, o, max_depth, scores):
+        return self._root("sqo_ab6_root", x, o, max_depth, scores)
 
     def ab2_root(self, x, o, max_depth, scores):
         return self._root("sqo_ab2_root", x, o, max_depth, scores)

@@ -148,6 +148,32 @@ def test_ab5_avoid_evaluator_live_oracle(dev, oracle):
     assert changed > 0          # the extra terms do matter on some of these positions
 
 
+def test_ab6_abbook_search_live_oracle(dev, oracle):
+    """src/abbook's search (abbook.go:104-123,215-275): AB-1 with boardValue+delta handed down"""
+    from squava_b200 import positions
+    sc = oracle.tables()["scores_ab"]
+    boards, _ = positions.midgame_batch(40, marks=(6, 8, 10, 12, 14, 16), seed=81)
+    changed = 0
+    for depth in (0, 1, 3, 6, 8):      # abbook's SetDepth gives 6 / 8 / 10 (abbook.go:80-90)
+        values, bv, bm, _ = dev.alphabeta_root(boards, 6, depth, sc)
+        for i in range(boards.shape[0]):
+            x, o = int(boards[i]["x"]), int(boards[i]["o"])
+            if depth == 8 and bin(x | o).count("1") < 10:
+                continue
+            ov, obm, obv, _ = oracle.ab6_root(x, o, depth, sc)
+            assert values[i].tolist() == ov, (depth, i)
+            assert (int(bm[i]), int(bv[i])) == (obm, obv)
+            changed += ov != oracle.ab1_root(x, o, depth, sc)[0]
+    assert changed > 0
+
+
+def test_subtree_carried_out_of_range_is_refused(dev):
+    t = subtree_array(dev, [(1 << 12, 1 << 6, 6, 2, 1, 20000)])
+    with pytest.raises(dev.SquavaError) as e:
+        dev.alphabeta_subtrees(t, 3, 6, [0] * 25)
+    assert e.value.status == -5
+
+
 def test_ab2_root_live_oracle(dev, oracle):
     from squava_b200 import positions
     sc = oracle.tables()["scores_ab"]
@@ -160,7 +186,7 @@ def test_ab2_root_live_oracle(dev, oracle):
             assert (int(bm[i]), int(bv[i])) == (obm, obv)
 
 
-@pytest.mark.parametrize("dialect", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("dialect", [1, 2, 3, 4, 5, 6])
 def test_subtrees_live_oracle(dev, oracle, dialect):
     from squava_b200 import positions
     rng = np.random.Generator(np.random.PCG64(dialect))
@@ -183,7 +209,7 @@ def test_subtrees_live_oracle(dev, oracle, dialect):
         assert int(v[i]) == ov, (dialect, i, rows[i])
 
 
-@pytest.mark.parametrize("dialect", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("dialect", [1, 2, 3, 4, 5, 6])
 def test_extreme_bias_tables_and_carried_values(dev, oracle, dialect):
     """bias entries up to +-120 and carried values in the thousands can outrank a win score: the
     exact shortcuts must switch themselves off and the values must still match"""
@@ -202,10 +228,10 @@ def test_extreme_bias_tables_and_carried_values(dev, oracle, dialect):
     v, _ = dev.alphabeta_subtrees(t, dialect, 7, sc)
     for i, (x, o, last, ply, side, carried) in enumerate(rows):
         assert int(v[i]) == oracle.ab_subtree(dialect, x, o, last, ply, side, carried, 7, sc)[0], (dialect, i)
-    if dialect in (1, 2, 5):
+    if dialect in (1, 2, 5, 6):
         boards, _ = positions.midgame_batch(12, marks=(12, 14, 16), seed=90 + dialect)
         values, _, _, _ = dev.alphabeta_root(boards, dialect, 8, sc)
-        f = {1: oracle.ab1_root, 2: oracle.ab2_root, 5: oracle.ab5_root}[dialect]
+        f = {1: oracle.ab1_root, 2: oracle.ab2_root, 5: oracle.ab5_root, 6: oracle.ab6_root}[dialect]
         for i in range(12):
             assert values[i].tolist() == f(int(boards[i]["x"]), int(boards[i]["o"]), 8, sc)[0], i
 

@@ -86,3 +86,34 @@ def test_playoff5_batch_mode_line_format():
         m = re.match(r"^%d AlphaBeta AlphaBeta 10 false (\d+) (-?[01])((?: \d[+-]?,\d[+-]?)+)$" % i, l)
         assert m, l
         assert len(m.group(3).split()) == int(m.group(1))
+
+
+def test_squavathr_book_transcripts_match_go():
+    """-B: the "My move" lines of bookStart / bookDefend (squavathr.go:662-810) against the
+    reference's own functions (golden made by make_ref_golden_abbook.py).  stdin ends where the
+    book asks for the next human move, so no search starts (EOF exits 0, squavathr.go:566-568)."""
+    V = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_go_abbook_vectors.json")))["squavathr_book"]
+    n = 0
+    for c in V:
+        used = len(c["replies"]) - c["unread"]
+        want = c["said"]
+        if c["role"] == "start":
+            # the book returned: the search (depth 12 from six marks) would be next; stop one read earlier
+            replies = c["replies"][:used] if c["count"] < 0 else c["replies"][:used - 1]
+            env = dict(os.environ, SQUAVA_BOOK_PICK=str(c["pick"]))
+            args = ["-B", "-C", "-D"]
+        else:
+            replies = [c["first"]] + c["replies"][:used]
+            if (1 + c["count"]) % 2 == 1:      # the computer would search next: stop at the book's only read
+                replies, want = [c["first"]], c["said"][:1]
+            env = dict(os.environ)
+            args = ["-B", "-D"]
+        stdin = "".join("%d %d\n" % (r // 5, r % 5) for r in replies)
+        exe = os.path.join(HOST, "squavathr")
+        p = subprocess.run([exe, *args], input=stdin, capture_output=True, text=True, timeout=120, env=env)
+        assert p.returncode == 0, p.stderr
+        assert p.stdout.startswith("Using opening book\n")
+        said = [[int(a), int(b)] for a, b in re.findall(r"My move: (-?\d) (-?\d)\n", p.stdout)]
+        assert said == want, (c, p.stdout)
+        n += 1
+    assert n > 40

@@ -209,3 +209,33 @@ def test_full_board_sentinels(oracle):
         assert v == -want
     v, _ = oracle.ab_subtree(1, x, o, last, 3, -1, 0, 9, sc)
     assert v == 20000
+
+
+def test_alternating_enumeration_is_complete_and_distinct(oracle):
+    """the rank -> board enumerator behind the exhaustive classification sweep"""
+    import ctypes as C
+    import itertools
+    L = oracle.L
+    L.sqo_count_alternating.restype = C.c_int64
+    L.sqo_enumerate_alternating.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_void_p]
+    assert sum(L.sqo_count_alternating(k) for k in range(11)) == 1_177_833_846
+    assert L.sqo_count_alternating(25) == 5_200_300
+    for k in range(5):
+        n = L.sqo_count_alternating(k)
+        b = np.empty(n, np.dtype([("x", "<u4"), ("o", "<u4")]))
+        L.sqo_enumerate_alternating(k, 0, n, b.ctypes.data)
+        got = set(zip(b["x"].tolist(), b["o"].tolist()))
+        nx = (k + 1) // 2
+        exp = set()
+        for cells in itertools.combinations(range(25), k):
+            for xs in itertools.combinations(cells, nx):
+                x = sum(1 << c for c in xs)
+                exp.add((x, sum(1 << c for c in cells) & ~x))
+        assert len(got) == n and got == exp
+    # ranges compose: two half calls equal one whole call
+    n = L.sqo_count_alternating(6)
+    a = np.empty(1000, np.dtype([("x", "<u4"), ("o", "<u4")])); c = a.copy()
+    L.sqo_enumerate_alternating(6, n - 1000, 1000, a.ctypes.data)
+    L.sqo_enumerate_alternating(6, n - 1000, 500, c.ctypes.data)
+    L.sqo_enumerate_alternating(6, n - 500, 500, c[500:].ctypes.data)
+    assert (a == c).all()
