@@ -115,6 +115,23 @@ int sq_alphabeta_root(const sq_board *positions, int64_t n, int dialect, int max
                       const int8_t scores[25], int32_t (*values)[25],
                       int32_t *best_value, uint32_t *best_mask, uint64_t *nodes);
 
+/* ---- NegaScout ----------------------------------------------------------- */
+/* Replaces (*NegaScout).ChooseMove's search, src/negascout/negascout.go:81-122 (reorderMoves
+ * :411-499, negaScout :232-266, staticValue :168-230), for a batch of positions with
+ * MAXIMIZER to move; max_depth = p.maxDepth as SetDepth leaves it (:69-79).  This search is
+ * not a plain minimax (null-window results are accepted two plies above the horizon, the
+ * root hands its running alpha to movekeeper), so the GPU replays the reference's recursion
+ * step for step, one warp per position, and every output is bit-exact including nodes[]:
+ * values[i][c] = the alpha recorded by moves.SetMove for root move c (SQ_NO_MOVE if not
+ * visited); visit_order[i][k] = k-th root cell searched, -1 padded (may be NULL);
+ * best_value / best_mask = movekeeper's max and the cells it holds; first_best[i] = the cell
+ * it returns when deterministic (-1: no legal move); nodes[i] = staticValue calls
+ * (p.leafNodeCount).  Output pointers other than values may be NULL.            */
+int sq_negascout_root(const sq_board *positions, int64_t n, int max_depth,
+                      const int8_t scores[25], int32_t (*values)[25], int8_t (*visit_order)[25],
+                      int32_t *best_value, uint32_t *best_mask, int8_t *first_best,
+                      uint64_t *nodes);
+
 /* One unit of squavathr's toDo channel (squavathr.go:17-24,448-466) or one of
  * opening2/opening3's top-level calls (opening2.go:62-71, opening3.go:104-109):
  * the board already holds the move at last_cell, side_to_move moves at `ply`,

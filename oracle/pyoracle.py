@@ -370,3 +370,109 @@ def opening3_subtrees():
                 computed[k][r] = MIN
                 out.append((f, r))
     return out
+
+
+# ---- NegaScout, src/negascout/negascout.go -------------------------------------------------
+NS_INITIAL_ORDER = [6, 8, 18, 16, 1, 3, 9, 19, 23, 21, 15, 5, 0, 4, 24, 20, 12, 7, 13, 17, 11, 2, 10, 14, 22]  # :392-399
+NS_DEADLY = [[5, 11, 17, 23], [21, 17, 13, 9], [1, 7, 13, 19], [15, 11, 7, 3]]                                  # :147-152
+
+
+def ns_reorder(bd):
+    """reorderMoves, negascout.go:411-499 -> (order for MINIMIZER, order for MAXIMIZER)"""
+    good, bad, dull = [], [], []
+    for c in NS_INITIAL_ORDER:
+        if bd[c] != UNSET:
+            continue
+        kind = None
+        for q in IQ[c]:
+            s = sum(bd[k] for k in q)
+            if s in (3, 2):
+                kind = good
+            elif s in (-3, -2):
+                kind = bad
+            if kind is not None:
+                break
+        if kind is None:
+            for t in IT[c]:
+                s = sum(bd[k] for k in t)
+                if s == -2:
+                    kind = good
+                elif s == 2:
+                    kind = bad
+                if kind is not None:
+                    break
+        (dull if kind is None else kind).append(c)
+    return bad + dull + good, good + dull + bad
+
+
+def ns_static(bd, ply, max_depth, scores):
+    """staticValue, negascout.go:168-230 -> (stop, value)"""
+    v = 0
+    for c in IMPORTANT:
+        for q in IQ[c]:
+            s = sum(bd[k] for k in q)
+            if s in (4, -4):
+                return True, bd[q[0]] * (WIN - ply)
+            if s in (3, -3):
+                v += s * 10
+    for c in IMPORTANT:
+        for t in IT[c]:
+            s = sum(bd[k] for k in t)
+            if s in (3, -3):
+                return True, -(s // 3) * (WIN - ply)
+    for d in NS_DEADLY:
+        outer, inner = bd[d[0]] + bd[d[3]], bd[d[1]] + bd[d[2]]
+        if inner in (2, -2) and outer == 0:
+            v -= inner // 2 * 5
+    if v == 0:
+        v = sum(bd[c] * scores[c] for c in range(25))
+    return ply > max_depth, v
+
+
+def ns_search(bd, ply, player, alpha, beta, max_depth, scores, orders, count):
+    """negaScout, negascout.go:232-266"""
+    count[0] += 1
+    stop, bv = ns_static(bd, ply, max_depth, scores)
+    if stop:
+        return player * bv
+    score, n = 3 * LOSS, beta
+    for c in orders[(player + 1) // 2]:
+        if bd[c] != UNSET:
+            continue
+        bd[c] = player
+        cur = -ns_search(bd, ply + 1, -player, -n, -alpha, max_depth, scores, orders, count)
+        if cur > score:
+            if n == beta or ply == max_depth - 2:
+                score = cur
+            else:
+                score = -ns_search(bd, ply + 1, -player, -beta, -cur, max_depth, scores, orders, count)
+        bd[c] = UNSET
+        alpha = max(alpha, score)
+        if alpha >= beta:
+            break
+        n = alpha + 1
+    return score
+
+
+def negascout_root(bd, max_depth, scores):
+    """ChooseMove, negascout.go:81-122 -> (values[25], visit order, leaves)"""
+    bd = list(bd)
+    orders = ns_reorder(bd)
+    values, visited, count = [NO_MOVE] * 25, [], [0]
+    beta, alpha, score = 2 * WIN, 2 * LOSS, 3 * LOSS
+    n = beta
+    for c in orders[1]:
+        if bd[c] != UNSET:
+            continue
+        bd[c] = MAX
+        cur = -ns_search(bd, 1, MIN, -n, -alpha, max_depth, scores, orders, count)
+        if cur > score:
+            score = cur if n == beta else -ns_search(bd, 1, MIN, -beta, -cur, max_depth, scores, orders, count)
+        bd[c] = UNSET
+        alpha = max(alpha, score)
+        values[c] = alpha
+        visited.append(c)
+        if alpha >= beta:
+            break
+        n = alpha + 1
+    return values, visited, count[0]

@@ -711,6 +711,147 @@ int32_t sqo_ab_subtree(int dialect, sqo_board b, int last_cell, int ply, int sid
     return v;
 }
 
+/* ------------------------------------------------------------------------ */
+/* NegaScout, src/negascout/negascout.go (playoff5's "N" player)             */
+/* ------------------------------------------------------------------------ */
+static const int k_ns_initial_order[25] = {6, 8, 18, 16, 1, 3, 9, 19, 23, 21, 15, 5, 0, 4, 24, 20,
+                                           12, 7, 13, 17, 11, 2, 10, 14, 22};   /* negascout.go:392-399 */
+static const int k_ns_deadly[4][4] = {{5, 11, 17, 23}, {21, 17, 13, 9}, {1, 7, 13, 19}, {15, 11, 7, 3}}; /* :147-152 */
+typedef struct {
+    int bd[25];
+    int max_depth;
+    const int *scores;
+    int64_t leaves;
+    int order[3][25], n_order;   /* orderedMoves[0] for MINIMIZER, [2] for MAXIMIZER (:403) */
+} ns_t;
+
+/* reorderMoves, negascout.go:411-499: good / dull / bad empty cells */
+static void ns_reorder(ns_t *s) {
+    int good[25], bad[25], dull[25], ng = 0, nb = 0, nd = 0;
+    for (int k = 0; k < 25; k++) {
+        int c = k_ns_initial_order[k];
+        if (s->bd[c] != UNSET) continue;
+        int interesting = 0;
+        for (int q = 0; q < g_iq_n[c] && !interesting; q++) {
+            const int *l = g_aq[g_iq[c][q]];
+            int sum = s->bd[l[0]] + s->bd[l[1]] + s->bd[l[2]] + s->bd[l[3]];
+            if (sum == 3 || sum == 2) { good[ng++] = c; interesting = 1; }
+            else if (sum == -3 || sum == -2) { bad[nb++] = c; interesting = 1; }
+        }
+        for (int t = 0; t < g_it_n[c] && !interesting; t++) {
+            const int *l = g_at[g_it[c][t]];
+            int sum = s->bd[l[0]] + s->bd[l[1]] + s->bd[l[2]];
+            if (sum == -2) { good[ng++] = c; interesting = 1; }
+            else if (sum == 2) { bad[nb++] = c; interesting = 1; }
+        }
+        if (!interesting) dull[nd++] = c;
+    }
+    int n = 0;
+    for (int i = 0; i < ng; i++) s->order[2][n++] = good[i];      /* MAXIMIZER: good, dull, bad */
+    for (int i = 0; i < nd; i++) s->order[2][n++] = dull[i];
+    for (int i = 0; i < nb; i++) s->order[2][n++] = bad[i];
+    n = 0;
+    for (int i = 0; i < nb; i++) s->order[0][n++] = bad[i];       /* MINIMIZER: bad, dull, good */
+    for (int i = 0; i < nd; i++) s->order[0][n++] = dull[i];
+    for (int i = 0; i < ng; i++) s->order[0][n++] = good[i];
+    s->n_order = n;
+}
+
+/* staticValue, negascout.go:168-230: whole-board evaluation; quads and triplets are visited
+ * once per "checkable" cell they contain, in that order. */
+static int ns_static(ns_t *s, int ply, int *value) {
+    int v = 0;
+    s->leaves++;
+    g_evals++;
+    for (int k = 0; k < 9; k++) {
+        int c = k_important[k];                                    /* checkableCells, :159-163 */
+        for (int q = 0; q < g_iq_n[c]; q++) {
+            const int *l = g_aq[g_iq[c][q]];
+            int sum = s->bd[l[0]] + s->bd[l[1]] + s->bd[l[2]] + s->bd[l[3]];
+            if (sum == 4 || sum == -4) { *value = s->bd[l[0]] * (WIN - ply); return 1; }
+            if (sum == 3 || sum == -3) v += sum * 10;
+        }
+    }
+    for (int k = 0; k < 9; k++) {
+        int c = k_important[k];
+        for (int t = 0; t < g_it_n[c]; t++) {
+            const int *l = g_at[g_it[c][t]];
+            int sum = s->bd[l[0]] + s->bd[l[1]] + s->bd[l[2]];
+            if (sum == 3 || sum == -3) { *value = -sum / 3 * (WIN - ply); return 1; }
+        }
+    }
+    for (int d = 0; d < 4; d++) {
+        const int *l = k_ns_deadly[d];
+        int outer = s->bd[l[0]] + s->bd[l[3]], inner = s->bd[l[1]] + s->bd[l[2]];
+        if ((inner == 2 || inner == -2) && outer == 0) v -= inner / 2 * 5;
+    }
+    if (v == 0)
+        for (int c = 0; c < 25; c++) v += s->bd[c] * s->scores[c];
+    *value = v;
+    return ply > s->max_depth;
+}
+
+/* negaScout, negascout.go:232-266 */
+static int ns_search(ns_t *s, int ply, int player, int alpha, int beta) {
+    int bv;
+    if (ns_static(s, ply, &bv)) return player * bv;
+    int score = 3 * LOSS, n = beta;
+    const int *order = s->order[player + 1];
+    for (int k = 0; k < s->n_order; k++) {
+        int c = order[k];
+        if (s->bd[c] != UNSET) continue;
+        s->bd[c] = player;
+        int cur = -ns_search(s, ply + 1, -player, -n, -alpha);
+        if (cur > score) {
+            if (n == beta || ply == s->max_depth - 2) score = cur;
+            else score = -ns_search(s, ply + 1, -player, -beta, -cur);
+        }
+        s->bd[c] = UNSET;
+        if (score > alpha) alpha = score;
+        if (alpha >= beta) break;
+        n = alpha + 1;
+    }
+    return score;
+}
+
+/* ChooseMove, negascout.go:81-122, with movekeeper.New(3*LOSS, ...) (movekeeper.go:26-52).
+ * values[c] = what SetMove was given for cell c (the running alpha), SQO_NO_MOVE for cells not
+ * visited; visit_order[k] = k-th visited cell (orderedMoves[2] order; -1 padded); *best_mask = the
+ * cells movekeeper holds at the end, *first_best = the one it returns when deterministic (-1 if none). */
+void sqo_negascout_root(sqo_board b, int max_depth, const int scores[25], int32_t values[25],
+                        int32_t visit_order[25], uint32_t *best_mask, int32_t *best_value,
+                        int32_t *first_best, int64_t *leaves) {
+    ns_t s; tables(); unpack(b, s.bd); g_evals = 0;
+    s.max_depth = max_depth; s.scores = scores; s.leaves = 0;
+    ns_reorder(&s);
+    for (int c = 0; c < 25; c++) { values[c] = SQO_NO_MOVE; visit_order[c] = -1; }
+    int beta = 2 * WIN, alpha = 2 * LOSS, score = 3 * LOSS, n = beta;
+    int max = 3 * LOSS, first = -1, nv = 0; uint32_t mask = 0;
+    for (int k = 0; k < s.n_order; k++) {
+        int c = s.order[2][k];
+        if (s.bd[c] != UNSET) continue;
+        s.bd[c] = MAXIMIZER;
+        int cur = -ns_search(&s, 1, MINIMIZER, -n, -alpha);
+        if (cur > score) {
+            if (n == beta) score = cur;
+            else score = -ns_search(&s, 1, MINIMIZER, -beta, -cur);
+        }
+        s.bd[c] = UNSET;
+        if (score > alpha) alpha = score;
+        values[c] = alpha; visit_order[nv++] = c;
+        if (alpha >= max) {                                       /* movekeeper.SetMove */
+            if (alpha > max) { max = alpha; mask = 0; first = c; }
+            mask |= 1u << c;
+        }
+        if (alpha >= beta) break;
+        n = alpha + 1;
+    }
+    if (best_mask) *best_mask = mask;
+    if (best_value) *best_value = mask ? max : 0;
+    if (first_best) *first_best = first;
+    if (leaves) *leaves = s.leaves;
+}
+
 /* opening3.go:66-128: a (first, reply) pair is skipped when some symmetry maps it
  * onto a pair already searched under ANY first move.                         */
 int sqo_opening3_subtrees(int first[150], int reply[150]) {

@@ -132,6 +132,15 @@ void sqo_ab6_root(sqo_board b, int max_depth, const int scores[25],
 void sqo_ab2_root(sqo_board b, int max_depth, const int scores[25],
                   int32_t values[25], uint32_t *best_mask, int32_t *best_value,
                   int64_t *leaves);
+/* src/negascout ChooseMove (negascout.go:81-122: reorderMoves :411-499, negaScout :232-266, the
+ * whole-board staticValue :168-230) with movekeeper.  The search is NOT a plain minimax (null
+ * windows accepted two plies above the horizon, a running alpha handed to SetMove), so every
+ * output depends on the visiting order: values[c] = the alpha recorded for root move c,
+ * visit_order = the root cells in the order searched (-1 padded), *best_mask = what movekeeper
+ * holds, *first_best = its deterministic choice (-1: no move), *leaves = staticValue calls.   */
+void sqo_negascout_root(sqo_board b, int max_depth, const int scores[25], int32_t values[25],
+                        int32_t visit_order[25], uint32_t *best_mask, int32_t *best_value,
+                        int32_t *first_best, int64_t *leaves);
 /* One explicit subtree: the board already holds the move `last_cell`; `side` is
  * to move at `ply`; `carried` is the boardValue argument.
  *  dialect 1: (*AlphaBeta).alphaBeta(ply, side, -20000, +20000, x, y, carried)  alphabeta.go:165

@@ -18,7 +18,7 @@ import numpy as np
 __all__ = [
     "SquavaError", "BOARD", "SUBTREE", "NO_MOVE", "lib", "lib_path", "init", "shutdown",
     "is_initialised", "classify", "playouts", "playouts_dev", "classify_dev",
-    "alphabeta_root", "alphabeta_subtrees", "int32_peak", "launch_count",
+    "alphabeta_root", "alphabeta_subtrees", "negascout_root", "int32_peak", "launch_count",
     "last_playout_kernel_ms", "debug_philox", "device_count", "sm_count", "EXPORTS",
 ]
 
@@ -35,7 +35,7 @@ AB_ALPHABETA, AB_SQUAVATHR, AB_OPENING3, AB_OPENING2, AB_ALPHABETA_AVOID, AB_ABB
 # every symbol include/squava_b200.h declares
 EXPORTS = [
     "sq_init", "sq_shutdown", "sq_strerror", "sq_last_error", "sq_abi_version", "sq_device_count",
-    "sq_sm_count", "sq_classify", "sq_playouts", "sq_alphabeta_root", "sq_alphabeta_subtrees",
+    "sq_sm_count", "sq_classify", "sq_playouts", "sq_alphabeta_root", "sq_alphabeta_subtrees", "sq_negascout_root",
     "sq_classify_dev", "sq_playouts_dev", "sq_int32_peak", "sq_launch_count",
     "sq_last_playout_kernel_ms", "sq_debug_philox",
 ]
@@ -75,6 +75,7 @@ def lib():
         L.sq_playouts.argtypes = [vp, vp, i64, u64, u64, vp]
         L.sq_alphabeta_root.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, vp]
         L.sq_alphabeta_subtrees.argtypes = [vp, i64, i32, i32, vp, vp, vp]
+        L.sq_negascout_root.argtypes = [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]
         L.sq_classify_dev.argtypes = [i32, vp, i64, vp, vp, vp, vp]
         L.sq_playouts_dev.argtypes = [i32, vp, vp, i64, u64, u64, u64, vp, vp]
         L.sq_int32_peak.argtypes = [i32, i32, i32, C.POINTER(C.c_double)]
@@ -183,6 +184,20 @@ def alphabeta_root(positions, dialect, max_depth, scores):
     _ck(lib().sq_alphabeta_root(b.ctypes.data, n, dialect, max_depth, s.ctypes.data, values.ctypes.data,
                                 bv.ctypes.data, bm.ctypes.data, nodes.ctypes.data), "sq_alphabeta_root")
     return values, bv, bm, nodes
+
+
+def negascout_root(positions, max_depth, scores):
+    """-> dict(values i32[n,25], visit_order i8[n,25], best_value, best_mask, first_best, nodes)"""
+    b = as_boards(positions)
+    n = b.shape[0]
+    s = _scores(scores)
+    r = dict(values=np.empty((n, 25), np.int32), visit_order=np.empty((n, 25), np.int8),
+             best_value=np.empty(n, np.int32), best_mask=np.empty(n, np.uint32), first_best=np.empty(n, np.int8),
+             nodes=np.empty(n, np.uint64))
+    _ck(lib().sq_negascout_root(b.ctypes.data, n, max_depth, s.ctypes.data, r["values"].ctypes.data,
+                                r["visit_order"].ctypes.data, r["best_value"].ctypes.data, r["best_mask"].ctypes.data,
+                                r["first_best"].ctypes.data, r["nodes"].ctypes.data), "sq_negascout_root")
+    return r
 
 
 def alphabeta_subtrees(subtrees, dialect, max_depth, scores):

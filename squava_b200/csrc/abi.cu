@@ -18,6 +18,7 @@
 
 #include "kernels.cuh"
 #include "alphabeta.cuh"
+#include "negascout.cuh"
 #include "sq_tables.h"
 
 namespace {
@@ -212,6 +213,8 @@ int sq_init(const int* device_ids, int n_devices, uint64_t seed) {
     sq::build_scan_tables(tables);
     sq::AbTables ab_tables;
     sq::build_ab_tables(ab_tables);
+    sq::NsTables ns_tables;
+    sq::build_ns_tables(ns_tables);
     for (int k = 0; k < n_devices; k++) {
         Device d;
         d.id = device_ids[k];
@@ -240,6 +243,7 @@ int sq_init(const int* device_ids, int n_devices, uint64_t seed) {
         CK(cudaMalloc((void**)&d.small, 16 + (size_t)kSmallLeaves * (32 + 8 + 1)));
         CK(cudaMemcpyToSymbol(sq::c_scan, &tables, sizeof tables));
         CK(cudaMemcpyToSymbol(sq::c_ab, &ab_tables, sizeof ab_tables));
+        CK(cudaMemcpyToSymbol(sq::c_ns, &ns_tables, sizeof ns_tables));
         size_t smem = (size_t)sq::kMaxEmpty * sq::kPlayoutThreads * sizeof(uint32_t);
         CK(cudaFuncSetAttribute(sq::playout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.playout_blocks_per_sm, sq::playout_kernel,
@@ -467,6 +471,65 @@ int sq_alphabeta_root(const sq_board* positions, int64_t n, int dialect, int max
         if (best_value) best_value[i] = mask ? mx : 0;
     }
     return SQ_OK;
+}
+
+int sq_negascout_root(const sq_board* positions, int64_t n, int max_depth, const int8_t scores[25],
+                      int32_t (*values)[25], int8_t (*visit_order)[25], int32_t* best_value,
+                      uint32_t* best_mask, int8_t* first_best, uint64_t* nodes) {
+    int rc = check_ready();
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!positions || !values)) || !scores) {
+        snprintf(t_err, sizeof t_err, "sq_negascout_root: null pointer"); return SQ_ERR_INVALID;
+    }
+    if (max_depth < 0 || max_depth > sq::kNsMaxDepth) { snprintf(t_err, sizeof t_err, "max_depth out of range [0,%d]", sq::kNsMaxDepth); return SQ_ERR_INVALID; }
+    for (int64_t i = 0; i < n; i++)
+        if ((positions[i].x & positions[i].o) || ((positions[i].x | positions[i].o) >> 25)) {
+            snprintf(t_err, sizeof t_err, "sq_negascout_root: position %lld is not a board", (long long)i);
+            return SQ_ERR_INVALID;
+        }
+    sq::NsScores sc;
+    memcpy(sc.s, scores, 25);
+    std::lock_guard<std::mutex> lk(g_mu);
+    const int m = (int)g_dev.size();
+    return for_each_device(m, [&](int k) -> int {
+        Device& d = g_dev[k];
+        int64_t lo, hi; share(n, m, k, lo, hi);
+        const int64_t cnt = hi - lo;
+        if (cnt <= 0) return SQ_OK;
+        int r;
+        CK(cudaSetDevice(d.id));
+        // one device block: [queue | nodes | values | best_value | best_mask | visit_order | first_best]
+        const size_t o_nodes = 16, o_values = o_nodes + 8 * cnt, o_bv = o_values + 100 * cnt, o_bm = o_bv + 4 * cnt,
+                     o_visit = o_bm + 4 * cnt, o_first = o_visit + 25 * cnt, total = o_first + cnt;
+        if ((r = reserve(d, 0, cnt * sizeof(sq_board)))) return r;
+        if ((r = reserve(d, 4, total))) return r;
+        uint8_t* blk = (uint8_t*)d.buf[4];
+        CK(cudaMemcpyAsync(d.buf[0], positions + lo, cnt * sizeof(sq_board), cudaMemcpyHostToDevice, d.stream));
+        CK(cudaMemsetAsync(blk, 0, 16, d.stream));
+        sq::NsOut out;
+        out.nodes = (unsigned long long*)(blk + o_nodes);
+        out.values = (int32_t(*)[25])(blk + o_values);
+        out.best_value = (int32_t*)(blk + o_bv);
+        out.best_mask = (uint32_t*)(blk + o_bm);
+        out.visit_order = (int8_t(*)[25])(blk + o_visit);
+        out.first_best = (int8_t*)(blk + o_first);
+        const int64_t want = (cnt + sq::kNsWarps - 1) / sq::kNsWarps, cap = (int64_t)d.sm_count * 16;
+        const int blocks = (int)(want < cap ? want : cap);
+        sq::negascout_kernel<<<blocks, sq::kNsWarps * 32, 0, d.stream>>>((const sq_board*)d.buf[0], (int)cnt, max_depth, sc, out,
+                                                                          (unsigned int*)blk);
+        g_launches += 1;
+        CK(cudaGetLastError());
+        std::vector<uint8_t> h(total);
+        CK(cudaMemcpyAsync(h.data(), blk, total, cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+        memcpy(values + lo, h.data() + o_values, 100 * cnt);
+        if (nodes) memcpy(nodes + lo, h.data() + o_nodes, 8 * cnt);
+        if (best_value) memcpy(best_value + lo, h.data() + o_bv, 4 * cnt);
+        if (best_mask) memcpy(best_mask + lo, h.data() + o_bm, 4 * cnt);
+        if (visit_order) memcpy(visit_order + lo, h.data() + o_visit, 25 * cnt);
+        if (first_best) memcpy(first_best + lo, h.data() + o_first, cnt);
+        return SQ_OK;
+    });
 }
 
 int sq_alphabeta_subtrees(const sq_subtree* subtrees, int64_t n, int dialect, int max_depth,

@@ -56,6 +56,9 @@ def load():
         f = getattr(L, name)
         f.argtypes = [Board, C.c_int, i32p, i32p, C.POINTER(C.c_uint32), i32p, C.POINTER(C.c_int64)]
         f.restype = None
+    L.sqo_negascout_root.argtypes = [Board, C.c_int, i32p, i32p, i32p, C.POINTER(C.c_uint32), i32p, i32p,
+                                     C.POINTER(C.c_int64)]
+    L.sqo_negascout_root.restype = None
     L.sqo_ab_subtree.argtypes = [C.c_int, Board, C.c_int, C.c_int, C.c_int, C.c_int32, C.c_int,
                                  i32p, C.POINTER(C.c_int64)]
     L.sqo_ab_subtree.restype = C.c_int32
@@ -157,6 +160,14 @@ class _Oracle:
 
     def ab2_root(self, x, o, max_depth, scores):
         return self._root("sqo_ab2_root", x, o, max_depth, scores)
+
+    def negascout_root(self, x, o, max_depth, scores):
+        """-> (values[25], visit order, best_mask, best_value, first_best, leaves)"""
+        sc = (C.c_int32 * 25)(*scores); vals = (C.c_int32 * 25)(); order = (C.c_int32 * 25)()
+        bm = C.c_uint32(); bv = C.c_int32(); fb = C.c_int32(); lv = C.c_int64()
+        self.L.sqo_negascout_root(Board(x, o), max_depth, sc, vals, order, C.byref(bm), C.byref(bv), C.byref(fb),
+                                  C.byref(lv))
+        return list(vals), [c for c in order if c >= 0], bm.value, bv.value, fb.value, lv.value
 
     def ab_subtree(self, dialect, x, o, last_cell, ply, side, carried, max_depth, scores):
         sc = (C.c_int32 * 25)(*scores); lv = C.c_int64()

@@ -1,0 +1,82 @@
+"""src/negascout's ChooseMove on the GPU (one warp per position) vs the CPU oracle: the search is
+order-dependent, so EVERYTHING must match: the alpha recorded per root move, the visiting order,
+movekeeper's set and deterministic choice, and the staticValue call count."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev(sq):
+    sq.init()
+    yield sq
+    sq.shutdown()
+
+
+def check(dev, oracle, boards, depth, sc):
+    r = dev.negascout_root(boards, depth, sc)
+    for i in range(boards.shape[0]):
+        vals, order, bm, bv, fb, leaves = oracle.negascout_root(int(boards[i]["x"]), int(boards[i]["o"]), depth, sc)
+        assert r["values"][i].tolist() == vals, (depth, i)
+        assert [int(c) for c in r["visit_order"][i] if c >= 0] == order
+        assert (int(r["best_mask"][i]), int(r["best_value"][i]), int(r["first_best"][i])) == (bm, bv, fb)
+        assert int(r["nodes"][i]) == leaves
+    return r
+
+
+def test_live_oracle_midgame(dev, oracle):
+    from squava_b200 import positions
+    sc = oracle.tables()["scores_ab"]
+    for marks, depth, count in [(16, 8, 24), (14, 6, 24), (12, 6, 16), (10, 6, 12), (10, 8, 6), (8, 4, 12), (6, 4, 8),
+                                (20, 10, 24), (22, 10, 16), (24, 10, 8), (4, 3, 6), (2, 3, 4), (0, 2, 1), (12, 0, 8), (12, 1, 8),
+                                (12, 2, 8), (12, 3, 8)]:
+        boards, _ = positions.midgame_batch(count, marks=(marks,), seed=1000 + marks * 16 + depth)
+        check(dev, oracle, boards, depth, sc)
+
+
+def test_setdepth_table_depths_from_opening_positions(dev, oracle):
+    """SetDepth gives 6 below four marks (negascout.go:69-79): the biggest trees the engine searches"""
+    from squava_b200 import positions
+    sc = oracle.tables()["scores_ab"]
+    boards, _ = positions.midgame_batch(4, marks=(2,), seed=5)
+    r = check(dev, oracle, boards, 6, sc)
+    assert int(r["nodes"].max()) > 100_000
+
+
+def test_random_bias_tables(dev, oracle):
+    from squava_b200 import positions
+    rng = np.random.Generator(np.random.PCG64(8))
+    for _ in range(4):
+        sc = [int(v) for v in rng.integers(-5, 6, size=25)]
+        boards, _ = positions.midgame_batch(12, marks=(10, 12, 14), seed=int(rng.integers(1 << 30)))
+        check(dev, oracle, boards, 5, sc)
+
+
+def test_boards_that_already_hold_lines_and_full_boards(dev, oracle):
+    """unreachable inputs: both colours own lines (the scan order decides), no empty cell"""
+    sc = oracle.tables()["scores_ab"]
+    rng = np.random.Generator(np.random.PCG64(9))
+    rows = []
+    while len(rows) < 200:
+        trits = rng.integers(0, 3, size=25)
+        x = sum(1 << c for c in range(25) if trits[c] == 1); o = sum(1 << c for c in range(25) if trits[c] == 2)
+        if bin(x | o).count("1") >= 12:
+            rows.append((x, o))
+    rows.append((0x1364d93, 0x1ffffff & ~0x1364d93))          # a full board
+    boards = np.array(rows, dtype=np.uint32).view(dev.BOARD).reshape(-1)
+    r = check(dev, oracle, boards, 4, sc)
+    assert int(r["first_best"][-1]) == -1 and int(r["best_mask"][-1]) == 0
+
+
+def test_batch_order_and_size_do_not_matter(dev, oracle):
+    from squava_b200 import positions
+    sc = oracle.tables()["scores_ab"]
+    boards, _ = positions.midgame_batch(700, marks=(12, 14, 16, 18), seed=77)
+    a = dev.negascout_root(boards, 6, sc)
+    b = dev.negascout_root(boards[::-1].copy(), 6, sc)
+    assert (a["values"] == b["values"][::-1]).all() and (a["nodes"] == b["nodes"][::-1]).all()
+    one = dev.negascout_root(boards[123:124], 6, sc)
+    assert (one["values"][0] == a["values"][123]).all() and int(one["nodes"][0]) == int(a["nodes"][123])
+    empty = dev.negascout_root(boards[:0], 6, sc)
+    assert empty["values"].shape == (0, 25)
