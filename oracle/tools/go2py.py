@@ -282,6 +282,8 @@ def translate_func(text, globals_written=()):
             py.append(ind + "%s += 1" % s[:-2])
         elif re.match(r"var\s+(\w+)\s+\*\w+$", s):
             py.append(ind + "%s = None" % re.match(r"var\s+(\w+)", s).group(1))
+        elif re.match(r"var\s+(\w+)\s+\[\]\[\d+\]\w+$", s):              # a nil slice of arrays
+            py.append(ind + "%s = []" % re.match(r"var\s+(\w+)", s).group(1))
         elif re.match(r"var\s+(\w+)\s+\[\]\w+$", s):
             py.append(ind + "%s = []" % re.match(r"var\s+(\w+)", s).group(1))
         elif re.match(r"var\s+(\w+(?:\s*,\s*\w+)+)\s+(int|float64)$", s):

@@ -46,6 +46,8 @@ constexpr int64_t kSmallLeaves = 1 << 16;      // per device
 
 constexpr unsigned kCounterRing = 256;
 
+static sq::NsTables g_ns_tables;   // host copy: which positions the fast NegaScout kernel may take
+
 std::mutex g_mu;
 std::vector<Device> g_dev;
 bool g_init = false;
@@ -215,6 +217,9 @@ int sq_init(const int* device_ids, int n_devices, uint64_t seed) {
     sq::build_ab_tables(ab_tables);
     sq::NsTables ns_tables;
     sq::build_ns_tables(ns_tables);
+    sq::NsCellTables ns_cell_tables;
+    sq::build_ns_cell_tables(ns_tables, ns_cell_tables);
+    g_ns_tables = ns_tables;
     for (int k = 0; k < n_devices; k++) {
         Device d;
         d.id = device_ids[k];
@@ -244,6 +249,7 @@ int sq_init(const int* device_ids, int n_devices, uint64_t seed) {
         CK(cudaMemcpyToSymbol(sq::c_scan, &tables, sizeof tables));
         CK(cudaMemcpyToSymbol(sq::c_ab, &ab_tables, sizeof ab_tables));
         CK(cudaMemcpyToSymbol(sq::c_ns, &ns_tables, sizeof ns_tables));
+        CK(cudaMemcpyToSymbol(sq::c_ns_cell, &ns_cell_tables, sizeof ns_cell_tables));
         size_t smem = (size_t)sq::kMaxEmpty * sq::kPlayoutThreads * sizeof(uint32_t);
         CK(cudaFuncSetAttribute(sq::playout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.playout_blocks_per_sm, sq::playout_kernel,
@@ -513,12 +519,33 @@ int sq_negascout_root(const sq_board* positions, int64_t n, int max_depth, const
         out.best_mask = (uint32_t*)(blk + o_bm);
         out.visit_order = (int8_t(*)[25])(blk + o_visit);
         out.first_best = (int8_t*)(blk + o_first);
-        const int64_t want = (cnt + sq::kNsWarps - 1) / sq::kNsWarps, cap = (int64_t)d.sm_count * 16;
-        const int blocks = (int)(want < cap ? want : cap);
-        sq::negascout_kernel<<<blocks, sq::kNsWarps * 32, 0, d.stream>>>((const sq_board*)d.buf[0], (int)cnt, max_depth, sc, out,
-                                                                          (unsigned int*)blk);
-        g_launches += 1;
-        CK(cudaGetLastError());
+        // positions the fast kernel cannot take (a complete line already on the board, or maxDepth 0) replay the
+        // recursion with the full evaluator; the rest take the incremental path.  Both read an index list.
+        std::vector<int> order((size_t)cnt);
+        int64_t n_fast = 0, n_slow = 0;
+        for (int64_t i = 0; i < cnt; i++) {
+            const sq_board& b = positions[lo + i];
+            bool line = false;
+            for (int q = 0; q < 28; q++) line |= !(g_ns_tables.quad[q] & ~b.x) || !(g_ns_tables.quad[q] & ~b.o);
+            for (int t = 0; t < 48; t++) line |= !(g_ns_tables.trip[t] & ~b.x) || !(g_ns_tables.trip[t] & ~b.o);
+            if (line || max_depth < 1) order[(size_t)(cnt - 1 - n_slow++)] = (int)i; else order[(size_t)n_fast++] = (int)i;
+        }
+        if ((r = reserve(d, 5, cnt * sizeof(int)))) return r;
+        CK(cudaMemcpyAsync(d.buf[5], order.data(), cnt * sizeof(int), cudaMemcpyHostToDevice, d.stream));
+        const int64_t cap = (int64_t)d.sm_count * 6;
+        auto grid = [&](int64_t units) { int64_t want = (units + sq::kNsWarps - 1) / sq::kNsWarps; return (int)(want < cap ? want : cap); };
+        if (n_fast) {
+            sq::negascout_fast_kernel<<<grid(n_fast), sq::kNsWarps * 32, 0, d.stream>>>(
+                (const sq_board*)d.buf[0], (const int*)d.buf[5], (int)n_fast, max_depth, sc, out, (unsigned int*)blk);
+            g_launches += 1;
+            CK(cudaGetLastError());
+        }
+        if (n_slow) {
+            sq::negascout_kernel<<<grid(n_slow), sq::kNsWarps * 32, 0, d.stream>>>(
+                (const sq_board*)d.buf[0], (const int*)d.buf[5] + n_fast, (int)n_slow, max_depth, sc, out, (unsigned int*)blk + 1);
+            g_launches += 1;
+            CK(cudaGetLastError());
+        }
         std::vector<uint8_t> h(total);
         CK(cudaMemcpyAsync(h.data(), blk, total, cudaMemcpyDeviceToHost, d.stream));
         CK(cudaStreamSynchronize(d.stream));

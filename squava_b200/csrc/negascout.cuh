@@ -93,9 +93,41 @@ struct NsOut {
     unsigned long long* nodes;
 };
 
+// reorderMoves (negascout.go:411-499): lane i classifies the i-th cell of the initial order as
+// good / bad / dull; the two ordered lists are stable partitions of that order.
+__device__ __forceinline__ void ns_reorder(uint32_t x, uint32_t o, int lane, uint8_t (*order)[32]) {
+    const uint32_t full = 0xffffffffu;
+    const int c = lane < 25 ? c_ns.initial_order[lane] : 0;
+    const bool empty = lane < 25 && !(((x | o) >> c) & 1u);
+    int kind = 0;                                             // +1 good, -1 bad, 0 dull
+    if (empty) {
+        for (int k = 0; k < c_ns.n_cell_quads[c] && kind == 0; k++) {
+            const uint32_t m = c_ns.cell_quads[c][k];
+            const int sum = __popc(m & x) - __popc(m & o);
+            if (sum == 3 || sum == 2) kind = 1; else if (sum == -3 || sum == -2) kind = -1;
+        }
+        for (int k = 0; k < c_ns.n_cell_trips[c] && kind == 0; k++) {
+            const uint32_t m = c_ns.cell_trips[c][k];
+            const int sum = __popc(m & x) - __popc(m & o);
+            if (sum == -2) kind = 1; else if (sum == 2) kind = -1;
+        }
+    }
+    const uint32_t good = __ballot_sync(full, empty && kind > 0), bad = __ballot_sync(full, empty && kind < 0);
+    const uint32_t dull = __ballot_sync(full, empty && kind == 0);
+    const uint32_t below = (1u << lane) - 1u;
+    const int ng = __popc(good), nb = __popc(bad), nd = __popc(dull);
+    if (empty) {
+        const int within = __popc((kind > 0 ? good : kind < 0 ? bad : dull) & below);
+        // MAXIMIZER: good, dull, bad.  MINIMIZER: bad, dull, good.
+        order[1][kind > 0 ? within : kind == 0 ? ng + within : ng + nd + within] = (uint8_t)c;
+        order[0][kind < 0 ? within : kind == 0 ? nb + within : nb + nd + within] = (uint8_t)c;
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(kNsWarps * 32)
-negascout_kernel(const sq_board* __restrict__ pos, int n_pos, int max_depth, NsScores sc, NsOut out,
-                 unsigned int* __restrict__ queue) {
+negascout_kernel(const sq_board* __restrict__ pos, const int* __restrict__ idx, int n_pos, int max_depth, NsScores sc,
+                 NsOut out, unsigned int* __restrict__ queue) {
     __shared__ NsFrame s_frames[kNsWarps][kNsMaxDepth + 2];
     __shared__ uint8_t s_order[kNsWarps][2][32];       // [0] MINIMIZER's list, [1] MAXIMIZER's
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -117,38 +149,11 @@ negascout_kernel(const sq_board* __restrict__ pos, int n_pos, int max_depth, NsS
         if (lane == 0) p = atomicAdd(queue, 1u);
         p = __shfl_sync(full, p, 0);
         if (p >= (unsigned)n_pos) break;
+        p = idx[p];
         uint32_t x = pos[p].x & kFull25, o = pos[p].o & kFull25;
         unsigned long long nodes = 0;
 
-        // ---- reorderMoves (negascout.go:411-499): lane i classifies the i-th cell of the initial order
-        {
-            const int c = lane < 25 ? c_ns.initial_order[lane] : 0;
-            const bool empty = lane < 25 && !(((x | o) >> c) & 1u);
-            int kind = 0;                                             // +1 good, -1 bad, 0 dull
-            if (empty) {
-                for (int k = 0; k < c_ns.n_cell_quads[c] && kind == 0; k++) {
-                    const uint32_t m = c_ns.cell_quads[c][k];
-                    const int sum = __popc(m & x) - __popc(m & o);
-                    if (sum == 3 || sum == 2) kind = 1; else if (sum == -3 || sum == -2) kind = -1;
-                }
-                for (int k = 0; k < c_ns.n_cell_trips[c] && kind == 0; k++) {
-                    const uint32_t m = c_ns.cell_trips[c][k];
-                    const int sum = __popc(m & x) - __popc(m & o);
-                    if (sum == -2) kind = 1; else if (sum == 2) kind = -1;
-                }
-            }
-            const uint32_t good = __ballot_sync(full, empty && kind > 0), bad = __ballot_sync(full, empty && kind < 0);
-            const uint32_t dull = __ballot_sync(full, empty && kind == 0);
-            const uint32_t below = (1u << lane) - 1u;
-            const int ng = __popc(good), nb = __popc(bad), nd = __popc(dull);
-            if (empty) {
-                const int within = __popc((kind > 0 ? good : kind < 0 ? bad : dull) & below);
-                // MAXIMIZER: good, dull, bad.  MINIMIZER: bad, dull, good.
-                s_order[warp][1][kind > 0 ? within : kind == 0 ? ng + within : ng + nd + within] = (uint8_t)c;
-                s_order[warp][0][kind < 0 ? within : kind == 0 ? nb + within : nb + nd + within] = (uint8_t)c;
-            }
-            __syncwarp();
-        }
+        ns_reorder(x, o, lane, s_order[warp]);
         const int n_moves = __popc(kFull25 & ~(x | o));
         int bias = __reduce_add_sync(full, lane < 25 ? (int)((x >> lane) & 1u) * my_score - (int)((o >> lane) & 1u) * my_score : 0);
 
@@ -270,6 +275,258 @@ negascout_kernel(const sq_board* __restrict__ pos, int n_pos, int max_depth, NsS
         }
         if (lane == 0) {
             out.best_value[p] = keeper_mask ? keeper_max : 0;        // movekeeper.go:40-44
+            out.best_mask[p] = keeper_mask;
+            out.first_best[p] = (int8_t)first_best;
+            out.nodes[p] = nodes;
+        }
+        __syncwarp();
+    }
+}
+
+// ---- the fast path ------------------------------------------------------------------------
+// Same recursion, same windows, same counts -- but no node is ever evaluated from scratch.  When a
+// node becomes the running loop, ONE lane-parallel pass evaluates all of its children at once:
+// lane i takes the i-th cell of the mover's ordered list and derives the child's staticValue from
+// the parent's (a position whose loop runs has no complete line, so only lines THROUGH the new
+// mark can complete or change their three-of-four state; the "deadly" diagonals through the cell
+// are recomputed).  Visiting a child is then a shared-memory read.
+// At the horizon (children of a node at ply == maxDepth all stop) even the loop disappears: the
+// running maximum, the cut-off point and the number of re-searches of negascout.go:240-262 are
+// prefix-maximum scans over the lanes.
+// Needs: root without a complete line, maxDepth >= 1 (otherwise negascout_kernel runs).
+struct NsCellTables {          // [k][cell], padded: conflict-free when lanes hold different cells
+    uint32_t quads[8][32];
+    int32_t quad_w[8][32];     // 30 * times the scan meets the quad
+    uint32_t trips[12][32];
+    uint32_t deadly_in[2][32], deadly_out[2][32];
+};
+__constant__ NsCellTables c_ns_cell;
+
+inline void build_ns_cell_tables(const NsTables& t, NsCellTables& c) {
+    memset(&c, 0, sizeof c);
+    for (int cell = 0; cell < 32; cell++) {
+        for (int k = 0; k < 8; k++) {
+            c.quads[k][cell] = (cell < 25 && k < t.n_cell_quads[cell]) ? t.cell_quads[cell][k] : kNsDummy;
+            for (int j = 0; j < 28; j++) if (t.quad[j] == c.quads[k][cell]) c.quad_w[k][cell] = 3 * t.quad_weight[j];
+        }
+        for (int k = 0; k < 12; k++) c.trips[k][cell] = (cell < 25 && k < t.n_cell_trips[cell]) ? t.cell_trips[cell][k] : kNsDummy;
+        int nd = 0;
+        for (int d = 0; d < 4 && cell < 25; d++)
+            if ((t.deadly_inner[d] | t.deadly_outer[d]) >> cell & 1u) {
+                c.deadly_in[nd][cell] = t.deadly_inner[d]; c.deadly_out[nd][cell] = t.deadly_outer[d]; nd++;
+            }
+    }
+}
+
+__device__ __forceinline__ int ns_deadly_term(uint32_t in, uint32_t out, uint32_t x, uint32_t o) {
+    const int inner = __popc(in & x) - __popc(in & o), outer = __popc(out & x) - __popc(out & o);
+    return (outer == 0 && (inner == 2 || inner == -2)) ? -(inner / 2) * 5 : 0;
+}
+
+struct NsChild { bool term; int cur; int sum; };   // cur: the child's value as the parent's loop sees it (-ret)
+
+// staticValue of (x, o) + mover `pl` on `cell`, from the parent's raw sum `vsum` and bias; cply = child's ply
+__device__ __forceinline__ NsChild ns_child(const NsCellTables& C, uint32_t x, uint32_t o, int pl, int cell, int vsum,
+                                            int bias_child, int cply) {
+    const uint32_t own = pl > 0 ? x : o, opp = pl > 0 ? o : x;
+    bool four = false, three = false;
+    int gain = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t q = C.quads[k][cell];
+        const int oc = __popc(q & own), pc = __popc(q & opp);
+        four |= (oc == 3) & (pc == 0);
+        if ((oc == 2 && pc == 0) || (oc == 0 && pc == 3)) gain += C.quad_w[k][cell];   // a new own three, or an opposing one blocked
+    }
+#pragma unroll
+    for (int k = 0; k < 12; k++) three |= __popc(C.trips[k][cell] & own) == 2;
+    const uint32_t bit = 1u << cell;
+    const uint32_t x2 = x | (pl > 0 ? bit : 0u), o2 = o | (pl > 0 ? 0u : bit);
+    int dd = 0;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const uint32_t in = C.deadly_in[j][cell], out = C.deadly_out[j][cell];
+        dd += ns_deadly_term(in, out, x2, o2) - ns_deadly_term(in, out, x, o);
+    }
+    NsChild r;
+    r.sum = vsum + pl * gain + dd;
+    r.term = four || three;
+    const int bv = four ? pl * (10000 - cply) : three ? -pl * (10000 - cply) : (r.sum == 0 ? bias_child : r.sum);
+    r.cur = pl * bv;
+    return r;
+}
+
+struct NsFastFrame { int alpha, beta, score, n, k, at_phase; uint32_t active, term; };
+
+__global__ void __launch_bounds__(kNsWarps * 32)
+negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ idx, int n_pos, int max_depth, NsScores sc,
+                      NsOut out, unsigned int* __restrict__ queue) {
+    __shared__ NsCellTables C;
+    __shared__ NsFastFrame s_frames[kNsWarps][kNsMaxDepth + 2];
+    __shared__ int s_cur[kNsWarps][kNsMaxDepth + 2][32], s_sum[kNsWarps][kNsMaxDepth + 2][32];
+    __shared__ uint8_t s_order[kNsWarps][2][32];
+    for (int i = threadIdx.x; i < (int)(sizeof(NsCellTables) / 4); i += blockDim.x) ((uint32_t*)&C)[i] = ((const uint32_t*)&c_ns_cell)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    NsFastFrame* const frames = s_frames[warp];
+    const uint32_t full = 0xffffffffu;
+    const int kNegInf = -(1 << 30);
+
+    const uint32_t my_quad = c_ns.quad[lane];
+    const int my_weight = c_ns.quad_weight[lane] * 3;
+    const uint32_t my_in = lane >= 28 ? c_ns.deadly_inner[lane - 28] : 0u;
+    const uint32_t my_out = lane >= 28 ? c_ns.deadly_outer[lane - 28] : 0u;
+    int my_score = 0;
+#pragma unroll
+    for (int c = 0; c < 25; c++) if (lane == c) my_score = sc.s[c];
+
+    for (;;) {
+        unsigned int p = 0;
+        if (lane == 0) p = atomicAdd(queue, 1u);
+        p = __shfl_sync(full, p, 0);
+        if (p >= (unsigned)n_pos) break;
+        p = idx[p];
+        uint32_t x = pos[p].x & kFull25, o = pos[p].o & kFull25;
+        unsigned long long nodes = 0;
+        ns_reorder(x, o, lane, s_order[warp]);
+        const int n_moves = __popc(kFull25 & ~(x | o));
+        int bias = __reduce_add_sync(full, lane < 25 ? (int)((x >> lane) & 1u) * my_score - (int)((o >> lane) & 1u) * my_score : 0);
+        // the root's raw sum (no complete line on it: the host checked)
+        int vsum;
+        {
+            const int cx = __popc(my_quad & x), co = __popc(my_quad & o);
+            int contrib = (cx == 3 && co == 0) ? my_weight : (co == 3 && cx == 0) ? -my_weight : 0;
+            if (lane >= 28) contrib += ns_deadly_term(my_in, my_out, x, o);
+            vsum = __reduce_add_sync(full, contrib);
+        }
+
+        int ply = 0;
+        int alpha = -2 * 10000, beta = 2 * 10000, score = -3 * 10000, n = beta, k = 0, at = 0, phase = 0;
+        uint32_t active = 0, term = 0;
+        int keeper_max = -3 * 10000, first_best = -1, n_visited = 0;
+        uint32_t keeper_mask = 0;
+        if (lane < 25) { out.values[p][lane] = SQ_NO_MOVE; out.visit_order[p][lane] = -1; }
+
+        // one pass over the children of the node that starts its loop at `ply` (mover pl)
+        auto children = [&](int at_ply, int raw_sum) {
+            const int pl = (at_ply & 1) ? -1 : 1;
+            const int c = lane < n_moves ? s_order[warp][pl > 0 ? 1 : 0][lane] : 0;
+            const bool act = lane < n_moves && !(((x | o) >> c) & 1u);
+            const NsChild ch = ns_child(C, x, o, pl, c, raw_sum, bias + pl * __shfl_sync(full, my_score, c), at_ply + 1);
+            active = __ballot_sync(full, act);
+            term = __ballot_sync(full, act && ch.term);
+            return ch;
+        };
+        {
+            const NsChild ch = children(0, vsum);
+            s_cur[warp][0][lane] = ch.cur; s_sum[warp][0][lane] = ch.sum;
+            __syncwarp();
+        }
+        int ret = 0, rs_cur = 0;
+        bool returned = false, enter = false;
+        for (;;) {
+            const int player = (ply & 1) ? -1 : 1;
+            if (!returned && !enter) {
+                const uint32_t cand = active & (full << k);
+                if (cand == 0) {                       // loop over: hand the score up
+                    if (ply == 0) break;
+                    ret = score;
+                    ply--;
+                    const NsFastFrame f = frames[ply];
+                    alpha = f.alpha; beta = f.beta; score = f.score; n = f.n; k = f.k;
+                    at = f.at_phase & 31; phase = f.at_phase >> 5; active = f.active; term = f.term;
+                    returned = true;
+                    continue;
+                }
+                at = __ffs(cand) - 1;
+                k = at + 1;
+                phase = 1;
+                enter = true;
+                const int cell = s_order[warp][player > 0 ? 1 : 0][at];
+                if (player > 0) x |= 1u << cell; else o |= 1u << cell;
+                bias += player * __shfl_sync(full, my_score, cell);
+            }
+            if (enter) {
+                const int ca = phase == 1 ? -n : -beta, cb = phase == 1 ? -alpha : -rs_cur;
+                const int cply = ply + 1;
+                enter = false;
+                nodes++;
+                if ((term >> at) & 1u) {               // the child is a finished game
+                    ret = -s_cur[warp][ply][at];
+                    returned = true;
+                } else if (cply == max_depth) {
+                    // the child's own children all stop: its whole loop (:240-262) as scans over the lanes
+                    const uint32_t act_save = active, term_save = term;
+                    const NsChild ch = children(cply, s_sum[warp][ply][at]);
+                    const uint32_t act = active;
+                    active = act_save; term = term_save;
+                    const bool mine = (act >> lane) & 1u;
+                    int incl = mine ? ch.cur : kNegInf;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int up = __shfl_up_sync(full, incl, d);
+                        if (lane >= d) incl = max(incl, up);
+                    }
+                    int excl = __shfl_up_sync(full, incl, 1);
+                    if (lane == 0) excl = kNegInf;
+                    const int first = __ffs(act) - 1;
+                    const int before = max(ca, excl);                        // alpha when this child is reached
+                    const bool visited = mine && (lane == first || before < cb);
+                    const bool again = visited && lane != first && ch.cur > excl && before + 1 != cb;   // re-searched (:251)
+                    const uint32_t vmask = __ballot_sync(full, visited), amask = __ballot_sync(full, again);
+                    nodes += __popc(vmask) + __popc(amask);
+                    ret = vmask ? __shfl_sync(full, incl, 31 - __clz(vmask)) : -3 * 10000;
+                    returned = true;
+                } else {
+                    NsFastFrame f;
+                    f.alpha = alpha; f.beta = beta; f.score = score; f.n = n; f.k = k; f.at_phase = at | (phase << 5);
+                    f.active = active; f.term = term;
+                    if (lane == 0) frames[ply] = f;
+                    const NsChild ch = children(cply, s_sum[warp][ply][at]);
+                    s_cur[warp][cply][lane] = ch.cur; s_sum[warp][cply][lane] = ch.sum;
+                    __syncwarp();
+                    ply = cply;
+                    alpha = ca; beta = cb; score = -3 * 10000; n = cb; k = 0;
+                    continue;
+                }
+            }
+            // `ret` came back to the running loop (:243-262)
+            returned = false;
+            if (phase == 1) {
+                const int cur = -ret;
+                if (cur > score) {
+                    if (n == beta || (ply > 0 && ply == max_depth - 2)) score = cur;
+                    else { phase = 2; rs_cur = cur; enter = true; continue; }
+                }
+            } else {
+                score = -ret;
+            }
+            const int cell = s_order[warp][player > 0 ? 1 : 0][at];
+            if (player > 0) x &= ~(1u << cell); else o &= ~(1u << cell);
+            bias -= player * __shfl_sync(full, my_score, cell);
+            if (score > alpha) alpha = score;
+            if (ply == 0) {                            // moves.SetMove(i, j, alpha), movekeeper.go:26-36
+                if (lane == 0) { out.values[p][cell] = alpha; out.visit_order[p][n_visited] = (int8_t)cell; }
+                n_visited++;
+                if (alpha >= keeper_max) {
+                    if (alpha > keeper_max) { keeper_max = alpha; keeper_mask = 0; first_best = cell; }
+                    keeper_mask |= 1u << cell;
+                }
+            }
+            if (alpha >= beta) {
+                if (ply == 0) break;
+                ret = score;
+                ply--;
+                const NsFastFrame f = frames[ply];
+                alpha = f.alpha; beta = f.beta; score = f.score; n = f.n; k = f.k;
+                at = f.at_phase & 31; phase = f.at_phase >> 5; active = f.active; term = f.term;
+                returned = true;
+                continue;
+            }
+            n = alpha + 1;
+        }
+        if (lane == 0) {
+            out.best_value[p] = keeper_mask ? keeper_max : 0;
             out.best_mask[p] = keeper_mask;
             out.first_best[p] = (int8_t)first_best;
             out.nodes[p] = nodes;

@@ -1,6 +1,6 @@
 // playoff5 -- engine-vs-engine harness over the Player interface (playoff5.go:31-126),
-// with the engines on the accelerated path: A (alpha-beta), B (alpha-beta + opening book),
-// G (alpha-beta + the "avoid" evaluator) and M (MCTS).  N (NegaScout) is not built.
+// with all five engine types: A (alpha-beta), N (NegaScout), B (alpha-beta + opening book),
+// G (alpha-beta + the "avoid" evaluator) and M (MCTS).
 #include <chrono>
 #include <cstdio>
 
@@ -10,11 +10,12 @@ using namespace squava;
 
 static Player* create(const std::string& t, int maxDepth, bool det) {     // playoff5.go:185-221
     if (t == "A" || t == "a") return new alphabeta::AlphaBeta(det, maxDepth);
+    if (t == "N" || t == "n") return new negascout::NegaScout(det, maxDepth);
     if (t == "B" || t == "b") return new abbook::AlphaBetaBook(det, maxDepth);
     if (t == "G" || t == "g") { auto* p = new alphabeta::AlphaBeta(det, maxDepth); p->SetAvoid(); return p; }
     if (t == "M" || t == "m") return new mcts::MCTS(det, maxDepth);
-    std::fprintf(stderr, "player type %s is outside the accelerated path (A, B, G and M only)\n", t.c_str());
-    std::exit(2);
+    std::fprintf(stderr, "panic: runtime error: invalid memory address or nil pointer dereference (player type %s)\n", t.c_str());
+    std::exit(2);                                   // the reference leaves the Player nil (playoff5.go:192-217)
 }
 
 // nonInteractiveGames, playoff5.go:128-183 -- quirks kept: `randomize` is passed where
@@ -69,8 +70,8 @@ int main(int argc, char** argv) {
     fl.Int("d", &maxDepth, "maximum lookahead depth (alpha/beta)");
     fl.Bool("D", &deterministic, "Play deterministically");
     fl.Bool("r", &randomize, "Randomize bias scores");
-    fl.String("1", &firstType, "first player type, A: alphabeta, B: A/B+book opening, G: A/B+avoid bad positions, M: MCTS");
-    fl.String("2", &secondType, "second player type, A: alphabeta, B: A/B+book opening, G: A/B+avoid bad positions, M: MCTS");
+    fl.String("1", &firstType, "first player type, A: alphabeta, N: negascout, B: A/B+book opening, G: A/B+avoid bad positions, M: MCTS");
+    fl.String("2", &secondType, "second player type, A: alphabeta, N: negascout, B: A/B+book opening, G: A/B+avoid bad positions, M: MCTS");
     fl.Int("n", &games, "play <number> games non-interactively");
     fl.Float("u1", &u1, "UCTK coefficient, player 1 (MCTS)");
     fl.Float("u2", &u2, "UCTK coefficient, player 2 (MCTS)");

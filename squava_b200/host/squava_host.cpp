@@ -415,4 +415,50 @@ void AlphaBetaBook::bookStart() {
 }
 
 }  // namespace abbook
+
+// ---- src/negascout -----------------------------------------------------------------------
+namespace negascout {
+
+int8_t scores[25];
+
+void NegaScout::SetDepth(int moveCounter) {        // negascout.go:69-79
+    if (moveCounter < 4) maxDepth_ = 6;
+    if (moveCounter > 3) maxDepth_ = 8;
+    if (moveCounter > 10) maxDepth_ = 10;
+}
+
+Move NegaScout::ChooseMove() {                     // negascout.go:81-122
+    sq_board b = bd_.raw();
+    int32_t values[1][25]; int8_t order[1][25]; int32_t bv = 0; uint32_t bm = 0; int8_t first = -1; uint64_t nodes = 0;
+    must(sq_negascout_root(&b, 1, maxDepth_, scores, values, order, &bv, &bm, &first, &nodes), "sq_negascout_root");
+    if (first < 0) { std::fprintf(stderr, "panic: index out of range [-1]\n"); std::exit(2); }   // MakeMove(-1, -1, ...)
+    int cell = first;
+    if (!deterministic_) {                         // movekeeper.go:46-49: a uniform member of the kept moves, in visit order
+        int kept[25], nk = 0;
+        for (int k = 0; k < 25 && order[0][k] >= 0; k++) if ((bm >> order[0][k]) & 1u) kept[nk++] = order[0][k];
+        cell = kept[intn(host_rng(), nk)];
+    }
+    MakeMove(cell / 5, cell % 5, MAXIMIZER);
+    return Move{cell / 5, cell % 5, bv, (int)nodes};
+}
+
+void NegaScout::PrintBoard() { std::printf("%s", bd_.str_grid().c_str()); }
+
+void NegaScout::SetScores(bool randomize) {        // negascout.go:371-388
+    if (randomize) {
+        static const int vals[11] = {-5, -4, -3 - 2, -1, 0, 1, 2, 3, 4, 5, 0};
+        for (int i = 0; i < 25; i++) scores[i] = (int8_t)vals[intn(host_rng(), 11)];
+    } else {
+        static const int8_t d[25] = {3, 3, 0, 3, 3, 3, 4, 1, 4, 3, 0, 1, 0, 1, 0, 3, 4, 1, 4, 3, 3, 3, 0, 3, 3};
+        std::memcpy(scores, d, 25);
+    }
+}
+
+int NegaScout::FindWinner() {                      // negascout.go:124-145: the flat-list scan of src/alphabeta
+    sq_board b = bd_.raw(); int8_t w = 0;
+    must(sq_classify(&b, 1, nullptr, nullptr, &w), "sq_classify");
+    return w;
+}
+
+}  // namespace negascout
 }  // namespace squava

@@ -191,6 +191,29 @@ extern int8_t scores[25];    // abbook.go:379
 
 }  // namespace abbook
 
+// ---- NegaScout ---------------------------------------------------------------------------
+namespace negascout {
+
+// src/negascout/negascout.go:20-122.  The whole ChooseMove search is one sq_negascout_root call.
+class NegaScout : public Player {
+public:
+    NegaScout(bool deterministic, int maxdepth) : maxDepth_(maxdepth), deterministic_(deterministic) {}
+    std::string Name() override { return "NegaScout"; }
+    void MakeMove(int x, int y, int player) override { bd_.set(5 * x + y, player); }
+    void SetDepth(int moveCounter) override;
+    Move ChooseMove() override;
+    void PrintBoard() override;
+    void SetScores(bool randomize) override;
+    int FindWinner() override;
+private:
+    Board bd_;
+    int maxDepth_;
+    bool deterministic_;
+};
+extern int8_t scores[25];    // negascout.go:369
+
+}  // namespace negascout
+
 // ---- tiny Go-style flag parser ("-i 100", "-i=100", "-C", "-C=false") ----------------
 class Flags {
 public:
