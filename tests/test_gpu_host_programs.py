@@ -117,3 +117,33 @@ def test_squavathr_book_transcripts_match_go():
         assert said == want, (c, p.stdout)
         n += 1
     assert n > 40
+
+
+def test_playoff5_negascout_vs_book_game_replays_on_the_oracle(oracle):
+    """playoff5 -1 N -2 B -D: every searched move, its value and its leaf count must be what the CPU
+    oracle gets for the same position at the depth SetDepth gives (negascout.go:69-79, abbook.go:80-90)"""
+    rc, out, err = run("playoff5", "-1", "N", "-2", "B", "-D")
+    assert rc == 0, err
+    sc = oracle.tables()["scores_ab"]
+    lines = re.findall(r"^([XO]) \((NegaScout|A/B\+Book)\) <(\d),(\d)> \((-?\d+)\) \[(\d+)\]", out, flags=re.M)
+    assert len(lines) >= 6 and lines[0][1] == "NegaScout" and lines[1][1] == "A/B+Book"
+    mine = {"X": [0, 0], "O": [0, 0]}            # [own marks, opponent marks] as each engine sees the board
+    searched = 0
+    for counter, (who, name, a, b, value, leaves) in enumerate(lines):
+        cell, value, leaves = 5 * int(a) + int(b), int(value), int(leaves)
+        own, opp = mine[who]
+        if name == "NegaScout":
+            depth = 6 if counter < 4 else 8 if counter <= 10 else 10
+            vals, order, bm, bv, fb, lv = oracle.negascout_root(own, opp, depth, sc)
+            assert (cell, value, leaves) == (fb, bv, lv), (counter, lines[counter])
+            searched += 1
+        elif leaves:                                # the book is over: src/abbook's search
+            depth = 6 if counter < 4 else 8 if counter <= 10 else 10
+            vals, bm, bv, lv = oracle.ab6_root(own, opp, depth, sc)
+            assert value == bv and cell == min(k for k in range(25) if bm >> k & 1), (counter, lines[counter])
+            searched += 1
+        other = "O" if who == "X" else "X"
+        mine[who][0] |= 1 << cell
+        mine[other][1] |= 1 << cell
+    assert searched >= 5
+    assert re.search(r"(player 1 X \(NegaScout\) wins|player 2 O \(A/B\+Book\) wins|Cat wins)", out)
