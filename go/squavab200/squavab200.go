@@ -119,6 +119,7 @@ const (
 	Opening3  = 3 // opening3.go
 	Opening2  = 4 // opening2.go
 	Avoid     = 5 // src/alphabeta after SetAvoid(): deltaValue2
+	ABBook    = 6 // src/abbook: boardValue+delta handed down
 )
 
 // AlphaBetaRoot replaces ChooseMove's loop (alphabeta.go:98-110) / chooseMove + the worker
@@ -139,6 +140,40 @@ func AlphaBetaRoot(positions []Board, dialect, maxDepth int, scores *[25]int8) [
 		(*C.uint64_t)(unsafe.Pointer(&nodes[0]))), "sq_alphabeta_root")
 	for i := range out {
 		out[i] = RootValues{values[i], bv[i], bm[i], nodes[i]}
+	}
+	return out
+}
+
+// NegaScoutResult is what (*NegaScout).ChooseMove needs from its search (negascout.go:81-122).
+type NegaScoutResult struct {
+	Values     [25]int32 // alpha handed to moves.SetMove per root cell, NoMove if not visited
+	VisitOrder [25]int8  // root cells in the order searched, -1 padded
+	BestValue  int32
+	BestMask   uint32 // the cells movekeeper holds
+	FirstBest  int8   // movekeeper's deterministic choice, -1 if the board is full
+	Nodes      uint64 // staticValue calls = p.leafNodeCount
+}
+
+// NegaScoutRoot replaces reorderMoves + the root loop + negaScout (negascout.go:86-116,232-266).
+func NegaScoutRoot(positions []Board, maxDepth int, scores *[25]int8) []NegaScoutResult {
+	n := len(positions)
+	out := make([]NegaScoutResult, n)
+	if n == 0 {
+		return out
+	}
+	values := make([][25]int32, n)
+	order := make([][25]int8, n)
+	bv := make([]int32, n)
+	bm := make([]uint32, n)
+	fb := make([]int8, n)
+	nodes := make([]uint64, n)
+	check(C.sq_negascout_root((*C.sq_board)(unsafe.Pointer(&positions[0])), C.int64_t(n), C.int(maxDepth),
+		(*C.int8_t)(unsafe.Pointer(&scores[0])), (*[25]C.int32_t)(unsafe.Pointer(&values[0])),
+		(*[25]C.int8_t)(unsafe.Pointer(&order[0])), (*C.int32_t)(unsafe.Pointer(&bv[0])),
+		(*C.uint32_t)(unsafe.Pointer(&bm[0])), (*C.int8_t)(unsafe.Pointer(&fb[0])),
+		(*C.uint64_t)(unsafe.Pointer(&nodes[0]))), "sq_negascout_root")
+	for i := range out {
+		out[i] = NegaScoutResult{values[i], order[i], bv[i], bm[i], fb[i], nodes[i]}
 	}
 	return out
 }
