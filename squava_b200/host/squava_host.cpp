@@ -272,6 +272,40 @@ int MCTS::FindWinner() {                                        // mcts.go:92-12
 }  // namespace mcts
 
 // ---- alpha-beta ---------------------------------------------------------------------------
+// One library call per (kind, depth, bias table) group of requests.
+void search_batch(const std::vector<SearchRequest>& req, std::vector<SearchResult>& res) {
+    const size_t n = req.size();
+    res.assign(n, SearchResult());
+    std::vector<char> done(n, 0);
+    for (size_t i = 0; i < n; i++) {
+        if (done[i]) continue;
+        std::vector<size_t> grp;
+        for (size_t j = i; j < n; j++)
+            if (!done[j] && req[j].kind == req[i].kind && req[j].depth == req[i].depth && req[j].scores == req[i].scores) {
+                grp.push_back(j); done[j] = 1;
+            }
+        const size_t m = grp.size();
+        std::vector<sq_board> b(m);
+        std::vector<int32_t> values(m * 25), bv(m);
+        std::vector<uint32_t> bm(m);
+        std::vector<uint64_t> nodes(m);
+        std::vector<int8_t> order(m * 25, -1), first(m, -1);
+        for (size_t k = 0; k < m; k++) b[k] = req[grp[k]].board;
+        if (req[i].kind == kSearchNegaScout)
+            must(sq_negascout_root(b.data(), (int64_t)m, req[i].depth, req[i].scores, (int32_t(*)[25])values.data(),
+                                   (int8_t(*)[25])order.data(), bv.data(), bm.data(), first.data(), nodes.data()), "sq_negascout_root");
+        else
+            must(sq_alphabeta_root(b.data(), (int64_t)m, req[i].kind, req[i].depth, req[i].scores, (int32_t(*)[25])values.data(),
+                                   bv.data(), bm.data(), nodes.data()), "sq_alphabeta_root");
+        for (size_t k = 0; k < m; k++) {
+            SearchResult& r = res[grp[k]];
+            std::memcpy(r.values, &values[k * 25], sizeof r.values);
+            std::memcpy(r.visit_order, &order[k * 25], sizeof r.visit_order);
+            r.best_value = bv[k]; r.best_mask = bm[k]; r.first_best = first[k]; r.nodes = nodes[k];
+        }
+    }
+}
+
 namespace alphabeta {
 
 int8_t scores[25] = {0};
@@ -286,16 +320,20 @@ void AlphaBeta::SetDepth(int moveCounter) {       // alphabeta.go:79-89
 }
 
 Move AlphaBeta::ChooseMove() {                    // alphabeta.go:92-117
-    sq_board b = bd_.raw();
-    int32_t values[1][25]; int32_t bv = 0; uint32_t bm = 0; uint64_t nodes = 0;
-    must(sq_alphabeta_root(&b, 1, dialect_, maxDepth_, scores_, values, &bv, &bm, &nodes), "sq_alphabeta_root");
+    std::vector<SearchRequest> req{Request()};
+    std::vector<SearchResult> res;
+    search_batch(req, res);
+    return Finish(res[0]);
+}
+
+Move AlphaBeta::Finish(const SearchResult& r) {   // moves.SetMove in row-major order, ChooseMove, MakeMove (:97-116)
     MoveKeeper moves(2 * LOSS, deterministic_, &host_rng());
-    for (int c = 0; c < 25; c++) if (values[0][c] != SQ_NO_MOVE) moves.SetMove(c / 5, c % 5, values[0][c]);
+    for (int c = 0; c < 25; c++) if (r.values[c] != SQ_NO_MOVE) moves.SetMove(c / 5, c % 5, r.values[c]);
     int a, bb, v;
     moves.ChooseMove(a, bb, v);
     if (a < 0) { std::fprintf(stderr, "panic: index out of range [-1]\n"); std::exit(2); }   // the reference indexes bd[-1]
     MakeMove(a, bb, MAXIMIZER);
-    return Move{a, bb, v, (int)nodes};
+    return Move{a, bb, v, (int)r.nodes};
 }
 
 void AlphaBeta::PrintBoard() { std::printf("%s", bd_.str_grid().c_str()); }
@@ -335,14 +373,18 @@ void AlphaBetaBook::SetDepth(int moveCounter) {    // abbook.go:80-90
     if (moveCounter > 10) maxDepth_ = 10;
 }
 
+bool AlphaBetaBook::BookMove(Move* mv) {           // abbook.go:95-105
+    if (!bookInProgress_) return false;
+    if (moveCount_ % 2 == 0) bookStart(); else bookDefend();
+    if (c_x_ == -1 || c_y_ == -1) return false;
+    MakeMove(c_x_, c_y_, MAXIMIZER);
+    *mv = Move{c_x_, c_y_, 0, 0};
+    return true;
+}
+
 Move AlphaBetaBook::ChooseMove() {                 // abbook.go:93-131
-    if (bookInProgress_) {
-        if (moveCount_ % 2 == 0) bookStart(); else bookDefend();
-        if (c_x_ != -1 && c_y_ != -1) {
-            MakeMove(c_x_, c_y_, MAXIMIZER);
-            return Move{c_x_, c_y_, 0, 0};
-        }
-    }
+    Move mv;
+    if (BookMove(&mv)) return mv;
     return AlphaBeta::ChooseMove();                // the same loop with dialect 6; MakeMove is virtual
 }
 
@@ -428,18 +470,22 @@ void NegaScout::SetDepth(int moveCounter) {        // negascout.go:69-79
 }
 
 Move NegaScout::ChooseMove() {                     // negascout.go:81-122
-    sq_board b = bd_.raw();
-    int32_t values[1][25]; int8_t order[1][25]; int32_t bv = 0; uint32_t bm = 0; int8_t first = -1; uint64_t nodes = 0;
-    must(sq_negascout_root(&b, 1, maxDepth_, scores, values, order, &bv, &bm, &first, &nodes), "sq_negascout_root");
-    if (first < 0) { std::fprintf(stderr, "panic: index out of range [-1]\n"); std::exit(2); }   // MakeMove(-1, -1, ...)
-    int cell = first;
+    std::vector<SearchRequest> req{Request()};
+    std::vector<SearchResult> res;
+    search_batch(req, res);
+    return Finish(res[0]);
+}
+
+Move NegaScout::Finish(const SearchResult& r) {
+    if (r.first_best < 0) { std::fprintf(stderr, "panic: index out of range [-1]\n"); std::exit(2); }   // MakeMove(-1, -1, ...)
+    int cell = r.first_best;
     if (!deterministic_) {                         // movekeeper.go:46-49: a uniform member of the kept moves, in visit order
         int kept[25], nk = 0;
-        for (int k = 0; k < 25 && order[0][k] >= 0; k++) if ((bm >> order[0][k]) & 1u) kept[nk++] = order[0][k];
+        for (int k = 0; k < 25 && r.visit_order[k] >= 0; k++) if ((r.best_mask >> r.visit_order[k]) & 1u) kept[nk++] = r.visit_order[k];
         cell = kept[intn(host_rng(), nk)];
     }
     MakeMove(cell / 5, cell % 5, MAXIMIZER);
-    return Move{cell / 5, cell % 5, bv, (int)nodes};
+    return Move{cell / 5, cell % 5, r.best_value, (int)r.nodes};
 }
 
 void NegaScout::PrintBoard() { std::printf("%s", bd_.str_grid().c_str()); }

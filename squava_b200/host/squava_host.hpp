@@ -62,6 +62,24 @@ public:
     virtual int FindWinner() = 0;
 };
 
+// Engines whose ChooseMove is "maybe a book move, else ONE library search" expose the two halves, so
+// that a harness can advance many games in lockstep with one batched library call per ply
+// (playoff5 -lockstep).  ChooseMove() itself is BookMove / Request / search / Finish.
+constexpr int kSearchNegaScout = 100;
+struct SearchRequest { sq_board board; int kind; int depth; const int8_t* scores; };   // kind: SQ_AB_* or kSearchNegaScout
+struct SearchResult {
+    int32_t values[25]; int8_t visit_order[25]; int32_t best_value; uint32_t best_mask; int8_t first_best; uint64_t nodes;
+};
+class BatchSearchable {
+public:
+    virtual ~BatchSearchable() {}
+    virtual bool BookMove(Move*) { return false; }     // true: a move was made without searching
+    virtual SearchRequest Request() = 0;
+    virtual Move Finish(const SearchResult& r) = 0;    // movekeeper + MakeMove
+};
+// one library call per (kind, depth, bias table) group; results in request order
+void search_batch(const std::vector<SearchRequest>& req, std::vector<SearchResult>& res);
+
 // src/movekeeper/movekeeper.go
 class MoveKeeper {
 public:
@@ -141,7 +159,7 @@ private:
 // ---- alpha-beta ---------------------------------------------------------------------
 namespace alphabeta {
 
-class AlphaBeta : public Player {      // alphabeta.go:20-117
+class AlphaBeta : public Player, public BatchSearchable {      // alphabeta.go:20-117
 public:
     AlphaBeta(bool deterministic, int maxdepth);
     std::string Name() override { return name_; }
@@ -152,6 +170,8 @@ public:
     void SetScores(bool randomize) override;
     int FindWinner() override;
     void SetAvoid() { name_ = "A/B+Avoid"; dialect_ = SQ_AB_ALPHABETA_AVOID; }   // alphabeta.go:473-475
+    SearchRequest Request() override { return SearchRequest{bd_.raw(), dialect_, maxDepth_, scores_}; }
+    Move Finish(const SearchResult& r) override;
     const Board& board() const { return bd_; }
 protected:
     Board bd_;
@@ -177,6 +197,7 @@ public:
     void MakeMove(int x, int y, int player) override { moveCount_++; bd_.set(5 * x + y, player); }   // :75-78
     void SetDepth(int moveCounter) override;
     Move ChooseMove() override;
+    bool BookMove(Move* mv) override;
     bool bookInProgress() const { return bookInProgress_; }
     void SetBookPick(int k) { pick_ = k; }      // tests: stands in for rand.Intn(4) (abbook.go:526); -1 = random
 private:
@@ -194,8 +215,10 @@ extern int8_t scores[25];    // abbook.go:379
 // ---- NegaScout ---------------------------------------------------------------------------
 namespace negascout {
 
+extern int8_t scores[25];    // negascout.go:369
+
 // src/negascout/negascout.go:20-122.  The whole ChooseMove search is one sq_negascout_root call.
-class NegaScout : public Player {
+class NegaScout : public Player, public BatchSearchable {
 public:
     NegaScout(bool deterministic, int maxdepth) : maxDepth_(maxdepth), deterministic_(deterministic) {}
     std::string Name() override { return "NegaScout"; }
@@ -205,12 +228,13 @@ public:
     void PrintBoard() override;
     void SetScores(bool randomize) override;
     int FindWinner() override;
+    SearchRequest Request() override { return SearchRequest{bd_.raw(), kSearchNegaScout, maxDepth_, scores}; }
+    Move Finish(const SearchResult& r) override;
 private:
     Board bd_;
     int maxDepth_;
     bool deterministic_;
 };
-extern int8_t scores[25];    // negascout.go:369
 
 }  // namespace negascout
 

@@ -147,3 +147,31 @@ def test_playoff5_negascout_vs_book_game_replays_on_the_oracle(oracle):
         mine[other][1] |= 1 << cell
     assert searched >= 5
     assert re.search(r"(player 1 X \(NegaScout\) wins|player 2 O \(A/B\+Book\) wins|Cat wins)", out)
+
+
+@pytest.mark.parametrize("pair", [("A", "G"), ("N", "B"), ("B", "N")])
+def test_playoff5_lockstep_equals_sequential(pair):
+    """-n with -r: createPlayers receives `randomize` as `deterministic` (playoff5.go:133), so the games are
+    deterministic; advancing them in lockstep (one batched call per ply) must print the same lines"""
+    a = run("playoff5", "-n", "3", "-1", pair[0], "-2", pair[1], "-r", "-seed", "3")
+    b = run("playoff5", "-n", "3", "-1", pair[0], "-2", pair[1], "-r", "-seed", "3", "-lockstep")
+    assert a[0] == 0 and b[0] == 0, (a[2], b[2])
+    assert a[1] == b[1] and len(a[1].splitlines()) == 3
+    c = run("playoff5", "-n", "3", "-1", pair[0], "-2", pair[1], "-r", "-seed", "3", "-lockstep", "-records")
+    recs = [l.split("\t") for l in c[1].splitlines()]
+    for line, rec in zip(a[1].splitlines(), recs):
+        f = line.split(" ")
+        count, winner = int(f[5]), int(f[6])
+        assert rec[0] == {1: "X", -1: "O", 0: "C"}[winner] and int(rec[1]) == count
+        assert rec[2:] == [m.replace("+", "").replace("-", "") for m in f[7:]]
+
+
+def test_recreate_replays_a_playoff5_line(tmp_path):
+    """recreate.go:10-96: non-move fields are reported and skipped but still counted, markers dropped"""
+    p = tmp_path / "game.txt"
+    p.write_text("3 A/B X 10 false 5 1 1,1 0+,0 2,2- 3,3 4,4\n")
+    rc, out, err = run("recreate", str(p))
+    assert rc == 0
+    assert [l for l in out.splitlines() if "move" in l] == ["X move 1,1", "O move 0,0", "X move 2,2", "O move 3,3", "X move 4,4"]
+    assert err.count("problem") == 7 and 'Move 2, "A/B", problem' in err
+    assert out.rstrip().endswith("O _ _ _ _ \n_ X _ _ _ \n_ _ X _ _ \n_ _ _ O _ \n_ _ _ _ X")
