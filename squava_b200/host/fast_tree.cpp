@@ -1,0 +1,419 @@
+// fast_tree.cpp -- the host side of leaf-parallel MCTS at scale (BASELINE configs[2]:
+// "10^9 iterations, host tree + GPU leaf batches of 64K").
+//
+// Same algorithm as UCT() in squava_host.cpp (src/mcts/mcts.go:123-199: select by UCB1 while a node
+// is fully expanded, expand one untried move picked uniformly, roll out, back-propagate), same
+// batched-mode conventions (visits counted at selection time = virtual loss, wins when the batch
+// returns, a node created inside a batch learns whether it is terminal from its own rollout).
+// What differs is the data structure, built for 10^9 nodes and many selecting threads:
+//   * nodes are 24-byte records in one lazily committed arena, addressed by 32-bit index;
+//   * the children of a node live in ONE contiguous block (slot = rank of the move among the
+//     node's empty cells), allocated when the first child is made: a UCB1 scan is a linear read;
+//   * counts are 32-bit atomics; a thread claims an untried move with one fetch_and, so any
+//     number of threads select / back-propagate concurrently without locks;
+//   * every batch is three phases -- parallel select, ONE sq_playouts call, parallel update.
+// With one thread, batch 1 and the test hooks it grows exactly the reference's tree (children in
+// creation order, first maximum wins ties): tests/test_host_uct_vs_reference.py.
+#include <sys/mman.h>
+#include <x86intrin.h>
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <thread>
+
+#include "squava_host.hpp"
+
+namespace squava {
+namespace mcts {
+
+namespace {
+
+constexpr uint32_t kFull = 0x1FFFFFFu;
+constexpr uint32_t kPending = 1u << 31;      // untried: the node's first rollout has not come back yet
+const double kEps = std::numeric_limits<double>::denorm_min();
+
+struct FNode {
+    std::atomic<uint32_t> visits;        // includes selections still in flight
+    std::atomic<uint32_t> wins;          // of the player who moved INTO this node (Update, mcts.go:268-271)
+    std::atomic<uint32_t> first_child;   // arena index of the child block, 0 = none yet
+    std::atomic<uint32_t> untried;       // moves nobody has claimed (25 bits) | kPending
+    uint32_t parent;
+    uint32_t info;                       // move (5 bits) | playerJustMoved == MAXIMIZER (bit 5) | creation rank (bits 6..10)
+};
+static_assert(sizeof(FNode) == 24, "node record");
+
+struct Rng {                              // xoshiro256**, one per selecting thread
+    uint64_t s[4];
+    explicit Rng(uint64_t seed) {
+        for (auto& w : s) { seed += 0x9e3779b97f4a7c15ull; uint64_t z = seed; z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull; z = (z ^ (z >> 27)) * 0x94d049bb133111ebull; w = z ^ (z >> 31); }
+    }
+    uint64_t next() {
+        auto rotl = [](uint64_t x, int k) { return (x << k) | (x >> (64 - k)); };
+        uint64_t r = rotl(s[1] * 5, 7) * 9, t = s[1] << 17;
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl(s[3], 45);
+        return r;
+    }
+    int intn(int n) {                     // unbiased, like rand.Intn (Lemire's multiply-shift with rejection)
+        uint64_t m = (uint64_t)(uint32_t)(next() >> 32) * (uint64_t)n;
+        if ((uint32_t)m < (uint32_t)n) {
+            const uint32_t t = (0u - (uint32_t)n) % (uint32_t)n;
+            while ((uint32_t)m < t) m = (uint64_t)(uint32_t)(next() >> 32) * (uint64_t)n;
+        }
+        return (int)(m >> 32);
+    }
+};
+
+inline int nth_set_bit(uint32_t m, int n) {
+    for (int i = 0; i < n; i++) m &= m - 1;
+    return __builtin_ctz(m);
+}
+
+// run fn(t) for t in [0, T) on T threads; the pool lives as long as the search
+class Pool {
+public:
+    explicit Pool(int n) : n_(n) {
+        for (int t = 1; t < n_; t++) th_.emplace_back([this, t] { loop(t); });
+    }
+    ~Pool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; gen_++; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    void run(const std::function<void(int)>& fn) {
+        if (n_ == 1) { fn(0); return; }
+        { std::lock_guard<std::mutex> lk(mu_); fn_ = &fn; left_ = n_ - 1; gen_++; }
+        cv_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [this] { return left_ == 0; });
+    }
+private:
+    void loop(int t) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)>* fn;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                fn = fn_;
+            }
+            (*fn)(t);
+            { std::lock_guard<std::mutex> lk(mu_); if (--left_ == 0) done_.notify_one(); }
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int)>* fn_ = nullptr;
+    uint64_t gen_ = 0;
+    int left_ = 0;
+    bool stop_ = false;
+};
+
+// UCB1 scan of one child block in single precision (throughput mode): w/v + K*sqrt(c*ln N / v) as
+// w*r*r + K*sqrt(c*ln N)*r with r = 1/sqrt(v) (rsqrt + one Newton step, 8 children per instruction).  The exact double form
+// (and the creation-order tie rule) is kept for the mode the tests pin against the reference.
+int best_child_scalar(const FNode* blk, int slots, float k_sqrt_lg) {
+    int best = -1; float bs = 0.f;
+    for (int k = 0; k < slots; k++) {
+        const float v = (float)blk[k].visits.load(std::memory_order_relaxed);
+        if (!(v > 0.f)) continue;                        // claimed, still being set up
+        const float inv = 1.0f / v;
+        const float sc = (float)blk[k].wins.load(std::memory_order_relaxed) * inv + k_sqrt_lg * std::sqrt(inv);
+        if (sc > bs) { bs = sc; best = k; }
+    }
+    return best;
+}
+
+__attribute__((target("avx2,fma")))
+int best_child_avx2(const FNode* blk, int slots, float k_sqrt_lg) {
+    alignas(32) float v[32], w[32], sc[32];
+    for (int k = 0; k < slots; k++) {
+        v[k] = (float)blk[k].visits.load(std::memory_order_relaxed);
+        w[k] = (float)blk[k].wins.load(std::memory_order_relaxed);
+    }
+    for (int k = slots; k < ((slots + 7) & ~7); k++) { v[k] = 0.f; w[k] = 0.f; }
+    const __m256 c = _mm256_set1_ps(k_sqrt_lg), half = _mm256_set1_ps(0.5f), three = _mm256_set1_ps(3.0f);
+    __m256 top = _mm256_set1_ps(-1.f);
+    for (int k = 0; k < slots; k += 8) {
+        const __m256 vv = _mm256_load_ps(v + k), ww = _mm256_load_ps(w + k);
+        __m256 rs = _mm256_rsqrt_ps(vv);                                   // 1/sqrt(v), 12 bits ...
+        rs = _mm256_mul_ps(_mm256_mul_ps(half, rs), _mm256_fnmadd_ps(_mm256_mul_ps(vv, rs), rs, three));   // ... one Newton step
+        const __m256 s = _mm256_fmadd_ps(_mm256_mul_ps(ww, rs), rs, _mm256_mul_ps(c, rs));                  // w/v + K*sqrt(lg/v)
+        const __m256 ok = _mm256_cmp_ps(vv, _mm256_setzero_ps(), _CMP_GT_OQ);
+        const __m256 m = _mm256_blendv_ps(_mm256_set1_ps(-1.f), s, ok);
+        _mm256_store_ps(sc + k, m);
+        top = _mm256_max_ps(top, m);
+    }
+    // first lane holding the maximum, without a data-dependent branch per child
+    __m256 t = _mm256_max_ps(top, _mm256_permute2f128_ps(top, top, 1));
+    t = _mm256_max_ps(t, _mm256_shuffle_ps(t, t, 0x4E));
+    t = _mm256_max_ps(t, _mm256_shuffle_ps(t, t, 0xB1));
+    if (!(_mm_cvtss_f32(_mm256_castps256_ps128(t)) > 0.f)) return -1;
+    for (int k = 0; k < slots; k += 8) {
+        const int hit = _mm256_movemask_ps(_mm256_cmp_ps(_mm256_load_ps(sc + k), t, _CMP_EQ_OQ));
+        if (hit) return k + __builtin_ctz((unsigned)hit);
+    }
+    return -1;
+}
+
+int best_child_float(const FNode* blk, int slots, float k_sqrt_lg) {
+    static const bool avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma");
+    return avx2 ? best_child_avx2(blk, slots, k_sqrt_lg) : best_child_scalar(blk, slots, k_sqrt_lg);
+}
+
+struct Chunk { uint64_t at = 0, end = 0; };            // a thread's private piece of the arena
+
+struct Leaf { uint32_t node; uint32_t x, o; int8_t to_move; bool fresh; uint8_t depth; };
+
+}  // namespace
+
+FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, const FastOptions& opt) {
+    static uint64_t stream_id = 1ull << 40;
+    const Hooks* hk = opt.hooks;
+    int T = opt.threads > 0 ? opt.threads : (int)std::thread::hardware_concurrency();
+    if (T < 1) T = 1;
+    if (hk && hk->intn) T = 1;                                   // a caller-supplied rand.Intn is one stream
+    const int P = opt.playouts_per_leaf < 1 ? 1 : opt.playouts_per_leaf;
+    const long long B0 = opt.batch < 1 ? 1 : opt.batch;
+    // worst case: every selection makes one node whose block has up to 24 slots... bounded in practice by
+    // (selections + 1) blocks of <= 25 slots; the arena is virtual memory, pages are touched on use
+    const uint64_t selections = (uint64_t)((itermax + P - 1) / P);
+    uint64_t cap = opt.max_nodes ? opt.max_nodes : selections * 26 + 64;
+    if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
+    FNode* nodes = (FNode*)mmap(nullptr, cap * sizeof(FNode), PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (nodes == MAP_FAILED) { std::fprintf(stderr, "fast_uct: cannot reserve %llu node slots\n", (unsigned long long)cap); std::exit(2); }
+    madvise(nodes, cap * sizeof(FNode), MADV_HUGEPAGE);          // random access over GBs: 2 MB pages if the kernel gives them
+    std::atomic<uint64_t> next_free{2};                         // 0 = null, 1 = root
+    std::atomic<bool> overflow{false};
+
+    const uint32_t root = 1;
+    {
+        bool terminal;
+        if (hk && hk->terminal) terminal = hk->terminal(rootstate.board);
+        else {
+            uint8_t flags = 0; sq_board rb = rootstate.board.raw();
+            must(sq_classify(&rb, 1, &flags, nullptr, nullptr), "sq_classify");
+            terminal = flags != 0;
+        }
+        nodes[root].untried.store(terminal ? 0u : rootstate.board.empty());
+        nodes[root].info = 31u | (rootstate.playerJustMoved == MAXIMIZER ? 32u : 0u);
+        nodes[root].parent = 0;
+    }
+    const double factor = opt.ucb_factor2 ? 2. : 1.;
+    const bool exact = opt.exact_ucb || (hk && hk->intn);
+
+    std::vector<Chunk> chunks((size_t)T);
+    std::vector<Rng> rngs;
+    for (int t = 0; t < T; t++) rngs.emplace_back(host_rng()());
+
+    // One walk from the root to a leaf is a chain of dependent cache misses (each level's child block is
+    // cold once the tree is large), so every thread advances a GROUP of walks in turn, one level per
+    // turn, prefetching the block the next turn will scan.  Visits are added on the way down (virtual
+    // loss, visible to every later step of every walk); wins follow when the batch returns.
+    struct Walk { uint32_t idx, x, o; int pjm; int depth; bool fresh, done; };
+    auto prefetch_block = [&](uint32_t fc, int slots) {
+        const char* p = (const char*)&nodes[fc];
+        const int bytes = slots * (int)sizeof(FNode);
+        for (int off = 0; off < bytes; off += 64) __builtin_prefetch(p + off, 0, 1);
+    };
+    auto start_walk = [&](Walk& w, uint32_t* path) {
+        w.idx = root; w.x = rootstate.board.x; w.o = rootstate.board.o; w.pjm = rootstate.playerJustMoved;
+        w.depth = 0; w.fresh = false; w.done = false;
+        // every walk passes the root: in throughput mode its visit is added once per thread and batch instead
+        if (exact) nodes[root].visits.fetch_add((uint32_t)P, std::memory_order_release);
+        path[w.depth++] = root;
+    };
+    // one level of one walk; returns true when the walk has reached its leaf
+    constexpr uint64_t kChunk = 1 << 16;
+    auto step = [&](Rng& rng, Chunk& ck, Walk& w, uint32_t* path) -> bool {
+        FNode& nd = nodes[w.idx];
+        const uint32_t u = nd.untried.load(std::memory_order_acquire);
+        if (u & kPending) return true;                       // still waiting for its first rollout: a leaf
+        const uint32_t um = u & kFull;
+        const uint32_t emp = kFull & ~(w.x | w.o);
+        if (um) {                                            // expand (mcts.go:166-171)
+            const int cnt = __builtin_popcount(um);
+            const int r = hk && hk->intn ? hk->intn(cnt) : rng.intn(cnt);
+            const int m = nth_set_bit(um, r);
+            const uint32_t bit = 1u << m;
+            if (!(nd.untried.fetch_and(~bit, std::memory_order_acq_rel) & bit)) return false;   // another thread took it: look again
+            const int slots = __builtin_popcount(emp);
+            uint32_t fc = nd.first_child.load(std::memory_order_acquire);
+            if (!fc) {
+                if (ck.at + (uint64_t)slots > ck.end) { ck.at = next_free.fetch_add(kChunk); ck.end = ck.at + kChunk; }
+                const uint64_t base = ck.at;
+                ck.at += (uint64_t)slots;
+                if (base + (uint64_t)slots >= cap) { overflow.store(true); nd.untried.fetch_or(bit); return true; }
+                uint32_t expect = 0;
+                if (nd.first_child.compare_exchange_strong(expect, (uint32_t)base, std::memory_order_acq_rel)) fc = (uint32_t)base;
+                else fc = expect;                            // lost the race: that block is simply not used
+            }
+            const uint32_t child = fc + (uint32_t)__builtin_popcount(emp & (bit - 1u));
+            w.pjm = -w.pjm;
+            if (w.pjm == MAXIMIZER) w.x |= bit; else w.o |= bit;
+            FNode& c = nodes[child];
+            c.parent = w.idx;
+            c.info = (uint32_t)m | (w.pjm == MAXIMIZER ? 32u : 0u) | ((uint32_t)(slots - cnt) << 6);
+            c.untried.store(kPending, std::memory_order_relaxed);
+            c.visits.store((uint32_t)P, std::memory_order_release);   // nobody touches a child before its visits are non-zero: a plain store, no locked RMW on a cold line
+            w.idx = child;
+            path[w.depth++] = child;
+            w.fresh = true;
+            return true;
+        }
+        const uint32_t fc = nd.first_child.load(std::memory_order_acquire);
+        if (!fc) return true;                                // terminal node: no moves at all
+        // select (mcts.go:158-161, bestMove :218-238): first maximum in creation order
+        const int slots = __builtin_popcount(emp);
+        // this walk's own visit is already on the node (added on the way down): the reference sees it only after the rollout
+        const uint32_t seen = nd.visits.load(std::memory_order_relaxed) - ((exact || w.idx != root) ? (uint32_t)P : 0u);
+        int best = -1;
+        if (exact) {
+            const double lg = factor * std::log((double)seen);
+            double bestscore = kEps; uint32_t best_rank = 0;
+            for (int k = 0; k < slots; k++) {
+                const FNode& c = nodes[fc + (uint32_t)k];
+                const uint32_t v = c.visits.load(std::memory_order_acquire);
+                if (!v) continue;                                // claimed, still being set up
+                const double sc = (double)c.wins.load(std::memory_order_relaxed) / ((double)v + kEps) + UCTK * std::sqrt(lg / ((double)v + kEps));
+                const uint32_t rank = (c.info >> 6) & 31u;
+                if (sc > bestscore || (best >= 0 && sc == bestscore && rank < best_rank)) { bestscore = sc; best = k; best_rank = rank; }
+            }
+        } else {
+            best = best_child_float(&nodes[fc], slots, (float)(UCTK * std::sqrt(factor * (double)std::log((float)seen))));
+        }
+        if (best < 0) {
+            if (T == 1) {                                    // the reference dereferences nil here (mcts.go:161)
+                std::fprintf(stderr, "Node has %d children\nplayer just moved %d\n", slots, w.pjm);
+                std::exit(2);
+            }
+            return false;
+        }
+        w.idx = fc + (uint32_t)best;
+        FNode& c = nodes[w.idx];
+        c.visits.fetch_add((uint32_t)P, std::memory_order_release);
+        const uint32_t bit = 1u << (c.info & 31u);
+        w.pjm = -w.pjm;
+        if (w.pjm == MAXIMIZER) w.x |= bit; else w.o |= bit;
+        path[w.depth++] = w.idx;
+        const uint32_t next = c.first_child.load(std::memory_order_relaxed);
+        if (next) prefetch_block(next, slots - 1);
+        return false;
+    };
+    constexpr int kPathLen = 27;
+    const int group = (hk && hk->intn) ? 1 : 16;
+
+    FastResult res;
+    std::memset(&res, 0, sizeof res);
+    Pool pool(T);
+    std::vector<Leaf> leaves;
+    std::vector<uint32_t> paths;
+    std::vector<sq_board> boards;
+    std::vector<int8_t> to_move;
+    std::vector<uint64_t> out;
+    long long done = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    while (done < itermax && !overflow.load()) {
+        long long remaining = itermax - done;
+        int p = P;
+        if (p > remaining) p = (int)remaining;
+        long long B = B0;
+        if (B * p > remaining) B = remaining / p;
+        if (B < 1) B = 1;
+        leaves.resize((size_t)B); boards.resize((size_t)B); to_move.resize((size_t)B); out.assign((size_t)B * 4, 0);
+        paths.resize((size_t)B * kPathLen);
+        auto t0 = now();
+        pool.run([&](int t) {
+            const long long lo = B * t / T, hi = B * (t + 1) / T;
+            Walk walks[16];
+            long long slot_of[16];
+            Chunk& ck = chunks[(size_t)t];
+            long long next = lo;
+            int active = 0;
+            for (; active < group && next < hi; active++, next++) { slot_of[active] = next; start_walk(walks[active], &paths[(size_t)next * kPathLen]); }
+            if (!exact && hi > lo) nodes[root].visits.fetch_add((uint32_t)((hi - lo) * P), std::memory_order_release);
+            while (active > 0) {
+                for (int g = 0; g < active; g++) {
+                    Walk& w = walks[g];
+                    const long long k = slot_of[g];
+                    if (!step(rngs[(size_t)t], ck, w, &paths[(size_t)k * kPathLen])) continue;
+                    Leaf& lf = leaves[(size_t)k];
+                    lf.node = w.idx; lf.x = w.x; lf.o = w.o; lf.to_move = (int8_t)-w.pjm; lf.fresh = w.fresh; lf.depth = (uint8_t)w.depth;
+                    boards[(size_t)k] = sq_board{w.x, w.o};
+                    to_move[(size_t)k] = lf.to_move;
+                    if (next < hi) { slot_of[g] = next; start_walk(w, &paths[(size_t)next * kPathLen]); next++; }
+                    else { walks[g] = walks[active - 1]; slot_of[g] = slot_of[active - 1]; active--; g--; }
+                }
+            }
+        });
+        auto t1 = now();
+        if (hk && hk->playouts) hk->playouts(boards.data(), to_move.data(), B, (uint64_t)p, stream_id++, (uint64_t(*)[4])out.data());
+        else must(sq_playouts(boards.data(), to_move.data(), B, (uint64_t)p, stream_id++, (uint64_t(*)[4])out.data()), "sq_playouts");
+        auto t2 = now();
+        pool.run([&](int t) {
+            const long long lo = B * t / T, hi = B * (t + 1) / T;
+            constexpr long long kAhead = 8;                  // the paths are known: pull their nodes in early
+            uint64_t root_wins = 0;
+            for (long long k = lo; k < hi; k++) {
+                if (k + kAhead < hi) {
+                    const uint32_t* pp = &paths[(size_t)(k + kAhead) * kPathLen];
+                    const int d = leaves[(size_t)(k + kAhead)].depth;
+                    for (int i = 0; i < d; i++) __builtin_prefetch(&nodes[pp[i]], 1, 1);
+                }
+                const Leaf& lf = leaves[(size_t)k];
+                const uint64_t* r = &out[(size_t)k * 4];
+                if (lf.fresh) nodes[lf.node].untried.store(r[3] != 0 ? (kFull & ~(lf.x | lf.o)) : 0u, std::memory_order_release);
+                const uint32_t* pp = &paths[(size_t)k * kPathLen];
+                root_wins += (nodes[root].info & 32u) ? r[0] : r[1];              // pp[0] is the root: one add per thread
+                for (int i = 1; i < lf.depth; i++) {                               // Update, mcts.go:190-192,268-271
+                    FNode& nd = nodes[pp[i]];
+                    const uint32_t add = (uint32_t)((nd.info & 32u) ? r[0] : r[1]);
+                    if (add) nd.wins.fetch_add(add, std::memory_order_relaxed);
+                }
+            }
+            if (root_wins) nodes[root].wins.fetch_add((uint32_t)root_wins, std::memory_order_relaxed);
+        });
+        auto t3 = now();
+        res.select_seconds += secs(t0, t1); res.gpu_seconds += secs(t1, t2); res.update_seconds += secs(t2, t3);
+        res.batches++;
+        done += B * p;
+    }
+    if (overflow.load()) { std::fprintf(stderr, "fast_uct: node arena exhausted (%llu slots)\n", (unsigned long long)cap); std::exit(2); }
+    res.iterations = done;
+    res.nodes = next_free.load();
+    res.threads = T;
+    // children of the root in creation order; the move returned is argmax UCB1 (mcts.go:196-198)
+    const uint32_t fc = nodes[root].first_child.load();
+    const int slots = __builtin_popcount(rootstate.board.empty());
+    int order[25], n = 0;
+    for (int k = 0; k < slots && fc; k++) if (nodes[fc + (uint32_t)k].visits.load()) order[n++] = k;
+    std::sort(order, order + n, [&](int a, int b) { return ((nodes[fc + (uint32_t)a].info >> 6) & 31u) < ((nodes[fc + (uint32_t)b].info >> 6) & 31u); });
+    const double lg = factor * std::log((double)nodes[root].visits.load());
+    double bestscore = kEps;
+    res.best_move = -1;
+    for (int i = 0; i < n; i++) {
+        const FNode& c = nodes[fc + (uint32_t)order[i]];
+        const double v = (double)c.visits.load(), w = (double)c.wins.load();
+        res.child_move[i] = (int)(c.info & 31u); res.child_visits[i] = v; res.child_wins[i] = w;
+        const double s = w / (v + kEps) + UCTK * std::sqrt(lg / (v + kEps));
+        if (s > bestscore) { bestscore = s; res.best_move = res.child_move[i]; res.value = (int)(1000. * s); }
+    }
+    res.n_children = n;
+    res.root_visits = (double)nodes[root].visits.load();
+    munmap(nodes, cap * sizeof(FNode));
+    if (res.best_move < 0) { std::fprintf(stderr, "Node has %d children\n", n); std::exit(2); }
+    return res;
+}
+
+}  // namespace mcts
+}  // namespace squava

@@ -42,6 +42,31 @@ int sqh_uct(uint32_t x, uint32_t o, int player_just_moved, int itermax, double u
     return 0;
 }
 
+// The same through the arena tree of fast_tree.cpp (one thread when callbacks are given).
+int sqh_fast_uct(uint32_t x, uint32_t o, int player_just_moved, long long itermax, double uctk, int factor2, int batch,
+                 int playouts_per_leaf, int threads, sqh_intn_fn intn, sqh_terminal_fn terminal, sqh_playouts_fn playouts,
+                 void* ud, int* n_children, int moves[25], double visits[25], double wins[25], int* best_move, int* value,
+                 double* root_visits, double seconds[3], unsigned long long* nodes) {
+    GameState st;
+    st.board.x = x; st.board.o = o; st.playerJustMoved = player_just_moved;
+    Hooks hk;
+    if (intn) hk.intn = [=](int n) { return intn(n, ud); };
+    if (terminal) hk.terminal = [=](const Board& b) { return terminal(b.x, b.o, ud) != 0; };
+    if (playouts) hk.playouts = [=](const sq_board* l, const int8_t* t, int64_t n, uint64_t p, uint64_t s, uint64_t (*out)[4]) {
+        playouts(l, t, n, p, s, out, ud);
+    };
+    FastOptions opt;
+    opt.batch = batch; opt.playouts_per_leaf = playouts_per_leaf; opt.ucb_factor2 = factor2 != 0; opt.threads = threads;
+    if (intn || terminal || playouts) opt.hooks = &hk;
+    FastResult r = fast_uct(st, itermax, uctk, opt);
+    for (int k = 0; k < r.n_children; k++) { moves[k] = r.child_move[k]; visits[k] = r.child_visits[k]; wins[k] = r.child_wins[k]; }
+    *n_children = r.n_children; *best_move = r.best_move; *value = r.value;
+    if (root_visits) *root_visits = r.root_visits;
+    if (seconds) { seconds[0] = r.select_seconds; seconds[1] = r.gpu_seconds; seconds[2] = r.update_seconds; }
+    if (nodes) *nodes = r.nodes;
+    return 0;
+}
+
 // Drives src/abbook's player (abbook.go:93-131) against a scripted opponent, the way the golden
 // vectors were made.  role 0: the engine moves first; role 1: the opponent does.  With
 // book_only != 0 the run stops before the first move that needs the search (no GPU needed).

@@ -14,6 +14,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <functional>
 #include <memory>
 #include <random>
@@ -132,6 +133,29 @@ struct Options {
 // child (owned by *root); leaves = rollouts performed; value = int(1000*UCB1) as mcts.go:198.
 Node* UCT(const GameState& rootstate, int itermax, double UCTK, std::unique_ptr<Node>& root,
           const Options& opt, int* leaves, int* value);
+
+// The same search on a tree built for 10^9 iterations and many host threads (fast_tree.cpp): 24-byte
+// nodes in an arena, contiguous child blocks, atomic counts, three phases per batch (parallel
+// select / one sq_playouts call / parallel update).  One decision, no tree reuse.
+struct FastOptions {
+    int batch = 65536;               // leaves per GPU call
+    int playouts_per_leaf = 1;
+    bool ucb_factor2 = true;
+    int threads = 0;                 // selecting / updating host threads; 0 = all hardware threads
+    uint64_t max_nodes = 0;          // arena slots (virtual memory); 0 = sized from the iteration count
+    bool exact_ucb = false;          // UCB1 in double, reference tie rule (always on under a caller-supplied rand.Intn)
+    const Hooks* hooks = nullptr;    // tests; a supplied intn forces one thread
+};
+struct FastResult {
+    int best_move, value;            // argmax UCB1 over the root's children, int(1000*UCB1) (mcts.go:196-198)
+    long long iterations, batches;
+    int n_children, child_move[25];  // root children in creation order
+    double child_visits[25], child_wins[25], root_visits;
+    double select_seconds, gpu_seconds, update_seconds;
+    uint64_t nodes;                  // arena slots handed out
+    int threads;
+};
+FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, const FastOptions& opt);
 
 class MCTS : public Player {           // mcts.go:32-90
 public:

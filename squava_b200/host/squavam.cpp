@@ -31,7 +31,8 @@ static int readMove(const Board& bd) {             // squavam.go:345-372
 }
 
 int main(int argc, char** argv) {
-    int iterMax = 10000, batch = 256, ppl = 1, gpus = 0, seed = -1;
+    int iterMax = 10000, batch = 256, ppl = 1, gpus = 0, seed = -1, threads = 0;
+    bool fast = false, stats = false;
     double uctk = 1.00;
     bool computerFirst = false;
     Flags fl;
@@ -40,6 +41,9 @@ int main(int argc, char** argv) {
     fl.Bool("C", &computerFirst, "Computer takes first move");
     fl.Int("batch", &batch, "leaves per GPU batch (1 = the reference's strictly sequential UCT)");
     fl.Int("ppl", &ppl, "playouts per leaf");
+    fl.Bool("fast", &fast, "arena tree with multi-threaded select/update (for 10^8..10^9 iterations); no tree reuse");
+    fl.Int("threads", &threads, "with -fast: host threads (default: all)");
+    fl.Bool("stats", &stats, "with -fast: print iterations, nodes and the time spent selecting / on the GPU / updating");
     fl.Int("gpus", &gpus, "number of GPUs (default 1)");
     fl.Int("seed", &seed, "seed for reproducible play (default: clock, as the reference)");
     fl.Parse(argc, argv);
@@ -56,6 +60,20 @@ int main(int argc, char** argv) {
         std::printf("%s\n", state.board.str().c_str());
         if (state.playerJustMoved == MAXIMIZER) {
             auto start = std::chrono::steady_clock::now();
+            if (fast) {
+                FastOptions fo; fo.batch = batch; fo.playouts_per_leaf = ppl; fo.ucb_factor2 = false; fo.threads = threads;
+                FastResult r = fast_uct(state, iterMax, uctk, fo);
+                m = r.best_move;
+                double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+                std::printf("My move: %d %d %s\n", m / 5, m % 5, go_duration(el).c_str());
+                if (stats)
+                    std::printf("fast tree: %lld iterations, %lld batches, %llu node slots, %d threads; select %.3fs (%.3g/s) gpu %.3fs update %.3fs\n",
+                                r.iterations, r.batches, (unsigned long long)r.nodes, r.threads, r.select_seconds,
+                                (double)r.iterations / ppl / (r.select_seconds > 0 ? r.select_seconds : 1e-9), r.gpu_seconds, r.update_seconds);
+                state.DoMove(m);
+                movesNode.reset();
+                continue;
+            }
             Node* best = UCT(state, iterMax, uctk, movesNode, opt, nullptr, nullptr);
             m = best->move;
             std::unique_ptr<Node> keep;

@@ -122,3 +122,67 @@ def test_python_mirror_grows_the_reference_tree():
         best = root.best_move(case["uctk"], case["which"] == "mcts")
         assert best.move == case["best"] and st.k == case["draws"]
         assert int(1000. * best.ucb1(case["uctk"], case["which"] == "mcts")) == case["value"]
+
+
+def run_fast(lib, case):
+    """the arena tree of fast_tree.cpp (one thread, batch 1) under the same stream"""
+    st = Stream()
+
+    def playouts(leaves, to_move, n, per_leaf, stream_id, out, ud):
+        b = np.ctypeslib.as_array(C.cast(leaves, C.POINTER(C.c_uint32)), shape=(n, 2))
+        t = np.ctypeslib.as_array(C.cast(to_move, C.POINTER(C.c_int8)), shape=(n,))
+        o = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint64)), shape=(n, 4))
+        for i in range(n):
+            o[i] = rollout(st, int(b[i, 0]), int(b[i, 1]), int(t[i]))
+    cb = (INTN(lambda n, ud: st.intn(n)), TERM(lambda x, o, ud: int(terminal(x, o))), PLAY(playouts))
+    moves = (C.c_int * 25)(); visits = (C.c_double * 25)(); wins = (C.c_double * 25)()
+    nch, best, value, rootv = C.c_int(), C.c_int(), C.c_int(), C.c_double()
+    lib.sqh_fast_uct.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_longlong, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 INTN, TERM, PLAY, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]
+    rc = lib.sqh_fast_uct(case["x"], case["o"], case["pjm"], case["itermax"], case["uctk"], int(case["which"] == "mcts"), 1, 1, 1,
+                          cb[0], cb[1], cb[2], None, C.byref(nch), moves, visits, wins, C.byref(best), C.byref(value),
+                          C.byref(rootv), None, None)
+    assert rc == 0
+    kids = [[moves[i], visits[i], wins[i]] for i in range(nch.value)]
+    return kids, best.value, value.value, st.k, rootv.value
+
+
+def test_fast_arena_tree_grows_the_reference_tree(host_lib):
+    """contiguous child blocks, 32-bit atomic counts, claim-by-fetch_and: still the reference's tree"""
+    for case in V["cases"]:
+        kids, best, value, draws, rootv = run_fast(host_lib, case)
+        assert kids == case["children"], (case["which"], hex(case["x"]), case["itermax"])
+        assert (best, value, draws) == (case["best"], case["value"], case["draws"])
+        assert rootv == case["root_visits"]
+
+
+def test_fast_arena_tree_many_threads_keeps_its_books(host_lib):
+    """throughput mode (4 threads, groups of interleaved walks, single-precision UCB1, deferred root
+    counts) with a synthetic rollout: every iteration is counted exactly once at every level"""
+    rng = np.random.Generator(np.random.PCG64(3))
+    tr = np.array([sum(1 << c for c in t) if not isinstance(t, int) else t for t in E.TRIPLETS], dtype=np.uint32)
+
+    def playouts(leaves, to_move, n, per_leaf, stream_id, out, ud):
+        b = np.ctypeslib.as_array(C.cast(leaves, C.POINTER(C.c_uint32)), shape=(n, 2))
+        o = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint64)), shape=(n, 4))
+        x, oo = b[:, 0][:, None], b[:, 1][:, None]
+        term = ((x & tr) == tr).any(axis=1) | ((oo & tr) == tr).any(axis=1) | ((b[:, 0] | b[:, 1]) == 0x1ffffff)
+        r = rng.integers(0, per_leaf + 1, size=n).astype(np.uint64)
+        o[:, 0] = r; o[:, 1] = np.uint64(per_leaf) - r; o[:, 2] = 0; o[:, 3] = np.where(term, 0, 3 * per_leaf)
+    cb = (TERM(lambda x, o, ud: int(terminal(x, o))), PLAY(playouts))
+    lib = host_lib
+    lib.sqh_fast_uct.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_longlong, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 INTN, TERM, PLAY, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]
+    for iters, batch, ppl in ((300_000, 4096, 1), (400_000, 1000, 4)):
+        moves = (C.c_int * 25)(); visits = (C.c_double * 25)(); wins = (C.c_double * 25)()
+        nch, best, value, rootv, nodes = C.c_int(), C.c_int(), C.c_int(), C.c_double(), C.c_ulonglong()
+        rc = lib.sqh_fast_uct(0, 0, 1, iters, 1.0, 0, batch, ppl, 4, INTN(0), cb[0], cb[1], None, C.byref(nch), moves, visits, wins,
+                              C.byref(best), C.byref(value), C.byref(rootv), None, C.byref(nodes))
+        assert rc == 0 and nch.value == 25 and sorted(moves[i] for i in range(25)) == list(range(25))
+        assert rootv.value == iters and sum(visits[i] for i in range(25)) == iters
+        assert all(0 <= wins[i] <= visits[i] for i in range(25))
+        assert best.value in range(25) and nodes.value > iters // ppl
