@@ -36,8 +36,12 @@ static const int firstMoves[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2,
 
 int main(int argc, char** argv) {
     int maxDepth = OPENING == 2 ? 9 : 10, gpus = 0;
+    std::string bookFile;
     Flags fl;
     fl.Int("d", &maxDepth, "maximum lookahead depth");
+#if OPENING == 3
+    fl.String("book", &bookFile, "also write an opening-book table (all 600 first-move/reply pairs, by symmetry) to this file");
+#endif
     fl.Int("gpus", &gpus, "number of GPUs (default 1)");
     fl.Parse(argc, argv);
     init_devices(gpus, 0);
@@ -98,6 +102,31 @@ int main(int argc, char** argv) {
             sum += nodes[k]; uniq++;
         }
         std::printf("Leaf nodes visited: %llu\nUnique moves computed: %d\nDuplicated moves: %d\n\n", sum, uniq, dup[fi]);
+    }
+    // the loop the reference leaves open.  The 85 computed pairs, carried through the 8
+    // symmetries the program itself uses to skip duplicates (opening3.go:379-451), give a value for
+    // every (first move, reply) pair: a table a -book reader (squavathr -book) can play from.
+    // Line format: "x1 y1 x2 y2 value depth", first mover's view (MAXIMIZER), 600 lines.
+    if (!bookFile.empty()) {
+        int table[25][25]; bool have[25][25];
+        std::memset(have, 0, sizeof have);
+        for (size_t r = 0; r < rows.size(); r++)
+            for (int m = 0; m < 8; m++) {
+                int a, b, c, d;
+                image(m, rows[r].x, rows[r].y, a, b); image(m, rows[r].p, rows[r].q, c, d);
+                if (!have[5 * a + b][5 * c + d]) { have[5 * a + b][5 * c + d] = true; table[5 * a + b][5 * c + d] = val[r]; }
+            }
+        FILE* fp = std::fopen(bookFile.c_str(), "w");
+        if (!fp) { std::fprintf(stderr, "open %s: cannot write\n", bookFile.c_str()); return 1; }
+        int missing = 0;
+        for (int f = 0; f < 25; f++)
+            for (int r = 0; r < 25; r++) {
+                if (f == r) continue;
+                if (!have[f][r]) { missing++; continue; }
+                std::fprintf(fp, "%d %d %d %d %d %d\n", f / 5, f % 5, r / 5, r % 5, table[f][r], maxDepth);
+            }
+        std::fclose(fp);
+        if (missing) std::fprintf(stderr, "book: %d pairs not covered by the symmetries\n", missing);
     }
 #endif
     sq_shutdown();

@@ -137,10 +137,41 @@ static int bookStart(Board& bd) {
     return moveCount;
 }
 
+// ---- -book FILE: play the first computer move from a table written by `opening3 -book` -----------
+// Lines "x1 y1 x2 y2 value depth", values from the first mover's point of view.  Moving first, the
+// computer takes the first move whose worst reply is best; answering a first move, the reply that is
+// worst for the first mover.  Ties: the first in row-major order (or a random one without -D).
+static bool bookTableMove(const std::string& file, const Board& bd, int moveCounter, bool deterministic, int& bx, int& by, int& bv) {
+    FILE* fp = std::fopen(file.c_str(), "r");
+    if (!fp) { std::fprintf(stderr, "open %s: no such file or directory\n", file.c_str()); std::exit(1); }
+    static int table[25][25]; static bool have[25][25];
+    int a, b, c, d, v, depth;
+    while (std::fscanf(fp, "%d %d %d %d %d %d", &a, &b, &c, &d, &v, &depth) == 6)
+        if (a >= 0 && a < 5 && b >= 0 && b < 5 && c >= 0 && c < 5 && d >= 0 && d < 5) { table[5 * a + b][5 * c + d] = v; have[5 * a + b][5 * c + d] = true; }
+    std::fclose(fp);
+    MoveKeeper moves(3 * LOSS, deterministic, &host_rng());
+    if (moveCounter == 0) {
+        for (int f = 0; f < 25; f++) {
+            int worst = 3 * WIN; bool any = false;
+            for (int r = 0; r < 25; r++) if (have[f][r]) { any = true; if (table[f][r] < worst) worst = table[f][r]; }
+            if (any) moves.SetMove(f / 5, f % 5, worst);
+        }
+    } else if (moveCounter == 1) {
+        int f = -1;
+        for (int cc = 0; cc < 25; cc++) if (bd.at(cc) == MINIMIZER) f = cc;
+        if (f < 0) return false;
+        for (int r = 0; r < 25; r++) if (have[f][r]) moves.SetMove(r / 5, r % 5, -table[f][r]);
+    } else {
+        return false;
+    }
+    moves.ChooseMove(bx, by, bv);
+    return bx >= 0;
+}
+
 int main(int argc, char** argv) {
     bool humanFirst = true, computerFirst = false, deterministic = false, noPrint = false, randomize = false, useBook = false;
     int maxDepthFlag = 15, threads = 0, gpus = 0, seed = -1;
-    std::string firstMove;
+    std::string firstMove, bookFile;
     Flags fl;
     fl.Bool("H", &humanFirst, "Human takes first move");
     fl.Bool("C", &computerFirst, "Computer takes first move");
@@ -151,6 +182,7 @@ int main(int argc, char** argv) {
     fl.Int("N", &threads, "Use this many threads (ignored: the root moves are one GPU batch)");
     fl.Bool("r", &randomize, "Randomize bias scores");
     fl.Bool("B", &useBook, "Use book start or defense");
+    fl.String("book", &bookFile, "play the computer's first move from this table (written by opening3 -book)");
     fl.Int("gpus", &gpus, "number of GPUs (default 1)");
     fl.Int("seed", &seed, "seed for reproducible play");
     fl.Parse(argc, argv);
@@ -197,6 +229,17 @@ int main(int argc, char** argv) {
         }
         if (endOfGame) break;
         humanFirst = true;
+        if (!bookFile.empty() && moveCounter < 2) {
+            int bx, by, bv;
+            if (bookTableMove(bookFile, bd, moveCounter, deterministic, bx, by, bv)) {
+                bd.set(5 * bx + by, MAXIMIZER);
+                moveCounter++;
+                if (printBoard) { std::printf("My move: %d %d (%d) [book]\n", bx, by, bv); std::printf("%s", bd.str_grid().c_str()); }
+                else std::printf("%d %d\n", bx, by);
+                std::fflush(stdout);
+                continue;
+            }
+        }
         auto start = std::chrono::steady_clock::now();
         // chooseMove(&bd, deterministic, maxDepth), squavathr.go:236-269
         sq_board b = bd.raw();

@@ -175,3 +175,36 @@ def test_recreate_replays_a_playoff5_line(tmp_path):
     assert [l for l in out.splitlines() if "move" in l] == ["X move 1,1", "O move 0,0", "X move 2,2", "O move 3,3", "X move 4,4"]
     assert err.count("problem") == 7 and 'Move 2, "A/B", problem' in err
     assert out.rstrip().endswith("O _ _ _ _ \n_ X _ _ _ \n_ _ X _ _ \n_ _ _ O _ \n_ _ _ _ X")
+
+
+def test_opening3_book_table_and_squavathr_book(tmp_path, oracle):
+    """opening3 -book writes a value for all 600 (first, reply) pairs by carrying the 85 computed
+    pairs through the program's own 8 symmetries; squavathr -book plays its first move from it"""
+    book = tmp_path / "book.txt"
+    rc, out, err = run("opening3", "-d", "4", "-book", str(book))
+    assert rc == 0, err
+    rows = [tuple(int(v) for v in l.split()) for l in book.read_text().splitlines()]
+    assert len(rows) == 600 and all(r[5] == 4 for r in rows)
+    table = {(5 * a + b, 5 * c + d): v for a, b, c, d, v, _ in rows}
+    # the computed pairs carry the values the program printed (and the oracle's)
+    sc = oracle.tables()["scores_opening"]
+    printed = re.findall(r"<(\d),(\d)>:<(\d),(\d)>\t(-?\d+) ", out)
+    assert len(printed) == 85
+    for a, b, c, d, v in printed:
+        f, r = 5 * int(a) + int(b), 5 * int(c) + int(d)
+        assert table[(f, r)] == int(v) == oracle.ab_subtree(3, 1 << f, 1 << r, r, 2, 1, sc[f], 4, sc)[0]
+    # closed under the symmetries: transpose and 180-degree rotation
+    for (f, r), v in table.items():
+        tf, tr = 5 * (f % 5) + f // 5, 5 * (r % 5) + r // 5
+        assert table[(tf, tr)] == v and table[(24 - f, 24 - r)] == v
+    # computer first: the first move whose worst reply is best
+    best = max(min(v for (f, r), v in table.items() if f == ff) for ff in range(25))
+    firsts = [ff for ff in range(25) if min(v for (f, r), v in table.items() if f == ff) == best]
+    rc, out, err = run("squavathr", "-C", "-D", "-book", str(book))
+    m = re.search(r"My move: (\d) (\d) \((-?\d+)\) \[book\]", out)
+    assert rc == 0 and m and 5 * int(m.group(1)) + int(m.group(2)) == firsts[0] and int(m.group(3)) == best
+    # human first at 1,1: the reply that is worst for the first mover
+    rc, out, err = run("squavathr", "-D", "-book", str(book), stdin="1 1\n")
+    m = re.search(r"My move: (\d) (\d) \((-?\d+)\) \[book\]", out)
+    worst = min(v for (f, r), v in table.items() if f == 6)
+    assert rc == 0 and m and int(m.group(3)) == -worst and table[(6, 5 * int(m.group(1)) + int(m.group(2)))] == worst
