@@ -6,6 +6,7 @@
 // alphabeta.cuh.  There is no CPU fallback anywhere in this file.
 #include "../../include/squava_b200.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -530,6 +531,11 @@ int sq_negascout_root(const sq_board* positions, int64_t n, int max_depth, const
             for (int t = 0; t < 48; t++) line |= !(g_ns_tables.trip[t] & ~b.x) || !(g_ns_tables.trip[t] & ~b.o);
             if (line || max_depth < 1) order[(size_t)(cnt - 1 - n_slow++)] = (int)i; else order[(size_t)n_fast++] = (int)i;
         }
+        // warps pull positions in list order: start the (probably) biggest searches first -- more empty cells,
+        // bigger tree -- so that the batch does not end on one late, large search
+        std::stable_sort(order.begin(), order.begin() + n_fast, [&](int a, int b) {
+            return __builtin_popcount(positions[lo + a].x | positions[lo + a].o) < __builtin_popcount(positions[lo + b].x | positions[lo + b].o);
+        });
         if ((r = reserve(d, 5, cnt * sizeof(int)))) return r;
         CK(cudaMemcpyAsync(d.buf[5], order.data(), cnt * sizeof(int), cudaMemcpyHostToDevice, d.stream));
         const int64_t cap = (int64_t)d.sm_count * 6;
