@@ -27,10 +27,16 @@ for devs in ([0], list(range(n_dev))):
     t0 = time.perf_counter()
     v = sq.alphabeta_root(ab_boards, 1, 10, sc)
     dta = time.perf_counter() - t0
-    res[len(devs)] = (p, c, v[:3], dt, dta)
+    v6 = sq.alphabeta_root(ab_boards[:64], 6, 8, sc)
+    t0 = time.perf_counter()
+    ns = sq.negascout_root(ab_boards, 8, sc)
+    dtn = time.perf_counter() - t0
+    small = sq.playouts(boards[:3], tm[:3], 1000, 9)         # the pinned small-call path, fewer leaves than devices
+    res[len(devs)] = (p, c, v[:3] + v6[:3] + (ns["values"], ns["visit_order"], ns["best_mask"], ns["first_best"], ns["nodes"], small), dt, dta, dtn)
     sq.shutdown()
 a, b = res[1], res[n_dev]
 ok = bool((a[0] == b[0]).all() and all((x == y).all() for x, y in zip(a[1], b[1])) and all((x == y).all() for x, y in zip(a[2], b[2])))
 print(json.dumps({"devices": n_dev, "identical_to_one_device": ok, "playouts_per_s_1": 4096 * 1e5 / a[3],
-                  "playouts_per_s_n": 4096 * 1e5 / b[3], "alphabeta_s_1": a[4], "alphabeta_s_n": b[4]}))
+                  "playouts_per_s_n": 4096 * 1e5 / b[3], "alphabeta_s_1": a[4], "alphabeta_s_n": b[4],
+                  "negascout_s_1": a[5], "negascout_s_n": b[5]}))
 sys.exit(0 if ok else 1)
