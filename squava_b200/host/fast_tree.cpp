@@ -121,10 +121,11 @@ private:
 // UCB1 scan of one child block in single precision (throughput mode): w/v + K*sqrt(c*ln N / v) as
 // w*r*r + K*sqrt(c*ln N)*r with r = 1/sqrt(v) (rsqrt + one Newton step, 8 children per instruction).  The exact double form
 // (and the creation-order tie rule) is kept for the mode the tests pin against the reference.
-int best_child_scalar(const FNode* blk, int slots, float k_sqrt_lg) {
+int best_child_scalar(const FNode* blk, int slots, float k_sqrt_lg, const uint32_t* dv) {
     int best = -1; float bs = 0.f;
     for (int k = 0; k < slots; k++) {
-        const float v = (float)blk[k].visits.load(std::memory_order_relaxed);
+        const uint32_t gv = blk[k].visits.load(std::memory_order_relaxed);
+        const float v = gv ? (float)(gv + (dv ? dv[k] : 0u)) : 0.f;
         if (!(v > 0.f)) continue;                        // claimed, still being set up
         const float inv = 1.0f / v;
         const float sc = (float)blk[k].wins.load(std::memory_order_relaxed) * inv + k_sqrt_lg * std::sqrt(inv);
@@ -134,10 +135,11 @@ int best_child_scalar(const FNode* blk, int slots, float k_sqrt_lg) {
 }
 
 __attribute__((target("avx2,fma")))
-int best_child_avx2(const FNode* blk, int slots, float k_sqrt_lg) {
+int best_child_avx2(const FNode* blk, int slots, float k_sqrt_lg, const uint32_t* dv) {
     alignas(32) float v[32], w[32], sc[32];
     for (int k = 0; k < slots; k++) {
-        v[k] = (float)blk[k].visits.load(std::memory_order_relaxed);
+        const uint32_t gv = blk[k].visits.load(std::memory_order_relaxed);       // 0: claimed, still being set up
+        v[k] = gv ? (float)(gv + (dv ? dv[k] : 0u)) : 0.f;
         w[k] = (float)blk[k].wins.load(std::memory_order_relaxed);
     }
     for (int k = slots; k < ((slots + 7) & ~7); k++) { v[k] = 0.f; w[k] = 0.f; }
@@ -165,12 +167,22 @@ int best_child_avx2(const FNode* blk, int slots, float k_sqrt_lg) {
     return -1;
 }
 
-int best_child_float(const FNode* blk, int slots, float k_sqrt_lg) {
+int best_child_float(const FNode* blk, int slots, float k_sqrt_lg, const uint32_t* dv) {
     static const bool avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma");
-    return avx2 ? best_child_avx2(blk, slots, k_sqrt_lg) : best_child_scalar(blk, slots, k_sqrt_lg);
+    return avx2 ? best_child_avx2(blk, slots, k_sqrt_lg, dv) : best_child_scalar(blk, slots, k_sqrt_lg, dv);
 }
 
 struct Chunk { uint64_t at = 0, end = 0; };            // a thread's private piece of the arena
+
+// Every walk crosses the first two levels, so their counters are the lines all cores fight over.  In
+// throughput mode each thread keeps its additions to those (at most 25 + 25*24) nodes privately and
+// hands them over once per batch: a thread sees the tree as of the start of the batch plus its own
+// selections in flight (virtual loss per thread).
+struct Shard {
+    uint32_t v1[32], v2[25][32];       // visits added to the root's children / grandchildren, by slot
+    uint64_t w1[32], w2[25][32];       // wins, update phase
+    Shard() { std::memset(this, 0, sizeof *this); }
+};
 
 struct Leaf { uint32_t node; uint32_t x, o; int8_t to_move; bool fresh; uint8_t depth; };
 
@@ -212,6 +224,7 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
     const bool exact = opt.exact_ucb || (hk && hk->intn);
 
     std::vector<Chunk> chunks((size_t)T);
+    std::vector<Shard> shards(exact ? 0 : (size_t)T);
     std::vector<Rng> rngs;
     for (int t = 0; t < T; t++) rngs.emplace_back(host_rng()());
 
@@ -219,7 +232,7 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
     // cold once the tree is large), so every thread advances a GROUP of walks in turn, one level per
     // turn, prefetching the block the next turn will scan.  Visits are added on the way down (virtual
     // loss, visible to every later step of every walk); wins follow when the batch returns.
-    struct Walk { uint32_t idx, x, o; int pjm; int depth; bool fresh, done; };
+    struct Walk { uint32_t idx, x, o; int pjm; int depth; int slot1; bool fresh, done; };
     auto prefetch_block = [&](uint32_t fc, int slots) {
         const char* p = (const char*)&nodes[fc];
         const int bytes = slots * (int)sizeof(FNode);
@@ -227,14 +240,14 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
     };
     auto start_walk = [&](Walk& w, uint32_t* path) {
         w.idx = root; w.x = rootstate.board.x; w.o = rootstate.board.o; w.pjm = rootstate.playerJustMoved;
-        w.depth = 0; w.fresh = false; w.done = false;
+        w.depth = 0; w.slot1 = 0; w.fresh = false; w.done = false;
         // every walk passes the root: in throughput mode its visit is added once per thread and batch instead
         if (exact) nodes[root].visits.fetch_add((uint32_t)P, std::memory_order_release);
         path[w.depth++] = root;
     };
     // one level of one walk; returns true when the walk has reached its leaf
     constexpr uint64_t kChunk = 1 << 16;
-    auto step = [&](Rng& rng, Chunk& ck, Walk& w, uint32_t* path) -> bool {
+    auto step = [&](Rng& rng, Chunk& ck, Shard* sh, Walk& w, uint32_t* path) -> bool {
         FNode& nd = nodes[w.idx];
         const uint32_t u = nd.untried.load(std::memory_order_acquire);
         if (u & kPending) return true;                       // still waiting for its first rollout: a leaf
@@ -265,6 +278,7 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
             c.info = (uint32_t)m | (w.pjm == MAXIMIZER ? 32u : 0u) | ((uint32_t)(slots - cnt) << 6);
             c.untried.store(kPending, std::memory_order_relaxed);
             c.visits.store((uint32_t)P, std::memory_order_release);   // nobody touches a child before its visits are non-zero: a plain store, no locked RMW on a cold line
+            if (w.depth == 1) w.slot1 = (int)(child - fc);
             w.idx = child;
             path[w.depth++] = child;
             w.fresh = true;
@@ -275,7 +289,10 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
         // select (mcts.go:158-161, bestMove :218-238): first maximum in creation order
         const int slots = __builtin_popcount(emp);
         // this walk's own visit is already on the node (added on the way down): the reference sees it only after the rollout
-        const uint32_t seen = nd.visits.load(std::memory_order_relaxed) - ((exact || w.idx != root) ? (uint32_t)P : 0u);
+        // w.depth == 1: at the root, 2: at one of its children -- the levels whose additions stay in the shard
+        uint32_t* dv = !sh ? nullptr : w.depth == 1 ? sh->v1 : w.depth == 2 ? sh->v2[w.slot1] : nullptr;
+        const uint32_t mine = (sh && w.depth == 2) ? sh->v1[w.slot1] : 0u;
+        const uint32_t seen = nd.visits.load(std::memory_order_relaxed) + mine - ((exact || w.idx != root) ? (uint32_t)P : 0u);
         int best = -1;
         if (exact) {
             const double lg = factor * std::log((double)seen);
@@ -289,7 +306,7 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
                 if (sc > bestscore || (best >= 0 && sc == bestscore && rank < best_rank)) { bestscore = sc; best = k; best_rank = rank; }
             }
         } else {
-            best = best_child_float(&nodes[fc], slots, (float)(UCTK * std::sqrt(factor * (double)std::log((float)seen))));
+            best = best_child_float(&nodes[fc], slots, (float)(UCTK * std::sqrt(factor * (double)std::log((float)seen))), dv);
         }
         if (best < 0) {
             if (T == 1) {                                    // the reference dereferences nil here (mcts.go:161)
@@ -300,7 +317,8 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
         }
         w.idx = fc + (uint32_t)best;
         FNode& c = nodes[w.idx];
-        c.visits.fetch_add((uint32_t)P, std::memory_order_release);
+        if (dv) { dv[best] += (uint32_t)P; if (w.depth == 1) w.slot1 = best; }
+        else c.visits.fetch_add((uint32_t)P, std::memory_order_release);
         const uint32_t bit = 1u << (c.info & 31u);
         w.pjm = -w.pjm;
         if (w.pjm == MAXIMIZER) w.x |= bit; else w.o |= bit;
@@ -338,6 +356,7 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
             Walk walks[16];
             long long slot_of[16];
             Chunk& ck = chunks[(size_t)t];
+            Shard* sh = exact ? nullptr : &shards[(size_t)t];
             long long next = lo;
             int active = 0;
             for (; active < group && next < hi; active++, next++) { slot_of[active] = next; start_walk(walks[active], &paths[(size_t)next * kPathLen]); }
@@ -346,13 +365,22 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
                 for (int g = 0; g < active; g++) {
                     Walk& w = walks[g];
                     const long long k = slot_of[g];
-                    if (!step(rngs[(size_t)t], ck, w, &paths[(size_t)k * kPathLen])) continue;
+                    if (!step(rngs[(size_t)t], ck, sh, w, &paths[(size_t)k * kPathLen])) continue;
                     Leaf& lf = leaves[(size_t)k];
                     lf.node = w.idx; lf.x = w.x; lf.o = w.o; lf.to_move = (int8_t)-w.pjm; lf.fresh = w.fresh; lf.depth = (uint8_t)w.depth;
                     boards[(size_t)k] = sq_board{w.x, w.o};
                     to_move[(size_t)k] = lf.to_move;
                     if (next < hi) { slot_of[g] = next; start_walk(w, &paths[(size_t)next * kPathLen]); next++; }
                     else { walks[g] = walks[active - 1]; slot_of[g] = slot_of[active - 1]; active--; g--; }
+                }
+            }
+            if (sh) {                                        // hand this thread's first- and second-level visits over
+                const uint32_t fc1 = nodes[root].first_child.load(std::memory_order_acquire);
+                for (int a = 0; a < 25 && fc1; a++) {
+                    if (sh->v1[a]) { nodes[fc1 + (uint32_t)a].visits.fetch_add(sh->v1[a], std::memory_order_release); sh->v1[a] = 0; }
+                    const uint32_t fc2 = nodes[fc1 + (uint32_t)a].first_child.load(std::memory_order_acquire);
+                    for (int b = 0; b < 25; b++)
+                        if (sh->v2[a][b]) { nodes[fc2 + (uint32_t)b].visits.fetch_add(sh->v2[a][b], std::memory_order_release); sh->v2[a][b] = 0; }
                 }
             }
         });
@@ -364,6 +392,8 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
             const long long lo = B * t / T, hi = B * (t + 1) / T;
             constexpr long long kAhead = 8;                  // the paths are known: pull their nodes in early
             uint64_t root_wins = 0;
+            Shard* sh = exact ? nullptr : &shards[(size_t)t];
+            const uint32_t fc1 = nodes[root].first_child.load(std::memory_order_acquire);
             for (long long k = lo; k < hi; k++) {
                 if (k + kAhead < hi) {
                     const uint32_t* pp = &paths[(size_t)(k + kAhead) * kPathLen];
@@ -375,13 +405,31 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
                 if (lf.fresh) nodes[lf.node].untried.store(r[3] != 0 ? (kFull & ~(lf.x | lf.o)) : 0u, std::memory_order_release);
                 const uint32_t* pp = &paths[(size_t)k * kPathLen];
                 root_wins += (nodes[root].info & 32u) ? r[0] : r[1];              // pp[0] is the root: one add per thread
-                for (int i = 1; i < lf.depth; i++) {                               // Update, mcts.go:190-192,268-271
+                int from = 1;
+                if (sh && lf.depth > 1) {                                          // first and second level: into the shard
+                    const int a = (int)(pp[1] - fc1);
+                    sh->w1[a] += (nodes[pp[1]].info & 32u) ? r[0] : r[1];
+                    from = 2;
+                    if (lf.depth > 2) {
+                        const int b = (int)(pp[2] - nodes[pp[1]].first_child.load(std::memory_order_relaxed));
+                        sh->w2[a][b] += (nodes[pp[2]].info & 32u) ? r[0] : r[1];
+                        from = 3;
+                    }
+                }
+                for (int i = from; i < lf.depth; i++) {                            // Update, mcts.go:190-192,268-271
                     FNode& nd = nodes[pp[i]];
                     const uint32_t add = (uint32_t)((nd.info & 32u) ? r[0] : r[1]);
                     if (add) nd.wins.fetch_add(add, std::memory_order_relaxed);
                 }
             }
             if (root_wins) nodes[root].wins.fetch_add((uint32_t)root_wins, std::memory_order_relaxed);
+            if (sh && fc1)
+                for (int a = 0; a < 25; a++) {
+                    if (sh->w1[a]) { nodes[fc1 + (uint32_t)a].wins.fetch_add((uint32_t)sh->w1[a], std::memory_order_relaxed); sh->w1[a] = 0; }
+                    const uint32_t fc2 = nodes[fc1 + (uint32_t)a].first_child.load(std::memory_order_relaxed);
+                    for (int b = 0; b < 25; b++)
+                        if (sh->w2[a][b]) { nodes[fc2 + (uint32_t)b].wins.fetch_add((uint32_t)sh->w2[a][b], std::memory_order_relaxed); sh->w2[a][b] = 0; }
+                }
         });
         auto t3 = now();
         res.select_seconds += secs(t0, t1); res.gpu_seconds += secs(t1, t2); res.update_seconds += secs(t2, t3);
