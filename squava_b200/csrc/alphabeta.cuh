@@ -685,16 +685,8 @@ inline unsigned long long ab_budget() {
 // (skips passes that would certainly abort).  Override with SQ_AB_SPLIT=<0..3>.
 inline int ab_choose_split(int empties, int rem) {
     const char* env = getenv("SQ_AB_SPLIT");
-    const int forced = (env && *env) ? atoi(env) : -1;
-    int split;
-    if (forced >= 0) split = forced;
-    else {
-        // rough size of the subtree: product of the branching factors, damped
-        double est = 1.0;
-        for (int k = 0; k < rem && empties - k > 0; k++) est *= 0.55 * (empties - k) + 0.45;
-        (void)est;
-        split = 0;   // adaptive passes do the splitting
-    }
+    int split = (env && *env) ? atoi(env) : 0;     // default 0: the adaptive passes do the splitting
+    if (split < 0) split = 0;
     if (split > rem - 1) split = rem - 1 < 0 ? 0 : rem - 1;
     if (split > empties - 1) split = empties - 1 < 0 ? 0 : empties - 1;
     if (split > 3) split = 3;
@@ -827,7 +819,7 @@ inline cudaError_t ab_dispatch(int dialect, AbRun R, AbWork& w, const void* d_in
 
 inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t scores[25], long long max_abs_carried = 0) {
     memset(&R, 0, sizeof R);
-    R.max_depth = dialect == 2 ? max_depth : max_depth;
+    R.max_depth = max_depth;       // squavathr's own decrement (squavathr.go:239) is applied by ab_root_search
     const bool opening = dialect == 3 || dialect == 4;
     R.sentinel = dialect == 4 ? kWin : 2 * kWin;
     R.win_lo = opening ? -kWin : -2 * kWin;
