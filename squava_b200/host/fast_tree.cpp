@@ -195,6 +195,7 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
     if (T < 1) T = 1;
     if (hk && hk->intn) T = 1;                                   // a caller-supplied rand.Intn is one stream
     const int P = opt.playouts_per_leaf < 1 ? 1 : opt.playouts_per_leaf;
+    if (itermax > 4000000000ll) { std::fprintf(stderr, "fast_uct: counts are 32 bits wide, at most 4e9 playouts per decision\n"); std::exit(2); }
     const long long B0 = opt.batch < 1 ? 1 : opt.batch;
     // worst case: every selection makes one node whose block has up to 24 slots... bounded in practice by
     // (selections + 1) blocks of <= 25 slots; the arena is virtual memory, pages are touched on use

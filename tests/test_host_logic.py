@@ -42,3 +42,31 @@ def test_emulator_statistics_match_exact_distribution(oracle):
         sigma = (p[k] * (1 - p[k]) / n) ** 0.5
         assert abs(out[k] / n - p[k]) <= 4 * sigma + 1e-12
     assert abs(out[3] / n - plies) < 0.05
+
+
+def test_recreate_program_follows_the_reference(tmp_path):
+    """recreate.go:10-96 (no GPU involved): one move per line when the file has several lines, else blank-separated;
+    a field that is not a move is reported and skipped BUT still counted, so it flips the X/O alternation
+    (markers[moveCounter%2], moveCounter starting at 1: the first move is drawn as O); "+"/"-" value markers
+    after a digit are dropped; at most 25 fields are looked at"""
+    import os
+    import subprocess
+    host = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "squava_b200", "host")
+    exe = os.path.join(host, "recreate")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", host, "-s", "recreate"])
+    p = tmp_path / "lines.txt"
+    p.write_text("1,1\n0+,0\n2,2-\nbad\n3,3\n")
+    r = subprocess.run([exe, str(p)], input="\n" * 10, capture_output=True, text=True, timeout=30)
+    assert r.returncode == 0
+    assert [l for l in r.stdout.splitlines() if "move" in l] == ["O move 1,1", "X move 0,0", "O move 2,2", "O move 3,3"]
+    assert 'Move 4, "bad", problem' in r.stderr and "Move 6" in r.stderr      # the empty field after the last newline
+    q = tmp_path / "record.txt"
+    q.write_text("X\t9\t" + "\t".join("%d,%d" % (i // 5, i % 5) for i in range(9)) + "\n")
+    r = subprocess.run([exe, str(q)], input="\n" * 30, capture_output=True, text=True, timeout=30)
+    # a tab-separated playoff4 record is ONE blank-separated field to recreate.go: it cannot replay it as is
+    assert r.returncode == 0 and "move" not in r.stdout and "problem" in r.stderr
+    s = tmp_path / "many.txt"
+    s.write_text(" ".join("%d,%d" % (i // 5, i % 5) for i in range(25)) + " 0,0 1,1")
+    r = subprocess.run([exe, str(s)], input="\n" * 40, capture_output=True, text=True, timeout=30)
+    assert len([l for l in r.stdout.splitlines() if "move" in l]) == 25
