@@ -316,19 +316,33 @@ int64_t sqo_count_alternating(int k) {
     if (k < 0 || k > 25) return 0;
     return (int64_t)(binom_tab[25][k] * binom_tab[k][(k + 1) / 2]);
 }
+/* next k-combination of 0..n-1 in lexicographic order (the order unrank_comb counts in); 0 when c was the last */
+static int next_comb(int *c, int n, int k) {
+    int i = k - 1;
+    while (i >= 0 && c[i] == n - k + i) i--;
+    if (i < 0) return 0;
+    c[i]++;
+    for (int j = i + 1; j < k; j++) c[j] = c[j - 1] + 1;
+    return 1;
+}
 void sqo_enumerate_alternating(int k, int64_t start, int64_t count, sqo_board *out) {
     binom_init();
+    if (count <= 0) return;
     int nx = (k + 1) / 2;
     uint64_t per = binom_tab[k][nx];
+    int cells[25], xs[25];
+    /* unrank the first board of the range, then step: the X-subset runs fastest */
+    unrank_comb((uint64_t)start / per, 25, k, cells);
+    unrank_comb((uint64_t)start % per, k, nx, xs);
     for (int64_t i = 0; i < count; i++) {
-        uint64_t r = (uint64_t)(start + i);
-        int cells[25], xs[25];
-        unrank_comb(r / per, 25, k, cells);
-        unrank_comb(r % per, k, nx, xs);
         uint32_t all = 0, x = 0;
         for (int j = 0; j < k; j++) all |= 1u << cells[j];
         for (int j = 0; j < nx; j++) x |= 1u << cells[xs[j]];
         out[i].x = x; out[i].o = all & ~x;
+        if (!next_comb(xs, k, nx)) {
+            for (int j = 0; j < nx; j++) xs[j] = j;
+            if (!next_comb(cells, 25, k)) break;         /* that was the last board with k marks */
+        }
     }
 }
 

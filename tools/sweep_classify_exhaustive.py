@@ -4,7 +4,7 @@ most K marks and X-count - O-count in {0, 1} (K=10: 1,177,833,846 boards), GPU t
 vs the CPU oracle, compared element-wise.  The oracle side (enumeration by rank + table-walk
 classification) runs on a thread pool; ctypes releases the GIL.
 
-usage: sweep_classify_exhaustive.py [K=10] [threads=nproc]"""
+usage: sweep_classify_exhaustive.py [K=10] [threads=nproc] [Kmin=0]   (marks Kmin..K)"""
 import ctypes as C
 import json
 import os
@@ -22,7 +22,8 @@ import squava_b200 as sq
 import oracle_lib
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 10
-T = int(sys.argv[2]) if len(sys.argv) > 2 else (os.cpu_count() or 1)
+T = int(sys.argv[2]) if len(sys.argv) > 2 and int(sys.argv[2]) > 0 else (os.cpu_count() or 1)
+KMIN = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 CH = 1 << 21
 o = oracle_lib.load()
 L = o.L
@@ -48,7 +49,7 @@ def chunk(job):
 
 
 jobs, per_k = [], {}
-for k in range(K + 1):
+for k in range(KMIN, K + 1):
     tot = L.sqo_count_alternating(k)
     per_k[k] = tot
     for s in range(0, tot, CH):
@@ -58,7 +59,7 @@ boards = mism = term = both = chk = 0
 with ThreadPoolExecutor(T) as ex:
     for n, bad, tm, bo, c in ex.map(chunk, jobs):
         boards += n; mism += bad; term += tm; both += bo; chk += c
-print(json.dumps({"max_marks": K, "boards": boards, "per_marks": per_k, "mismatches": mism, "terminal": term,
+print(json.dumps({"min_marks": KMIN, "max_marks": K, "boards": boards, "per_marks": per_k, "mismatches": mism, "terminal": term,
                   "scan_orders_disagree_on": both, "checksum": chk, "threads": T,
                   "seconds": round(time.time() - t0, 1)}))
 sq.shutdown()
