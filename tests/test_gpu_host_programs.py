@@ -208,3 +208,14 @@ def test_opening3_book_table_and_squavathr_book(tmp_path, oracle):
     m = re.search(r"My move: (\d) (\d) \((-?\d+)\) \[book\]", out)
     worst = min(v for (f, r), v in table.items() if f == 6)
     assert rc == 0 and m and int(m.group(3)) == -worst and table[(6, 5 * int(m.group(1)) + int(m.group(2)))] == worst
+
+
+def test_playoff5_lockstep_with_an_mcts_player():
+    """MCTS players keep their own trees and are stepped game by game inside the lockstep loop"""
+    rc, out, err = run("playoff5", "-n", "2", "-1", "M", "-2", "A", "-lockstep", "-seed", "2")
+    assert rc == 0, err
+    lines = out.splitlines()
+    assert len(lines) == 2
+    for g, line in enumerate(lines):
+        f = line.split(" ")
+        assert f[:3] == [str(g), "MCTS", "AlphaBeta"] and int(f[5]) == len(f) - 7 and f[6] in ("1", "-1", "0")
