@@ -219,3 +219,13 @@ def test_playoff5_lockstep_with_an_mcts_player():
     for g, line in enumerate(lines):
         f = line.split(" ")
         assert f[:3] == [str(g), "MCTS", "AlphaBeta"] and int(f[5]) == len(f) - 7 and f[6] in ("1", "-1", "0")
+
+
+def test_squavam_fast_arena_tree_decision():
+    """squavam -fast: one decision through the arena tree on all host threads, real GPU rollouts"""
+    rc, out, err = run("squavam", "-C", "-i", "300000", "-u", "1.0", "-batch", "8192", "-fast", "-stats", "-seed", "4")
+    assert rc == 0, err
+    m = re.search(r"My move: (\d) (\d) (\S+)", out)
+    s = re.search(r"fast tree: (\d+) iterations, (\d+) batches, (\d+) node slots, (\d+) threads", out)
+    assert m and s and int(s.group(1)) == 300000 and int(s.group(2)) == 37 and int(s.group(3)) > 300000
+    assert 0 <= int(m.group(1)) <= 4 and 0 <= int(m.group(2)) <= 4
