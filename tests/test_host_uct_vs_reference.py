@@ -186,3 +186,49 @@ def test_fast_arena_tree_many_threads_keeps_its_books(host_lib):
         assert rootv.value == iters and sum(visits[i] for i in range(25)) == iters
         assert all(0 <= wins[i] <= visits[i] for i in range(25))
         assert best.value in range(25) and nodes.value > iters // ppl
+
+
+def test_fast_arena_tree_throughput_mode_searches_like_the_exact_mode(host_lib):
+    """same synthetic game (the chance that X wins a rollout depends on who holds the inner ring), same budget:
+    the 4-thread / batched / single-precision / sharded search must spend its visits on the same first
+    moves as the sequential double-precision one"""
+    good = sum(1 << c for c in (6, 7, 8, 11, 13, 16, 17, 18))
+    tr = np.array([sum(1 << c for c in t) if not isinstance(t, int) else t for t in E.TRIPLETS], dtype=np.uint32)
+    rng = np.random.Generator(np.random.PCG64(12))
+
+    def playouts(leaves, to_move, n, per_leaf, stream_id, out, ud):
+        b = np.ctypeslib.as_array(C.cast(leaves, C.POINTER(C.c_uint32)), shape=(n, 2))
+        o = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint64)), shape=(n, 4))
+        x, oo = b[:, 0], b[:, 1]
+        term = ((x[:, None] & tr) == tr).any(axis=1) | ((oo[:, None] & tr) == tr).any(axis=1) | ((x | oo) == 0x1ffffff)
+        edge = np.bitwise_count(x & np.uint32(good)).astype(np.float64) - np.bitwise_count(oo & np.uint32(good))
+        p = 1.0 / (1.0 + np.exp(-0.9 * edge))
+        xw = rng.binomial(per_leaf, p).astype(np.uint64)
+        o[:, 0] = xw; o[:, 1] = np.uint64(per_leaf) - xw; o[:, 2] = 0; o[:, 3] = np.where(term, 0, 3 * per_leaf)
+    lib = host_lib
+    lib.sqh_fast_uct.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_longlong, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 INTN, TERM, PLAY, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]
+    term_cb, play_cb = TERM(lambda x, o, ud: int(terminal(x, o))), PLAY(playouts)
+    pick = np.random.Generator(np.random.PCG64(13))
+    share = {}
+    for mode, (batch, threads, intn) in {"exact": (1, 1, INTN(lambda n, ud: int(pick.integers(n)))), "fast": (2048, 4, INTN(0))}.items():
+        moves = (C.c_int * 25)(); visits = (C.c_double * 25)(); wins = (C.c_double * 25)()
+        nch, best, value, rootv = C.c_int(), C.c_int(), C.c_int(), C.c_double()
+        # MINIMIZER just moved: X (the side the inner ring favours) is to move at the root
+        rc = lib.sqh_fast_uct(0, 0, -1, 60_000, 0.7, 1, batch, 1, threads, intn, term_cb, play_cb, None, C.byref(nch), moves, visits,
+                              wins, C.byref(best), C.byref(value), C.byref(rootv), None, None)
+        assert rc == 0 and nch.value == 25
+        v = np.zeros(25)
+        for i in range(25):
+            v[moves[i]] = visits[i]
+        share[mode] = v / v.sum()
+        assert good >> best.value & 1, (mode, best.value)             # both settle on an inner-ring cell
+    a, b = share["exact"], share["fast"]
+    inner = [c for c in range(25) if good >> c & 1]
+    # the eight inner-ring cells are worth the same, so WHICH of them gets the most visits is a coin toss (virtual
+    # loss spreads a batch over them); what must agree is how much of the budget the ring gets as a whole
+    assert a[inner].sum() > 0.6 and b[inner].sum() > 0.6 and abs(a[inner].sum() - b[inner].sum()) < 0.2
+    outer = [c for c in range(25) if not good >> c & 1]
+    assert a[outer].max() < 0.05 and b[outer].max() < 0.05
