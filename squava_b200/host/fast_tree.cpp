@@ -136,22 +136,25 @@ int best_child_scalar(const FNode* blk, int slots, float k_sqrt_lg, const uint32
 
 __attribute__((target("avx2,fma")))
 int best_child_avx2(const FNode* blk, int slots, float k_sqrt_lg, const uint32_t* dv) {
-    alignas(32) float v[32], w[32], sc[32];
-    for (int k = 0; k < slots; k++) {
-        const uint32_t gv = blk[k].visits.load(std::memory_order_relaxed);       // 0: claimed, still being set up
-        v[k] = gv ? (float)(gv + (dv ? dv[k] : 0u)) : 0.f;
-        w[k] = (float)blk[k].wins.load(std::memory_order_relaxed);
-    }
-    for (int k = slots; k < ((slots + 7) & ~7); k++) { v[k] = 0.f; w[k] = 0.f; }
+    alignas(32) float sc[32];
+    alignas(32) static const uint32_t zero[32] = {0};
+    if (!dv) dv = zero;
     const __m256 c = _mm256_set1_ps(k_sqrt_lg), half = _mm256_set1_ps(0.5f), three = _mm256_set1_ps(3.0f);
+    const __m256i stride = _mm256_setr_epi32(0, 6, 12, 18, 24, 30, 36, 42);      // records are 6 dwords: visits, wins, ...
     __m256 top = _mm256_set1_ps(-1.f);
+    const int* base = reinterpret_cast<const int*>(blk);
     for (int k = 0; k < slots; k += 8) {
-        const __m256 vv = _mm256_load_ps(v + k), ww = _mm256_load_ps(w + k);
+        // lanes past the block read the next records of the arena (mapped, possibly foreign): masked out below
+        const __m256i live = _mm256_cmpgt_epi32(_mm256_set1_epi32(slots - k), _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7));
+        const __m256i gv = _mm256_mask_i32gather_epi32(_mm256_setzero_si256(), base + 6 * k, stride, live, 4);
+        const __m256i gw = _mm256_mask_i32gather_epi32(_mm256_setzero_si256(), base + 6 * k + 1, stride, live, 4);
+        const __m256i some = _mm256_andnot_si256(_mm256_cmpeq_epi32(gv, _mm256_setzero_si256()), live);   // visits != 0: the child is set up
+        const __m256 vv = _mm256_cvtepi32_ps(_mm256_add_epi32(gv, _mm256_loadu_si256((const __m256i*)(dv + k))));
+        const __m256 ww = _mm256_cvtepi32_ps(gw);
         __m256 rs = _mm256_rsqrt_ps(vv);                                   // 1/sqrt(v), 12 bits ...
         rs = _mm256_mul_ps(_mm256_mul_ps(half, rs), _mm256_fnmadd_ps(_mm256_mul_ps(vv, rs), rs, three));   // ... one Newton step
         const __m256 s = _mm256_fmadd_ps(_mm256_mul_ps(ww, rs), rs, _mm256_mul_ps(c, rs));                  // w/v + K*sqrt(lg/v)
-        const __m256 ok = _mm256_cmp_ps(vv, _mm256_setzero_ps(), _CMP_GT_OQ);
-        const __m256 m = _mm256_blendv_ps(_mm256_set1_ps(-1.f), s, ok);
+        const __m256 m = _mm256_blendv_ps(_mm256_set1_ps(-1.f), s, _mm256_castsi256_ps(some));
         _mm256_store_ps(sc + k, m);
         top = _mm256_max_ps(top, m);
     }
