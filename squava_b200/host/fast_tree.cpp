@@ -236,7 +236,7 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
     // cold once the tree is large), so every thread advances a GROUP of walks in turn, one level per
     // turn, prefetching the block the next turn will scan.  Visits are added on the way down (virtual
     // loss, visible to every later step of every walk); wins follow when the batch returns.
-    struct Walk { uint32_t idx, x, o; int pjm; int depth; int slot1; bool fresh, done; };
+    struct Walk { uint32_t idx, x, o; int pjm; int depth; int slot1, slot2; bool fresh, done; };
     auto prefetch_block = [&](uint32_t fc, int slots) {
         const char* p = (const char*)&nodes[fc];
         const int bytes = slots * (int)sizeof(FNode);
@@ -244,7 +244,7 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
     };
     auto start_walk = [&](Walk& w, uint32_t* path) {
         w.idx = root; w.x = rootstate.board.x; w.o = rootstate.board.o; w.pjm = rootstate.playerJustMoved;
-        w.depth = 0; w.slot1 = 0; w.fresh = false; w.done = false;
+        w.depth = 0; w.slot1 = 0; w.slot2 = 0; w.fresh = false; w.done = false;
         // every walk passes the root: in throughput mode its visit is added once per thread and batch instead
         if (exact) nodes[root].visits.fetch_add((uint32_t)P, std::memory_order_release);
         path[w.depth++] = root;
@@ -282,7 +282,7 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
             c.info = (uint32_t)m | (w.pjm == MAXIMIZER ? 32u : 0u) | ((uint32_t)(slots - cnt) << 6);
             c.untried.store(kPending, std::memory_order_relaxed);
             c.visits.store((uint32_t)P, std::memory_order_release);   // nobody touches a child before its visits are non-zero: a plain store, no locked RMW on a cold line
-            if (w.depth == 1) w.slot1 = (int)(child - fc);
+            if (w.depth == 1) w.slot1 = (int)(child - fc); else if (w.depth == 2) w.slot2 = (int)(child - fc);
             w.idx = child;
             path[w.depth++] = child;
             w.fresh = true;
@@ -295,8 +295,13 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
         // this walk's own visit is already on the node (added on the way down): the reference sees it only after the rollout
         // w.depth == 1: at the root, 2: at one of its children -- the levels whose additions stay in the shard
         uint32_t* dv = !sh ? nullptr : w.depth == 1 ? sh->v1 : w.depth == 2 ? sh->v2[w.slot1] : nullptr;
-        const uint32_t mine = (sh && w.depth == 2) ? sh->v1[w.slot1] : 0u;
-        const uint32_t seen = nd.visits.load(std::memory_order_relaxed) + mine - ((exact || w.idx != root) ? (uint32_t)P : 0u);
+        // visits this thread still holds in its shard for THIS node (its own walk's included)
+        const uint32_t mine = !sh ? 0u : w.depth == 2 ? sh->v1[w.slot1] : w.depth == 3 ? sh->v2[w.slot1][w.slot2] : 0u;
+        uint32_t seen = nd.visits.load(std::memory_order_relaxed) + mine - ((exact || w.idx != root) ? (uint32_t)P : 0u);
+        // Other threads' visits to a first- or second-level node sit in THEIR shards until the batch ends, so a node
+        // can be fully expanded while this thread has seen next to nothing of it.  Every child was made by a walk
+        // through the node: that many visits it has had for certain (keeps ln N positive, the scores above 0).
+        if (!exact && seen < (uint32_t)slots * (uint32_t)P + 1u) seen = (uint32_t)slots * (uint32_t)P + 1u;
         int best = -1;
         if (exact) {
             const double lg = factor * std::log((double)seen);
@@ -312,16 +317,21 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
         } else {
             best = best_child_float(&nodes[fc], slots, (float)(UCTK * std::sqrt(factor * (double)std::log((float)seen))), dv);
         }
+        if (best < 0 && !exact) {
+            // no child scored above zero: take any child that is set up rather than wait (a walk that waits keeps
+            // its thread's shard from being handed over, which others may be waiting for)
+            for (int k = 0; k < slots && best < 0; k++) if (nodes[fc + (uint32_t)k].visits.load(std::memory_order_acquire)) best = k;
+        }
         if (best < 0) {
             if (T == 1) {                                    // the reference dereferences nil here (mcts.go:161)
                 std::fprintf(stderr, "Node has %d children\nplayer just moved %d\n", slots, w.pjm);
                 std::exit(2);
             }
-            return false;
+            return false;                                    // every child is still being set up by another thread
         }
         w.idx = fc + (uint32_t)best;
         FNode& c = nodes[w.idx];
-        if (dv) { dv[best] += (uint32_t)P; if (w.depth == 1) w.slot1 = best; }
+        if (dv) { dv[best] += (uint32_t)P; if (w.depth == 1) w.slot1 = best; else w.slot2 = best; }
         else c.visits.fetch_add((uint32_t)P, std::memory_order_release);
         const uint32_t bit = 1u << (c.info & 31u);
         w.pjm = -w.pjm;
