@@ -5,7 +5,8 @@ would have made exactly that call, so values, visit order and leaf counts stay b
 split depth S: wasted nodes and the critical path (sum over waves of the largest unit) relative to the sequential
 node count.  Finding: exact, but the waves contain searches the sequential order never makes (after a
 cut-off, or with a window that later moved) and these are often LARGER than anything it does make: critical path
-0.2-1.6x sequential with 2-8x wasted nodes on mid-game positions -- not worth a kernel.
+anywhere from 0.02x to 1.6x sequential (typically 0.2-0.9x) with up to 8x wasted nodes on mid-game positions --
+too erratic to build a kernel on.
 
 usage: proto_negascout_ybw.py [seed]"""
 import sys, time
