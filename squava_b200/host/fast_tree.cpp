@@ -331,6 +331,9 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
         }
         w.idx = fc + (uint32_t)best;
         FNode& c = nodes[w.idx];
+        // the scan saw this child's visits non-zero through plain (vector) loads; this load pairs with the
+        // creator's release store, so the child's parent / info fields are visible before they are read
+        (void)c.visits.load(std::memory_order_acquire);
         if (dv) { dv[best] += (uint32_t)P; if (w.depth == 1) w.slot1 = best; else w.slot2 = best; }
         else c.visits.fetch_add((uint32_t)P, std::memory_order_release);
         const uint32_t bit = 1u << (c.info & 31u);
