@@ -47,8 +47,14 @@ func FromGrid(bd *[5][5]int) Board {
 	return FromCells(&flat)
 }
 
-func check(rc C.int, what string) {
-	if rc != C.SQ_OK {
+// call runs ONE library call and, if it failed, reads the error detail.  sq_last_error() is a
+// thread-local of the C library, so the goroutine is pinned to its OS thread across the pair:
+// without that the scheduler may move it between the two cgo calls and the detail read would be
+// empty or another call's.
+func call(what string, f func() C.int) {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	if rc := f(); rc != C.SQ_OK {
 		// the reference has no error returns: failure is panic or os.Exit
 		panic(fmt.Sprintf("%s: %s (%s)", what, C.GoString(C.sq_strerror(rc)), C.GoString(C.sq_last_error())))
 	}
@@ -56,17 +62,19 @@ func check(rc C.int, what string) {
 
 // Init selects the GPUs (nil = device 0) and the seed of every random stream.
 func Init(devices []int, seed uint64) {
-	runtime.LockOSThread()
-	defer runtime.UnlockOSThread()
 	if len(devices) == 0 {
-		check(C.sq_init(nil, 0, C.uint64_t(seed)), "sq_init")
+		call("sq_init", func() C.int {
+		return C.sq_init(nil, 0, C.uint64_t(seed))
+	})
 		return
 	}
 	ids := make([]C.int, len(devices))
 	for i, d := range devices {
 		ids[i] = C.int(d)
 	}
-	check(C.sq_init(&ids[0], C.int(len(ids)), C.uint64_t(seed)), "sq_init")
+	call("sq_init", func() C.int {
+		return C.sq_init(&ids[0], C.int(len(ids)), C.uint64_t(seed))
+	})
 }
 
 // Shutdown releases the devices.
@@ -79,9 +87,11 @@ func Classify(boards []Board) (flags []uint8, winnerMCTS, winnerAB []int8) {
 	if n == 0 {
 		return
 	}
-	check(C.sq_classify((*C.sq_board)(unsafe.Pointer(&boards[0])), C.int64_t(n),
+	call("sq_classify", func() C.int {
+		return C.sq_classify((*C.sq_board)(unsafe.Pointer(&boards[0])), C.int64_t(n),
 		(*C.uint8_t)(unsafe.Pointer(&flags[0])), (*C.int8_t)(unsafe.Pointer(&winnerMCTS[0])),
-		(*C.int8_t)(unsafe.Pointer(&winnerAB[0]))), "sq_classify")
+		(*C.int8_t)(unsafe.Pointer(&winnerAB[0])))
+	})
 	return
 }
 
@@ -95,9 +105,11 @@ func Playouts(leaves []Board, toMove []int8, perLeaf, streamID uint64) []Counts 
 	if n == 0 {
 		return out
 	}
-	check(C.sq_playouts((*C.sq_board)(unsafe.Pointer(&leaves[0])), (*C.int8_t)(unsafe.Pointer(&toMove[0])),
+	call("sq_playouts", func() C.int {
+		return C.sq_playouts((*C.sq_board)(unsafe.Pointer(&leaves[0])), (*C.int8_t)(unsafe.Pointer(&toMove[0])),
 		C.int64_t(n), C.uint64_t(perLeaf), C.uint64_t(streamID),
-		(*[4]C.uint64_t)(unsafe.Pointer(&out[0]))), "sq_playouts")
+		(*[4]C.uint64_t)(unsafe.Pointer(&out[0])))
+	})
 	return out
 }
 
@@ -134,10 +146,12 @@ func AlphaBetaRoot(positions []Board, dialect, maxDepth int, scores *[25]int8) [
 	bv := make([]int32, n)
 	bm := make([]uint32, n)
 	nodes := make([]uint64, n)
-	check(C.sq_alphabeta_root((*C.sq_board)(unsafe.Pointer(&positions[0])), C.int64_t(n), C.int(dialect),
+	call("sq_alphabeta_root", func() C.int {
+		return C.sq_alphabeta_root((*C.sq_board)(unsafe.Pointer(&positions[0])), C.int64_t(n), C.int(dialect),
 		C.int(maxDepth), (*C.int8_t)(unsafe.Pointer(&scores[0])), (*[25]C.int32_t)(unsafe.Pointer(&values[0])),
 		(*C.int32_t)(unsafe.Pointer(&bv[0])), (*C.uint32_t)(unsafe.Pointer(&bm[0])),
-		(*C.uint64_t)(unsafe.Pointer(&nodes[0]))), "sq_alphabeta_root")
+		(*C.uint64_t)(unsafe.Pointer(&nodes[0])))
+	})
 	for i := range out {
 		out[i] = RootValues{values[i], bv[i], bm[i], nodes[i]}
 	}
@@ -167,11 +181,13 @@ func NegaScoutRoot(positions []Board, maxDepth int, scores *[25]int8) []NegaScou
 	bm := make([]uint32, n)
 	fb := make([]int8, n)
 	nodes := make([]uint64, n)
-	check(C.sq_negascout_root((*C.sq_board)(unsafe.Pointer(&positions[0])), C.int64_t(n), C.int(maxDepth),
+	call("sq_negascout_root", func() C.int {
+		return C.sq_negascout_root((*C.sq_board)(unsafe.Pointer(&positions[0])), C.int64_t(n), C.int(maxDepth),
 		(*C.int8_t)(unsafe.Pointer(&scores[0])), (*[25]C.int32_t)(unsafe.Pointer(&values[0])),
 		(*[25]C.int8_t)(unsafe.Pointer(&order[0])), (*C.int32_t)(unsafe.Pointer(&bv[0])),
 		(*C.uint32_t)(unsafe.Pointer(&bm[0])), (*C.int8_t)(unsafe.Pointer(&fb[0])),
-		(*C.uint64_t)(unsafe.Pointer(&nodes[0]))), "sq_negascout_root")
+		(*C.uint64_t)(unsafe.Pointer(&nodes[0])))
+	})
 	for i := range out {
 		out[i] = NegaScoutResult{values[i], order[i], bv[i], bm[i], fb[i], nodes[i]}
 	}
@@ -195,8 +211,10 @@ func AlphaBetaSubtrees(st []Subtree, dialect, maxDepth int, scores *[25]int8) (v
 	if n == 0 {
 		return
 	}
-	check(C.sq_alphabeta_subtrees((*C.sq_subtree)(unsafe.Pointer(&st[0])), C.int64_t(n), C.int(dialect),
+	call("sq_alphabeta_subtrees", func() C.int {
+		return C.sq_alphabeta_subtrees((*C.sq_subtree)(unsafe.Pointer(&st[0])), C.int64_t(n), C.int(dialect),
 		C.int(maxDepth), (*C.int8_t)(unsafe.Pointer(&scores[0])), (*C.int32_t)(unsafe.Pointer(&value[0])),
-		(*C.uint64_t)(unsafe.Pointer(&nodes[0]))), "sq_alphabeta_subtrees")
+		(*C.uint64_t)(unsafe.Pointer(&nodes[0])))
+	})
 	return
 }

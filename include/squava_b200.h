@@ -12,8 +12,10 @@
  *     nothing aborts.  sq_strerror() names a status; sq_last_error() gives the
  *     CUDA detail of the calling thread's last failure.
  *   - The caller owns every buffer; the library keeps no pointer after a call
- *     returns (the cgo pointer rule).  Calls may arrive on any OS thread and are
- *     serialised per device inside the library.
+ *     returns (the cgo pointer rule).  Calls may arrive on any OS thread.  Calls on
+ *     different devices never wait for each other; on one device up to four calls
+ *     are in flight at a time (each on its own stream and staging buffers), further
+ *     ones queue.  Only sq_init / sq_shutdown exclude everything else.
  *   - There is NO CPU fallback: without a usable sm_100 device sq_init() fails
  *     and every compute call returns SQ_ERR_NOT_INIT.
  *   - Board: two 25-bit masks, bit c = 5*x + y with x the first coordinate
@@ -29,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SQ_ABI_VERSION 1
+#define SQ_ABI_VERSION 2
 
 typedef enum sq_status {
     SQ_OK = 0,
@@ -66,11 +68,16 @@ typedef struct sq_board { uint32_t x, o; } sq_board;
 /* device_ids == NULL / n_devices <= 0: use device 0.  seed keys every random
  * stream (the reference seeds math/rand from the clock, squavam.go:48).  With
  * n_devices > 1 the host-buffer calls below shard their units over the devices
- * (contiguous ranges, no collective); results do not depend on n_devices.   */
+ * (contiguous ranges; explicit subtrees by estimated size; no collective); results do not
+ * depend on n_devices.                                                     */
 int sq_init(const int *device_ids, int n_devices, uint64_t seed);
 void sq_shutdown(void);
 const char *sq_strerror(int status);
 const char *sq_last_error(void);
+/* The same message copied into the caller's buffer.  sq_last_error() reads a thread-local: a cgo
+ * caller whose goroutine may migrate between two C calls either pins its OS thread around the pair
+ * (runtime.LockOSThread) or calls this from the same C stub as the failing call.               */
+int sq_last_error_copy(char *buf, int len);
 int sq_abi_version(void);
 int sq_device_count(void);          /* devices this library was initialised on */
 int sq_sm_count(int slot);          /* multiprocessors of device slot (0 <= slot < sq_device_count()) */
@@ -98,6 +105,15 @@ int sq_classify(const sq_board *boards, int64_t n, uint8_t *flags,
  * sub-stream): the same call returns the same counts on any number of devices. */
 int sq_playouts(const sq_board *leaves, const int8_t *to_move, int64_t n_leaves,
                 uint64_t playouts_per_leaf, uint64_t stream_id, uint64_t (*out)[4]);
+
+/* One playout per leaf (what UCT's loop does per iteration, mcts.go:173-192) with the result packed
+ * into ONE byte per leaf instead of four counters: bits 0-1 = 1 MAXIMIZER won, 2 MINIMIZER won,
+ * 3 draw (GetResult 0.0 for both); bits 2-7 = plies played (0 <=> the leaf was terminal, which is
+ * what a freshly expanded node needs to know).  Same random stream as sq_playouts(.., 1, ..):
+ * outcome[i] encodes exactly the counts that call would return.  For hosts that feed 64K-leaf
+ * batches at 10^7 leaves/s (configs[2]): 1 B instead of 32 B back per leaf.                    */
+int sq_playouts_packed(const sq_board *leaves, const int8_t *to_move, int64_t n_leaves,
+                       uint64_t stream_id, uint8_t *outcome);
 
 /* ---- fixed-depth alpha-beta -------------------------------------------- */
 /* Replaces ChooseMove's per-root-move loop: src/alphabeta/alphabeta.go:92-117

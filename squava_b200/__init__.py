@@ -17,7 +17,7 @@ import numpy as np
 
 __all__ = [
     "SquavaError", "BOARD", "SUBTREE", "NO_MOVE", "lib", "lib_path", "init", "shutdown",
-    "is_initialised", "classify", "playouts", "playouts_dev", "classify_dev",
+    "is_initialised", "classify", "playouts", "playouts_packed", "playouts_dev", "classify_dev",
     "alphabeta_root", "alphabeta_subtrees", "negascout_root", "int32_peak", "launch_count",
     "last_playout_kernel_ms", "debug_philox", "device_count", "sm_count", "EXPORTS",
 ]
@@ -37,7 +37,7 @@ EXPORTS = [
     "sq_init", "sq_shutdown", "sq_strerror", "sq_last_error", "sq_abi_version", "sq_device_count",
     "sq_sm_count", "sq_classify", "sq_playouts", "sq_alphabeta_root", "sq_alphabeta_subtrees", "sq_negascout_root",
     "sq_classify_dev", "sq_playouts_dev", "sq_int32_peak", "sq_launch_count",
-    "sq_last_playout_kernel_ms", "sq_debug_philox",
+    "sq_last_playout_kernel_ms", "sq_debug_philox", "sq_playouts_packed", "sq_last_error_copy",
 ]
 
 
@@ -73,6 +73,8 @@ def lib():
         L.sq_sm_count.argtypes = [i32]
         L.sq_classify.argtypes = [vp, i64, vp, vp, vp]
         L.sq_playouts.argtypes = [vp, vp, i64, u64, u64, vp]
+        L.sq_playouts_packed.argtypes = [vp, vp, i64, u64, vp]
+        L.sq_last_error_copy.argtypes = [C.c_char_p, i32]
         L.sq_alphabeta_root.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, vp]
         L.sq_alphabeta_subtrees.argtypes = [vp, i64, i32, i32, vp, vp, vp]
         L.sq_negascout_root.argtypes = [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]
@@ -145,6 +147,18 @@ def playouts(boards, to_move, playouts_per_leaf, stream_id=0, out=None):
         out = np.empty((n, 4), np.uint64)
     _ck(lib().sq_playouts(b.ctypes.data, tm.ctypes.data, n, int(playouts_per_leaf), int(stream_id),
                           out.ctypes.data), "sq_playouts")
+    return out
+
+
+def playouts_packed(boards, to_move, stream_id=0):
+    """One playout per leaf -> u8[n]: bits 0-1 outcome (1 MAX won, 2 MIN won, 3 draw), bits 2-7 plies."""
+    b = as_boards(boards)
+    tm = np.ascontiguousarray(to_move, dtype=np.int8)
+    n = b.shape[0]
+    if tm.shape[0] != n:
+        raise ValueError("to_move length")
+    out = np.empty(n, np.uint8)
+    _ck(lib().sq_playouts_packed(b.ctypes.data, tm.ctypes.data, n, int(stream_id), out.ctypes.data), "sq_playouts_packed")
     return out
 
 

@@ -10,7 +10,9 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -24,9 +26,12 @@
 
 namespace {
 
-struct Device {
-    int id = -1;
-    int sm_count = 0;
+// A call context: everything one call in flight on a device needs -- its own stream, staging
+// buffers, pinned block, timing events and scheduling counters.  A device carries kCtx of them, so
+// calls arriving on different host threads overlap on the SAME device (and calls on different
+// devices never meet at all); a context is held for the duration of one call.
+struct Ctx {
+    std::mutex mu;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the most recent playout kernel
     bool timed = false;
@@ -35,30 +40,61 @@ struct Device {
     // staging for host-pointer calls (grown on demand)
     void* buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t cap[6] = {0, 0, 0, 0, 0, 0};
-    int playout_blocks_per_sm = 0;
-    int ab_blocks_per_sm = 0;
     // small-call path: pinned host staging [boards | to_move | out] and one device block
     // [counter | out | boards | to_move], so a call is memcpy-in, H2D, memset, kernel, D2H
     uint8_t* pin = nullptr;
     uint8_t* small = nullptr;
 };
 
-constexpr int64_t kSmallLeaves = 1 << 16;      // per device
+constexpr int kCtx = 4;
+
+struct Device {
+    int id = -1;
+    int sm_count = 0;
+    int playout_blocks_per_sm = 0;
+    int ab_blocks_per_sm = 0;
+    Ctx ctx[kCtx];
+    std::atomic<unsigned> rr{0};
+    std::atomic<int> last_timed{-1};            // context that ran the most recent playout kernel
+};
+
+constexpr int64_t kSmallLeaves = 1 << 16;      // per call and device
 
 constexpr unsigned kCounterRing = 256;
 
 static sq::NsTables g_ns_tables;   // host copy: which positions the fast NegaScout kernel may take
 
-std::mutex g_mu;
-std::vector<Device> g_dev;
+// g_state: exclusive for sq_init / sq_shutdown, shared for the duration of every other call, so the
+// device table cannot change under a call in flight.  Below it every context has its own mutex.
+std::shared_mutex g_state;
+std::vector<std::unique_ptr<Device>> g_dev;
 bool g_init = false;
 uint64_t g_seed = 0;
 std::atomic<uint64_t> g_launches{0};
 thread_local char t_err[512] = "";
 
+// Takes a free context of the device; when all are busy, queues on one of them.
+struct CtxHold {
+    Ctx* c = nullptr;
+    std::unique_lock<std::mutex> lk;
+    Ctx* operator->() const { return c; }
+    Ctx& operator*() const { return *c; }
+};
+CtxHold acquire(Device& d) {
+    CtxHold h;
+    for (int i = 0; i < kCtx; i++) {
+        std::unique_lock<std::mutex> lk(d.ctx[i].mu, std::try_to_lock);
+        if (lk.owns_lock()) { h.c = &d.ctx[i]; h.lk = std::move(lk); return h; }
+    }
+    const unsigned k = d.rr.fetch_add(1) % kCtx;
+    h.lk = std::unique_lock<std::mutex>(d.ctx[k].mu);
+    h.c = &d.ctx[k];
+    return h;
+}
+
 int fail_cuda(cudaError_t e, const char* what) {
     snprintf(t_err, sizeof t_err, "%s: %s", what, cudaGetErrorString(e));
-    return SQ_ERR_CUDA;
+    return e == cudaErrorMemoryAllocation ? SQ_ERR_NOMEM : SQ_ERR_CUDA;
 }
 #define CK(call)                                             \
     do {                                                     \
@@ -66,13 +102,13 @@ int fail_cuda(cudaError_t e, const char* what) {
         if (e_ != cudaSuccess) return fail_cuda(e_, #call);  \
     } while (0)
 
-int reserve(Device& d, int which, size_t bytes) {
-    if (d.cap[which] >= bytes) return SQ_OK;
-    if (d.buf[which]) CK(cudaFree(d.buf[which]));
-    d.buf[which] = nullptr; d.cap[which] = 0;
+int reserve(Ctx& c, int which, size_t bytes) {
+    if (c.cap[which] >= bytes) return SQ_OK;
+    if (c.buf[which]) { CK(cudaStreamSynchronize(c.stream)); CK(cudaFree(c.buf[which])); }
+    c.buf[which] = nullptr; c.cap[which] = 0;
     size_t want = bytes + bytes / 4 + 256;
-    CK(cudaMalloc(&d.buf[which], want));
-    d.cap[which] = want;
+    CK(cudaMalloc(&c.buf[which], want));
+    c.cap[which] = want;
     return SQ_OK;
 }
 
@@ -93,13 +129,14 @@ int launch_classify(Device& d, const sq_board* boards, int64_t n, uint8_t* flags
     return SQ_OK;
 }
 
-// counter == nullptr: zero `out`, take a counter from the ring and zero it.  Otherwise the caller
-// has already zeroed both (they sit in one block: one memset).
-int launch_playouts(Device& d, const sq_board* leaves, const int8_t* to_move, int64_t n_leaves,
+// counter == nullptr: zero `out`, take a counter from the context's ring and zero it.  Otherwise the
+// caller has already zeroed both (they sit in one block: one memset).  packed != nullptr: one playout
+// per leaf, the outcome goes to packed[i] as one byte instead of out[i][0..3] (sq_playouts_packed).
+int launch_playouts(Device& d, Ctx& c, int ctx_index, const sq_board* leaves, const int8_t* to_move, int64_t n_leaves,
                     uint64_t leaf_index_base, uint64_t per_leaf, uint64_t stream_id,
-                    uint64_t* out, cudaStream_t st, unsigned long long* counter = nullptr) {
+                    uint64_t* out, cudaStream_t st, unsigned long long* counter = nullptr, uint8_t* packed = nullptr) {
     if (n_leaves <= 0) return SQ_OK;
-    if (!counter) CK(cudaMemsetAsync(out, 0, (size_t)n_leaves * 4 * sizeof(uint64_t), st));
+    if (!counter && out) CK(cudaMemsetAsync(out, 0, (size_t)n_leaves * 4 * sizeof(uint64_t), st));
     if (per_leaf == 0) return SQ_OK;
     sq::PlayoutParams P;
     P.leaves = leaves; P.to_move = to_move; P.n_leaves = n_leaves;
@@ -116,10 +153,11 @@ int launch_playouts(Device& d, const sq_board* leaves, const int8_t* to_move, in
     unsigned long long items = (unsigned long long)n_leaves * S;
     P.n_rounds = (int64_t)((items + 31) / 32);
     P.out = reinterpret_cast<unsigned long long*>(out);
+    P.packed = packed;
     if (counter) P.round_counter = counter;
     else {
         // each launch gets its own counter: launches on different streams may overlap on the device
-        P.round_counter = d.counters + (d.launch_seq++ % kCounterRing);
+        P.round_counter = c.counters + (c.launch_seq++ % kCounterRing);
         CK(cudaMemsetAsync(P.round_counter, 0, sizeof(unsigned long long), st));
     }
     const int warps_per_block = sq::kPlayoutThreads / 32;
@@ -127,17 +165,18 @@ int launch_playouts(Device& d, const sq_board* leaves, const int8_t* to_move, in
     int64_t need = (P.n_rounds + warps_per_block - 1) / warps_per_block;
     if (blocks > need) blocks = need;
     size_t smem = (size_t)sq::kMaxEmpty * sq::kPlayoutThreads * sizeof(uint32_t);
-    CK(cudaEventRecord(d.ev0, st));
+    CK(cudaEventRecord(c.ev0, st));
     sq::playout_kernel<<<(unsigned)blocks, sq::kPlayoutThreads, smem, st>>>(P);
     g_launches++;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(d.ev1, st));
-    d.timed = true;
+    CK(cudaEventRecord(c.ev1, st));
+    c.timed = true;
+    d.last_timed.store(ctx_index);
     return SQ_OK;
 }
 
-// The alpha-beta search is host-driven (one synchronisation per pass), so with several devices
-// each share runs on its own host thread.  fn(k) returns a status; its message is kept.
+// Host-buffer calls over several devices: each share runs on its own host thread (the alpha-beta search
+// is host-driven, one synchronisation per pass).  fn(k) returns a status; its message is kept.
 template <typename F>
 int for_each_device(int m, F fn) {
     if (m == 1) return fn(0);
@@ -152,6 +191,7 @@ int for_each_device(int m, F fn) {
     return SQ_OK;
 }
 
+// callers hold g_state (shared)
 int check_ready() {
     if (!g_init) { snprintf(t_err, sizeof t_err, "sq_init() has not succeeded"); return SQ_ERR_NOT_INIT; }
     return SQ_OK;
@@ -163,22 +203,70 @@ int check_slot(int slot) {
     return SQ_OK;
 }
 
-void destroy_all() {
-    for (auto& d : g_dev) {
-        if (d.id < 0) continue;
-        cudaSetDevice(d.id);
-        if (d.stream) cudaStreamSynchronize(d.stream);
-        for (int i = 0; i < 6; i++) if (d.buf[i]) cudaFree(d.buf[i]);
-        if (d.counters) cudaFree(d.counters);
-        if (d.small) cudaFree(d.small);
-        if (d.pin) cudaFreeHost(d.pin);
-        if (d.ev0) cudaEventDestroy(d.ev0);
-        if (d.ev1) cudaEventDestroy(d.ev1);
-        if (d.stream) cudaStreamDestroy(d.stream);
+void destroy_device(Device& d) {
+    if (d.id < 0) return;
+    cudaSetDevice(d.id);
+    for (auto& c : d.ctx) {
+        if (c.stream) cudaStreamSynchronize(c.stream);
+        for (int i = 0; i < 6; i++) if (c.buf[i]) cudaFree(c.buf[i]);
+        if (c.counters) cudaFree(c.counters);
+        if (c.small) cudaFree(c.small);
+        if (c.pin) cudaFreeHost(c.pin);
+        if (c.ev0) cudaEventDestroy(c.ev0);
+        if (c.ev1) cudaEventDestroy(c.ev1);
+        if (c.stream) cudaStreamDestroy(c.stream);
+        c.stream = nullptr; c.ev0 = c.ev1 = nullptr; c.timed = false; c.counters = nullptr; c.launch_seq = 0;
+        for (int i = 0; i < 6; i++) { c.buf[i] = nullptr; c.cap[i] = 0; }
+        c.pin = c.small = nullptr;
     }
+    d.id = -1;
+}
+
+void destroy_all() {
+    for (auto& d : g_dev) destroy_device(*d);
     g_dev.clear();
     g_init = false;
 }
+
+int init_device(Device& d, const sq::ScanTables& tables, const sq::AbTables& ab_tables, const sq::NsTables& ns_tables,
+                const sq::NsCellTables& ns_cell_tables) {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, d.id));
+    if (prop.major != 10) {
+        snprintf(t_err, sizeof t_err, "device %d is sm_%d%d; this library carries sm_100a code only", d.id, prop.major, prop.minor);
+        return SQ_ERR_NO_DEVICE;
+    }
+    d.sm_count = prop.multiProcessorCount;
+    CK(cudaSetDevice(d.id));
+    {   // keep the alpha-beta workspace in the stream-ordered pool between calls
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, d.id));
+        uint64_t keep = ~0ull;
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    for (auto& c : d.ctx) {
+        CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&c.ev0));
+        CK(cudaEventCreate(&c.ev1));
+        CK(cudaMalloc(&c.counters, kCounterRing * sizeof(unsigned long long)));
+        CK(cudaMemset(c.counters, 0, kCounterRing * sizeof(unsigned long long)));
+        CK(cudaHostAlloc((void**)&c.pin, (size_t)kSmallLeaves * (8 + 1 + 32), cudaHostAllocDefault));
+        CK(cudaMalloc((void**)&c.small, 16 + (size_t)kSmallLeaves * (32 + 8 + 1)));
+    }
+    CK(cudaMemcpyToSymbol(sq::c_scan, &tables, sizeof tables));
+    CK(cudaMemcpyToSymbol(sq::c_ab, &ab_tables, sizeof ab_tables));
+    CK(cudaMemcpyToSymbol(sq::c_ns, &ns_tables, sizeof ns_tables));
+    CK(cudaMemcpyToSymbol(sq::c_ns_cell, &ns_cell_tables, sizeof ns_cell_tables));
+    size_t smem = (size_t)sq::kMaxEmpty * sq::kPlayoutThreads * sizeof(uint32_t);
+    CK(cudaFuncSetAttribute(sq::playout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.playout_blocks_per_sm, sq::playout_kernel,
+                                                     sq::kPlayoutThreads, smem));
+    if (d.playout_blocks_per_sm < 1) d.playout_blocks_per_sm = 1;
+    CK(sq::ab_configure(&d.ab_blocks_per_sm));
+    return SQ_OK;
+}
+
+bool bad_board(const sq_board& b) { return (b.x & b.o) || ((b.x | b.o) >> 25); }
 
 }  // namespace
 
@@ -199,9 +287,14 @@ const char* sq_strerror(int status) {
     }
 }
 const char* sq_last_error(void) { return t_err; }
+int sq_last_error_copy(char* buf, int len) {
+    if (!buf || len <= 0) return SQ_ERR_INVALID;
+    snprintf(buf, (size_t)len, "%s", t_err);
+    return SQ_OK;
+}
 
 int sq_init(const int* device_ids, int n_devices, uint64_t seed) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_state);
     destroy_all();
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -222,42 +315,17 @@ int sq_init(const int* device_ids, int n_devices, uint64_t seed) {
     sq::build_ns_cell_tables(ns_tables, ns_cell_tables);
     g_ns_tables = ns_tables;
     for (int k = 0; k < n_devices; k++) {
-        Device d;
-        d.id = device_ids[k];
-        if (d.id < 0 || d.id >= count) { destroy_all(); snprintf(t_err, sizeof t_err, "device id %d out of range", d.id); return SQ_ERR_INVALID; }
-        cudaDeviceProp prop;
-        CK(cudaGetDeviceProperties(&prop, d.id));
-        if (prop.major != 10) {
+        if (device_ids[k] < 0 || device_ids[k] >= count) {
             destroy_all();
-            snprintf(t_err, sizeof t_err, "device %d is sm_%d%d; this library carries sm_100a code only", d.id, prop.major, prop.minor);
-            return SQ_ERR_NO_DEVICE;
+            snprintf(t_err, sizeof t_err, "device id %d out of range", device_ids[k]);
+            return SQ_ERR_INVALID;
         }
-        d.sm_count = prop.multiProcessorCount;
-        CK(cudaSetDevice(d.id));
-        CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
-        {   // keep the alpha-beta workspace in the stream-ordered pool between calls
-            cudaMemPool_t pool;
-            CK(cudaDeviceGetDefaultMemPool(&pool, d.id));
-            uint64_t keep = ~0ull;
-            CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        }
-        CK(cudaEventCreate(&d.ev0));
-        CK(cudaEventCreate(&d.ev1));
-        CK(cudaMalloc(&d.counters, kCounterRing * sizeof(unsigned long long)));
-        CK(cudaMemset(d.counters, 0, kCounterRing * sizeof(unsigned long long)));
-        CK(cudaHostAlloc((void**)&d.pin, (size_t)kSmallLeaves * (8 + 1 + 32), cudaHostAllocDefault));
-        CK(cudaMalloc((void**)&d.small, 16 + (size_t)kSmallLeaves * (32 + 8 + 1)));
-        CK(cudaMemcpyToSymbol(sq::c_scan, &tables, sizeof tables));
-        CK(cudaMemcpyToSymbol(sq::c_ab, &ab_tables, sizeof ab_tables));
-        CK(cudaMemcpyToSymbol(sq::c_ns, &ns_tables, sizeof ns_tables));
-        CK(cudaMemcpyToSymbol(sq::c_ns_cell, &ns_cell_tables, sizeof ns_cell_tables));
-        size_t smem = (size_t)sq::kMaxEmpty * sq::kPlayoutThreads * sizeof(uint32_t);
-        CK(cudaFuncSetAttribute(sq::playout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.playout_blocks_per_sm, sq::playout_kernel,
-                                                         sq::kPlayoutThreads, smem));
-        if (d.playout_blocks_per_sm < 1) d.playout_blocks_per_sm = 1;
-        CK(sq::ab_configure(&d.ab_blocks_per_sm));
-        g_dev.push_back(d);
+        // the device joins the table BEFORE anything fallible is created on it: whatever a failed
+        // start-up leaves behind is released by destroy_all()
+        g_dev.emplace_back(new Device());
+        g_dev.back()->id = device_ids[k];
+        int rc = init_device(*g_dev.back(), tables, ab_tables, ns_tables, ns_cell_tables);
+        if (rc) { destroy_all(); return rc; }
     }
     g_seed = seed;
     g_init = true;
@@ -265,25 +333,29 @@ int sq_init(const int* device_ids, int n_devices, uint64_t seed) {
 }
 
 void sq_shutdown(void) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_state);
     destroy_all();
 }
 
-int sq_device_count(void) { return g_init ? (int)g_dev.size() : 0; }
+int sq_device_count(void) {
+    std::shared_lock<std::shared_mutex> sl(g_state);
+    return g_init ? (int)g_dev.size() : 0;
+}
 int sq_sm_count(int slot) {
+    std::shared_lock<std::shared_mutex> sl(g_state);
     if (check_slot(slot)) return 0;
-    return g_dev[slot].sm_count;
+    return g_dev[slot]->sm_count;
 }
 uint64_t sq_launch_count(void) { return g_launches.load(); }
 
 // ---- device-resident forms -------------------------------------------------
 int sq_classify_dev(int slot, const sq_board* boards, int64_t n, uint8_t* flags, int8_t* wm,
                     int8_t* wa, void* stream) {
+    std::shared_lock<std::shared_mutex> sl(g_state);
     int rc = check_slot(slot);
     if (rc) return rc;
     if (n < 0 || (n > 0 && !boards)) { snprintf(t_err, sizeof t_err, "sq_classify_dev: null boards"); return SQ_ERR_INVALID; }
-    std::lock_guard<std::mutex> lk(g_mu);
-    Device& d = g_dev[slot];
+    Device& d = *g_dev[slot];
     CK(cudaSetDevice(d.id));
     return launch_classify(d, boards, n, flags, wm, wa, (cudaStream_t)stream);
 }
@@ -291,140 +363,169 @@ int sq_classify_dev(int slot, const sq_board* boards, int64_t n, uint8_t* flags,
 int sq_playouts_dev(int slot, const sq_board* leaves, const int8_t* to_move, int64_t n_leaves,
                     uint64_t leaf_index_base, uint64_t per_leaf, uint64_t stream_id, uint64_t* out,
                     void* stream) {
+    std::shared_lock<std::shared_mutex> sl(g_state);
     int rc = check_slot(slot);
     if (rc) return rc;
     if (n_leaves < 0 || (n_leaves > 0 && (!leaves || !to_move || !out))) {
         snprintf(t_err, sizeof t_err, "sq_playouts_dev: null pointer"); return SQ_ERR_INVALID;
     }
-    std::lock_guard<std::mutex> lk(g_mu);
-    Device& d = g_dev[slot];
+    Device& d = *g_dev[slot];
+    CtxHold c = acquire(d);                    // for its counter ring and timing events only
     CK(cudaSetDevice(d.id));
-    return launch_playouts(d, leaves, to_move, n_leaves, leaf_index_base, per_leaf, stream_id, out,
+    return launch_playouts(d, *c, (int)(c.c - d.ctx), leaves, to_move, n_leaves, leaf_index_base, per_leaf, stream_id, out,
                            (cudaStream_t)stream);
 }
 
 // ---- host-buffer forms -------------------------------------------------------
 int sq_classify(const sq_board* boards, int64_t n, uint8_t* flags, int8_t* wm, int8_t* wa) {
+    std::shared_lock<std::shared_mutex> sl(g_state);
     int rc = check_ready();
     if (rc) return rc;
     if (n < 0 || (n > 0 && !boards)) { snprintf(t_err, sizeof t_err, "sq_classify: null boards"); return SQ_ERR_INVALID; }
-    std::lock_guard<std::mutex> lk(g_mu);
     int m = (int)g_dev.size();
+    std::vector<CtxHold> held((size_t)m);
     for (int k = 0; k < m; k++) {
-        Device& d = g_dev[k];
+        Device& d = *g_dev[k];
         int64_t lo, hi; share(n, m, k, lo, hi);
         int64_t cnt = hi - lo;
         if (cnt <= 0) continue;
+        held[k] = acquire(d);
+        Ctx& c = *held[k];
         CK(cudaSetDevice(d.id));
         if (cnt <= kSmallLeaves) {          // small call: pinned staging, one copy each way
-            memcpy(d.pin, boards + lo, cnt * sizeof(sq_board));
-            uint8_t* din = d.small + 16 + (size_t)cnt * 32;
-            uint8_t* dres = d.small + 16;
-            CK(cudaMemcpyAsync(din, d.pin, cnt * sizeof(sq_board), cudaMemcpyHostToDevice, d.stream));
-            rc = launch_classify(d, (const sq_board*)din, cnt, dres, (int8_t*)dres + cnt, (int8_t*)dres + 2 * cnt, d.stream);
+            memcpy(c.pin, boards + lo, cnt * sizeof(sq_board));
+            uint8_t* din = c.small + 16 + (size_t)cnt * 32;
+            uint8_t* dres = c.small + 16;
+            CK(cudaMemcpyAsync(din, c.pin, cnt * sizeof(sq_board), cudaMemcpyHostToDevice, c.stream));
+            rc = launch_classify(d, (const sq_board*)din, cnt, dres, (int8_t*)dres + cnt, (int8_t*)dres + 2 * cnt, c.stream);
             if (rc) return rc;
-            CK(cudaMemcpyAsync(d.pin + (size_t)kSmallLeaves * 9, dres, cnt * 3, cudaMemcpyDeviceToHost, d.stream));
+            CK(cudaMemcpyAsync(c.pin + (size_t)kSmallLeaves * 9, dres, cnt * 3, cudaMemcpyDeviceToHost, c.stream));
             continue;
         }
-        if ((rc = reserve(d, 0, cnt * sizeof(sq_board)))) return rc;
-        if ((rc = reserve(d, 1, cnt * 3))) return rc;
-        uint8_t* dout = (uint8_t*)d.buf[1];
-        CK(cudaMemcpyAsync(d.buf[0], boards + lo, cnt * sizeof(sq_board), cudaMemcpyHostToDevice, d.stream));
-        rc = launch_classify(d, (const sq_board*)d.buf[0], cnt, dout, (int8_t*)dout + cnt, (int8_t*)dout + 2 * cnt, d.stream);
+        if ((rc = reserve(c, 0, cnt * sizeof(sq_board)))) return rc;
+        if ((rc = reserve(c, 1, cnt * 3))) return rc;
+        uint8_t* dout = (uint8_t*)c.buf[1];
+        CK(cudaMemcpyAsync(c.buf[0], boards + lo, cnt * sizeof(sq_board), cudaMemcpyHostToDevice, c.stream));
+        rc = launch_classify(d, (const sq_board*)c.buf[0], cnt, dout, (int8_t*)dout + cnt, (int8_t*)dout + 2 * cnt, c.stream);
         if (rc) return rc;
     }
     // second sweep: a device-to-host copy into pageable memory waits for its stream, so all
     // devices are launched before the first result is collected
     for (int k = 0; k < m; k++) {
-        Device& d = g_dev[k];
+        Device& d = *g_dev[k];
         int64_t lo, hi; share(n, m, k, lo, hi);
         int64_t cnt = hi - lo;
         if (cnt <= 0) continue;
+        Ctx& c = *held[k];
         CK(cudaSetDevice(d.id));
         if (cnt <= kSmallLeaves) {
-            CK(cudaStreamSynchronize(d.stream));
-            const uint8_t* h = d.pin + (size_t)kSmallLeaves * 9;
+            CK(cudaStreamSynchronize(c.stream));
+            const uint8_t* h = c.pin + (size_t)kSmallLeaves * 9;
             if (flags) memcpy(flags + lo, h, cnt);
             if (wm) memcpy(wm + lo, h + cnt, cnt);
             if (wa) memcpy(wa + lo, h + 2 * cnt, cnt);
             continue;
         }
-        uint8_t* dout = (uint8_t*)d.buf[1];
-        if (flags) CK(cudaMemcpyAsync(flags + lo, dout, cnt, cudaMemcpyDeviceToHost, d.stream));
-        if (wm) CK(cudaMemcpyAsync(wm + lo, dout + cnt, cnt, cudaMemcpyDeviceToHost, d.stream));
-        if (wa) CK(cudaMemcpyAsync(wa + lo, dout + 2 * cnt, cnt, cudaMemcpyDeviceToHost, d.stream));
+        uint8_t* dout = (uint8_t*)c.buf[1];
+        if (flags) CK(cudaMemcpyAsync(flags + lo, dout, cnt, cudaMemcpyDeviceToHost, c.stream));
+        if (wm) CK(cudaMemcpyAsync(wm + lo, dout + cnt, cnt, cudaMemcpyDeviceToHost, c.stream));
+        if (wa) CK(cudaMemcpyAsync(wa + lo, dout + 2 * cnt, cnt, cudaMemcpyDeviceToHost, c.stream));
     }
-    for (int k = 0; k < m; k++) { CK(cudaSetDevice(g_dev[k].id)); CK(cudaStreamSynchronize(g_dev[k].stream)); }
+    for (int k = 0; k < m; k++)
+        if (held[k].c) { CK(cudaSetDevice(g_dev[k]->id)); CK(cudaStreamSynchronize(held[k]->stream)); }
+    return SQ_OK;
+}
+
+// shared body of sq_playouts (out: u64[n][4]) and sq_playouts_packed (packed: u8[n], one playout per leaf)
+static int playouts_host(const char* who, const sq_board* leaves, const int8_t* to_move, int64_t n_leaves,
+                         uint64_t per_leaf, uint64_t stream_id, uint64_t (*out)[4], uint8_t* packed) {
+    std::shared_lock<std::shared_mutex> sl(g_state);
+    int rc = check_ready();
+    if (rc) return rc;
+    if (n_leaves < 0 || (n_leaves > 0 && (!leaves || !to_move || (!out && !packed)))) {
+        snprintf(t_err, sizeof t_err, "%s: null pointer", who); return SQ_ERR_INVALID;
+    }
+    for (int64_t i = 0; i < n_leaves; i++) {
+        if (bad_board(leaves[i]) || (to_move[i] != 1 && to_move[i] != -1)) {
+            snprintf(t_err, sizeof t_err, "%s: leaf %lld is not a board / to_move not +-1", who, (long long)i);
+            return SQ_ERR_INVALID;
+        }
+    }
+    const size_t res_bytes = packed ? 1 : 32;           // per leaf, device -> host
+    int m = (int)g_dev.size();
+    std::vector<CtxHold> held((size_t)m);
+    for (int k = 0; k < m; k++) {
+        Device& d = *g_dev[k];
+        int64_t lo, hi; share(n_leaves, m, k, lo, hi);
+        int64_t cnt = hi - lo;
+        if (cnt <= 0) continue;
+        held[k] = acquire(d);
+        Ctx& c = *held[k];
+        const int ci = (int)(held[k].c - d.ctx);
+        CK(cudaSetDevice(d.id));
+        if (cnt <= kSmallLeaves) {
+            // small call: pinned staging, one copy in, one memset, one copy out
+            uint8_t* hin = c.pin;                              // [boards | to_move]
+            memcpy(hin, leaves + lo, cnt * sizeof(sq_board));
+            memcpy(hin + cnt * sizeof(sq_board), to_move + lo, cnt);
+            unsigned long long* dcounter = (unsigned long long*)c.small;
+            uint8_t* dres = c.small + 16;
+            uint8_t* din = c.small + 16 + (size_t)cnt * 32;
+            CK(cudaMemcpyAsync(din, hin, cnt * 9, cudaMemcpyHostToDevice, c.stream));
+            CK(cudaMemsetAsync(c.small, 0, 16 + (size_t)cnt * res_bytes, c.stream));
+            rc = launch_playouts(d, c, ci, (const sq_board*)din, (const int8_t*)(din + cnt * sizeof(sq_board)), cnt, (uint64_t)lo,
+                                 per_leaf, stream_id, packed ? nullptr : (uint64_t*)dres, c.stream, dcounter, packed ? dres : nullptr);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(c.pin + (size_t)kSmallLeaves * 9, dres, cnt * res_bytes, cudaMemcpyDeviceToHost, c.stream));
+            continue;
+        }
+        if ((rc = reserve(c, 0, cnt * sizeof(sq_board)))) return rc;
+        if ((rc = reserve(c, 1, cnt))) return rc;
+        if ((rc = reserve(c, 2, cnt * res_bytes))) return rc;
+        CK(cudaMemcpyAsync(c.buf[0], leaves + lo, cnt * sizeof(sq_board), cudaMemcpyHostToDevice, c.stream));
+        CK(cudaMemcpyAsync(c.buf[1], to_move + lo, cnt, cudaMemcpyHostToDevice, c.stream));
+        if (packed) CK(cudaMemsetAsync(c.buf[2], 0, cnt, c.stream));
+        rc = launch_playouts(d, c, ci, (const sq_board*)c.buf[0], (const int8_t*)c.buf[1], cnt, (uint64_t)lo,
+                             per_leaf, stream_id, packed ? nullptr : (uint64_t*)c.buf[2], c.stream, nullptr,
+                             packed ? (uint8_t*)c.buf[2] : nullptr);
+        if (rc) return rc;
+    }
+    for (int k = 0; k < m; k++) {      // collect after every device has been launched
+        Device& d = *g_dev[k];
+        int64_t lo, hi; share(n_leaves, m, k, lo, hi);
+        int64_t cnt = hi - lo;
+        if (cnt <= 0) continue;
+        Ctx& c = *held[k];
+        uint8_t* dst = packed ? packed + lo : (uint8_t*)(out + lo);
+        CK(cudaSetDevice(d.id));
+        if (cnt <= kSmallLeaves) {
+            CK(cudaStreamSynchronize(c.stream));
+            memcpy(dst, c.pin + (size_t)kSmallLeaves * 9, cnt * res_bytes);
+            continue;
+        }
+        CK(cudaMemcpyAsync(dst, c.buf[2], cnt * res_bytes, cudaMemcpyDeviceToHost, c.stream));
+    }
+    for (int k = 0; k < m; k++)
+        if (held[k].c) { CK(cudaSetDevice(g_dev[k]->id)); CK(cudaStreamSynchronize(held[k]->stream)); }
     return SQ_OK;
 }
 
 int sq_playouts(const sq_board* leaves, const int8_t* to_move, int64_t n_leaves,
                 uint64_t per_leaf, uint64_t stream_id, uint64_t (*out)[4]) {
-    int rc = check_ready();
-    if (rc) return rc;
-    if (n_leaves < 0 || (n_leaves > 0 && (!leaves || !to_move || !out))) {
-        snprintf(t_err, sizeof t_err, "sq_playouts: null pointer"); return SQ_ERR_INVALID;
-    }
-    for (int64_t i = 0; i < n_leaves; i++) {
-        if ((leaves[i].x & leaves[i].o) || ((leaves[i].x | leaves[i].o) >> 25) ||
-            (to_move[i] != 1 && to_move[i] != -1)) {
-            snprintf(t_err, sizeof t_err, "sq_playouts: leaf %lld is not a board / to_move not +-1", (long long)i);
-            return SQ_ERR_INVALID;
-        }
-    }
-    std::lock_guard<std::mutex> lk(g_mu);
-    int m = (int)g_dev.size();
-    for (int k = 0; k < m; k++) {
-        Device& d = g_dev[k];
-        int64_t lo, hi; share(n_leaves, m, k, lo, hi);
-        int64_t cnt = hi - lo;
-        if (cnt <= 0) continue;
-        CK(cudaSetDevice(d.id));
-        if (cnt <= kSmallLeaves) {
-            // small call: pinned staging, one copy in, one memset, one copy out
-            uint8_t* hin = d.pin;                              // [boards | to_move]
-            memcpy(hin, leaves + lo, cnt * sizeof(sq_board));
-            memcpy(hin + cnt * sizeof(sq_board), to_move + lo, cnt);
-            unsigned long long* dcounter = (unsigned long long*)d.small;
-            uint64_t* dout = (uint64_t*)(d.small + 16);
-            uint8_t* din = d.small + 16 + (size_t)cnt * 32;
-            CK(cudaMemcpyAsync(din, hin, cnt * 9, cudaMemcpyHostToDevice, d.stream));
-            CK(cudaMemsetAsync(d.small, 0, 16 + (size_t)cnt * 32, d.stream));
-            rc = launch_playouts(d, (const sq_board*)din, (const int8_t*)(din + cnt * sizeof(sq_board)), cnt, (uint64_t)lo,
-                                 per_leaf, stream_id, dout, d.stream, dcounter);
-            if (rc) return rc;
-            CK(cudaMemcpyAsync(d.pin + (size_t)kSmallLeaves * 9, dout, cnt * 32, cudaMemcpyDeviceToHost, d.stream));
-            continue;
-        }
-        if ((rc = reserve(d, 0, cnt * sizeof(sq_board)))) return rc;
-        if ((rc = reserve(d, 1, cnt))) return rc;
-        if ((rc = reserve(d, 2, cnt * 4 * sizeof(uint64_t)))) return rc;
-        CK(cudaMemcpyAsync(d.buf[0], leaves + lo, cnt * sizeof(sq_board), cudaMemcpyHostToDevice, d.stream));
-        CK(cudaMemcpyAsync(d.buf[1], to_move + lo, cnt, cudaMemcpyHostToDevice, d.stream));
-        rc = launch_playouts(d, (const sq_board*)d.buf[0], (const int8_t*)d.buf[1], cnt, (uint64_t)lo,
-                             per_leaf, stream_id, (uint64_t*)d.buf[2], d.stream);
-        if (rc) return rc;
-    }
-    for (int k = 0; k < m; k++) {      // collect after every device has been launched
-        Device& d = g_dev[k];
-        int64_t lo, hi; share(n_leaves, m, k, lo, hi);
-        int64_t cnt = hi - lo;
-        if (cnt <= 0) continue;
-        CK(cudaSetDevice(d.id));
-        if (cnt <= kSmallLeaves) {
-            CK(cudaStreamSynchronize(d.stream));
-            memcpy(out + lo, d.pin + (size_t)kSmallLeaves * 9, cnt * 32);
-            continue;
-        }
-        CK(cudaMemcpyAsync(out + lo, d.buf[2], cnt * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.stream));
-    }
-    for (int k = 0; k < m; k++) { CK(cudaSetDevice(g_dev[k].id)); CK(cudaStreamSynchronize(g_dev[k].stream)); }
-    return SQ_OK;
+    if (n_leaves > 0 && !out) { snprintf(t_err, sizeof t_err, "sq_playouts: null pointer"); return SQ_ERR_INVALID; }
+    return playouts_host("sq_playouts", leaves, to_move, n_leaves, per_leaf, stream_id, out, nullptr);
+}
+
+int sq_playouts_packed(const sq_board* leaves, const int8_t* to_move, int64_t n_leaves,
+                       uint64_t stream_id, uint8_t* outcome) {
+    if (n_leaves > 0 && !outcome) { snprintf(t_err, sizeof t_err, "sq_playouts_packed: null pointer"); return SQ_ERR_INVALID; }
+    return playouts_host("sq_playouts_packed", leaves, to_move, n_leaves, 1, stream_id, nullptr, outcome);
 }
 
 int sq_alphabeta_root(const sq_board* positions, int64_t n, int dialect, int max_depth,
                       const int8_t scores[25], int32_t (*values)[25], int32_t* best_value,
                       uint32_t* best_mask, uint64_t* nodes) {
+    std::shared_lock<std::shared_mutex> sl(g_state);
     int rc = check_ready();
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!positions || !values)) || !scores) {
@@ -437,32 +538,32 @@ int sq_alphabeta_root(const sq_board* positions, int64_t n, int dialect, int max
     }
     if (max_depth < 0 || max_depth > sq::kAbMaxDepth) { snprintf(t_err, sizeof t_err, "max_depth out of range [0,%d]", sq::kAbMaxDepth); return SQ_ERR_INVALID; }
     for (int64_t i = 0; i < n; i++)
-        if ((positions[i].x & positions[i].o) || ((positions[i].x | positions[i].o) >> 25)) {
+        if (bad_board(positions[i])) {
             snprintf(t_err, sizeof t_err, "sq_alphabeta_root: position %lld is not a board", (long long)i);
             return SQ_ERR_INVALID;
         }
-    std::lock_guard<std::mutex> lk(g_mu);
     const int m = (int)g_dev.size();
     rc = for_each_device(m, [&](int k) -> int {
-        Device& d = g_dev[k];
+        Device& d = *g_dev[k];
         int64_t lo, hi; share(n, m, k, lo, hi);
         int64_t cnt = hi - lo;
         if (cnt <= 0) return SQ_OK;
         int r;
+        CtxHold c = acquire(d);
         CK(cudaSetDevice(d.id));
-        if ((r = reserve(d, 0, cnt * sizeof(sq_board)))) return r;
-        if ((r = reserve(d, 2, cnt * 25 * sizeof(int32_t)))) return r;
-        if ((r = reserve(d, 3, cnt * sizeof(unsigned long long)))) return r;
-        CK(cudaMemcpyAsync(d.buf[0], positions + lo, cnt * sizeof(sq_board), cudaMemcpyHostToDevice, d.stream));
+        if ((r = reserve(*c, 0, cnt * sizeof(sq_board)))) return r;
+        if ((r = reserve(*c, 2, cnt * 25 * sizeof(int32_t)))) return r;
+        if ((r = reserve(*c, 3, cnt * sizeof(unsigned long long)))) return r;
+        CK(cudaMemcpyAsync(c->buf[0], positions + lo, cnt * sizeof(sq_board), cudaMemcpyHostToDevice, c->stream));
         uint64_t launches = 0;
-        cudaError_t e = sq::ab_root_search(positions + lo, (const sq_board*)d.buf[0], cnt, dialect, max_depth, scores,
-                                           (int32_t*)d.buf[2], (unsigned long long*)d.buf[3],
-                                           d.sm_count * d.ab_blocks_per_sm, d.stream, &launches);
+        cudaError_t e = sq::ab_root_search(positions + lo, (const sq_board*)c->buf[0], cnt, dialect, max_depth, scores,
+                                           (int32_t*)c->buf[2], (unsigned long long*)c->buf[3],
+                                           d.sm_count * d.ab_blocks_per_sm, c->stream, &launches);
         g_launches += launches;
         if (e != cudaSuccess) return fail_cuda(e, "ab_root_search");
-        CK(cudaMemcpyAsync(values + lo, d.buf[2], cnt * 25 * sizeof(int32_t), cudaMemcpyDeviceToHost, d.stream));
-        if (nodes) CK(cudaMemcpyAsync(nodes + lo, d.buf[3], cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.stream));
-        CK(cudaStreamSynchronize(d.stream));
+        CK(cudaMemcpyAsync(values + lo, c->buf[2], cnt * 25 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        if (nodes) CK(cudaMemcpyAsync(nodes + lo, c->buf[3], cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
         return SQ_OK;
     });
     if (rc) return rc;
@@ -483,6 +584,7 @@ int sq_alphabeta_root(const sq_board* positions, int64_t n, int dialect, int max
 int sq_negascout_root(const sq_board* positions, int64_t n, int max_depth, const int8_t scores[25],
                       int32_t (*values)[25], int8_t (*visit_order)[25], int32_t* best_value,
                       uint32_t* best_mask, int8_t* first_best, uint64_t* nodes) {
+    std::shared_lock<std::shared_mutex> sl(g_state);
     int rc = check_ready();
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!positions || !values)) || !scores) {
@@ -490,29 +592,29 @@ int sq_negascout_root(const sq_board* positions, int64_t n, int max_depth, const
     }
     if (max_depth < 0 || max_depth > sq::kNsMaxDepth) { snprintf(t_err, sizeof t_err, "max_depth out of range [0,%d]", sq::kNsMaxDepth); return SQ_ERR_INVALID; }
     for (int64_t i = 0; i < n; i++)
-        if ((positions[i].x & positions[i].o) || ((positions[i].x | positions[i].o) >> 25)) {
+        if (bad_board(positions[i])) {
             snprintf(t_err, sizeof t_err, "sq_negascout_root: position %lld is not a board", (long long)i);
             return SQ_ERR_INVALID;
         }
     sq::NsScores sc;
     memcpy(sc.s, scores, 25);
-    std::lock_guard<std::mutex> lk(g_mu);
     const int m = (int)g_dev.size();
     return for_each_device(m, [&](int k) -> int {
-        Device& d = g_dev[k];
+        Device& d = *g_dev[k];
         int64_t lo, hi; share(n, m, k, lo, hi);
         const int64_t cnt = hi - lo;
         if (cnt <= 0) return SQ_OK;
         int r;
+        CtxHold c = acquire(d);
         CK(cudaSetDevice(d.id));
         // one device block: [queue | nodes | values | best_value | best_mask | visit_order | first_best]
         const size_t o_nodes = 16, o_values = o_nodes + 8 * cnt, o_bv = o_values + 100 * cnt, o_bm = o_bv + 4 * cnt,
                      o_visit = o_bm + 4 * cnt, o_first = o_visit + 25 * cnt, total = o_first + cnt;
-        if ((r = reserve(d, 0, cnt * sizeof(sq_board)))) return r;
-        if ((r = reserve(d, 4, total))) return r;
-        uint8_t* blk = (uint8_t*)d.buf[4];
-        CK(cudaMemcpyAsync(d.buf[0], positions + lo, cnt * sizeof(sq_board), cudaMemcpyHostToDevice, d.stream));
-        CK(cudaMemsetAsync(blk, 0, 16, d.stream));
+        if ((r = reserve(*c, 0, cnt * sizeof(sq_board)))) return r;
+        if ((r = reserve(*c, 4, total))) return r;
+        uint8_t* blk = (uint8_t*)c->buf[4];
+        CK(cudaMemcpyAsync(c->buf[0], positions + lo, cnt * sizeof(sq_board), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync(blk, 0, 16, c->stream));
         sq::NsOut out;
         out.nodes = (unsigned long long*)(blk + o_nodes);
         out.values = (int32_t(*)[25])(blk + o_values);
@@ -536,25 +638,25 @@ int sq_negascout_root(const sq_board* positions, int64_t n, int max_depth, const
         std::stable_sort(order.begin(), order.begin() + n_fast, [&](int a, int b) {
             return __builtin_popcount(positions[lo + a].x | positions[lo + a].o) < __builtin_popcount(positions[lo + b].x | positions[lo + b].o);
         });
-        if ((r = reserve(d, 5, cnt * sizeof(int)))) return r;
-        CK(cudaMemcpyAsync(d.buf[5], order.data(), cnt * sizeof(int), cudaMemcpyHostToDevice, d.stream));
+        if ((r = reserve(*c, 5, cnt * sizeof(int)))) return r;
+        CK(cudaMemcpyAsync(c->buf[5], order.data(), cnt * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         const int64_t cap = (int64_t)d.sm_count * 6;
         auto grid = [&](int64_t units) { int64_t want = (units + sq::kNsWarps - 1) / sq::kNsWarps; return (int)(want < cap ? want : cap); };
         if (n_fast) {
-            sq::negascout_fast_kernel<<<grid(n_fast), sq::kNsWarps * 32, 0, d.stream>>>(
-                (const sq_board*)d.buf[0], (const int*)d.buf[5], (int)n_fast, max_depth, sc, out, (unsigned int*)blk);
+            sq::negascout_fast_kernel<<<grid(n_fast), sq::kNsWarps * 32, 0, c->stream>>>(
+                (const sq_board*)c->buf[0], (const int*)c->buf[5], (int)n_fast, max_depth, sc, out, (unsigned int*)blk);
             g_launches += 1;
             CK(cudaGetLastError());
         }
         if (n_slow) {
-            sq::negascout_kernel<<<grid(n_slow), sq::kNsWarps * 32, 0, d.stream>>>(
-                (const sq_board*)d.buf[0], (const int*)d.buf[5] + n_fast, (int)n_slow, max_depth, sc, out, (unsigned int*)blk + 1);
+            sq::negascout_kernel<<<grid(n_slow), sq::kNsWarps * 32, 0, c->stream>>>(
+                (const sq_board*)c->buf[0], (const int*)c->buf[5] + n_fast, (int)n_slow, max_depth, sc, out, (unsigned int*)blk + 1);
             g_launches += 1;
             CK(cudaGetLastError());
         }
         std::vector<uint8_t> h(total);
-        CK(cudaMemcpyAsync(h.data(), blk, total, cudaMemcpyDeviceToHost, d.stream));
-        CK(cudaStreamSynchronize(d.stream));
+        CK(cudaMemcpyAsync(h.data(), blk, total, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
         memcpy(values + lo, h.data() + o_values, 100 * cnt);
         if (nodes) memcpy(nodes + lo, h.data() + o_nodes, 8 * cnt);
         if (best_value) memcpy(best_value + lo, h.data() + o_bv, 4 * cnt);
@@ -567,6 +669,7 @@ int sq_negascout_root(const sq_board* positions, int64_t n, int max_depth, const
 
 int sq_alphabeta_subtrees(const sq_subtree* subtrees, int64_t n, int dialect, int max_depth,
                           const int8_t scores[25], int32_t* value, uint64_t* nodes) {
+    std::shared_lock<std::shared_mutex> sl(g_state);
     int rc = check_ready();
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!subtrees || !value)) || !scores) {
@@ -581,99 +684,133 @@ int sq_alphabeta_subtrees(const sq_subtree* subtrees, int64_t n, int dialect, in
             snprintf(t_err, sizeof t_err, "sq_alphabeta_subtrees: subtree %lld: |carried| > 15000", (long long)i);
             return SQ_ERR_UNSUPPORTED;
         }
-        bool ok = !(s.b.x & s.b.o) && !((s.b.x | s.b.o) >> 25) && s.last_cell >= 0 && s.last_cell < 25 &&
+        bool ok = !bad_board(s.b) && s.last_cell >= 0 && s.last_cell < 25 &&
                   (((s.b.x | s.b.o) >> s.last_cell) & 1u) && (s.side_to_move == 1 || s.side_to_move == -1) &&
                   s.ply >= 0 && s.ply <= max_depth;
         if (!ok) { snprintf(t_err, sizeof t_err, "sq_alphabeta_subtrees: subtree %lld malformed", (long long)i); return SQ_ERR_INVALID; }
     }
-    std::lock_guard<std::mutex> lk(g_mu);
+    // Several devices: the subtrees are dealt out by estimated size (a deeper remaining search and more
+    // empty cells first, largest to the least loaded device), not by index -- opening3's 85 subtrees differ by
+    // orders of magnitude.  One device: the caller's order.
     const int m = (int)g_dev.size();
+    std::vector<std::vector<int64_t>> mine((size_t)m);
+    if (m == 1) { mine[0].resize((size_t)n); for (int64_t i = 0; i < n; i++) mine[0][(size_t)i] = i; }
+    else {
+        std::vector<int64_t> idx((size_t)n);
+        std::vector<double> est((size_t)n), load((size_t)m, 0.0);
+        for (int64_t i = 0; i < n; i++) {
+            idx[(size_t)i] = i;
+            const int empt = 25 - __builtin_popcount(subtrees[i].b.x | subtrees[i].b.o);
+            const int rem = std::min(max_depth - subtrees[i].ply, empt);
+            double e = 1; for (int k = 0; k < rem; k++) e *= 0.45 * (empt - k) + 1;      // rough: pruning leaves ~ half the children
+            est[(size_t)i] = e;
+        }
+        std::stable_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return est[(size_t)a] > est[(size_t)b]; });
+        for (int64_t i : idx) {
+            int best = 0;
+            for (int k = 1; k < m; k++) if (load[(size_t)k] < load[(size_t)best]) best = k;
+            mine[(size_t)best].push_back(i); load[(size_t)best] += est[(size_t)i];
+        }
+    }
     return for_each_device(m, [&](int k) -> int {
-        Device& d = g_dev[k];
-        int64_t lo, hi; share(n, m, k, lo, hi);
-        int64_t cnt = hi - lo;
+        Device& d = *g_dev[k];
+        const std::vector<int64_t>& ix = mine[(size_t)k];
+        const int64_t cnt = (int64_t)ix.size();
         if (cnt <= 0) return SQ_OK;
         int r;
+        std::vector<sq_subtree> st((size_t)cnt);
+        for (int64_t q = 0; q < cnt; q++) st[(size_t)q] = subtrees[ix[(size_t)q]];
+        CtxHold c = acquire(d);
         CK(cudaSetDevice(d.id));
-        if ((r = reserve(d, 0, cnt * sizeof(sq_subtree)))) return r;
-        if ((r = reserve(d, 2, cnt * sizeof(int32_t)))) return r;
-        if ((r = reserve(d, 3, cnt * sizeof(unsigned long long)))) return r;
-        CK(cudaMemcpyAsync(d.buf[0], subtrees + lo, cnt * sizeof(sq_subtree), cudaMemcpyHostToDevice, d.stream));
+        if ((r = reserve(*c, 0, cnt * sizeof(sq_subtree)))) return r;
+        if ((r = reserve(*c, 2, cnt * sizeof(int32_t)))) return r;
+        if ((r = reserve(*c, 3, cnt * sizeof(unsigned long long)))) return r;
+        CK(cudaMemcpyAsync(c->buf[0], st.data(), cnt * sizeof(sq_subtree), cudaMemcpyHostToDevice, c->stream));
         uint64_t launches = 0;
-        cudaError_t e = sq::ab_subtree_search(subtrees + lo, (const sq_subtree*)d.buf[0], cnt, dialect, max_depth, scores,
-                                              (int32_t*)d.buf[2], (unsigned long long*)d.buf[3],
-                                              d.sm_count * d.ab_blocks_per_sm, d.stream, &launches);
+        cudaError_t e = sq::ab_subtree_search(st.data(), (const sq_subtree*)c->buf[0], cnt, dialect, max_depth, scores,
+                                              (int32_t*)c->buf[2], (unsigned long long*)c->buf[3],
+                                              d.sm_count * d.ab_blocks_per_sm, c->stream, &launches);
         g_launches += launches;
         if (e != cudaSuccess) return fail_cuda(e, "ab_subtree_search");
-        CK(cudaMemcpyAsync(value + lo, d.buf[2], cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, d.stream));
-        if (nodes) CK(cudaMemcpyAsync(nodes + lo, d.buf[3], cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, d.stream));
-        CK(cudaStreamSynchronize(d.stream));
+        std::vector<int32_t> hv((size_t)cnt); std::vector<uint64_t> hn((size_t)cnt);
+        CK(cudaMemcpyAsync(hv.data(), c->buf[2], cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(hn.data(), c->buf[3], cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int64_t q = 0; q < cnt; q++) { value[ix[(size_t)q]] = hv[(size_t)q]; if (nodes) nodes[ix[(size_t)q]] = hn[(size_t)q]; }
         return SQ_OK;
     });
 }
 
 // ---- measurement helpers -------------------------------------------------------
 int sq_int32_peak(int slot, int kind, int reps, double* ops_per_s) {
+    std::shared_lock<std::shared_mutex> sl(g_state);
     int rc = check_slot(slot);
     if (rc) return rc;
     if (!ops_per_s || kind < 0 || kind > 2) return SQ_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(g_mu);
-    Device& d = g_dev[slot];
+    Device& d = *g_dev[slot];
+    CtxHold c = acquire(d);
     CK(cudaSetDevice(d.id));
-    if ((rc = reserve(d, 4, 256))) return rc;
+    if ((rc = reserve(*c, 4, 256))) return rc;
     const int iters = 4096, threads = 1024;
     const int blocks = d.sm_count * 2;
     double best = 0;
     if (reps < 1) reps = 1;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (int r = 0; r < reps + 1; r++) {
-        CK(cudaEventRecord(d.ev0, d.stream));
-        uint32_t* o = (uint32_t*)d.buf[4];
-        if (kind == 0) sq::int32_peak_kernel<0><<<blocks, threads, 0, d.stream>>>(o, 12345u + r, iters);
-        else if (kind == 1) sq::int32_peak_kernel<1><<<blocks, threads, 0, d.stream>>>(o, 12345u + r, iters);
-        else sq::int32_peak_kernel<2><<<blocks, threads, 0, d.stream>>>(o, 12345u + r, iters);
+        CK(cudaEventRecord(e0, c->stream));
+        uint32_t* o = (uint32_t*)c->buf[4];
+        if (kind == 0) sq::int32_peak_kernel<0><<<blocks, threads, 0, c->stream>>>(o, 12345u + r, iters);
+        else if (kind == 1) sq::int32_peak_kernel<1><<<blocks, threads, 0, c->stream>>>(o, 12345u + r, iters);
+        else sq::int32_peak_kernel<2><<<blocks, threads, 0, c->stream>>>(o, 12345u + r, iters);
         g_launches++;
         CK(cudaGetLastError());
-        CK(cudaEventRecord(d.ev1, d.stream));
-        CK(cudaEventSynchronize(d.ev1));
+        CK(cudaEventRecord(e1, c->stream));
+        CK(cudaEventSynchronize(e1));
         float ms = 0;
-        CK(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
         double ops = (double)blocks * threads * (double)iters * 16.0 * 8.0;
         if (r > 0 && ms > 0 && ops / (ms * 1e-3) > best) best = ops / (ms * 1e-3);
     }
-    d.timed = false;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
     *ops_per_s = best;
     return SQ_OK;
 }
 
 int sq_last_playout_kernel_ms(int slot, float* ms) {
+    std::shared_lock<std::shared_mutex> sl(g_state);
     int rc = check_slot(slot);
     if (rc) return rc;
     if (!ms) return SQ_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(g_mu);
-    Device& d = g_dev[slot];
-    if (!d.timed) { snprintf(t_err, sizeof t_err, "no playout kernel has run on slot %d", slot); return SQ_ERR_INVALID; }
+    Device& d = *g_dev[slot];
+    const int ci = d.last_timed.load();
+    if (ci < 0) { snprintf(t_err, sizeof t_err, "no playout kernel has run on slot %d", slot); return SQ_ERR_INVALID; }
+    Ctx& c = d.ctx[ci];
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (!c.timed) { snprintf(t_err, sizeof t_err, "no playout kernel has run on slot %d", slot); return SQ_ERR_INVALID; }
     CK(cudaSetDevice(d.id));
-    CK(cudaEventSynchronize(d.ev1));
-    CK(cudaEventElapsedTime(ms, d.ev0, d.ev1));
+    CK(cudaEventSynchronize(c.ev1));
+    CK(cudaEventElapsedTime(ms, c.ev0, c.ev1));
     return SQ_OK;
 }
 
 int sq_debug_philox(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]) {
+    std::shared_lock<std::shared_mutex> sl(g_state);
     int rc = check_ready();
     if (rc) return rc;
     if (!counter || !key || !out) return SQ_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(g_mu);
-    Device& d = g_dev[0];
+    Device& d = *g_dev[0];
+    CtxHold c = acquire(d);
     CK(cudaSetDevice(d.id));
-    if ((rc = reserve(d, 4, 256))) return rc;
-    uint32_t* b = (uint32_t*)d.buf[4];
-    CK(cudaMemcpyAsync(b, counter, 16, cudaMemcpyHostToDevice, d.stream));
-    CK(cudaMemcpyAsync(b + 4, key, 8, cudaMemcpyHostToDevice, d.stream));
-    sq::philox_debug_kernel<<<1, 1, 0, d.stream>>>(b, b + 4, b + 8);
+    if ((rc = reserve(*c, 4, 256))) return rc;
+    uint32_t* b = (uint32_t*)c->buf[4];
+    CK(cudaMemcpyAsync(b, counter, 16, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(b + 4, key, 8, cudaMemcpyHostToDevice, c->stream));
+    sq::philox_debug_kernel<<<1, 1, 0, c->stream>>>(b, b + 4, b + 8);
     g_launches++;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out, b + 8, 16, cudaMemcpyDeviceToHost, d.stream));
-    CK(cudaStreamSynchronize(d.stream));
+    CK(cudaMemcpyAsync(out, b + 8, 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return SQ_OK;
 }
 

@@ -108,7 +108,7 @@ struct AbRun {
     int* pending;                    // unfinished children
     int* units;                      // indices of DFS units
     int* aborted;                    // units that ran out of budget in this pass: split one ply deeper
-    unsigned int* counters;          // [0] n_nodes [1] n_units [2] queue head [3] n_aborted
+    unsigned int* counters;          // [0] n_nodes [1] n_units [2] queue head [3] n_aborted [4] node pool overflowed
     int* out;                        // final values
     unsigned long long* node_count;  // evaluator calls per group
     int node_capacity;
@@ -215,7 +215,10 @@ __device__ __forceinline__ void ab_bounds(const AbRun& R, int node, int& alpha, 
 
 __device__ __forceinline__ int ab_new_node(const AbRun& R, const AbNode& n) {
     unsigned int idx = atomicAdd(&R.counters[0], 1u);
-    if (idx >= (unsigned)R.node_capacity) return -1;  // cannot happen: the host checks the room before every expansion
+    if (idx >= (unsigned)R.node_capacity) {           // the host checks the room before every expansion; if its sizing is
+        atomicExch(&R.counters[4], 1u);               // ever wrong the run is failed (SQ_ERR_NOMEM), never silently short
+        return -1;
+    }
     R.nodes[idx] = n;
     R.value[idx] = n.side > 0 ? -R.sentinel : R.sentinel;
     R.pending[idx] = 0;
@@ -505,8 +508,11 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
             const AbNode n = R.nodes[unit];
             int a0 = R.win_lo, b0 = R.win_hi;
             ab_bounds(R, unit, a0, b0);
-            if (a0 >= b0) {           // already cut off: hand up a value that changes nothing
-                ab_complete(R, unit, n.side > 0 ? -30000 : 30000);
+            if (a0 >= b0) {
+                // Already cut off by its ancestors' slots (or by a root-window edge: a MIN ancestor at -20000).
+                // It hands up a value its parent's atomicMin/Max ignores -- the parent is the other kind of
+                // node -- so the unit contributes nothing, as if the sequential search had never reached it.
+                ab_complete(R, unit, n.side > 0 ? 30000 : -30000);
                 continue;
             }
             int v0 = 0, carried_down = 0;
@@ -712,20 +718,49 @@ inline void ab_free(AbWork& w, cudaStream_t st) {
 
 #define SQ_AB_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ab_free(w, st); return e_; } } while (0)
 
+// Node pool: starts at what the level-0 nodes need (at least kAbPoolStart slots) and doubles on demand up to
+// the ceiling (ab_pool_nodes()); the arrays move, the node indices stay valid.
+inline cudaError_t ab_alloc(AbWork& w, long long capacity, cudaStream_t st) {
+    cudaError_t e;
+    if ((e = cudaMallocAsync(&w.nodes, sizeof(AbNode) * capacity, st)) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(&w.value, sizeof(int) * capacity, st)) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(&w.pending, sizeof(int) * capacity, st)) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(&w.units, sizeof(int) * capacity, st)) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(&w.aborted, sizeof(int) * capacity, st)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+inline cudaError_t ab_grow(AbWork& w, long long used, int n_aborted, long long new_capacity, cudaStream_t st) {
+    AbWork g;
+    cudaError_t e = ab_alloc(g, new_capacity, st);
+    if (e != cudaSuccess) { ab_free(g, st); return e; }
+    cudaMemcpyAsync(g.nodes, w.nodes, sizeof(AbNode) * used, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(g.value, w.value, sizeof(int) * used, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(g.pending, w.pending, sizeof(int) * used, cudaMemcpyDeviceToDevice, st);
+    e = cudaMemcpyAsync(g.aborted, w.aborted, sizeof(int) * n_aborted, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { ab_free(g, st); return e; }
+    g.counters = w.counters; g.split = w.split;
+    w.counters = nullptr; w.split = nullptr;
+    ab_free(w, st);
+    w = g;
+    return cudaSuccess;
+}
+
+constexpr long long kAbPoolStart = 1ll << 20;
+
 template <int DIALECT>
 cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n, const int8_t* h_split,
-                         long long capacity, int grid_cap, int min_ply, cudaStream_t st, uint64_t* launches) {
-    SQ_AB_CK(cudaMallocAsync(&w.nodes, sizeof(AbNode) * capacity, st));
-    SQ_AB_CK(cudaMallocAsync(&w.value, sizeof(int) * capacity, st));
-    SQ_AB_CK(cudaMallocAsync(&w.pending, sizeof(int) * capacity, st));
-    SQ_AB_CK(cudaMallocAsync(&w.units, sizeof(int) * capacity, st));
-    SQ_AB_CK(cudaMallocAsync(&w.aborted, sizeof(int) * capacity, st));
+                         long long capacity, long long ceiling, int grid_cap, int min_ply, cudaStream_t st, uint64_t* launches) {
+    SQ_AB_CK(ab_alloc(w, capacity, st));
     SQ_AB_CK(cudaMallocAsync(&w.counters, sizeof(unsigned int) * 8, st));
     SQ_AB_CK(cudaMallocAsync(&w.split, n, st));
     SQ_AB_CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned int) * 8, st));
     SQ_AB_CK(cudaMemcpyAsync(w.split, h_split, n, cudaMemcpyHostToDevice, st));
-    R.nodes = w.nodes; R.value = w.value; R.pending = w.pending; R.units = w.units; R.aborted = w.aborted;
-    R.counters = w.counters; R.node_capacity = (int)capacity;
+    auto bind = [&] {
+        R.nodes = w.nodes; R.value = w.value; R.pending = w.pending; R.units = w.units; R.aborted = w.aborted;
+        R.counters = w.counters; R.node_capacity = (int)capacity;
+    };
+    bind();
     if (roots) {
         int threads = n * 25;
         ab_roots_kernel<DIALECT><<<(threads + kAbThreads - 1) / kAbThreads, kAbThreads, 0, st>>>(
@@ -736,7 +771,7 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
     }
     (*launches)++;
     SQ_AB_CK(cudaGetLastError());
-    unsigned int h_counters[4] = {0, 0, 0, 0};
+    unsigned int h_counters[5] = {0, 0, 0, 0, 0};
     int lo = 0;
     for (int level = 0; level < 3; level++) {        // static pre-split (usually none)
         SQ_AB_CK(cudaMemcpyAsync(h_counters, w.counters, sizeof h_counters, cudaMemcpyDeviceToHost, st));
@@ -766,6 +801,7 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
     for (int pass = 0;; pass++) {
         SQ_AB_CK(cudaMemcpyAsync(h_counters, w.counters, sizeof h_counters, cudaMemcpyDeviceToHost, st));
         SQ_AB_CK(cudaStreamSynchronize(st));
+        if (h_counters[4]) { ab_free(w, st); return cudaErrorMemoryAllocation; }     // a node did not fit: never a silent short tree
         const int n_units = (int)h_counters[1];
         if (n_units == 0) break;
         // few units: split early (most lanes are idle anyway); many: let lanes run longer
@@ -788,7 +824,15 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
         if (n_aborted == 0) break;
         const unsigned int zero3[3] = {0, 0, 0};
         SQ_AB_CK(cudaMemcpyAsync(w.counters + 1, zero3, sizeof zero3, cudaMemcpyHostToDevice, st));
-        if ((long long)h_counters[0] + 25ll * n_aborted > capacity) {
+        const long long want = (long long)h_counters[0] + 25ll * n_aborted;
+        if (want > capacity && capacity < ceiling) {      // grow the pool: the arrays move, indices stay valid
+            long long bigger = capacity;
+            while (bigger < want && bigger < ceiling) bigger *= 2;
+            if (bigger > ceiling) bigger = ceiling;
+            if (ab_grow(w, (long long)h_counters[0], n_aborted, bigger, st) == cudaSuccess) { capacity = bigger; bind(); lap("grow", (int)(capacity >> 10), 0); }
+            else cudaGetLastError();                      // no memory for a bigger pool: carry on with what there is
+        }
+        if (want > capacity) {
             // no room to split further: finish the stragglers without a budget
             SQ_AB_CK(cudaMemcpyAsync(w.units, w.aborted, sizeof(int) * n_aborted, cudaMemcpyDeviceToDevice, st));
             const unsigned int nu = (unsigned)n_aborted;
@@ -805,15 +849,27 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
     return cudaSuccess;
 }
 
+constexpr long long kAbChunkNodesDefault = 64ll << 20;   // ceiling of node slots per chunk: level-0 nodes + what adaptive splitting may draw (~2.5 GB when all used)
+
+inline long long ab_pool_nodes() {      // SQ_AB_POOL_NODES shrinks the pool (tests of the no-room path)
+    const char* env = getenv("SQ_AB_POOL_NODES");
+    long long v = (env && *env) ? atoll(env) : kAbChunkNodesDefault;
+    return v < 4096 ? 4096 : v;
+}
+
 inline cudaError_t ab_dispatch(int dialect, AbRun R, AbWork& w, const void* d_in, bool roots, int n,
-                               const int8_t* h_split, long long capacity, int grid_cap, int min_ply,
+                               const int8_t* h_split, long long needed, int grid_cap, int min_ply,
                                cudaStream_t st, uint64_t* launches) {
+    // ceiling: SQ_AB_POOL_NODES (default 64 Mi slots, ~2.5 GB), never below what the level-0 nodes need;
+    // the run starts with max(needed, kAbPoolStart) slots and grows towards the ceiling only if it splits that far
+    const long long ceiling = std::max(needed + 16, ab_pool_nodes());
+    const long long capacity = std::min(ceiling, std::max(needed + 16, kAbPoolStart));
     switch (dialect) {
-    case 1: return ab_run_chunk<1>(R, w, d_in, roots, n, h_split, capacity, grid_cap, min_ply, st, launches);
-    case 2: return ab_run_chunk<2>(R, w, d_in, roots, n, h_split, capacity, grid_cap, min_ply, st, launches);
-    case 5: return ab_run_chunk<5>(R, w, d_in, roots, n, h_split, capacity, grid_cap, min_ply, st, launches);
-    case 6: return ab_run_chunk<6>(R, w, d_in, roots, n, h_split, capacity, grid_cap, min_ply, st, launches);
-    default: return ab_run_chunk<3>(R, w, d_in, roots, n, h_split, capacity, grid_cap, min_ply, st, launches);
+    case 1: return ab_run_chunk<1>(R, w, d_in, roots, n, h_split, capacity, ceiling, grid_cap, min_ply, st, launches);
+    case 2: return ab_run_chunk<2>(R, w, d_in, roots, n, h_split, capacity, ceiling, grid_cap, min_ply, st, launches);
+    case 5: return ab_run_chunk<5>(R, w, d_in, roots, n, h_split, capacity, ceiling, grid_cap, min_ply, st, launches);
+    case 6: return ab_run_chunk<6>(R, w, d_in, roots, n, h_split, capacity, ceiling, grid_cap, min_ply, st, launches);
+    default: return ab_run_chunk<3>(R, w, d_in, roots, n, h_split, capacity, ceiling, grid_cap, min_ply, st, launches);
     }
 }
 
@@ -835,14 +891,6 @@ inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t score
     const bool cumulative = dialect == 2 || dialect == 3 || dialect == 4 || dialect == 6;
     const long long worst = (cumulative ? (long long)(max_depth + 1) * per_eval : 2 * per_eval) + max_abs_carried;
     R.shortcuts = worst < kWin - max_depth - 1 && !getenv("SQ_AB_NO_SHORTCUTS");
-}
-
-constexpr long long kAbChunkNodesDefault = 64ll << 20;   // node slots per chunk: level-0 nodes + the pool adaptive splitting draws on (~2.5 GB)
-
-inline long long ab_pool_nodes() {      // SQ_AB_POOL_NODES shrinks the pool (tests of the no-room path)
-    const char* env = getenv("SQ_AB_POOL_NODES");
-    long long v = (env && *env) ? atoll(env) : kAbChunkNodesDefault;
-    return v < 4096 ? 4096 : v;
 }
 
 // worst-case node count below one level-0 node with e empties and `split` expanded plies
@@ -876,7 +924,7 @@ inline cudaError_t ab_root_search(const sq_board* h_pos, const sq_board* d_pos, 
         AbRun Rc = R;
         Rc.out = d_values + lo * 25;
         Rc.node_count = d_nodes + lo;
-        e = ab_dispatch(dialect, Rc, w, d_pos + lo, true, (int)(hi - lo), split.data() + lo, cap + 16 > kAbChunkNodes ? cap + 16 : kAbChunkNodes, grid_cap, 1, st, launches);
+        e = ab_dispatch(dialect, Rc, w, d_pos + lo, true, (int)(hi - lo), split.data() + lo, cap, grid_cap, 1, st, launches);
         if (e != cudaSuccess) return e;
         lo = hi;
     }
@@ -910,7 +958,7 @@ inline cudaError_t ab_subtree_search(const sq_subtree* h_st, const sq_subtree* d
         Rc.node_count = d_nodes + lo;
         int min_ply = 127;
         for (long long q = lo; q < hi; q++) if (h_st[q].ply < min_ply) min_ply = h_st[q].ply;
-        e = ab_dispatch(dialect, Rc, w, d_st + lo, false, (int)(hi - lo), split.data() + lo, cap + 16 > kAbChunkNodes ? cap + 16 : kAbChunkNodes, grid_cap, min_ply, st, launches);
+        e = ab_dispatch(dialect, Rc, w, d_st + lo, false, (int)(hi - lo), split.data() + lo, cap, grid_cap, min_ply, st, launches);
         if (e != cudaSuccess) return e;
         lo = hi;
     }

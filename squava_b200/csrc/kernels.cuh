@@ -113,6 +113,8 @@ struct PlayoutParams {
     int64_t n_rounds;
     unsigned long long* round_counter;
     unsigned long long* out;   // [n_leaves][4]
+    uint8_t* packed;           // non-null (per_leaf == 1 only): one outcome byte per leaf instead of `out`:
+                               // bits 0-1 = 1 MAXIMIZER won, 2 MINIMIZER won, 3 draw; bits 2-7 = plies played
 };
 
 #ifndef SQ_PLAYOUT_CTAS_PER_SM
@@ -236,6 +238,11 @@ playout_kernel(PlayoutParams P) {
         uint32_t ow = first_is_x ? second_wins : first_wins;
         uint32_t dr = played - first_wins - second_wins;   // playouts that filled the board lineless
         xw += direct_x; ow += direct_o; dr += direct_d;
+        if (P.packed) {                                   // one playout per leaf: the lane owns its leaf's byte
+            if (have) P.packed[leaf64] = (uint8_t)((xw ? 1u : ow ? 2u : 3u) | (plies << 2));
+            __syncwarp();
+            continue;
+        }
         uint32_t key = have ? (uint32_t)leaf64 : 0xffffffffu;
         uint32_t peers = __match_any_sync(0xffffffffu, key);
         uint32_t sx = __reduce_add_sync(peers, xw);

@@ -176,6 +176,7 @@ int best_child_float(const FNode* blk, int slots, float k_sqrt_lg, const uint32_
 }
 
 struct Chunk { uint64_t at = 0, end = 0; };            // a thread's private piece of the arena
+constexpr uint64_t kChunk = 1 << 16;                   // slots per piece
 
 // Every walk crosses the first two levels, so their counters are the lines all cores fight over.  In
 // throughput mode each thread keeps its additions to those (at most 25 + 25*24) nodes privately and
@@ -203,7 +204,8 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
     // worst case: every selection makes one node whose block has up to 24 slots... bounded in practice by
     // (selections + 1) blocks of <= 25 slots; the arena is virtual memory, pages are touched on use
     const uint64_t selections = (uint64_t)((itermax + P - 1) / P);
-    uint64_t cap = opt.max_nodes ? opt.max_nodes : selections * 26 + 64;
+    // every thread claims arena space in private kChunk-slot pieces: each may leave one piece mostly unused
+    uint64_t cap = opt.max_nodes ? opt.max_nodes : selections * 26 + 64 + (uint64_t)T * kChunk;
     if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
     FNode* nodes = (FNode*)mmap(nullptr, cap * sizeof(FNode), PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (nodes == MAP_FAILED) { std::fprintf(stderr, "fast_uct: cannot reserve %llu node slots\n", (unsigned long long)cap); std::exit(2); }
@@ -250,7 +252,6 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
         path[w.depth++] = root;
     };
     // one level of one walk; returns true when the walk has reached its leaf
-    constexpr uint64_t kChunk = 1 << 16;
     auto step = [&](Rng& rng, Chunk& ck, Shard* sh, Walk& w, uint32_t* path) -> bool {
         FNode& nd = nodes[w.idx];
         const uint32_t u = nd.untried.load(std::memory_order_acquire);

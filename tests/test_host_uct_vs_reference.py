@@ -177,10 +177,12 @@ def test_fast_arena_tree_many_threads_keeps_its_books(host_lib):
                                  INTN, TERM, PLAY, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
                                  C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
                                  C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]
-    for iters, batch, ppl in ((300_000, 4096, 1), (400_000, 1000, 4)):
+    # the third case is squavam -fast's own default budget on a many-core host: every thread claims a private
+    # 65536-slot piece of the arena, which the arena must have room for however small the budget is
+    for iters, batch, ppl, threads in ((300_000, 4096, 1, 4), (400_000, 1000, 4, 4), (10_000, 256, 1, 16), (10_000, 256, 1, 8)):
         moves = (C.c_int * 25)(); visits = (C.c_double * 25)(); wins = (C.c_double * 25)()
         nch, best, value, rootv, nodes = C.c_int(), C.c_int(), C.c_int(), C.c_double(), C.c_ulonglong()
-        rc = lib.sqh_fast_uct(0, 0, 1, iters, 1.0, 0, batch, ppl, 4, INTN(0), cb[0], cb[1], None, C.byref(nch), moves, visits, wins,
+        rc = lib.sqh_fast_uct(0, 0, 1, iters, 1.0, 0, batch, ppl, threads, INTN(0), cb[0], cb[1], None, C.byref(nch), moves, visits, wins,
                               C.byref(best), C.byref(value), C.byref(rootv), None, C.byref(nodes))
         assert rc == 0 and nch.value == 25 and sorted(moves[i] for i in range(25)) == list(range(25))
         assert rootv.value == iters and sum(visits[i] for i in range(25)) == iters
