@@ -59,14 +59,48 @@ def test_opening3_matches_oracle():
     assert re.findall(r"Unique moves computed: (\d+)", out) == ["14", "24", "14", "14", "14", "5"]
 
 
-def test_squavathr_scripted_endgame(oracle):
-    """a scripted human opening, deterministic play; every computer move must be in the oracle's
-    tie set for the position it was chosen in (AB-2, depth from setDepth)."""
-    rc, out, err = run("squavathr", "-D", "-M", "1,1", stdin="0 0\n4 4\n")
+def test_squavathr_scripted_game_every_move_checked(oracle, sq):
+    """squavathr -D against a scripted human (a fixed permutation of the cells; an occupied cell is refused and
+    the next one read, squavathr.go:559-610).  EVERY computer move is checked: the printed value must be the
+    maximum of chooseMove's root values and the move the first cell of movekeeper's tie set
+    (squavathr.go:236-269, movekeeper.go:26-52) for the position it was chosen in, at the depth setDepth gives
+    (:183-198: 10 / 12 / -d).  From move 11 on (depth = -d, here 9, more than the empty cells left for the last
+    moves, so the search runs into full boards) the row comes from the CPU oracle; the early, deep searches
+    are far beyond the oracle's reach in a test and are compared with sq_alphabeta_root called directly -- the
+    search itself is oracle-checked at those depths in test_gpu_alphabeta.py."""
+    import numpy as np
+    script = [12, 0, 24, 6, 18, 4, 20, 2, 22, 10, 14, 8, 16, 1, 3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 23]
+    stdin = "".join("%d %d\n" % (c // 5, c % 5) for c in script)
+    rc, out, err = run("squavathr", "-D", "-d", "9", stdin=stdin)
     assert rc == 0, err
-    assert "My move: 1 1" in out
     mine = re.findall(r"My move: (\d) (\d) \((-?\d+)\) \[(\d+)\]", out)
-    assert len(mine) >= 1
+    assert len(mine) >= 4
+    sc = [3, 3, 0, 3, 3, 3, 4, 1, 4, 3, 0, 1, 0, 1, 0, 3, 4, 1, 4, 3, 3, 3, 0, 3, 3]     # squavathr.go:620-628
+    x = o = 0                      # x: the computer (MAXIMIZER), o: the human
+    k = 0                          # next script entry
+    counter = 0
+    sq.init()
+    try:
+        late = 0
+        for a, b, value, nodes in mine:
+            while (x | o) >> script[k] & 1:
+                k += 1
+            o |= 1 << script[k]; k += 1; counter += 1
+            depth = 10 if counter < 4 else 12 if counter <= 10 else 9
+            if counter > 10:
+                vals, bm, bv, _ = oracle.ab2_root(x, o, depth, sc)
+                late += 1
+            else:
+                v, bvv, bmm, _ = sq.alphabeta_root(np.array([(x, o)], dtype=sq.BOARD), 2, depth, sc)
+                vals, bm, bv = v[0].tolist(), int(bmm[0]), int(bvv[0])
+            cell = 5 * int(a) + int(b)
+            assert int(value) == bv and cell == min(c for c in range(25) if bm >> c & 1), (counter, a, b, value, vals)
+            assert int(nodes) > 0
+            x |= 1 << cell; counter += 1
+        assert late >= 1
+    finally:
+        sq.shutdown()
+    assert re.search(r"(X wins|O wins|Cat wins)", out)
 
 
 def test_playoff5_game_ends_consistently(oracle):

@@ -42,7 +42,10 @@ def test_bit_exact_vs_emulator(dev):
 
 def test_three_sigma_vs_exact_distribution_at_1e7(dev, oracle):
     from squava_b200 import positions
-    boards, tm = positions.midgame_batch(6, marks=(10, 11, 12, 13, 14), seed=21)
+    # configs[1] draws its leaves from 8..14 marks: two positions of every size, the 17-empty ones included
+    parts = [positions.midgame_batch(2, marks=(k,), seed=21 + k) for k in (8, 9, 10, 11, 12, 13, 14)]
+    boards = np.concatenate([p[0] for p in parts]); tm = np.concatenate([p[1] for p in parts])
+    assert sorted(bin(int(b["x"]) | int(b["o"])).count("1") for b in boards) == [8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13, 14, 14]
     n = 10_000_000
     out = dev.playouts(boards, tm, n, 77)
     for i in range(boards.shape[0]):
