@@ -20,10 +20,17 @@ One JSON line on stdout (rank 0).  Keys follow the driver's contract; see DESIGN
   cpu_baseline  the CPU oracle (a C port of the Go reference's table-walk playout) on
              all host threads, bounded sample.  Rank 0, N=1 only.
 
+  secondary  the other BASELINE configs, each timed once and parity-checked inside the run
+             (N=1: c0 squavam decision, c2_1e8 host tree, c3 alpha-beta batch; every N: c4 opening3
+             sharded over the ranks with an NCCL merge, and `strong`: the SAME 4096 leaves split
+             over the ranks).  --no-secondary skips them.
+
 --impl reference times that same CPU port as the reference arm (the Go reference cannot
 be built here: no Go toolchain).
 """
 import argparse
+import ctypes
+import hashlib
 import json
 import os
 import sys
@@ -118,6 +125,203 @@ def cpu_port_rate(boards, to_move, target_s, threads, seed=1):
     return boards.shape[0] * per_leaf / dt, per_leaf, dt
 
 
+def source_hash():
+    """sha256 of the sources the playout kernel is compiled from: a committed ncu count is only used
+    while it describes THIS kernel (profiles/playout_kernel_traffic.json carries the hash it was taken at)."""
+    h = hashlib.sha256()
+    for f in ("kernels.cuh", "sq_device.cuh"):
+        h.update(open(os.path.join(ROOT, "squava_b200", "csrc", f), "rb").read())
+    return h.hexdigest()
+
+
+def oracle_handle():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    return oracle_lib.load()
+
+
+def lpt_assign(weights, ranks):
+    """largest first, each to the least loaded rank -> list of index lists"""
+    order = sorted(range(len(weights)), key=lambda i: -weights[i])
+    load, mine = [0.0] * ranks, [[] for _ in range(ranks)]
+    for i in order:
+        k = min(range(ranks), key=lambda r: load[r])
+        mine[k].append(i); load[k] += weights[i]
+    return mine
+
+
+SCORES_AB = [3, 3, 0, 3, 3, 3, 4, 1, 4, 3, 0, 1, 0, 1, 0, 3, 4, 1, 4, 3, 3, 3, 0, 3, 3]          # alphabeta.go:343-349
+SCORES_OPENING = [3, 3, 0, 3, 3, 3, 4, 1, 4, 3, 0, 1, 0, 1, 2, 3, 4, 1, 4, 3, 3, 3, 0, 3, 3]     # opening3.go:366-372
+AB_OPS_PER_EVAL = 48                                                                            # SURVEY.md 8(d)
+
+
+def secondary_c3(sq, peak_ops):
+    """configs[3]: 1024 positions (8/10/12/14 marks), src/alphabeta depth 10, one sq_alphabeta_root call with host
+    buffers.  Parity: the CPU oracle searches a bounded sample (smallest trees first, all host threads, ~6 s) and
+    every sampled row + tie mask is compared; the eight-mark trees are covered by tests/golden/c3_*.json in the
+    test suite.  Rate: reference-order evaluator calls (the oracle's sequential count for the whole batch, measured
+    once and committed with the hash of the positions) per second."""
+    from concurrent.futures import ThreadPoolExecutor
+    from squava_b200 import positions
+    boards, _ = positions.midgame_batch(1024, marks=(8, 10, 12, 14), seed=0xC4)
+    sq.alphabeta_root(boards[:8], 1, 4, SCORES_AB)                               # warm-up
+    best, l0 = None, sq.launch_count()
+    for rep in range(3):
+        t0 = time.perf_counter()
+        values, bv, bm, nodes = sq.alphabeta_root(boards, 1, 10, SCORES_AB)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    launches = (sq.launch_count() - l0) // 3
+    rec = {"workload": "configs[3]: 1024 positions (8/10/12/14 marks), AB-1 depth 10, sq_alphabeta_root (host buffers)",
+           "seconds": best, "gpu_evaluator_calls": int(nodes.sum()), "gpu_launches": launches}
+    ref = None
+    try:
+        ref = json.load(open(os.path.join(ROOT, "tests", "golden", "c3_reference_order_counts.json")))
+        if ref.get("positions_sha256") != hashlib.sha256(boards.tobytes()).hexdigest():
+            ref = None
+    except Exception:
+        ref = None
+    if ref:
+        evals = ref["oracle_evaluator_calls"]
+        rec["ref_order_evals_per_s"] = evals / best
+        rec["roofline"] = {"bound": "int32_issue", "ops_per_eval": AB_OPS_PER_EVAL, "achieved": AB_OPS_PER_EVAL * evals / best / 1e12,
+                           "peak": peak_ops / 1e12, "unit": "Tops/s", "frac": AB_OPS_PER_EVAL * evals / best / peak_ops,
+                           "frac_gpu_evals": AB_OPS_PER_EVAL * int(nodes.sum()) / best / peak_ops,
+                           "note": "reference-order evaluator calls (oracle's sequential count, %s) x 48 ops" % ref["source"]}
+    # bounded oracle sample: positions with the most marks first (smallest trees), until ~6 s of wall time
+    o = oracle_handle()
+    order = sorted(range(1024), key=lambda i: -bin(int(boards[i]["x"]) | int(boards[i]["o"])).count("1"))
+    threads = host_threads()
+    t0 = time.perf_counter()
+    done, evals_cpu, mism = 0, 0, 0
+
+    def one(i):
+        vals, obm, obv, _ = o.ab1_root(int(boards[i]["x"]), int(boards[i]["o"]), 10, SCORES_AB)
+        return i, vals, obm, obv, o.last_evals()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        pos = 0
+        while pos < len(order) and time.perf_counter() - t0 < 6.0:
+            chunk = order[pos:pos + 4 * threads]
+            pos += len(chunk)
+            for i, vals, obm, obv, ev in ex.map(one, chunk):
+                done += 1; evals_cpu += ev
+                if values[i].tolist() != vals or int(bm[i]) != obm or int(bv[i]) != obv:
+                    mism += 1
+    cpu_s = time.perf_counter() - t0
+    rec["mismatching_positions"] = mism
+    rec["parity_sample"] = "%d of 1024 positions (most marks first) searched by the CPU oracle in this run" % done
+    rec["cpu_baseline"] = {"value": evals_cpu / cpu_s, "unit": "evaluator calls/s", "cores": threads, "kind": "port",
+                           "sample": "%d positions, %.1f s" % (done, cpu_s)}
+    return rec
+
+
+def opening3_subtrees(sq):
+    """opening3.go:66-128: the (first move, reply) pairs not equivalent under the program's 8 symmetries
+    (opening3.go:379-451) to a pair computed earlier: 85 = 14 + 24 + 14 + 14 + 14 + 5."""
+    def images(c):
+        x, y = divmod(c, 5)
+        return [5 * a + b for a, b in ((x, y), (y, 4 - x), (4 - x, 4 - y), (4 - y, x), (4 - x, y), (x, 4 - y), (4 - y, 4 - x), (y, x))]
+    done, pairs = set(), []
+    for f in (0, 1, 2, 6, 7, 12):                       # firstMoves, opening3.go:456-463
+        for r in range(25):
+            if r == f or any((a, b) in done for a, b in zip(images(f), images(r))):
+                continue
+            done.add((f, r)); pairs.append((f, r))
+    assert len(pairs) == 85
+    st = np.zeros(len(pairs), sq.SUBTREE)
+    for i, (f, r) in enumerate(pairs):
+        st[i] = (1 << f, 1 << r, r, 2, 1, 0, SCORES_OPENING[f])
+    return pairs, st
+
+
+def secondary_c4(sq, rank, world, dev, dist, torch, peak_ops):
+    """configs[4], alpha-beta half: opening3's 85 subtrees (AB-3, -d 10) sharded over the ranks -- by the node counts of
+    a depth-7 pilot search (largest subtree first, each to the least loaded rank), every rank searching its share on
+    its own GPU -- and ONE NCCL all-reduce of the zero-padded value vector.  Parity: all 85 values against the
+    oracle's depth-10 vectors (tests/golden/c4_opening3_depth10.json)."""
+    pairs, st = opening3_subtrees(sq)
+    sq.alphabeta_subtrees(st[:4], 3, 5, SCORES_OPENING)                          # warm-up
+    t0 = time.perf_counter()
+    _, pilot = sq.alphabeta_subtrees(st, 3, 7, SCORES_OPENING)                   # every rank: the same weights
+    mine = lpt_assign([float(v) for v in pilot], world)[rank]
+    vals = torch.zeros(len(pairs), dtype=torch.int64, device=dev)
+    nodes = torch.zeros(len(pairs), dtype=torch.int64, device=dev)
+    if mine:
+        v, n = sq.alphabeta_subtrees(st[mine], 3, 10, SCORES_OPENING)
+        vals[mine] = torch.from_numpy(v.astype(np.int64)).to(dev)
+        nodes[mine] = torch.from_numpy(n.astype(np.int64)).to(dev)
+    if world > 1:
+        dist.all_reduce(vals); dist.all_reduce(nodes)
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs = float(t.item())
+    got = vals.cpu().numpy().tolist()
+    rec = {"workload": "configs[4] alpha-beta: opening3's 85 subtrees, AB-3 depth 10, sharded over %d rank(s) by pilot-search size, NCCL merge" % world,
+           "seconds": secs, "gpu_evaluator_calls": int(nodes.sum().item()), "subtrees_on_rank0": len(mine) if rank == 0 else None}
+    gp = os.path.join(ROOT, "tests", "golden", "c4_opening3_depth10.json")
+    if os.path.exists(gp):
+        g = json.load(open(gp))
+        want = {(c["first"], c["reply"]): c["value"] for c in g["cases"]}
+        rec["mismatching_subtrees"] = sum(1 for (f, r), v in zip(pairs, got) if want[(f, r)] != v)
+        rec["ref_order_evals_per_s"] = g["total_evals"] / secs
+        rec["roofline"] = {"bound": "int32_issue", "ops_per_eval": AB_OPS_PER_EVAL, "achieved": AB_OPS_PER_EVAL * g["total_evals"] / secs / 1e12,
+                           "peak": peak_ops * world / 1e12, "unit": "Tops/s", "frac": AB_OPS_PER_EVAL * g["total_evals"] / secs / (peak_ops * world)}
+        rec["cpu_baseline"] = {"value": g["total_evals"] / g["wall_seconds"], "unit": "evaluator calls/s", "cores": g["procs"], "kind": "port",
+                               "sample": "all 85 subtrees, measured when the golden vectors were made (%.0f s; not on this box)" % g["wall_seconds"]}
+    else:
+        rec["mismatching_subtrees"] = None
+    return rec
+
+
+def host_lib():
+    L = ctypes.CDLL(os.path.join(ROOT, "squava_b200", "host", "libsquava_host.so"))
+    C = ctypes
+    L.sqh_uct.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                          C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                          C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.sqh_fast_uct.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_longlong, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                               C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                               C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]
+    return L
+
+
+def secondary_c0_c2(sq, iters_c2):
+    """configs[0]: one squavam move decision from the empty board, -i 10000 -u 1.0, computer first (UCT with squavam.go's
+    UCB1, leaf batches of 256), and configs[2] at 1e8 iterations: ONE host tree, one playout per leaf, GPU leaf batches
+    of 65536 (the arena tree of squavam -fast).  Both through the C++ host library that squavam itself is built from.
+    Consistency checks inside the run: every iteration is counted once (root visits == iterations, children sum to it)."""
+    C = ctypes
+    L = host_lib()
+    moves = (C.c_int * 25)(); visits = (C.c_double * 25)(); wins = (C.c_double * 25)()
+    nch, best, value, leaves = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    out = {}
+    ts = []
+    for rep in range(3):
+        t0 = time.perf_counter()
+        rc = L.sqh_uct(0, 0, 1, 10000, 1.0, 0, 256, 1, None, None, None, None, C.byref(nch), moves, visits, wins,
+                       C.byref(best), C.byref(value), C.byref(leaves))
+        ts.append(time.perf_counter() - t0)
+        assert rc == 0 and leaves.value == 10000 and sum(visits[i] for i in range(nch.value)) == 10000
+    out["c0"] = {"workload": "configs[0]: squavam -C -i 10000 -u 1.0, one move decision from the empty board (leaf batches of 256)",
+                 "seconds": min(ts), "iterations_per_s": 10000 / min(ts), "best_move": best.value}
+    rootv, nodes = C.c_double(), C.c_ulonglong()
+    secs = (C.c_double * 3)()
+    t0 = time.perf_counter()
+    rc = L.sqh_fast_uct(0, 0, 1, iters_c2, 1.0, 0, 65536, 1, 0, None, None, None, None, C.byref(nch), moves, visits, wins,
+                        C.byref(best), C.byref(value), C.byref(rootv), secs, C.byref(nodes))
+    dt = time.perf_counter() - t0
+    assert rc == 0 and rootv.value == iters_c2 and sum(visits[i] for i in range(nch.value)) == iters_c2
+    assert all(0 <= wins[i] <= visits[i] for i in range(nch.value))
+    out["c2_1e8"] = {"workload": "configs[2] at %.0e iterations: one host tree, one playout per leaf, GPU leaf batches of 65536" % iters_c2,
+                     "seconds": dt, "iterations_per_s": iters_c2 / dt, "host_threads": host_threads(),
+                     "select_seconds": secs[0], "gpu_seconds": secs[1], "update_seconds": secs[2], "tree_node_slots": int(nodes.value),
+                     "best_move": best.value}
+    return out
+
+
 def run_reference(args):
     """Reference arm: the CPU port of the Go playout loop on all host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -166,6 +370,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--per-leaf", type=int, default=PER_LEAF, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configs (c0, c2_1e8, c3, c4, strong)")
+    ap.add_argument("--c2-iterations", type=float, default=1e8, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -294,30 +500,42 @@ def main():
     peak_alu = sq.int32_peak(kind=0, reps=3)
     peak_fma = sq.int32_peak(kind=1, reps=3)
     alg_ops = OPS_PER_PLY * plies_per_step + OPS_PER_PLAYOUT * N_LEAVES * per_leaf
-    achieved = alg_ops / (kernel_ms * 1e-3)
-    traffic, warp_inst = None, None
+    model_rate = alg_ops / (kernel_ms * 1e-3)
+    # What the kernel really issues: thread-instructions per ply counted by ncu (smsp__inst_executed of one
+    # launch of this workload) -- used only while the committed count was taken from THIS source (hash).
+    traffic, inst_per_ply, prof_note = None, None, "no committed ncu count"
     tp = os.path.join(ROOT, "profiles", "playout_kernel_traffic.json")
-    if os.path.exists(tp) and per_leaf == PER_LEAF:
+    if os.path.exists(tp):
         try:
             prof = json.load(open(tp))
-            traffic = prof.get("dram_bytes_per_launch")
-            warp_inst = prof.get("warp_instructions_per_launch")
-        except Exception:
-            traffic = None
+            if prof.get("source_sha256") == source_hash():
+                traffic = prof.get("dram_bytes_per_launch")
+                inst_per_ply = prof["warp_instructions_per_launch"] * 32.0 / prof["plies_per_launch"]
+                prof_note = prof.get("source")
+            else:
+                prof_note = "committed ncu count is stale (kernel source changed since it was taken): not used"
+        except Exception as e:
+            prof_note = "unreadable: %s" % e
+    if inst_per_ply and per_leaf == PER_LEAF:
+        # achieved = executed thread-instructions per second: a true fraction of the issue ceiling (<= 1)
+        executed = inst_per_ply * plies_per_step
+        achieved, basis = executed / (kernel_ms * 1e-3), "executed thread-instructions (ncu count per ply x plies of this run)"
+    else:
+        achieved, basis = min(model_rate, peak_mixed), "SURVEY 8d op model, capped at the peak (no fresh ncu count)"
     roofline = {
         "bound": "int32_issue", "achieved": achieved / 1e12, "peak": peak_mixed / 1e12, "unit": "Tops/s",
-        "frac": achieved / peak_mixed, "traffic": traffic,
+        "frac": achieved / peak_mixed, "traffic": traffic, "basis": basis,
         "kernel": "sq::playout_kernel", "kernel_ms": kernel_ms, "kernel_ms_last_internal_events": last_kernel_ms,
-        "algorithmic_ops_per_launch": alg_ops, "ops_model": "64 per ply + 16 per playout (SURVEY.md 8d)",
+        "model_ops_per_launch": alg_ops, "ops_model": "64 per ply + 16 per playout (SURVEY.md 8d)",
+        "model_tops": model_rate / 1e12, "model_over_peak": model_rate / peak_mixed,
+        "model_note": "the kernel issues fewer instructions per ply than the survey's 64+16 budget, so the model rate can exceed the issue peak; frac is the executed-instruction fraction",
         "plies_per_launch": plies_per_step, "peak_source": "sq_int32_peak measured in this run (LOP3+IMAD interleaved)",
         "peak_alu_only_tops": peak_alu / 1e12, "peak_fma_only_tops": peak_fma / 1e12,
-        "algorithmic_bytes_per_launch": N_LEAVES * (9 + 32),
+        "algorithmic_bytes_per_launch": N_LEAVES * (9 + 32), "ncu_count": prof_note,
     }
-    if warp_inst:
-        # what the kernel really issues (ncu smsp__inst_executed of the same launch) against the same peak
-        roofline["executed_thread_inst_per_launch"] = warp_inst * 32
-        roofline["executed_thread_inst_per_ply"] = warp_inst * 32 / plies_per_step
-        roofline["frac_executed"] = warp_inst * 32 / (kernel_ms * 1e-3) / peak_mixed
+    if inst_per_ply:
+        roofline["executed_thread_inst_per_ply"] = inst_per_ply
+    assert roofline["frac"] <= 1.0 + 1e-9
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -332,6 +550,48 @@ def main():
                 "d2h_bytes_per_step": N_LEAVES * 32 * world, "steps": Ke, "api": "sq_playouts (host buffers, C ABI)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
     }
+
+    if not args.no_secondary:
+        sec = {}
+        # ---- strong scaling: the SAME 4096 leaves x 1e6 playouts, split over the ranks, one NCCL merge per step ----
+        s_lo, s_hi = N_LEAVES * rank // world, N_LEAVES * (rank + 1) // world
+        sb, st_ = boards_all[s_lo:s_hi], tm_all[s_lo:s_hi]
+        ds_b = torch.from_numpy(sb.view(np.uint32).reshape(-1, 2).view(np.int32).copy()).to(dev)
+        ds_t = torch.from_numpy(st_.copy()).to(dev)
+        ds_m = torch.zeros((N_LEAVES, 4), dtype=torch.int64, device=dev)
+
+        def strong_step(i):
+            flush.fill_(i & 0xff)
+            if world > 1:
+                ds_m.zero_()
+            sq.playouts_dev(ds_b.data_ptr(), ds_t.data_ptr(), s_hi - s_lo, per_leaf, ds_m[s_lo:s_hi].data_ptr(),
+                            leaf_index_base=s_lo, stream_id=5000 + i, stream=stream)
+            if world > 1:
+                dist.all_reduce(ds_m)
+        Ks = max(3, K // 2)
+        for i in range(3):
+            strong_step(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(Ks):
+            strong_step(3 + i)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        got = ds_m.cpu().numpy()
+        assert (got[:, :3].sum(axis=1) == per_leaf).all()
+        sec["strong"] = {"workload": "the SAME 4096 leaves x %d playouts split over %d rank(s), NCCL all-reduce of the [4096,4] counts per step" % (per_leaf, world),
+                         "value": N_LEAVES * per_leaf * Ks / (float(t.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(t.item()) / Ks, "steps": Ks,
+                         "scaling": "strong"}
+        # ---- configs[4]: every rank takes its share of opening3's subtrees ----
+        sec["c4"] = secondary_c4(sq, rank, world, dev, dist, torch, peak_mixed)
+        if rank == 0 and world == 1:
+            sec["c3"] = secondary_c3(sq, peak_mixed)
+            sec.update(secondary_c0_c2(sq, int(args.c2_iterations)))
+        line["secondary"] = sec
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = host_threads()

@@ -68,6 +68,20 @@ def test_c3_eight_mark_positions_depth10_live_oracle(dev, oracle):
         assert values[j].tolist() == ov and (int(bm[j]), int(bv[j])) == (obm, obv)
 
 
+def test_c4_opening3_depth10_golden(dev):
+    """configs[4] at BASELINE size: opening3 -d 10 (the program's default), all 85 subtrees, against the oracle's
+    committed vectors (tests/golden/c4_opening3_depth10.json, oracle/tools/make_golden_c4.py)"""
+    g = json.load(open(os.path.join(HERE, "golden", "c4_opening3_depth10.json")))["cases"]
+    assert len(g) == 85 and all(c["depth"] == 10 for c in g)
+    so = [3, 3, 0, 3, 3, 3, 4, 1, 4, 3, 0, 1, 0, 1, 2, 3, 4, 1, 4, 3, 3, 3, 0, 3, 3]
+    st = np.zeros(85, dev.SUBTREE)
+    for i, c in enumerate(g):
+        st[i] = (1 << c["first"], 1 << c["reply"], c["reply"], 2, 1, 0, so[c["first"]])
+    v, nodes = dev.alphabeta_subtrees(st, 3, 10, so)
+    assert v.tolist() == [c["value"] for c in g]
+    assert (nodes > 0).all()
+
+
 def test_near_full_boards_search_deeper_than_the_empties(dev, oracle):
     """max_depth > empty cells: the search runs into full boards (node value -+20000, which outranks a win) and
     root windows get cut at their edge -- squavathr -d 15 and playoff depth 12 do this in every endgame.
