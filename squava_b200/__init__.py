@@ -23,7 +23,8 @@ __all__ = [
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-lib_path = os.path.join(_HERE, "libsquava_b200.so")
+# SQUAVA_B200_LIB: another build of the same library (kernel tuning variants, tools/playout_variants.sh)
+lib_path = os.environ.get("SQUAVA_B200_LIB") or os.path.join(_HERE, "libsquava_b200.so")
 
 BOARD = np.dtype([("x", "<u4"), ("o", "<u4")])
 SUBTREE = np.dtype([("x", "<u4"), ("o", "<u4"), ("last_cell", "i1"), ("ply", "i1"),

@@ -150,6 +150,7 @@ int launch_playouts(Device& d, Ctx& c, int ctx_index, const sq_board* leaves, co
     P.key1 = (uint32_t)(g_seed >> 32);
     P.ctr3 = (uint32_t)stream_id;
     P.one = 1u;
+    sq::playout_round_keys(P);
     unsigned long long items = (unsigned long long)n_leaves * S;
     P.n_rounds = (int64_t)((items + 31) / 32);
     P.out = reinterpret_cast<unsigned long long*>(out);

@@ -31,6 +31,7 @@
 #include "../../include/squava_b200.h"
 #include "sq_device.cuh"
 #include "sq_tables.h"
+#include "ab_horizon.cuh"
 
 namespace sq {
 
@@ -116,7 +117,9 @@ struct AbRun {
     int sentinel;        // |value| of a node with no legal move: 20000, or 10000 (opening2)
     int win_lo, win_hi;  // the dialect's root window
     int shortcuts;       // exact shortcuts allowed (see ab_move_classes); off when |heuristic sums| could reach a win score
+    int fast_horizon;    // horizon-1 nodes are valued in one bit-parallel shot (ab_horizon.cuh): needs the shortcuts and a bias table spanning < 30
     int8_t scores[25];
+    HorizonTables hz;
 };
 
 // ---- evaluators -----------------------------------------------------------------
@@ -608,12 +611,31 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                         if (kPenalties) ret += eval_penalties(T, side > 0 ? xs : os, (side > 0 ? os : xs) | j0, cell, side);
                         evals++;
                         returning = true;
+                    } else if (!kPenalties && R.fast_horizon && cply == R.max_depth - 1 && (emp_after & (emp_after - 1u))) {
+                        // the child is a horizon-1 node that cannot run out of cells: its value in one shot
+                        const uint32_t own2 = side > 0 ? os : xs, opp2 = side > 0 ? xs : os;      // the child's mover is the other side
+                        const uint32_t f0 = emp_after & (0u - emp_after), rest = emp_after ^ f0, f1 = rest & (0u - rest);
+                        const AbWalk w0 = ab_walk(W, own2 | f0, opp2, __ffs(f0) - 1);
+                        const int first_cnt = __popc(w0.e1 & ~f1) + __popc(w0.e2 & ~f1);
+                        int konst = -30 * (__popc(w.e1) + __popc(w.e2)) - R.scores[cell];
+                        if (AbTraits<DIALECT>::delayed_sum) konst -= side * d;
+                        const int rel = horizon_node_value<true>(own2, opp2, emp_after, kWin - (cply + 1), konst, w.e1, w.e2, first_cnt, R.hz);
+                        ret = -side * rel;
+                        evals += 2 + __popc(emp_after);
+                        returning = true;
                     }
                 } else {
                     int dv = side * (30 * (__popc(w.e1) + __popc(w.e2)) + R.scores[cell]);
                     if (kPenalties) dv += eval_penalties(T, side > 0 ? xs : os, side > 0 ? os : xs, cell, side);
                     if (cply == R.max_depth) { ret = dv + carried; returning = true; }
                     else if (emp_after == 0) { ret = side > 0 ? R.sentinel : -R.sentinel; returning = true; }
+                    else if (!kPenalties && R.fast_horizon && cply == R.max_depth - 1 && (emp_after & (emp_after - 1u))) {
+                        const uint32_t own2 = side > 0 ? os : xs, opp2 = side > 0 ? xs : os;
+                        const int rel = horizon_node_value<false>(own2, opp2, kFull25 & ~(xs | os), kWin - (cply + 1), -side * (dv + carried), 0u, 0u, 0, R.hz);
+                        ret = -side * rel;
+                        evals += 1 + __popc(emp_after);
+                        returning = true;
+                    }
                     else d = dv + carried;
                 }
                 if (!returning) {
@@ -891,6 +913,8 @@ inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t score
     const bool cumulative = dialect == 2 || dialect == 3 || dialect == 4 || dialect == 6;
     const long long worst = (cumulative ? (long long)(max_depth + 1) * per_eval : 2 * per_eval) + max_abs_carried;
     R.shortcuts = worst < kWin - max_depth - 1 && !getenv("SQ_AB_NO_SHORTCUTS");
+    build_horizon_tables(scores, R.hz);
+    R.fast_horizon = R.shortcuts && R.hz.ok && !getenv("SQ_AB_NO_FAST_HORIZON");
 }
 
 // worst-case node count below one level-0 node with e empties and `split` expanded plies

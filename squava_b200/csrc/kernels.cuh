@@ -108,6 +108,8 @@ struct PlayoutParams {
     uint32_t quota_lo;         // N / S
     uint32_t quota_extra;      // N % S: items j < quota_extra run quota_lo + 1
     uint32_t key0, key1, ctr3;
+    uint32_t rk[20];           // Philox round keys (key0 + r*W0, key1 + r*W1), r = 0..9: read straight from the
+                               // constant bank by the round's LOP3, so the key schedule costs no instruction
     uint32_t one;              // == 1, but opaque to ptxas: x*one+y is issued as IMAD on the FMA pipe,
                                // which balances it against the ALU pipe (LOP3/SEL/ISETP) -- see DESIGN.md
     int64_t n_rounds;
@@ -117,11 +119,118 @@ struct PlayoutParams {
                                // bits 0-1 = 1 MAXIMIZER won, 2 MINIMIZER won, 3 draw; bits 2-7 = plies played
 };
 
+inline void playout_round_keys(PlayoutParams& P) {
+    for (int r = 0; r < 10; r++) { P.rk[2 * r] = P.key0 + (uint32_t)r * kPhiloxW0; P.rk[2 * r + 1] = P.key1 + (uint32_t)r * kPhiloxW1; }
+}
+
+// Philox4x32-10 with the round keys precomputed (same function as philox4x32_10)
+__device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&rk)[20], uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(kPhiloxM0, c0), lo0 = kPhiloxM0 * c0;
+        uint32_t hi1 = __umulhi(kPhiloxM1, c2), lo1 = kPhiloxM1 * c2;
+        c0 = hi1 ^ c1 ^ rk[2 * r];
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ rk[2 * r + 1];
+        c3 = lo0;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
 #ifndef SQ_PLAYOUT_CTAS_PER_SM
 #define SQ_PLAYOUT_CTAS_PER_SM 4
 #endif
+// tuning knobs of the ply loop (pipe balance; the random stream and the results do not depend on them)
+#ifndef SQ_PL_ADDR_ALU
+#define SQ_PL_ADDR_ALU 1      // element addresses by shift+add on the ALU pipe instead of IMAD
+#endif
+#ifndef SQ_PL_ACC_ALU
+#define SQ_PL_ACC_ALU 0       // win counter by predicated add (ALU) instead of predicated IMAD
+#endif
+#ifndef SQ_PL_SHF
+#define SQ_PL_SHF 0           // how many of the eight line-test shifts of a ply are forced onto the ALU pipe (SHF)
+#endif
+
+__device__ __forceinline__ uint32_t shl_alu(uint32_t x, int k) {      // x << k as SHF (ALU pipe); ptxas keeps it there
+    uint32_t r;
+    asm("shf.l.clamp.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(0u), "r"(x), "r"((uint32_t)k));
+    return r;
+}
+
+struct PlyState {
+    uint32_t a, b, n, inc_w, acc, acc_fin, plies;
+    int remi;
+};
+
+// Twelve plies from one Philox block.  CAREFUL = false: no lane can finish its quota inside this block (every
+// lane has more than 12 playouts to go), so the end-of-quota snapshot is not compiled in at all.
+template <bool CAREFUL>
+__device__ __forceinline__ void ply_block(PlyState& S, const uint32_t (&w)[4], uint32_t leaf_a, uint32_t leaf_b, uint32_t n0,
+                                          uint32_t sbase, uint32_t one, uint32_t blk_after) {
+    constexpr uint32_t kStride = kPlayoutThreads * 4;
+    uint32_t a = S.a, b = S.b, n = S.n, inc_w = S.inc_w, acc = S.acc, acc_fin = S.acc_fin, plies = S.plies;
+    int remi = S.remi;
+#pragma unroll
+    for (int wi = 0; wi < 4; wi++) {
+        uint32_t r = w[wi];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            // draw: idx = floor(r*n / 2^32), r <- r*n mod 2^32
+            const uint32_t idx = __umulhi(r, n);
+            r = r * n;
+#if SQ_PL_ADDR_ALU
+            const uint32_t ai = shl_alu(idx, 10) + sbase;
+            const uint32_t al = shl_alu(n, 10) + (sbase - kStride);
+#else
+            const uint32_t ai = idx * kStride + sbase;
+            const uint32_t al = n * kStride + (sbase - kStride);
+#endif
+            uint32_t bit, last;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(bit) : "r"(ai));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(last) : "r"(al));
+            asm volatile("st.shared.u32 [%0], %1;" :: "r"(ai), "r"(last));
+            asm volatile("st.shared.u32 [%0], %1;" :: "r"(al), "r"(bit));
+            const uint32_t m = a + bit;          // bit is an empty cell: + is |
+#if SQ_PL_SHF > 0
+            Pairs p;
+            p.h = m & (m << 1);
+            p.v = m & (SQ_PL_SHF >= 1 ? shl_alu(m, 6) : (m << 6));
+            p.d = m & (SQ_PL_SHF >= 2 ? shl_alu(m, 7) : (m << 7));
+            p.a = m & (SQ_PL_SHF >= 3 ? shl_alu(m, 5) : (m << 5));
+#else
+            const Pairs p = pairs(m);
+#endif
+            const uint32_t t3 = any3(p), t4 = any4(p);
+            const uint32_t n1 = n - 1u;
+            const bool line = t3 != 0;
+            const bool term = line | (n1 == 0);
+            const uint32_t inc_l = inc_w ^ 0x10001u;
+            const uint32_t inc = t4 ? inc_w : inc_l;
+#if SQ_PL_ACC_ALU
+            asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q add.u32 %0, %0, %2;\n\t}" : "+r"(acc) : "r"(t3), "r"(inc));
+#else
+            asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q mad.lo.u32 %0, %2, %3, %0;\n\t}"
+                : "+r"(acc) : "r"(t3), "r"(inc), "r"(one));
+#endif
+            if (CAREFUL) {
+                const bool fin = term & (remi == 1);
+                const uint32_t plies_now = blk_after * 12u - 11u + (uint32_t)(wi * 3 + d);
+                asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %4, 0;\n\t@q mov.u32 %0, %2;\n\t@q mov.u32 %1, %3;\n\t}"
+                    : "+r"(acc_fin), "+r"(plies) : "r"(acc), "r"(plies_now), "r"((uint32_t)fin));
+            }
+            asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q add.s32 %0, %0, -1;\n\t}"
+                : "+r"(remi) : "r"((uint32_t)term));
+            a = term ? leaf_a : b;
+            b = term ? leaf_b : m;
+            n = term ? n0 : n1;
+            inc_w = term ? 1u : inc_l;
+        }
+    }
+    S.a = a; S.b = b; S.n = n; S.inc_w = inc_w; S.acc = acc; S.acc_fin = acc_fin; S.plies = plies; S.remi = remi;
+}
+
 __global__ void __launch_bounds__(kPlayoutThreads, SQ_PLAYOUT_CTAS_PER_SM)
-playout_kernel(PlayoutParams P) {
+playout_kernel(const __grid_constant__ PlayoutParams P) {
     extern __shared__ uint32_t s_arr[];  // [kMaxEmpty][blockDim.x]
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -178,59 +287,34 @@ playout_kernel(PlayoutParams P) {
         // its counters are SNAPSHOT (two predicated moves) at the ply its last playout ends.
         // Plies need no counter at all: every iteration of an unfinished lane is one ply, so
         // the snapshot takes the (warp-uniform) iteration number.
-        uint32_t a = leaf_a, b = leaf_b, n = n0;
-        uint32_t inc_w = 1u;          // what the mover's win adds: 1 = first player, 0x10000 = second
-        uint32_t acc = 0;
-        uint32_t acc_fin = 0, plies = 0;   // snapshots: every iteration of an unfinished lane is one ply
-        int remi = (int)rem;          // playouts still to finish; <= 0: done
+        // Two phases: while EVERY playing lane still has more than 12 playouts to go no lane can finish inside
+        // the next block of 12 plies, and the block runs without the snapshot logic; the last few blocks of a
+        // round run the careful version.  Lanes with nothing to play (no leaf, terminal leaf) idle along.
+        PlyState S;
+        S.a = leaf_a; S.b = leaf_b; S.n = n0;
+        S.inc_w = 1u;                 // what the mover's win adds: 1 = first player, 0x10000 = second
+        S.acc = 0; S.acc_fin = 0; S.plies = 0;
+        S.remi = (int)rem;            // playouts still to finish; <= 0: done
         uint32_t blk = 0;
         const uint32_t c1 = j, c2 = (uint32_t)(P.leaf_index_base + leaf64);
         const uint32_t one = P.one;
         const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(arr);   // element k at sbase + k*kStride
-        constexpr uint32_t kStride = kPlayoutThreads * 4;
-        while (__any_sync(0xffffffffu, remi > 0)) {
+        const bool idle = rem == 0;
+        while (__all_sync(0xffffffffu, idle | (S.remi > 12))) {
+            if (__all_sync(0xffffffffu, idle)) break;
             uint32_t w[4];
-            philox4x32_10(blk, c1, c2, P.ctr3, P.key0, P.key1, w);
+            philox4x32_10_rk(blk, c1, c2, P.ctr3, P.rk, w);
             blk++;
-#pragma unroll
-            for (int wi = 0; wi < 4; wi++) {
-                uint32_t r = w[wi];
-#pragma unroll
-                for (int d = 0; d < 3; d++) {
-                    // draw: idx = floor(r*n / 2^32), r <- r*n mod 2^32
-                    const uint32_t idx = __umulhi(r, n);
-                    r = r * n;
-                    const uint32_t ai = idx * kStride + sbase;
-                    const uint32_t al = n * kStride + (sbase - kStride);
-                    uint32_t bit, last;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(bit) : "r"(ai));
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(last) : "r"(al));
-                    asm volatile("st.shared.u32 [%0], %1;" :: "r"(ai), "r"(last));
-                    asm volatile("st.shared.u32 [%0], %1;" :: "r"(al), "r"(bit));
-                    const uint32_t m = a + bit;          // bit is an empty cell: + is |
-                    const Pairs p = pairs(m);
-                    const uint32_t t3 = any3(p), t4 = any4(p);
-                    const uint32_t n1 = n - 1u;
-                    const bool line = t3 != 0;
-                    const bool term = line | (n1 == 0);
-                    const uint32_t inc_l = inc_w ^ 0x10001u;
-                    const uint32_t inc = t4 ? inc_w : inc_l;
-                    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q mad.lo.u32 %0, %2, %3, %0;\n\t}"
-                        : "+r"(acc) : "r"(t3), "r"(inc), "r"(one));
-                    const bool fin = term & (remi == 1);
-                    const uint32_t plies_now = blk * 12u - 11u + (uint32_t)(wi * 3 + d);   // blk already advanced
-                    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %4, 0;\n\t@q mov.u32 %0, %2;\n\t@q mov.u32 %1, %3;\n\t}"
-                        : "+r"(acc_fin), "+r"(plies) : "r"(acc), "r"(plies_now), "r"((uint32_t)fin));
-                    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q add.s32 %0, %0, -1;\n\t}"
-                        : "+r"(remi) : "r"((uint32_t)term));
-                    a = term ? leaf_a : b;
-                    b = term ? leaf_b : m;
-                    n = term ? n0 : n1;
-                    inc_w = term ? 1u : inc_l;
-                }
-            }
+            ply_block<false>(S, w, leaf_a, leaf_b, n0, sbase, one, blk);
         }
-        acc = acc_fin;
+        if (idle) S.remi = 0;
+        while (__any_sync(0xffffffffu, S.remi > 0)) {
+            uint32_t w[4];
+            philox4x32_10_rk(blk, c1, c2, P.ctr3, P.rk, w);
+            blk++;
+            ply_block<true>(S, w, leaf_a, leaf_b, n0, sbase, one, blk);
+        }
+        const uint32_t acc = S.acc_fin, plies = S.plies;
 
         // ---- fold into per-leaf counts ------------------------------------------
         uint32_t first_wins = acc & 0xffffu, second_wins = acc >> 16;

@@ -59,48 +59,66 @@ def test_opening3_matches_oracle():
     assert re.findall(r"Unique moves computed: (\d+)", out) == ["14", "24", "14", "14", "14", "5"]
 
 
-def test_squavathr_scripted_game_every_move_checked(oracle, sq):
-    """squavathr -D against a scripted human (a fixed permutation of the cells; an occupied cell is refused and
-    the next one read, squavathr.go:559-610).  EVERY computer move is checked: the printed value must be the
-    maximum of chooseMove's root values and the move the first cell of movekeeper's tie set
+def test_squavathr_game_every_move_checked(oracle, sq):
+    """squavathr -D driven move by move over its stdin/stdout protocol by a cautious human (the first empty cell
+    that does not complete a 3-line of its own, so the game lasts).  EVERY computer move is checked: the printed
+    value must be the maximum of chooseMove's root values and the move the first cell of movekeeper's tie set
     (squavathr.go:236-269, movekeeper.go:26-52) for the position it was chosen in, at the depth setDepth gives
-    (:183-198: 10 / 12 / -d).  From move 11 on (depth = -d, here 9, more than the empty cells left for the last
-    moves, so the search runs into full boards) the row comes from the CPU oracle; the early, deep searches
-    are far beyond the oracle's reach in a test and are compared with sq_alphabeta_root called directly -- the
-    search itself is oracle-checked at those depths in test_gpu_alphabeta.py."""
+    (:183-198: 10 / 12 / -d).  From move 11 on (depth = -d 15, more than the empty cells left: the search runs
+    into full boards) the row comes from the CPU oracle; the early, deep searches are far beyond the oracle's
+    reach in a test and are compared with sq_alphabeta_root called directly -- the search itself is oracle-checked
+    at those depths in test_gpu_alphabeta.py and test_gpu_configs.py."""
     import numpy as np
-    script = [12, 0, 24, 6, 18, 4, 20, 2, 22, 10, 14, 8, 16, 1, 3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 23]
-    stdin = "".join("%d %d\n" % (c // 5, c % 5) for c in script)
-    rc, out, err = run("squavathr", "-D", "-d", "9", stdin=stdin)
-    assert rc == 0, err
-    mine = re.findall(r"My move: (\d) (\d) \((-?\d+)\) \[(\d+)\]", out)
-    assert len(mine) >= 4
+    from squava_b200 import positions
+    exe = os.path.join(HOST, "squavathr")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", HOST, "-s"])
+    p = subprocess.Popen([exe, "-D", "-d", "15"], stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     sc = [3, 3, 0, 3, 3, 3, 4, 1, 4, 3, 0, 1, 0, 1, 0, 3, 4, 1, 4, 3, 3, 3, 0, 3, 3]     # squavathr.go:620-628
+
+    def read_until_prompt():
+        buf = ""
+        while not buf.endswith("Your move: "):
+            ch = p.stdout.read(1)
+            if ch == "":
+                break
+            buf += ch
+        return buf
     x = o = 0                      # x: the computer (MAXIMIZER), o: the human
-    k = 0                          # next script entry
-    counter = 0
+    counter, late, moves_checked = 0, 0, 0
+    order = [12, 0, 24, 6, 18, 4, 20, 2, 22, 10, 14, 8, 16, 1, 3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 23]
     sq.init()
     try:
-        late = 0
-        for a, b, value, nodes in mine:
-            while (x | o) >> script[k] & 1:
-                k += 1
-            o |= 1 << script[k]; k += 1; counter += 1
-            depth = 10 if counter < 4 else 12 if counter <= 10 else 9
+        text = read_until_prompt()
+        while text.endswith("Your move: "):
+            empties = [c for c in order if not (x | o) >> c & 1]
+            safe = [c for c in empties if not positions.has_line(o | 1 << c)]
+            h = (safe or empties)[0]
+            o |= 1 << h; counter += 1
+            p.stdin.write("%d %d\n" % (h // 5, h % 5)); p.stdin.flush()
+            text = read_until_prompt()
+            m = re.search(r"My move: (\d) (\d) \((-?\d+)\) \[(\d+)\]", text)
+            if not m:
+                break                                   # the human's move ended the game
+            depth = 10 if counter < 4 else 12 if counter <= 10 else 15
             if counter > 10:
                 vals, bm, bv, _ = oracle.ab2_root(x, o, depth, sc)
                 late += 1
             else:
                 v, bvv, bmm, _ = sq.alphabeta_root(np.array([(x, o)], dtype=sq.BOARD), 2, depth, sc)
                 vals, bm, bv = v[0].tolist(), int(bmm[0]), int(bvv[0])
-            cell = 5 * int(a) + int(b)
-            assert int(value) == bv and cell == min(c for c in range(25) if bm >> c & 1), (counter, a, b, value, vals)
-            assert int(nodes) > 0
-            x |= 1 << cell; counter += 1
-        assert late >= 1
+            cell = 5 * int(m.group(1)) + int(m.group(2))
+            assert int(m.group(3)) == bv and cell == min(c for c in range(25) if bm >> c & 1), (counter, m.group(0), vals)
+            assert int(m.group(4)) > 0
+            x |= 1 << cell; counter += 1; moves_checked += 1
+        rest = text + p.stdout.read()
+        assert p.wait(timeout=60) == 0, p.stderr.read()
+        assert moves_checked >= 5 and late >= 1, (moves_checked, late)
+        assert re.search(r"(X wins|O wins|Cat wins)", rest)
     finally:
         sq.shutdown()
-    assert re.search(r"(X wins|O wins|Cat wins)", out)
+        if p.poll() is None:
+            p.kill()
 
 
 def test_playoff5_game_ends_consistently(oracle):
