@@ -115,6 +115,16 @@ int sq_playouts(const sq_board *leaves, const int8_t *to_move, int64_t n_leaves,
 int sq_playouts_packed(const sq_board *leaves, const int8_t *to_move, int64_t n_leaves,
                        uint64_t stream_id, uint8_t *outcome);
 
+/* The two calls above on ONE device of those sq_init() named (slot = index into that list) instead of
+ * sharded over all of them: what a root-parallel host uses -- one tree, one host-thread group and one
+ * device per searcher (squavam2.go:93-112 runs N searchers for one decision), root statistics merged
+ * once per decision.  The stream depends on (seed, stream_id, leaf index) only, so a leaf gives the same
+ * counts on every device.                                                                         */
+int sq_playouts_on(int slot, const sq_board *leaves, const int8_t *to_move, int64_t n_leaves,
+                   uint64_t playouts_per_leaf, uint64_t stream_id, uint64_t (*out)[4]);
+int sq_playouts_packed_on(int slot, const sq_board *leaves, const int8_t *to_move, int64_t n_leaves,
+                          uint64_t stream_id, uint8_t *outcome);
+
 /* ---- fixed-depth alpha-beta -------------------------------------------- */
 /* Replaces ChooseMove's per-root-move loop: src/alphabeta/alphabeta.go:92-117
  * (dialect 1, or 5 = the same engine after SetAvoid(); max_depth = p.maxDepth as SetDepth

@@ -38,7 +38,7 @@ EXPORTS = [
     "sq_init", "sq_shutdown", "sq_strerror", "sq_last_error", "sq_abi_version", "sq_device_count",
     "sq_sm_count", "sq_classify", "sq_playouts", "sq_alphabeta_root", "sq_alphabeta_subtrees", "sq_negascout_root",
     "sq_classify_dev", "sq_playouts_dev", "sq_int32_peak", "sq_launch_count",
-    "sq_last_playout_kernel_ms", "sq_debug_philox", "sq_playouts_packed", "sq_last_error_copy",
+    "sq_last_playout_kernel_ms", "sq_debug_philox", "sq_playouts_packed", "sq_last_error_copy", "sq_playouts_on", "sq_playouts_packed_on",
 ]
 
 
@@ -76,6 +76,8 @@ def lib():
         L.sq_playouts.argtypes = [vp, vp, i64, u64, u64, vp]
         L.sq_playouts_packed.argtypes = [vp, vp, i64, u64, vp]
         L.sq_last_error_copy.argtypes = [C.c_char_p, i32]
+        L.sq_playouts_on.argtypes = [i32, vp, vp, i64, u64, u64, vp]
+        L.sq_playouts_packed_on.argtypes = [i32, vp, vp, i64, u64, vp]
         L.sq_alphabeta_root.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, vp]
         L.sq_alphabeta_subtrees.argtypes = [vp, i64, i32, i32, vp, vp, vp]
         L.sq_negascout_root.argtypes = [vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]
@@ -137,8 +139,9 @@ def classify(boards):
     return f, wm, wa
 
 
-def playouts(boards, to_move, playouts_per_leaf, stream_id=0, out=None):
-    """-> u64[n, 4] = {MAX wins, MIN wins, draws, plies} per leaf (host buffers)."""
+def playouts(boards, to_move, playouts_per_leaf, stream_id=0, out=None, slot=None):
+    """-> u64[n, 4] = {MAX wins, MIN wins, draws, plies} per leaf (host buffers).  slot: run on that one
+    device instead of sharding over all (sq_playouts_on)."""
     b = as_boards(boards)
     tm = np.ascontiguousarray(to_move, dtype=np.int8)
     n = b.shape[0]
@@ -146,8 +149,12 @@ def playouts(boards, to_move, playouts_per_leaf, stream_id=0, out=None):
         raise ValueError("to_move length")
     if out is None:
         out = np.empty((n, 4), np.uint64)
-    _ck(lib().sq_playouts(b.ctypes.data, tm.ctypes.data, n, int(playouts_per_leaf), int(stream_id),
-                          out.ctypes.data), "sq_playouts")
+    if slot is None:
+        _ck(lib().sq_playouts(b.ctypes.data, tm.ctypes.data, n, int(playouts_per_leaf), int(stream_id),
+                              out.ctypes.data), "sq_playouts")
+    else:
+        _ck(lib().sq_playouts_on(int(slot), b.ctypes.data, tm.ctypes.data, n, int(playouts_per_leaf), int(stream_id),
+                                 out.ctypes.data), "sq_playouts_on")
     return out
 
 

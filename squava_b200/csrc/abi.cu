@@ -439,9 +439,9 @@ int sq_classify(const sq_board* boards, int64_t n, uint8_t* flags, int8_t* wm, i
 
 // shared body of sq_playouts (out: u64[n][4]) and sq_playouts_packed (packed: u8[n], one playout per leaf)
 static int playouts_host(const char* who, const sq_board* leaves, const int8_t* to_move, int64_t n_leaves,
-                         uint64_t per_leaf, uint64_t stream_id, uint64_t (*out)[4], uint8_t* packed) {
+                         uint64_t per_leaf, uint64_t stream_id, uint64_t (*out)[4], uint8_t* packed, int only_slot = -1) {
     std::shared_lock<std::shared_mutex> sl(g_state);
-    int rc = check_ready();
+    int rc = only_slot < 0 ? check_ready() : check_slot(only_slot);
     if (rc) return rc;
     if (n_leaves < 0 || (n_leaves > 0 && (!leaves || !to_move || (!out && !packed)))) {
         snprintf(t_err, sizeof t_err, "%s: null pointer", who); return SQ_ERR_INVALID;
@@ -454,10 +454,15 @@ static int playouts_host(const char* who, const sq_board* leaves, const int8_t* 
     }
     const size_t res_bytes = packed ? 1 : 32;           // per leaf, device -> host
     int m = (int)g_dev.size();
+    // only_slot >= 0: the whole call on that one device (root-parallel hosts keep one tree per device)
+    auto part = [&](int k, int64_t& lo, int64_t& hi) {
+        if (only_slot < 0) share(n_leaves, m, k, lo, hi);
+        else { lo = 0; hi = k == only_slot ? n_leaves : 0; }
+    };
     std::vector<CtxHold> held((size_t)m);
     for (int k = 0; k < m; k++) {
         Device& d = *g_dev[k];
-        int64_t lo, hi; share(n_leaves, m, k, lo, hi);
+        int64_t lo, hi; part(k, lo, hi);
         int64_t cnt = hi - lo;
         if (cnt <= 0) continue;
         held[k] = acquire(d);
@@ -493,7 +498,7 @@ static int playouts_host(const char* who, const sq_board* leaves, const int8_t* 
     }
     for (int k = 0; k < m; k++) {      // collect after every device has been launched
         Device& d = *g_dev[k];
-        int64_t lo, hi; share(n_leaves, m, k, lo, hi);
+        int64_t lo, hi; part(k, lo, hi);
         int64_t cnt = hi - lo;
         if (cnt <= 0) continue;
         Ctx& c = *held[k];
@@ -521,6 +526,18 @@ int sq_playouts_packed(const sq_board* leaves, const int8_t* to_move, int64_t n_
                        uint64_t stream_id, uint8_t* outcome) {
     if (n_leaves > 0 && !outcome) { snprintf(t_err, sizeof t_err, "sq_playouts_packed: null pointer"); return SQ_ERR_INVALID; }
     return playouts_host("sq_playouts_packed", leaves, to_move, n_leaves, 1, stream_id, nullptr, outcome);
+}
+
+int sq_playouts_on(int slot, const sq_board* leaves, const int8_t* to_move, int64_t n_leaves,
+                   uint64_t per_leaf, uint64_t stream_id, uint64_t (*out)[4]) {
+    if (slot < 0 || (n_leaves > 0 && !out)) { snprintf(t_err, sizeof t_err, "sq_playouts_on: bad slot / null pointer"); return SQ_ERR_INVALID; }
+    return playouts_host("sq_playouts_on", leaves, to_move, n_leaves, per_leaf, stream_id, out, nullptr, slot);
+}
+
+int sq_playouts_packed_on(int slot, const sq_board* leaves, const int8_t* to_move, int64_t n_leaves,
+                          uint64_t stream_id, uint8_t* outcome) {
+    if (slot < 0 || (n_leaves > 0 && !outcome)) { snprintf(t_err, sizeof t_err, "sq_playouts_packed_on: bad slot / null pointer"); return SQ_ERR_INVALID; }
+    return playouts_host("sq_playouts_packed_on", leaves, to_move, n_leaves, 1, stream_id, nullptr, outcome, slot);
 }
 
 int sq_alphabeta_root(const sq_board* positions, int64_t n, int dialect, int max_depth,
@@ -690,32 +707,9 @@ int sq_alphabeta_subtrees(const sq_subtree* subtrees, int64_t n, int dialect, in
                   s.ply >= 0 && s.ply <= max_depth;
         if (!ok) { snprintf(t_err, sizeof t_err, "sq_alphabeta_subtrees: subtree %lld malformed", (long long)i); return SQ_ERR_INVALID; }
     }
-    // Several devices: the subtrees are dealt out by estimated size (a deeper remaining search and more
-    // empty cells first, largest to the least loaded device), not by index -- opening3's 85 subtrees differ by
-    // orders of magnitude.  One device: the caller's order.
-    const int m = (int)g_dev.size();
-    std::vector<std::vector<int64_t>> mine((size_t)m);
-    if (m == 1) { mine[0].resize((size_t)n); for (int64_t i = 0; i < n; i++) mine[0][(size_t)i] = i; }
-    else {
-        std::vector<int64_t> idx((size_t)n);
-        std::vector<double> est((size_t)n), load((size_t)m, 0.0);
-        for (int64_t i = 0; i < n; i++) {
-            idx[(size_t)i] = i;
-            const int empt = 25 - __builtin_popcount(subtrees[i].b.x | subtrees[i].b.o);
-            const int rem = std::min(max_depth - subtrees[i].ply, empt);
-            double e = 1; for (int k = 0; k < rem; k++) e *= 0.45 * (empt - k) + 1;      // rough: pruning leaves ~ half the children
-            est[(size_t)i] = e;
-        }
-        std::stable_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return est[(size_t)a] > est[(size_t)b]; });
-        for (int64_t i : idx) {
-            int best = 0;
-            for (int k = 1; k < m; k++) if (load[(size_t)k] < load[(size_t)best]) best = k;
-            mine[(size_t)best].push_back(i); load[(size_t)best] += est[(size_t)i];
-        }
-    }
-    return for_each_device(m, [&](int k) -> int {
+    // one device's share: the subtrees ix[] searched to `depth`, results scattered back by index
+    auto run_on = [&](int k, const std::vector<int64_t>& ix, int depth, int32_t* val_out, uint64_t* nodes_out) -> int {
         Device& d = *g_dev[k];
-        const std::vector<int64_t>& ix = mine[(size_t)k];
         const int64_t cnt = (int64_t)ix.size();
         if (cnt <= 0) return SQ_OK;
         int r;
@@ -728,7 +722,7 @@ int sq_alphabeta_subtrees(const sq_subtree* subtrees, int64_t n, int dialect, in
         if ((r = reserve(*c, 3, cnt * sizeof(unsigned long long)))) return r;
         CK(cudaMemcpyAsync(c->buf[0], st.data(), cnt * sizeof(sq_subtree), cudaMemcpyHostToDevice, c->stream));
         uint64_t launches = 0;
-        cudaError_t e = sq::ab_subtree_search(st.data(), (const sq_subtree*)c->buf[0], cnt, dialect, max_depth, scores,
+        cudaError_t e = sq::ab_subtree_search(st.data(), (const sq_subtree*)c->buf[0], cnt, dialect, depth, scores,
                                               (int32_t*)c->buf[2], (unsigned long long*)c->buf[3],
                                               d.sm_count * d.ab_blocks_per_sm, c->stream, &launches);
         g_launches += launches;
@@ -737,9 +731,45 @@ int sq_alphabeta_subtrees(const sq_subtree* subtrees, int64_t n, int dialect, in
         CK(cudaMemcpyAsync(hv.data(), c->buf[2], cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaMemcpyAsync(hn.data(), c->buf[3], cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        for (int64_t q = 0; q < cnt; q++) { value[ix[(size_t)q]] = hv[(size_t)q]; if (nodes) nodes[ix[(size_t)q]] = hn[(size_t)q]; }
+        for (int64_t q = 0; q < cnt; q++) {
+            if (val_out) val_out[ix[(size_t)q]] = hv[(size_t)q];
+            if (nodes_out) nodes_out[ix[(size_t)q]] = hn[(size_t)q];
+        }
         return SQ_OK;
-    });
+    };
+    const int m = (int)g_dev.size();
+    std::vector<int64_t> all((size_t)n);
+    for (int64_t i = 0; i < n; i++) all[(size_t)i] = i;
+    if (m == 1 || n <= 1) return run_on(0, all, max_depth, value, nodes);
+    // Several devices: whole subtrees are dealt out by SIZE, not by index -- opening3's 85 subtrees differ by
+    // orders of magnitude although they all have 23 empty cells.  The size estimate is a PILOT search of
+    // every subtree three plies shallower on the first device (a few hundred times cheaper than the search
+    // itself): its evaluator counts are the weights; largest first, each to the least loaded device.
+    std::vector<double> est((size_t)n, 1.0);
+    int min_rem = 1 << 30;
+    for (int64_t i = 0; i < n; i++) min_rem = std::min(min_rem, max_depth - (int)subtrees[i].ply);
+    if (min_rem > 4) {
+        std::vector<uint64_t> pilot((size_t)n, 0);
+        rc = run_on(0, all, max_depth - 3, nullptr, pilot.data());
+        if (rc) return rc;
+        for (int64_t i = 0; i < n; i++) est[(size_t)i] = 1.0 + (double)pilot[(size_t)i];
+    } else {
+        for (int64_t i = 0; i < n; i++) {
+            const int empt = 25 - __builtin_popcount(subtrees[i].b.x | subtrees[i].b.o);
+            const int rem = std::min(max_depth - (int)subtrees[i].ply, empt);
+            double e = 1; for (int k = 0; k < rem; k++) e *= 0.45 * (empt - k) + 1;
+            est[(size_t)i] = e;
+        }
+    }
+    std::vector<std::vector<int64_t>> mine((size_t)m);
+    std::vector<double> load((size_t)m, 0.0);
+    std::stable_sort(all.begin(), all.end(), [&](int64_t a, int64_t b) { return est[(size_t)a] > est[(size_t)b]; });
+    for (int64_t i : all) {
+        int best = 0;
+        for (int k = 1; k < m; k++) if (load[(size_t)k] < load[(size_t)best]) best = k;
+        mine[(size_t)best].push_back(i); load[(size_t)best] += est[(size_t)i];
+    }
+    return for_each_device(m, [&](int k) -> int { return run_on(k, mine[(size_t)k], max_depth, value, nodes); });
 }
 
 // ---- measurement helpers -------------------------------------------------------

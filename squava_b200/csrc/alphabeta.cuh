@@ -23,6 +23,7 @@
 // orderedCells child order).
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -109,7 +110,10 @@ struct AbRun {
     int* pending;                    // unfinished children
     int* units;                      // indices of DFS units
     int* aborted;                    // units that ran out of budget in this pass: split one ply deeper
-    unsigned int* counters;          // [0] n_nodes [1] n_units [2] queue head [3] n_aborted [4] node pool overflowed
+    int* kids;                       // first child of a split node (its children are contiguous, eldest first), -1: none
+    int* held;                       // younger children of a split node still waiting for the eldest to finish
+    int* released;                   // younger children set free in this pass: units of the next one
+    unsigned int* counters;          // [0] n_nodes [1] n_units [2] queue head [3] n_aborted [4] node pool overflowed [5] n_released [6] smallest ply among the next pass's units
     int* out;                        // final values
     unsigned long long* node_count;  // evaluator calls per group
     int node_capacity;
@@ -117,6 +121,7 @@ struct AbRun {
     int sentinel;        // |value| of a node with no legal move: 20000, or 10000 (opening2)
     int win_lo, win_hi;  // the dialect's root window
     int shortcuts;       // exact shortcuts allowed (see ab_move_classes); off when |heuristic sums| could reach a win score
+    int ybw;             // young brothers wait: a split node's younger children start only when the eldest has finished
     int fast_horizon;    // horizon-1 nodes are valued in one bit-parallel shot (ab_horizon.cuh): needs the shortcuts and a bias table spanning < 30
     int8_t scores[25];
     HorizonTables hz;
@@ -198,6 +203,18 @@ __device__ void ab_complete(const AbRun& R, int node, int value) {
         if (R.nodes[parent].side > 0) atomicMax(&R.value[parent], value);
         else atomicMin(&R.value[parent], value);
         __threadfence();
+        // Young brothers wait: the eldest child of a split node has finished, so its value now bounds the parent's
+        // slot -- the younger children become units of the next pass and start with that bound (only the thread
+        // that completes the eldest gets here: no race on held[]).
+        if (R.kids[parent] == node) {
+            const int nh = R.held[parent];
+            if (nh > 0) {
+                R.held[parent] = 0;
+                const unsigned at = atomicAdd(&R.counters[5], (unsigned)nh);
+                for (int k = 0; k < nh; k++) R.released[at + k] = node + 1 + k;
+                atomicMin(&R.counters[6], (unsigned)R.nodes[node].ply);
+            }
+        }
         int old = atomicSub(&R.pending[parent], 1);
         if (old != 1) return;
         __threadfence();
@@ -225,9 +242,12 @@ __device__ __forceinline__ int ab_new_node(const AbRun& R, const AbNode& n) {
     R.nodes[idx] = n;
     R.value[idx] = n.side > 0 ? -R.sentinel : R.sentinel;
     R.pending[idx] = 0;
+    R.kids[idx] = -1;
+    R.held[idx] = 0;
     if (n.split == 0) {
         unsigned int u = atomicAdd(&R.counters[1], 1u);
         R.units[u] = (int)idx;
+        atomicMin(&R.counters[6], (unsigned)n.ply);
     }
     return (int)idx;
 }
@@ -382,10 +402,22 @@ ab_expand_kernel(AbRun R, const int* __restrict__ list, int lo, int count) {
             R.value[idx] = -best;                 // children fold into this with atomicMin/Max
         }
     }
-    R.pending[idx] = __popc(empties);
+    // the children take one contiguous run of slots, eldest (first in the dialect's visiting order) first
+    const int nch = __popc(empties);
+    const unsigned base = atomicAdd(&R.counters[0], (unsigned)nch);
+    if (base + (unsigned)nch > (unsigned)R.node_capacity) {   // the host checks the room before every expansion; if its
+        atomicExch(&R.counters[4], 1u);                       // sizing is ever wrong the run is failed, never silently short
+        return;
+    }
+    // adaptive split of a unit that proved too big: only the eldest child starts now, the others when it is done
+    const bool hold = list != nullptr && R.ybw && nch >= 2;
+    R.kids[idx] = (int)base;
+    R.held[idx] = hold ? nch - 1 : 0;
+    R.pending[idx] = nch;
     __threadfence();
     const bool pend_is_x = (n.x >> n.cell) & 1u;
     const int sign = pend_is_x ? 1 : -1;
+    int j = 0;
     for (int k = 0; k < 25; k++) {               // children in the dialect's visiting order
         const int cell = AbTraits<DIALECT>::ordered ? T.order[k] : k;
         const uint32_t bit = 1u << cell;
@@ -407,8 +439,16 @@ ab_expand_kernel(AbRun R, const int* __restrict__ list, int lo, int count) {
         } else {
             c.carried = carried_down;
         }
-        ab_new_node(R, c);
+        const int ci = (int)base + j;
+        R.nodes[ci] = c;
+        R.value[ci] = c.side > 0 ? -R.sentinel : R.sentinel;
+        R.pending[ci] = 0;
+        R.kids[ci] = -1;
+        R.held[ci] = 0;
+        if (c.split == 0 && (!hold || j == 0)) R.units[atomicAdd(&R.counters[1], 1u)] = ci;
+        j++;
     }
+    if (n.split == 1) atomicMin(&R.counters[6], (unsigned)(n.ply + 1));
     atomicAdd(&R.node_count[n.group], evals);
 }
 
@@ -621,7 +661,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                         if (AbTraits<DIALECT>::delayed_sum) konst -= side * d;
                         const int rel = horizon_node_value<true>(own2, opp2, emp_after, kWin - (cply + 1), konst, w.e1, w.e2, first_cnt, R.hz);
                         ret = -side * rel;
-                        evals += 2 + __popc(emp_after);
+                        evals += 3;          // about three table walks of instructions
                         returning = true;
                     }
                 } else {
@@ -633,7 +673,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                         const uint32_t own2 = side > 0 ? os : xs, opp2 = side > 0 ? xs : os;
                         const int rel = horizon_node_value<false>(own2, opp2, kFull25 & ~(xs | os), kWin - (cply + 1), -side * (dv + carried), 0u, 0u, 0, R.hz);
                         ret = -side * rel;
-                        evals += 1 + __popc(emp_after);
+                        evals += 2;
                         returning = true;
                     }
                     else d = dv + carried;
@@ -724,7 +764,7 @@ inline int ab_choose_split(int empties, int rem) {
 struct AbWork {   // device allocations of one chunk
     AbNode* nodes = nullptr; int* value = nullptr; int* pending = nullptr; int* units = nullptr;
     unsigned int* counters = nullptr; int8_t* split = nullptr;
-    int* aborted = nullptr;
+    int* aborted = nullptr; int* kids = nullptr; int* held = nullptr; int* released = nullptr;
 };
 
 inline void ab_free(AbWork& w, cudaStream_t st) {
@@ -735,6 +775,9 @@ inline void ab_free(AbWork& w, cudaStream_t st) {
     if (w.counters) cudaFreeAsync(w.counters, st);
     if (w.split) cudaFreeAsync(w.split, st);
     if (w.aborted) cudaFreeAsync(w.aborted, st);
+    if (w.kids) cudaFreeAsync(w.kids, st);
+    if (w.held) cudaFreeAsync(w.held, st);
+    if (w.released) cudaFreeAsync(w.released, st);
     w = AbWork();
 }
 
@@ -749,16 +792,22 @@ inline cudaError_t ab_alloc(AbWork& w, long long capacity, cudaStream_t st) {
     if ((e = cudaMallocAsync(&w.pending, sizeof(int) * capacity, st)) != cudaSuccess) return e;
     if ((e = cudaMallocAsync(&w.units, sizeof(int) * capacity, st)) != cudaSuccess) return e;
     if ((e = cudaMallocAsync(&w.aborted, sizeof(int) * capacity, st)) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(&w.kids, sizeof(int) * capacity, st)) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(&w.held, sizeof(int) * capacity, st)) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(&w.released, sizeof(int) * capacity, st)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
-inline cudaError_t ab_grow(AbWork& w, long long used, int n_aborted, long long new_capacity, cudaStream_t st) {
+inline cudaError_t ab_grow(AbWork& w, long long used, int n_aborted, int n_units, long long new_capacity, cudaStream_t st) {
     AbWork g;
     cudaError_t e = ab_alloc(g, new_capacity, st);
     if (e != cudaSuccess) { ab_free(g, st); return e; }
     cudaMemcpyAsync(g.nodes, w.nodes, sizeof(AbNode) * used, cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(g.value, w.value, sizeof(int) * used, cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(g.pending, w.pending, sizeof(int) * used, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(g.kids, w.kids, sizeof(int) * used, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(g.held, w.held, sizeof(int) * used, cudaMemcpyDeviceToDevice, st);
+    if (n_units > 0) cudaMemcpyAsync(g.units, w.units, sizeof(int) * n_units, cudaMemcpyDeviceToDevice, st);
     e = cudaMemcpyAsync(g.aborted, w.aborted, sizeof(int) * n_aborted, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) { ab_free(g, st); return e; }
     g.counters = w.counters; g.split = w.split;
@@ -770,16 +819,24 @@ inline cudaError_t ab_grow(AbWork& w, long long used, int n_aborted, long long n
 
 constexpr long long kAbPoolStart = 1ll << 20;
 
+// the pool size the last search of this process ended with: the next one starts there instead of growing again
+inline std::atomic<long long>& ab_hint() { static std::atomic<long long> h{0}; return h; }
+inline void ab_hint_store(long long capacity) { ab_hint().store(capacity); }
+
 template <int DIALECT>
 cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n, const int8_t* h_split,
                          long long capacity, long long ceiling, int grid_cap, int min_ply, cudaStream_t st, uint64_t* launches) {
     SQ_AB_CK(ab_alloc(w, capacity, st));
     SQ_AB_CK(cudaMallocAsync(&w.counters, sizeof(unsigned int) * 8, st));
     SQ_AB_CK(cudaMallocAsync(&w.split, n, st));
-    SQ_AB_CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned int) * 8, st));
+    {
+        const unsigned int init8[8] = {0, 0, 0, 0, 0, 0, 127, 0};
+        SQ_AB_CK(cudaMemcpyAsync(w.counters, init8, sizeof init8, cudaMemcpyHostToDevice, st));
+    }
     SQ_AB_CK(cudaMemcpyAsync(w.split, h_split, n, cudaMemcpyHostToDevice, st));
     auto bind = [&] {
         R.nodes = w.nodes; R.value = w.value; R.pending = w.pending; R.units = w.units; R.aborted = w.aborted;
+        R.kids = w.kids; R.held = w.held; R.released = w.released;
         R.counters = w.counters; R.node_capacity = (int)capacity;
     };
     bind();
@@ -793,7 +850,7 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
     }
     (*launches)++;
     SQ_AB_CK(cudaGetLastError());
-    unsigned int h_counters[5] = {0, 0, 0, 0, 0};
+    unsigned int h_counters[7] = {0, 0, 0, 0, 0, 0, 127};
     int lo = 0;
     for (int level = 0; level < 3; level++) {        // static pre-split (usually none)
         SQ_AB_CK(cudaMemcpyAsync(h_counters, w.counters, sizeof h_counters, cudaMemcpyDeviceToHost, st));
@@ -805,9 +862,11 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
         SQ_AB_CK(cudaGetLastError());
         lo = hi;
     }
-    // Adaptive passes: every unit gets `budget` evaluator calls; the ones that need more are
-    // split one ply deeper and their children (now with their siblings' bounds in the parent
-    // slots) form the next pass.  Small subtrees keep sequential pruning, big ones get spread.
+    // Adaptive passes: every unit gets `budget` evaluator calls; the ones that need more are split one ply
+    // deeper.  Of a split unit's children only the ELDEST becomes a unit of the next pass; the younger ones wait
+    // until it has finished (ab_complete sets them free) and then start with its value as their bound -- young
+    // brothers wait, at pass granularity.  Small subtrees keep sequential pruning, big ones are spread over the
+    // machine one generation at a time, with bounds that are nearly as good as the sequential search's.
     const bool trace = getenv("SQ_AB_TRACE") != nullptr;
     auto t_prev = std::chrono::steady_clock::now();
     auto lap = [&](const char* what, int a, int b) {
@@ -819,18 +878,27 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
     lap("setup", n, (int)capacity);
     const unsigned long long fixed_budget = ab_budget();
     bool unlimited = false;
-    int plies_split = 0;      // how many plies below the level-0 nodes this pass's units sit (at least)
-    for (int pass = 0;; pass++) {
+    int passes = 0;
+    for (;;) {
         SQ_AB_CK(cudaMemcpyAsync(h_counters, w.counters, sizeof h_counters, cudaMemcpyDeviceToHost, st));
         SQ_AB_CK(cudaStreamSynchronize(st));
         if (h_counters[4]) { ab_free(w, st); return cudaErrorMemoryAllocation; }     // a node did not fit: never a silent short tree
-        const int n_units = (int)h_counters[1];
+        int n_units = (int)h_counters[1];
+        const int n_released = (int)h_counters[5];
+        if (n_released > 0) {                          // younger brothers set free during the last pass / expansion
+            SQ_AB_CK(cudaMemcpyAsync(w.units + n_units, w.released, sizeof(int) * n_released, cudaMemcpyDeviceToDevice, st));
+            n_units += n_released;
+        }
         if (n_units == 0) break;
+        // (units re-queued without a budget are not in the ply count: size for the shallowest possible unit then)
+        const int unit_ply = (unlimited || (int)h_counters[6] > 126) ? min_ply : (int)h_counters[6];
+        const unsigned int zero7[7] = {h_counters[0], 0, 0, 0, 0, 0, 127};  // n_nodes stays; units, queue head, aborted, released, min ply restart
+        SQ_AB_CK(cudaMemcpyAsync(w.counters, zero7, sizeof zero7, cudaMemcpyHostToDevice, st));
         // few units: split early (most lanes are idle anyway); many: let lanes run longer
         unsigned long long budget = fixed_budget ? fixed_budget : n_units < (1 << 15) ? 256 : n_units < (1 << 18) ? 1024 : 4096;
         if (unlimited) budget = ~0ull;
         // frames a unit can push: one per ply from its own down to max_depth - 1
-        int n_frames = R.max_depth - (min_ply + plies_split) + 1;
+        int n_frames = R.max_depth - unit_ply + 1;
         if (n_frames > kAbMaxDepth + 2) n_frames = kAbMaxDepth + 2;
         if (n_frames < 2) n_frames = 2;
         long long blocks = ((long long)n_units + kAbThreads - 1) / kAbThreads;
@@ -838,35 +906,42 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
         ab_dfs_kernel<DIALECT><<<(unsigned)blocks, kAbThreads, (size_t)n_frames * AbFrameWords<DIALECT>::n * kAbThreads * 4, st>>>(
             R, n_units, budget, n_frames);
         (*launches)++;
+        passes++;
         SQ_AB_CK(cudaGetLastError());
         SQ_AB_CK(cudaMemcpyAsync(h_counters, w.counters, sizeof h_counters, cudaMemcpyDeviceToHost, st));
         SQ_AB_CK(cudaStreamSynchronize(st));
         const int n_aborted = (int)h_counters[3];
         lap("dfs", n_units, n_aborted);
-        if (n_aborted == 0) break;
-        const unsigned int zero3[3] = {0, 0, 0};
-        SQ_AB_CK(cudaMemcpyAsync(w.counters + 1, zero3, sizeof zero3, cudaMemcpyHostToDevice, st));
+        if (n_aborted == 0) continue;                 // nothing to split; units set free by this pass are picked up at the top
         const long long want = (long long)h_counters[0] + 25ll * n_aborted;
         if (want > capacity && capacity < ceiling) {      // grow the pool: the arrays move, indices stay valid
             long long bigger = capacity;
             while (bigger < want && bigger < ceiling) bigger *= 2;
             if (bigger > ceiling) bigger = ceiling;
-            if (ab_grow(w, (long long)h_counters[0], n_aborted, bigger, st) == cudaSuccess) { capacity = bigger; bind(); lap("grow", (int)(capacity >> 10), 0); }
-            else cudaGetLastError();                      // no memory for a bigger pool: carry on with what there is
+            // the units list is empty here (consumed by the pass); released[] is re-read from the old arrays below
+            int* old_released = w.released; w.released = nullptr;
+            if (ab_grow(w, (long long)h_counters[0], n_aborted, 0, bigger, st) == cudaSuccess) {
+                if (h_counters[5]) cudaMemcpyAsync(w.released, old_released, sizeof(int) * h_counters[5], cudaMemcpyDeviceToDevice, st);
+                cudaFreeAsync(old_released, st);
+                capacity = bigger; bind(); lap("grow", (int)(capacity >> 10), 0);
+            } else { cudaGetLastError(); w.released = old_released; }   // no memory for a bigger pool: carry on with what there is
         }
         if (want > capacity) {
-            // no room to split further: finish the stragglers without a budget
+            // no room to split further: finish the stragglers without a budget (they become units again)
             SQ_AB_CK(cudaMemcpyAsync(w.units, w.aborted, sizeof(int) * n_aborted, cudaMemcpyDeviceToDevice, st));
             const unsigned int nu = (unsigned)n_aborted;
             SQ_AB_CK(cudaMemcpyAsync(w.counters + 1, &nu, sizeof nu, cudaMemcpyHostToDevice, st));
             unlimited = true;
             continue;
         }
+        // each split goes at least one ply deeper than the shallowest unit so far; with brothers waiting the deepest
+        // chain grows by one ply per split, which only makes this frame bound generous
         ab_expand_kernel<DIALECT><<<(n_aborted + kAbThreads - 1) / kAbThreads, kAbThreads, 0, st>>>(R, w.aborted, 0, n_aborted);
-        plies_split++;
         (*launches)++;
         SQ_AB_CK(cudaGetLastError());
     }
+    if (trace) fprintf(stderr, "[ab] %d passes, pool %lld of %lld slots\n", passes, (long long)h_counters[0], capacity);
+    ab_hint_store(capacity);
     ab_free(w, st);
     return cudaSuccess;
 }
@@ -885,7 +960,7 @@ inline cudaError_t ab_dispatch(int dialect, AbRun R, AbWork& w, const void* d_in
     // ceiling: SQ_AB_POOL_NODES (default 64 Mi slots, ~2.5 GB), never below what the level-0 nodes need;
     // the run starts with max(needed, kAbPoolStart) slots and grows towards the ceiling only if it splits that far
     const long long ceiling = std::max(needed + 16, ab_pool_nodes());
-    const long long capacity = std::min(ceiling, std::max(needed + 16, kAbPoolStart));
+    const long long capacity = std::min(ceiling, std::max(std::max(needed + 16, kAbPoolStart), ab_hint().load()));
     switch (dialect) {
     case 1: return ab_run_chunk<1>(R, w, d_in, roots, n, h_split, capacity, ceiling, grid_cap, min_ply, st, launches);
     case 2: return ab_run_chunk<2>(R, w, d_in, roots, n, h_split, capacity, ceiling, grid_cap, min_ply, st, launches);
@@ -915,6 +990,7 @@ inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t score
     R.shortcuts = worst < kWin - max_depth - 1 && !getenv("SQ_AB_NO_SHORTCUTS");
     build_horizon_tables(scores, R.hz);
     R.fast_horizon = R.shortcuts && R.hz.ok && !getenv("SQ_AB_NO_FAST_HORIZON");
+    R.ybw = !getenv("SQ_AB_NO_YBW");
 }
 
 // worst-case node count below one level-0 node with e empties and `split` expanded plies

@@ -142,7 +142,10 @@ __device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint3
 #endif
 // tuning knobs of the ply loop (pipe balance; the random stream and the results do not depend on them)
 #ifndef SQ_PL_ADDR_ALU
-#define SQ_PL_ADDR_ALU 1      // element addresses by shift+add on the ALU pipe instead of IMAD
+#define SQ_PL_ADDR_ALU 0      // element addresses by shift+add on the ALU pipe instead of IMAD (measured: IMAD is better)
+#endif
+#ifndef SQ_PL_LINE3
+#define SQ_PL_LINE3 1         // line test from three-input ANDs of the shifted mask (22 instructions) instead of pair masks (24)
 #endif
 #ifndef SQ_PL_ACC_ALU
 #define SQ_PL_ACC_ALU 0       // win counter by predicated add (ALU) instead of predicated IMAD
@@ -191,16 +194,24 @@ __device__ __forceinline__ void ply_block(PlyState& S, const uint32_t (&w)[4], u
             asm volatile("st.shared.u32 [%0], %1;" :: "r"(ai), "r"(last));
             asm volatile("st.shared.u32 [%0], %1;" :: "r"(al), "r"(bit));
             const uint32_t m = a + bit;          // bit is an empty cell: + is |
-#if SQ_PL_SHF > 0
+#if SQ_PL_LINE3
+            // r_d = m & m<<d & m<<2d: bit at the END of every run of >= 3 in direction d; a run of >= 4 also has m<<3d
+            const uint32_t h1 = m << 1, h2 = m << 2, h3 = m << 3, v1 = m << 6, v2 = m << 12, v3 = m << 18;
+            const uint32_t d1 = m << 7, d2 = m << 14, d3 = m << 21, a1 = m << 5, a2 = m << 10, a3 = m << 15;
+            const uint32_t rh = m & h1 & h2, rv = m & v1 & v2, rd = m & d1 & d2, ra = m & a1 & a2;
+            const uint32_t t3 = rh | rv | rd | ra;
+            const uint32_t t4 = (rh & h3) | (rv & v3) | (rd & d3) | (ra & a3);
+#elif SQ_PL_SHF > 0
             Pairs p;
             p.h = m & (m << 1);
             p.v = m & (SQ_PL_SHF >= 1 ? shl_alu(m, 6) : (m << 6));
             p.d = m & (SQ_PL_SHF >= 2 ? shl_alu(m, 7) : (m << 7));
             p.a = m & (SQ_PL_SHF >= 3 ? shl_alu(m, 5) : (m << 5));
+            const uint32_t t3 = any3(p), t4 = any4(p);
 #else
             const Pairs p = pairs(m);
-#endif
             const uint32_t t3 = any3(p), t4 = any4(p);
+#endif
             const uint32_t n1 = n - 1u;
             const bool line = t3 != 0;
             const bool term = line | (n1 == 0);

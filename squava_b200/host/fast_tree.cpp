@@ -193,7 +193,8 @@ struct Leaf { uint32_t node; uint32_t x, o; int8_t to_move; bool fresh; uint8_t 
 }  // namespace
 
 FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, const FastOptions& opt) {
-    static uint64_t stream_id = 1ull << 40;
+    static std::atomic<uint64_t> stream_counter{1ull << 40};
+    auto next_stream = [&] { return opt.stream_base + stream_counter.fetch_add(1); };
     const Hooks* hk = opt.hooks;
     int T = opt.threads > 0 ? opt.threads : (int)std::thread::hardware_concurrency();
     if (T < 1) T = 1;
@@ -232,7 +233,8 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
     std::vector<Chunk> chunks((size_t)T);
     std::vector<Shard> shards(exact ? 0 : (size_t)T);
     std::vector<Rng> rngs;
-    for (int t = 0; t < T; t++) rngs.emplace_back(host_rng()());
+    if (opt.rng_seed) { std::mt19937_64 g(opt.rng_seed); for (int t = 0; t < T; t++) rngs.emplace_back(g()); }
+    else for (int t = 0; t < T; t++) rngs.emplace_back(host_rng()());
 
     // One walk from the root to a leaf is a chain of dependent cache misses (each level's child block is
     // cold once the tree is large), so every thread advances a GROUP of walks in turn, one level per
@@ -356,6 +358,7 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
     std::vector<sq_board> boards;
     std::vector<int8_t> to_move;
     std::vector<uint64_t> out;
+    std::vector<uint8_t> packed;
     long long done = 0;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
@@ -403,8 +406,21 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
             }
         });
         auto t1 = now();
-        if (hk && hk->playouts) hk->playouts(boards.data(), to_move.data(), B, (uint64_t)p, stream_id++, (uint64_t(*)[4])out.data());
-        else must(sq_playouts(boards.data(), to_move.data(), B, (uint64_t)p, stream_id++, (uint64_t(*)[4])out.data()), "sq_playouts");
+        const uint64_t sid = next_stream();
+        if (hk && hk->playouts) hk->playouts(boards.data(), to_move.data(), B, (uint64_t)p, sid, (uint64_t(*)[4])out.data());
+        else if (p == 1) {
+            // one playout per leaf: one outcome byte per leaf comes back (1 B instead of 32 B), unpacked below
+            packed.resize((size_t)B);
+            if (opt.device_slot >= 0) must(sq_playouts_packed_on(opt.device_slot, boards.data(), to_move.data(), B, sid, packed.data()), "sq_playouts_packed_on");
+            else must(sq_playouts_packed(boards.data(), to_move.data(), B, sid, packed.data()), "sq_playouts_packed");
+            for (long long k = 0; k < B; k++) {
+                const uint8_t c = packed[(size_t)k];
+                uint64_t* r = &out[(size_t)k * 4];
+                r[0] = (c & 3) == 1; r[1] = (c & 3) == 2; r[2] = (c & 3) == 3; r[3] = c >> 2;
+            }
+        }
+        else if (opt.device_slot >= 0) must(sq_playouts_on(opt.device_slot, boards.data(), to_move.data(), B, (uint64_t)p, sid, (uint64_t(*)[4])out.data()), "sq_playouts_on");
+        else must(sq_playouts(boards.data(), to_move.data(), B, (uint64_t)p, sid, (uint64_t(*)[4])out.data()), "sq_playouts");
         auto t2 = now();
         pool.run([&](int t) {
             const long long lo = B * t / T, hi = B * (t + 1) / T;
@@ -479,6 +495,54 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
     munmap(nodes, cap * sizeof(FNode));
     if (res.best_move < 0) { std::fprintf(stderr, "Node has %d children\n", n); std::exit(2); }
     return res;
+}
+
+RootParallelResult root_parallel_uct(const GameState& rootstate, long long itermax, double UCTK, const FastOptions& opt,
+                                     int n_searchers) {
+    if (n_searchers < 1) n_searchers = 1;
+    const int devices = std::max(1, sq_device_count());
+    int T = opt.threads > 0 ? opt.threads : (int)std::thread::hardware_concurrency();
+    if (T < n_searchers) T = n_searchers;
+    RootParallelResult R;
+    R.searcher.resize((size_t)n_searchers);
+    const uint64_t seed0 = opt.rng_seed ? opt.rng_seed : host_rng()();
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int i = 0; i < n_searchers; i++)
+        th.emplace_back([&, i] {
+            FastOptions o = opt;
+            o.threads = T * (i + 1) / n_searchers - T * i / n_searchers;
+            o.device_slot = opt.hooks ? -1 : i % devices;
+            o.stream_base = opt.stream_base + ((uint64_t)(i + 1) << 48);
+            o.rng_seed = seed0 + 0x9e3779b97f4a7c15ull * (uint64_t)(i + 1);
+            const long long share = itermax * (i + 1) / n_searchers - itermax * i / n_searchers;
+            R.searcher[(size_t)i] = fast_uct(rootstate, share, UCTK, o);
+        });
+    for (auto& t : th) t.join();
+    R.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    // merge: sum the root children's statistics by move, then bestMove over the sums
+    FastResult& M = R.merged;
+    std::memset(&M, 0, sizeof M);
+    double v[25] = {0}, w[25] = {0};
+    for (const FastResult& r : R.searcher) {
+        for (int k = 0; k < r.n_children; k++) { v[r.child_move[k]] += r.child_visits[k]; w[r.child_move[k]] += r.child_wins[k]; }
+        M.iterations += r.iterations; M.batches += r.batches; M.root_visits += r.root_visits; M.nodes += r.nodes;
+        M.select_seconds = std::max(M.select_seconds, r.select_seconds); M.gpu_seconds = std::max(M.gpu_seconds, r.gpu_seconds);
+        M.update_seconds = std::max(M.update_seconds, r.update_seconds); M.threads += r.threads;
+    }
+    const double factor = opt.ucb_factor2 ? 2. : 1.;
+    const double lg = factor * std::log(M.root_visits);
+    double bestscore = kEps;
+    M.best_move = -1;
+    for (int m = 0; m < 25; m++) {
+        if (!(v[m] > 0)) continue;
+        const int i = M.n_children++;
+        M.child_move[i] = m; M.child_visits[i] = v[m]; M.child_wins[i] = w[m];
+        const double s = w[m] / (v[m] + kEps) + UCTK * std::sqrt(lg / (v[m] + kEps));
+        if (s > bestscore) { bestscore = s; M.best_move = m; M.value = (int)(1000. * s); }
+    }
+    if (M.best_move < 0) { std::fprintf(stderr, "Node has %d children\n", M.n_children); std::exit(2); }
+    return R;
 }
 
 }  // namespace mcts

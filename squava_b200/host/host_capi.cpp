@@ -2,6 +2,8 @@
 // injectable callbacks, so the TREE logic (select / expand / backprop / UCB1, mcts.go:123-271)
 // can be compared with the reference's on a CPU box: the rollout, the terminal test and
 // rand.Intn come from the caller.  With null callbacks it runs on the GPU like squavam does.
+#include <chrono>
+
 #include "squava_host.hpp"
 
 using namespace squava;
@@ -64,6 +66,43 @@ int sqh_fast_uct(uint32_t x, uint32_t o, int player_just_moved, long long iterma
     if (root_visits) *root_visits = r.root_visits;
     if (seconds) { seconds[0] = r.select_seconds; seconds[1] = r.gpu_seconds; seconds[2] = r.update_seconds; }
     if (nodes) *nodes = r.nodes;
+    return 0;
+}
+
+// Root-parallel: n_searchers independent arena trees (searcher i on device slot i % devices; with callbacks all on
+// the callbacks), statistics merged by move.  device_slot >= 0 pins a ONE-searcher call to that device and
+// stream_base separates the random streams of searchers living in different processes (torchrun ranks).
+int sqh_root_parallel_uct(uint32_t x, uint32_t o, int player_just_moved, long long itermax, double uctk, int factor2, int batch,
+                          int playouts_per_leaf, int threads, int n_searchers, int device_slot, unsigned long long stream_base,
+                          unsigned long long rng_seed, sqh_terminal_fn terminal, sqh_playouts_fn playouts, void* ud,
+                          double visits[25], double wins[25], int* best_move, int* value, double* root_visits, double* seconds) {
+    GameState st;
+    st.board.x = x; st.board.o = o; st.playerJustMoved = player_just_moved;
+    Hooks hk;
+    if (terminal) hk.terminal = [=](const Board& b) { return terminal(b.x, b.o, ud) != 0; };
+    if (playouts) hk.playouts = [=](const sq_board* l, const int8_t* t, int64_t n, uint64_t p, uint64_t s, uint64_t (*out)[4]) {
+        playouts(l, t, n, p, s, out, ud);
+    };
+    FastOptions opt;
+    opt.batch = batch; opt.playouts_per_leaf = playouts_per_leaf; opt.ucb_factor2 = factor2 != 0; opt.threads = threads;
+    opt.stream_base = stream_base; opt.rng_seed = rng_seed;
+    if (terminal || playouts) opt.hooks = &hk;
+    FastResult m;
+    double secs;
+    if (n_searchers <= 1 && device_slot >= 0) {
+        opt.device_slot = device_slot;
+        auto t0 = std::chrono::steady_clock::now();
+        m = fast_uct(st, itermax, uctk, opt);
+        secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    } else {
+        RootParallelResult r = root_parallel_uct(st, itermax, uctk, opt, n_searchers);
+        m = r.merged; secs = r.seconds;
+    }
+    for (int c = 0; c < 25; c++) { visits[c] = 0; wins[c] = 0; }
+    for (int k = 0; k < m.n_children; k++) { visits[m.child_move[k]] = m.child_visits[k]; wins[m.child_move[k]] = m.child_wins[k]; }
+    *best_move = m.best_move; *value = m.value;
+    if (root_visits) *root_visits = m.root_visits;
+    if (seconds) *seconds = secs;
     return 0;
 }
 

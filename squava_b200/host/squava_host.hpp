@@ -145,6 +145,9 @@ struct FastOptions {
     uint64_t max_nodes = 0;          // arena slots (virtual memory); 0 = sized from the iteration count
     bool exact_ucb = false;          // UCB1 in double, reference tie rule (always on under a caller-supplied rand.Intn)
     const Hooks* hooks = nullptr;    // tests; a supplied intn forces one thread
+    int device_slot = -1;            // >= 0: every GPU call of this search on that one device (root-parallel: one tree per device)
+    uint64_t stream_base = 0;        // added to the random-stream ids of this search: searchers of one decision must not share streams
+    uint64_t rng_seed = 0;           // != 0: seeds this search's host RNGs (else they are drawn from the process-wide host RNG)
 };
 struct FastResult {
     int best_move, value;            // argmax UCB1 over the root's children, int(1000*UCB1) (mcts.go:196-198)
@@ -156,6 +159,21 @@ struct FastResult {
     int threads;
 };
 FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, const FastOptions& opt);
+
+// Root-parallel MCTS (the shape of squavam2.go:93-112 -- N searchers, ONE decision -- without its shared, locked
+// tree): n_searchers independent arena trees are grown from the same root, searcher i on device slot
+// i % sq_device_count() with its own share of the host threads, its own host RNG and its own random streams,
+// itermax / n_searchers iterations each.  The root children's {visits, wins} are then summed move by move and the
+// move returned is argmax UCB1 over the merged statistics (mcts.go:196-198,218-238).  One process drives all the
+// devices, so the merge is a sum in host memory; under torchrun (one process per GPU, bench.py) the same 2 x 25
+// vector is merged with one NCCL all-reduce instead.
+struct RootParallelResult {
+    FastResult merged;               // child_* merged by move (ascending move order), best_move / value from the merged statistics
+    std::vector<FastResult> searcher;
+    double seconds;
+};
+RootParallelResult root_parallel_uct(const GameState& rootstate, long long itermax, double UCTK, const FastOptions& opt,
+                                     int n_searchers);
 
 class MCTS : public Player {           // mcts.go:32-90
 public:

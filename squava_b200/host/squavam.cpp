@@ -32,7 +32,7 @@ static int readMove(const Board& bd) {             // squavam.go:345-372
 
 int main(int argc, char** argv) {
     int iterMax = 10000, batch = 256, ppl = 1, gpus = 0, seed = -1, threads = 0;
-    bool fast = false, stats = false;
+    bool fast = false, stats = false, rootParallel = false;
     double uctk = 1.00;
     bool computerFirst = false;
     Flags fl;
@@ -44,6 +44,7 @@ int main(int argc, char** argv) {
     fl.Bool("fast", &fast, "arena tree with multi-threaded select/update (for 10^8..10^9 iterations); no tree reuse");
     fl.Int("threads", &threads, "with -fast: host threads (default: all)");
     fl.Bool("stats", &stats, "with -fast: print iterations, nodes and the time spent selecting / on the GPU / updating");
+    fl.Bool("root-parallel", &rootParallel, "with -fast -gpus N: N independent trees, one per GPU, root statistics merged once per decision (squavam2.go's N searchers without the shared tree)");
     fl.Int("gpus", &gpus, "number of GPUs (default 1)");
     fl.Int("seed", &seed, "seed for reproducible play (default: clock, as the reference)");
     fl.Parse(argc, argv);
@@ -62,7 +63,16 @@ int main(int argc, char** argv) {
             auto start = std::chrono::steady_clock::now();
             if (fast) {
                 FastOptions fo; fo.batch = batch; fo.playouts_per_leaf = ppl; fo.ucb_factor2 = false; fo.threads = threads;
-                FastResult r = fast_uct(state, iterMax, uctk, fo);
+                FastResult r;
+                if (rootParallel) {
+                    RootParallelResult rp = root_parallel_uct(state, iterMax, uctk, fo, sq_device_count());
+                    r = rp.merged;
+                    if (stats)
+                        for (size_t i = 0; i < rp.searcher.size(); i++)
+                            std::printf("searcher %zu: %lld iterations, best %d %d, select %.3fs gpu %.3fs update %.3fs\n", i, rp.searcher[i].iterations,
+                                        rp.searcher[i].best_move / 5, rp.searcher[i].best_move % 5, rp.searcher[i].select_seconds,
+                                        rp.searcher[i].gpu_seconds, rp.searcher[i].update_seconds);
+                } else r = fast_uct(state, iterMax, uctk, fo);
                 m = r.best_move;
                 double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
                 std::printf("My move: %d %d %s\n", m / 5, m % 5, go_duration(el).c_str());

@@ -234,3 +234,45 @@ def test_fast_arena_tree_throughput_mode_searches_like_the_exact_mode(host_lib):
     assert a[inner].sum() > 0.6 and b[inner].sum() > 0.6 and abs(a[inner].sum() - b[inner].sum()) < 0.2
     outer = [c for c in range(25) if not good >> c & 1]
     assert a[outer].max() < 0.05 and b[outer].max() < 0.05
+
+
+def test_root_parallel_searchers_merge_their_root_statistics(host_lib):
+    """root-parallel MCTS (N searchers, one decision: squavam2.go:93-112 without the shared tree): every iteration
+    is counted once over all searchers, the merged statistics equal the sum of what the searchers report, and the
+    merged decision lands where a single tree with the whole budget lands (synthetic game: the inner ring wins)"""
+    good = sum(1 << c for c in (6, 7, 8, 11, 13, 16, 17, 18))
+    tr = np.array([sum(1 << c for c in t) if not isinstance(t, int) else t for t in E.TRIPLETS], dtype=np.uint32)
+    rng = np.random.Generator(np.random.PCG64(21))
+    streams = set()
+
+    def playouts(leaves, to_move, n, per_leaf, stream_id, out, ud):
+        streams.add(stream_id >> 48)                     # searcher i draws from stream ids (i + 1) << 48 ...
+        b = np.ctypeslib.as_array(C.cast(leaves, C.POINTER(C.c_uint32)), shape=(n, 2))
+        o = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint64)), shape=(n, 4))
+        x, oo = b[:, 0], b[:, 1]
+        term = ((x[:, None] & tr) == tr).any(axis=1) | ((oo[:, None] & tr) == tr).any(axis=1) | ((x | oo) == 0x1ffffff)
+        edge = np.bitwise_count(x & np.uint32(good)).astype(np.float64) - np.bitwise_count(oo & np.uint32(good))
+        xw = rng.binomial(per_leaf, 1.0 / (1.0 + np.exp(-0.9 * edge))).astype(np.uint64)
+        o[:, 0] = xw; o[:, 1] = np.uint64(per_leaf) - xw; o[:, 2] = 0; o[:, 3] = np.where(term, 0, 3 * per_leaf)
+    lib = host_lib
+    lib.sqh_root_parallel_uct.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_longlong, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_int, C.c_ulonglong, C.c_ulonglong, TERM, PLAY, C.c_void_p, C.POINTER(C.c_double),
+                                          C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                          C.POINTER(C.c_double)]
+    term_cb, play_cb = TERM(lambda x, o, ud: int(terminal(x, o))), PLAY(playouts)
+    share = {}
+    for n_searchers in (1, 4):
+        streams.clear()
+        visits = (C.c_double * 25)(); wins = (C.c_double * 25)()
+        best, value, rootv, secs = C.c_int(), C.c_int(), C.c_double(), C.c_double()
+        rc = lib.sqh_root_parallel_uct(0, 0, -1, 120_000, 0.7, 1, 1024, 2, 4, n_searchers, -1, 0, 77, term_cb, play_cb, None,
+                                       visits, wins, C.byref(best), C.byref(value), C.byref(rootv), C.byref(secs))
+        assert rc == 0
+        v = np.array(list(visits)); w = np.array(list(wins))
+        assert rootv.value == 120_000 and v.sum() == 120_000 and (w <= v).all() and (v > 0).all()
+        assert len(streams) == n_searchers              # disjoint random streams per searcher
+        assert good >> best.value & 1
+        share[n_searchers] = v / v.sum()
+    inner = [c for c in range(25) if good >> c & 1]
+    assert share[1][inner].sum() > 0.6 and share[4][inner].sum() > 0.6
+    assert abs(share[1][inner].sum() - share[4][inner].sum()) < 0.2

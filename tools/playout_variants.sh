@@ -7,13 +7,11 @@ cd "$(dirname "$0")/.."
 mkdir -p variants
 declare -A V
 V[base]=""
-V[addr_imad]="-DSQ_PL_ADDR_ALU=0"
-V[acc_alu]="-DSQ_PL_ACC_ALU=1"
-V[shf1]="-DSQ_PL_SHF=1"
-V[shf2]="-DSQ_PL_SHF=2"
-V[acc_alu_shf1]="-DSQ_PL_ACC_ALU=1 -DSQ_PL_SHF=1"
+V[line3_off]="-DSQ_PL_LINE3=0"
 V[ctas5]="-DSQ_PLAYOUT_CTAS_PER_SM=5"
-V[ctas3]="-DSQ_PLAYOUT_CTAS_PER_SM=3"
+V[ctas5_line3_off]="-DSQ_PLAYOUT_CTAS_PER_SM=5 -DSQ_PL_LINE3=0"
+V[ctas6_line3_off]="-DSQ_PLAYOUT_CTAS_PER_SM=6 -DSQ_PL_LINE3=0"
+V[acc_alu_line3_off]="-DSQ_PL_ACC_ALU=1 -DSQ_PL_LINE3=0"
 if [ "$1" = "run" ]; then
     for k in "${!V[@]}"; do
         export SQUAVA_B200_LIB="$PWD/variants/libsquava_b200_$k.so"
