@@ -275,6 +275,55 @@ def secondary_c4(sq, rank, world, dev, dist, torch, peak_ops):
     return rec
 
 
+def secondary_c4_mcts(sq, rank, world, dev, dist, torch, playouts_per_position):
+    """configs[4], MCTS half: root-parallel MCTS from opening3's 85 two-mark positions.  Every rank grows its OWN tree
+    per position on its own GPU (C++ arena tree of the host library, leaf batches of 1024 leaves x 65536 playouts,
+    its own host RNG seed and random-stream ids), then the per-root-move {visits, wins} vectors of all positions --
+    85 x 2 x 25 doubles -- are merged with ONE NCCL all-reduce and the move is chosen from the merged statistics
+    (argmax UCB1, mcts.go:196-198).  Checked inside the run: every iteration is counted once."""
+    C = ctypes
+    L = host_lib()
+    L.sqh_root_parallel_uct.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_longlong, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_ulonglong, C.c_ulonglong, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                        C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    pairs, _ = opening3_subtrees(sq)
+    ppl, batch = 65536, 1024
+    iters = int(playouts_per_position)
+    stats = np.zeros((len(pairs), 2, 25), np.float64)
+    visits = (C.c_double * 25)(); wins = (C.c_double * 25)()
+    best, value, rootv, secs = C.c_int(), C.c_int(), C.c_double(), C.c_double()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i, (f, r) in enumerate(pairs):
+        rc = L.sqh_root_parallel_uct(1 << f, 1 << r, -1, iters, 1.0, 1, batch, ppl, 0, 1, 0, ((rank + 1) << 56) | (i << 44),
+                                     1000 + 85 * rank + i, None, None, None, visits, wins, C.byref(best), C.byref(value),
+                                     C.byref(rootv), C.byref(secs))
+        assert rc == 0 and rootv.value == iters
+        stats[i, 0] = list(visits); stats[i, 1] = list(wins)
+    t_stats = torch.from_numpy(stats).to(dev)
+    if world > 1:
+        dist.all_reduce(t_stats)                                       # the merge: 85 x 2 x 25 doubles
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    merged = t_stats.cpu().numpy()
+    assert (merged[:, 0].sum(axis=1) == iters * world).all() and (merged[:, 1] <= merged[:, 0]).all()
+    moves = []
+    for i in range(len(pairs)):
+        v, w = merged[i, 0], merged[i, 1]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            u = np.where(v > 0, w / v + np.sqrt(2.0 * np.log(v.sum()) / v), -1.0)
+        moves.append(int(np.argmax(u)))
+    secs_all = float(t.item())
+    return {"workload": "configs[4] MCTS: root-parallel trees from the 85 opening3 positions, %.3g playouts per position and rank (leaf batches of %d x %d), %d rank(s), one NCCL all-reduce of the 85x2x25 root statistics" % (iters, batch, ppl, world),
+            "seconds": secs_all, "value": len(pairs) * iters * world / secs_all, "unit": UNIT, "playouts_per_s_per_gpu": len(pairs) * iters / secs_all,
+            "chosen_moves": moves}
+
+
 def host_lib():
     L = ctypes.CDLL(os.path.join(ROOT, "squava_b200", "host", "libsquava_host.so"))
     C = ctypes
@@ -588,6 +637,7 @@ def main():
                          "scaling": "strong"}
         # ---- configs[4]: every rank takes its share of opening3's subtrees ----
         sec["c4"] = secondary_c4(sq, rank, world, dev, dist, torch, peak_mixed)
+        sec["c4"]["mcts"] = secondary_c4_mcts(sq, rank, world, dev, dist, torch, 2 ** 30)
         if rank == 0 and world == 1:
             sec["c3"] = secondary_c3(sq, peak_mixed)
             sec.update(secondary_c0_c2(sq, int(args.c2_iterations)))

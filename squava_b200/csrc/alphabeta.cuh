@@ -990,7 +990,9 @@ inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t score
     R.shortcuts = worst < kWin - max_depth - 1 && !getenv("SQ_AB_NO_SHORTCUTS");
     build_horizon_tables(scores, R.hz);
     R.fast_horizon = R.shortcuts && R.hz.ok && !getenv("SQ_AB_NO_FAST_HORIZON");
-    R.ybw = !getenv("SQ_AB_NO_YBW");
+    // measured (profiles/r02_alphabeta_ybw_passes.md): with a barrier between passes the brothers' wait costs more
+    // time than the pruning it buys except in very deep searches, so it is opt-in for the pass-driven search
+    R.ybw = getenv("SQ_AB_YBW") != nullptr;
 }
 
 // worst-case node count below one level-0 node with e empties and `split` expanded plies

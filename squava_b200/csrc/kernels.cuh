@@ -138,7 +138,7 @@ __device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint3
 }
 
 #ifndef SQ_PLAYOUT_CTAS_PER_SM
-#define SQ_PLAYOUT_CTAS_PER_SM 4
+#define SQ_PLAYOUT_CTAS_PER_SM 5      // 40 warps per SM (48 registers per thread): measured best of 3..6
 #endif
 // tuning knobs of the ply loop (pipe balance; the random stream and the results do not depend on them)
 #ifndef SQ_PL_ADDR_ALU

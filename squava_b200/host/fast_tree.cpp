@@ -348,7 +348,10 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
         return false;
     };
     constexpr int kPathLen = 27;
-    const int group = (hk && hk->intn) ? 1 : 16;
+    // walks a thread keeps in flight / paths it prefetches ahead while updating: memory-level parallelism knobs
+    auto env_int = [](const char* name, int dflt, int lo, int hi) { const char* e = std::getenv(name); int v = e && *e ? std::atoi(e) : dflt; return v < lo ? lo : v > hi ? hi : v; };
+    const int group = (hk && hk->intn) ? 1 : env_int("SQUAVA_FAST_GROUP", 16, 1, 64);
+    const long long kAhead = env_int("SQUAVA_FAST_AHEAD", 8, 1, 64);
 
     FastResult res;
     std::memset(&res, 0, sizeof res);
@@ -374,8 +377,8 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
         auto t0 = now();
         pool.run([&](int t) {
             const long long lo = B * t / T, hi = B * (t + 1) / T;
-            Walk walks[16];
-            long long slot_of[16];
+            Walk walks[64];
+            long long slot_of[64];
             Chunk& ck = chunks[(size_t)t];
             Shard* sh = exact ? nullptr : &shards[(size_t)t];
             long long next = lo;
@@ -424,7 +427,7 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
         auto t2 = now();
         pool.run([&](int t) {
             const long long lo = B * t / T, hi = B * (t + 1) / T;
-            constexpr long long kAhead = 8;                  // the paths are known: pull their nodes in early
+            // the paths are known: their nodes are pulled in kAhead paths early
             uint64_t root_wins = 0;
             Shard* sh = exact ? nullptr : &shards[(size_t)t];
             const uint32_t fc1 = nodes[root].first_child.load(std::memory_order_acquire);
