@@ -113,7 +113,9 @@ struct AbRun {
     int* kids;                       // first child of a split node (its children are contiguous, eldest first), -1: none
     int* held;                       // younger children of a split node still waiting for the eldest to finish
     int* released;                   // younger children set free in this pass: units of the next one
-    unsigned int* counters;          // [0] n_nodes [1] n_units [2] queue head [3] n_aborted [4] node pool overflowed [5] n_released [6] smallest ply among the next pass's units
+    unsigned int* counters;          // [0] n_nodes [1] n_units = queue tail [2] queue head [3] n_aborted [4] node pool overflowed
+                                     // [5] n_released [6] smallest ply among the next pass's units
+                                     // queue-driven search: [7] units alive (queued or being searched) [8] watchdog fired [9] heartbeat
     int* out;                        // final values
     unsigned long long* node_count;  // evaluator calls per group
     int node_capacity;
@@ -121,6 +123,9 @@ struct AbRun {
     int sentinel;        // |value| of a node with no legal move: 20000, or 10000 (opening2)
     int win_lo, win_hi;  // the dialect's root window
     int shortcuts;       // exact shortcuts allowed (see ab_move_classes); off when |heuristic sums| could reach a win score
+    int queued;          // queue-driven search: ONE persistent kernel, units flow through a device-side queue (see ab_dfs_kernel)
+    unsigned int min_budget;   // queue-driven: evaluator calls a unit spends before it may be split for hungry lanes
+    long long stall_cycles;    // queue-driven watchdog: idle lanes give up when the heartbeat stands still this long
     int ybw;             // young brothers wait: a split node's younger children start only when the eldest has finished
     int fast_horizon;    // horizon-1 nodes are valued in one bit-parallel shot (ab_horizon.cuh): needs the shortcuts and a bias table spanning < 30
     int8_t scores[25];
@@ -195,6 +200,16 @@ __device__ __forceinline__ void load_tables(AbTables& dst) {
 // ---- node bookkeeping ---------------------------------------------------------------
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
+// A node becomes a unit: of the next pass (pass-driven search) or of the running kernel (queue-driven: the slot
+// write is what a lane holding that ticket is polling for, so everything about the node is fenced before it).
+__device__ __forceinline__ void ab_enqueue(const AbRun& R, int idx, int ply) {
+    if (R.queued) atomicAdd(&R.counters[7], 1u);
+    const unsigned slot = atomicAdd(&R.counters[1], 1u);
+    __threadfence();
+    *reinterpret_cast<volatile int*>(&R.units[slot]) = idx;
+    if (!R.queued) atomicMin(&R.counters[6], (unsigned)ply);
+}
+
 // A finished node hands its value to its parent; the last child to finish carries on upward.
 __device__ void ab_complete(const AbRun& R, int node, int value) {
     for (;;) {
@@ -210,9 +225,13 @@ __device__ void ab_complete(const AbRun& R, int node, int value) {
             const int nh = R.held[parent];
             if (nh > 0) {
                 R.held[parent] = 0;
-                const unsigned at = atomicAdd(&R.counters[5], (unsigned)nh);
-                for (int k = 0; k < nh; k++) R.released[at + k] = node + 1 + k;
-                atomicMin(&R.counters[6], (unsigned)R.nodes[node].ply);
+                if (R.queued) {
+                    for (int k = 0; k < nh; k++) ab_enqueue(R, node + 1 + k, 0);
+                } else {
+                    const unsigned at = atomicAdd(&R.counters[5], (unsigned)nh);
+                    for (int k = 0; k < nh; k++) R.released[at + k] = node + 1 + k;
+                    atomicMin(&R.counters[6], (unsigned)R.nodes[node].ply);
+                }
             }
         }
         int old = atomicSub(&R.pending[parent], 1);
@@ -244,11 +263,7 @@ __device__ __forceinline__ int ab_new_node(const AbRun& R, const AbNode& n) {
     R.pending[idx] = 0;
     R.kids[idx] = -1;
     R.held[idx] = 0;
-    if (n.split == 0) {
-        unsigned int u = atomicAdd(&R.counters[1], 1u);
-        R.units[u] = (int)idx;
-        atomicMin(&R.counters[6], (unsigned)n.ply);
-    }
+    if (n.split == 0) ab_enqueue(R, (int)idx, n.ply);
     return (int)idx;
 }
 
@@ -445,11 +460,69 @@ ab_expand_kernel(AbRun R, const int* __restrict__ list, int lo, int count) {
         R.pending[ci] = 0;
         R.kids[ci] = -1;
         R.held[ci] = 0;
-        if (c.split == 0 && (!hold || j == 0)) R.units[atomicAdd(&R.counters[1], 1u)] = ci;
+        if (c.split == 0 && (!hold || j == 0)) ab_enqueue(R, ci, c.ply);
         j++;
     }
-    if (n.split == 1) atomicMin(&R.counters[6], (unsigned)(n.ply + 1));
     atomicAdd(&R.node_count[n.group], evals);
+}
+
+// Queue-driven search: a lane hands its unit over to hungry lanes.  The unit's node gets children for the root
+// moves the lane has NOT finished (`cells`, API layout: the untried ones and the one it was inside), its value slot
+// is seeded with what the finished ones gave (a bound like any other child's), and the children go to the queue --
+// all of them if there is a bound already, else the eldest only (the brothers wait for it, see ab_complete).
+// Returns false when the node pool has no room: the lane then simply carries on searching.
+template <int DIALECT>
+__device__ __noinline__ bool ab_split_unit(const AbTables& T, const AbRun& R, int unit, uint32_t cells, int seed_value,
+                                           bool have_seed, int carried_down, unsigned long long* evals) {
+    const AbNode n = R.nodes[unit];
+    const int nch = __popc(cells);
+    unsigned base = *reinterpret_cast<volatile unsigned*>(&R.counters[0]);
+    for (;;) {                                                   // reserve nch contiguous slots, or none
+        if (base + (unsigned)nch > (unsigned)R.node_capacity) return false;
+        const unsigned seen = atomicCAS(&R.counters[0], base, base + (unsigned)nch);
+        if (seen == base) break;
+        base = seen;
+    }
+    const bool hold = R.ybw && !have_seed && nch >= 2;
+    R.kids[unit] = (int)base;
+    R.held[unit] = hold ? nch - 1 : 0;
+    if (have_seed) { if (n.side > 0) atomicMax(&R.value[unit], seed_value); else atomicMin(&R.value[unit], seed_value); }
+    R.pending[unit] = nch;
+    __threadfence();
+    const bool pend_is_x = (n.x >> n.cell) & 1u;
+    const int sign = pend_is_x ? 1 : -1;
+    int j = 0;
+    for (int k = 0; k < 25; k++) {               // children in the dialect's visiting order
+        const int cell = AbTraits<DIALECT>::ordered ? T.order[k] : k;
+        const uint32_t bit = 1u << cell;
+        if (!(cells & bit)) continue;
+        AbNode c;
+        c.x = n.x | (n.side > 0 ? bit : 0u);
+        c.o = n.o | (n.side > 0 ? 0u : bit);
+        c.cell = (int8_t)cell;
+        c.ply = n.ply + 1;
+        c.side = -n.side;
+        c.split = 0;
+        c.parent = unit;
+        c.group = n.group;
+        if (AbTraits<DIALECT>::delayed) {   // the unit's pending move re-evaluated with this child's mark on
+            Eval e = eval_lines(T, pend_is_x ? c.x : c.o, pend_is_x ? c.o : c.x, n.cell, sign, n.ply);
+            c.carried = e.value + sign * R.scores[n.cell] + (AbTraits<DIALECT>::delayed_sum ? n.carried : 0);
+            if (AbTraits<DIALECT>::penalties) c.carried += eval_penalties(T, pend_is_x ? c.x : c.o, pend_is_x ? c.o : c.x, n.cell, sign);
+            (*evals)++;
+        } else {
+            c.carried = carried_down;
+        }
+        const int ci = (int)base + j;
+        R.nodes[ci] = c;
+        R.value[ci] = c.side > 0 ? -R.sentinel : R.sentinel;
+        R.pending[ci] = 0;
+        R.kids[ci] = -1;
+        R.held[ci] = 0;
+        if (!hold || j == 0) ab_enqueue(R, ci, c.ply);
+        j++;
+    }
+    return true;
 }
 
 // Sequential alpha-beta per lane over the queued units.
@@ -507,7 +580,17 @@ __device__ __forceinline__ AbWalk ab_walk(const AbWalkTables& W, uint32_t own, u
 
 template <int DIALECT> struct AbFrameWords { static constexpr int n = AbTraits<DIALECT>::delayed ? 5 : 3; };
 
-template <int DIALECT>
+//
+// QUEUED = false: pass-driven.  The host launches one pass per generation of units; a unit that exceeds `budget`
+// is handed back (aborted[]) and split by ab_expand_kernel before the next pass.
+// QUEUED = true: queue-driven.  ONE persistent launch per search.  units[] is a ticket queue in global memory:
+// counters[1] = tail (bumped by whoever makes a unit: the root kernels, a lane that splits its unit, ab_complete
+// setting waiting brothers free), counters[2] = head (a lane without work draws a ticket and polls ITS slot until
+// a unit lands there), counters[7] = units alive; the search is over when that count reaches zero.  A lane splits
+// its unit only when it has spent min_budget evaluator calls on it AND some lane is hungry (head > tail): small
+// subtrees and busy machines keep sequential pruning, big subtrees on an idle machine are spread one generation
+// at a time, eldest child first (young brothers wait), with no host round trip and no barrier in between.
+template <int DIALECT, bool QUEUED>
 __global__ void __launch_bounds__(kAbThreads)
 ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
     __shared__ AbTables T;
@@ -532,6 +615,11 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
     unsigned long long evals = 0;
     bool fresh = false;                        // the register frame was just entered
     (void)n_frames;
+    // queue-driven search
+    unsigned ticket = 0xffffffffu;             // the queue slot this lane is waiting on
+    bool no_split = false;                     // the node pool had no room: finish the unit alone
+    unsigned iter = 0;
+    unsigned beat_seen = 0; long long beat_at = 0;
 
     auto order_mask = [&](uint32_t cells) -> uint32_t {   // API layout -> child-order space
         if (!kOrdered) return cells;
@@ -544,10 +632,32 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
         int ret = 0;
         bool returning = false;   // `ret` is to be handed to frame sp ...
         bool restore = false;     // ... which is in shared memory (a pushed child came back)
+        iter++;
         if (sp < 0) {
-            unsigned int u = atomicAdd(&R.counters[2], 1u);
-            if (u >= (unsigned)n_units) break;
-            unit = R.units[u];
+            if (QUEUED) {
+                // a waiting lane shares its warp with working ones: it looks at its slot on every eighth turn only
+                if (ticket != 0xffffffffu && (iter & 7u) != 0) continue;
+                if (ticket == 0xffffffffu) ticket = atomicAdd(&R.counters[2], 1u);
+                const int got = ticket < (unsigned)R.node_capacity ? *reinterpret_cast<const volatile int*>(&R.units[ticket]) : -1;
+                if (got < 0) {
+                    // nothing in my slot yet: done if no unit is alive anywhere; else wait (other lanes of the warp step on)
+                    if (ld_volatile(reinterpret_cast<const int*>(&R.counters[7])) <= 0 || ld_volatile(reinterpret_cast<const int*>(&R.counters[8])) != 0) break;
+                    // watchdog: working lanes advance the heartbeat; if it stands still for stall_cycles, give up
+                    const unsigned beat = (unsigned)ld_volatile(reinterpret_cast<const int*>(&R.counters[9]));
+                    const long long now = clock64();
+                    if (beat != beat_seen || beat_at == 0) { beat_seen = beat; beat_at = now; }
+                    else if (now - beat_at > R.stall_cycles) { atomicExch(&R.counters[8], 1u); break; }
+                    __nanosleep(200);
+                    continue;
+                }
+                __threadfence();
+                ticket = 0xffffffffu; no_split = false; beat_at = 0;
+                unit = got;
+            } else {
+                unsigned int u = atomicAdd(&R.counters[2], 1u);
+                if (u >= (unsigned)n_units) break;
+                unit = R.units[u];
+            }
             const AbNode n = R.nodes[unit];
             int a0 = R.win_lo, b0 = R.win_hi;
             ab_bounds(R, unit, a0, b0);
@@ -556,6 +666,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                 // It hands up a value its parent's atomicMin/Max ignores -- the parent is the other kind of
                 // node -- so the unit contributes nothing, as if the sequential search had never reached it.
                 ab_complete(R, unit, n.side > 0 ? 30000 : -30000);
+                if (QUEUED) atomicSub(&R.counters[7], 1u);
                 continue;
             }
             int v0 = 0, carried_down = 0;
@@ -563,6 +674,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
             if (ab_enter<DIALECT>(T, R, n, v0, carried_down)) {
                 atomicAdd(&R.node_count[group], evals);
                 ab_complete(R, unit, v0);
+                if (QUEUED) atomicSub(&R.counters[7], 1u);
                 continue;
             }
             x = n.x; o = n.o; base_ply = n.ply; base_side = n.side;
@@ -579,11 +691,37 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
             fresh = true;
             continue;
         }
-        if (evals > budget) {          // too big for one lane: hand the unit back to be split one ply deeper
+        if (!QUEUED && evals > budget) {   // too big for one lane: hand the unit back to be split one ply deeper
             atomicAdd(&R.node_count[group], evals);
             R.aborted[atomicAdd(&R.counters[3], 1u)] = unit;
             sp = -1;
             continue;
+        }
+        if (QUEUED && (iter & 31u) == 0) {
+            if ((iter & 255u) == 0) *reinterpret_cast<volatile unsigned*>(&R.counters[9]) = (unsigned)clock64();   // heartbeat of the working lanes
+            if (ld_volatile(reinterpret_cast<const int*>(&R.counters[8])) != 0) break;            // the watchdog fired somewhere
+            // hungry lanes (tickets drawn beyond the tail) and this unit has had its minimum: split it
+            if (!no_split && !fresh && evals >= R.min_budget &&
+                (unsigned)ld_volatile(reinterpret_cast<const int*>(&R.counters[2])) > (unsigned)ld_volatile(reinterpret_cast<const int*>(&R.counters[1]))) {
+                uint32_t rmoves; int rvalue, rcarried;
+                if (sp == 0) { rmoves = moves; rvalue = value; rcarried = carried; }
+                else {
+                    const uint32_t w0 = SQ_FR(0, 0);
+                    rmoves = (w0 & kFull25) | (1u << (w0 >> 25));                 // the child the lane is inside goes back too
+                    rvalue = (int)(short)(SQ_FR(0, 1) & 0xffffu);
+                    rcarried = (int)(short)(SQ_FR(0, 2) >> 16);
+                }
+                uint32_t cells = rmoves;
+                if (kOrdered) { cells = 0; for (uint32_t m = rmoves; m; m &= m - 1) cells |= 1u << T.order[__ffs(m) - 1]; }
+                const bool have_seed = rvalue != (base_side > 0 ? -R.sentinel : R.sentinel);
+                if (cells && ab_split_unit<DIALECT>(T, R, unit, cells, rvalue, have_seed, rcarried, &evals)) {
+                    atomicAdd(&R.node_count[group], evals);
+                    atomicSub(&R.counters[7], 1u);          // after its children were counted in
+                    sp = -1;
+                    continue;
+                }
+                no_split = true;
+            }
         }
 
         const int ply = base_ply + sp;
@@ -699,6 +837,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
             if (sp < 0) {
                 atomicAdd(&R.node_count[group], evals);
                 ab_complete(R, unit, ret);
+                if (QUEUED) atomicSub(&R.counters[7], 1u);
                 break;
             }
             const int s = (sp & 1) ? -base_side : base_side;
@@ -727,16 +866,23 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
 }
 
 // ---- host orchestration ---------------------------------------------------------------
+template <int DIALECT>
+inline cudaError_t ab_configure_dialect(int max_smem) {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(ab_dfs_kernel<DIALECT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(ab_dfs_kernel<DIALECT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+}
+
 inline cudaError_t ab_configure(int* blocks_per_sm) {
     int b1 = 0;
     const int max_smem = (kAbMaxDepth + 2) * 5 * kAbThreads * 4;
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(ab_dfs_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ab_dfs_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ab_dfs_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ab_dfs_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(ab_dfs_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, ab_dfs_kernel<1>, kAbThreads, 10 * 5 * kAbThreads * 4);
+    if ((e = ab_configure_dialect<1>(max_smem)) != cudaSuccess) return e;
+    if ((e = ab_configure_dialect<2>(max_smem)) != cudaSuccess) return e;
+    if ((e = ab_configure_dialect<3>(max_smem)) != cudaSuccess) return e;
+    if ((e = ab_configure_dialect<5>(max_smem)) != cudaSuccess) return e;
+    if ((e = ab_configure_dialect<6>(max_smem)) != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, ab_dfs_kernel<1, false>, kAbThreads, 10 * 5 * kAbThreads * 4);
     if (e != cudaSuccess) return e;
     *blocks_per_sm = b1 < 1 ? 1 : b1;
     return cudaSuccess;
@@ -903,7 +1049,7 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
         if (n_frames < 2) n_frames = 2;
         long long blocks = ((long long)n_units + kAbThreads - 1) / kAbThreads;
         if (blocks > grid_cap) blocks = grid_cap;
-        ab_dfs_kernel<DIALECT><<<(unsigned)blocks, kAbThreads, (size_t)n_frames * AbFrameWords<DIALECT>::n * kAbThreads * 4, st>>>(
+        ab_dfs_kernel<DIALECT, false><<<(unsigned)blocks, kAbThreads, (size_t)n_frames * AbFrameWords<DIALECT>::n * kAbThreads * 4, st>>>(
             R, n_units, budget, n_frames);
         (*launches)++;
         passes++;
@@ -946,6 +1092,67 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
     return cudaSuccess;
 }
 
+// Queue-driven search of one chunk: the root kernel makes the level-0 nodes and queues them, ONE persistent launch of
+// ab_dfs_kernel<., true> searches them to the end (splitting on the device as lanes run dry), the host only reads
+// the flags afterwards.  The node pool cannot grow while the kernel runs: it is sized from the request and from what
+// the last search of this process needed; if it does fill up, units simply stop being split (correct, less parallel)
+// and the next search starts with a bigger pool.
+constexpr long long kAbQueuePoolStart = 4ll << 20;
+
+template <int DIALECT>
+cudaError_t ab_run_queue(AbRun R, AbWork& w, const void* d_in, bool roots, int n, const int8_t* h_split,
+                         long long capacity, int sm_count, int min_ply, cudaStream_t st, uint64_t* launches) {
+    (void)h_split;
+    SQ_AB_CK(ab_alloc(w, capacity, st));
+    SQ_AB_CK(cudaMallocAsync(&w.counters, sizeof(unsigned int) * 16, st));
+    SQ_AB_CK(cudaMallocAsync(&w.split, n, st));
+    SQ_AB_CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned int) * 16, st));
+    SQ_AB_CK(cudaMemsetAsync(w.split, 0, n, st));
+    SQ_AB_CK(cudaMemsetAsync(w.units, 0xff, sizeof(int) * capacity, st));          // every queue slot: empty
+    R.nodes = w.nodes; R.value = w.value; R.pending = w.pending; R.units = w.units; R.aborted = w.aborted;
+    R.kids = w.kids; R.held = w.held; R.released = w.released;
+    R.counters = w.counters; R.node_capacity = (int)capacity;
+    R.queued = 1;
+    R.ybw = getenv("SQ_AB_NO_YBW") == nullptr;
+    { const char* e = getenv("SQ_AB_MIN_BUDGET"); R.min_budget = e && *e ? (unsigned)atoi(e) : 96u; }
+    R.stall_cycles = 8000000000ll;                  // ~4 s without any working lane's heartbeat: a stuck queue, not a long search
+    if (roots) {
+        int threads = n * 25;
+        ab_roots_kernel<DIALECT><<<(threads + kAbThreads - 1) / kAbThreads, kAbThreads, 0, st>>>(R, (const sq_board*)d_in, w.split, n);
+    } else {
+        ab_subtree_nodes_kernel<<<(n + kAbThreads - 1) / kAbThreads, kAbThreads, 0, st>>>(R, (const sq_subtree*)d_in, w.split, n);
+    }
+    (*launches)++;
+    SQ_AB_CK(cudaGetLastError());
+    int n_frames = R.max_depth - min_ply + 1;       // units sit at any ply from the level-0 nodes down
+    if (n_frames > kAbMaxDepth + 2) n_frames = kAbMaxDepth + 2;
+    if (n_frames < 2) n_frames = 2;
+    const size_t smem = (size_t)n_frames * AbFrameWords<DIALECT>::n * kAbThreads * 4;
+    int per_sm = 1;
+    SQ_AB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ab_dfs_kernel<DIALECT, true>, kAbThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (long long)sm_count * per_sm;             // every block resident: nobody polls for a block that has not started
+    const long long most = ((long long)n * 25 * 4 + kAbThreads - 1) / kAbThreads;   // a small request does not need the whole machine polling
+    if (blocks > most) blocks = most < 1 ? 1 : most;
+    const bool trace = getenv("SQ_AB_TRACE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    ab_dfs_kernel<DIALECT, true><<<(unsigned)blocks, kAbThreads, smem, st>>>(R, 0, 0ull, n_frames);
+    (*launches)++;
+    SQ_AB_CK(cudaGetLastError());
+    unsigned int h_counters[16];
+    SQ_AB_CK(cudaMemcpyAsync(h_counters, w.counters, sizeof h_counters, cudaMemcpyDeviceToHost, st));
+    SQ_AB_CK(cudaStreamSynchronize(st));
+    if (trace)
+        fprintf(stderr, "[ab] queue: %d level-0 inputs, %u nodes of %lld, %u units queued, %u tickets drawn, %u alive at the end, %u blocks, %.3f ms\n",
+                n, h_counters[0], capacity, h_counters[1], h_counters[2], h_counters[7], (unsigned)blocks,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    ab_free(w, st);
+    if (h_counters[8] || h_counters[7]) return cudaErrorLaunchTimeout;   // the watchdog fired / units left over: never a silent wrong answer
+    // remember what this search needed: twice the nodes it used, so that the next one has room to split freely
+    ab_hint_store(std::max<long long>(2ll * h_counters[0], kAbQueuePoolStart));
+    return cudaSuccess;
+}
+
 constexpr long long kAbChunkNodesDefault = 64ll << 20;   // ceiling of node slots per chunk: level-0 nodes + what adaptive splitting may draw (~2.5 GB when all used)
 
 inline long long ab_pool_nodes() {      // SQ_AB_POOL_NODES shrinks the pool (tests of the no-room path)
@@ -960,6 +1167,19 @@ inline cudaError_t ab_dispatch(int dialect, AbRun R, AbWork& w, const void* d_in
     // ceiling: SQ_AB_POOL_NODES (default 64 Mi slots, ~2.5 GB), never below what the level-0 nodes need;
     // the run starts with max(needed, kAbPoolStart) slots and grows towards the ceiling only if it splits that far
     const long long ceiling = std::max(needed + 16, ab_pool_nodes());
+    if (!getenv("SQ_AB_PASSES") && !getenv("SQ_AB_BUDGET") && !getenv("SQ_AB_SPLIT")) {
+        // queue-driven search (default).  SQ_AB_PASSES / SQ_AB_BUDGET / SQ_AB_SPLIT select the pass-driven one.
+        const long long cap_q = std::min(ceiling, std::max(std::max(2 * needed + 16, kAbQueuePoolStart), ab_hint().load()));
+        int dev_id = 0, sm_count = 148;
+        if (cudaGetDevice(&dev_id) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev_id) != cudaSuccess) return cudaGetLastError();
+        switch (dialect) {
+        case 1: return ab_run_queue<1>(R, w, d_in, roots, n, h_split, cap_q, sm_count, min_ply, st, launches);
+        case 2: return ab_run_queue<2>(R, w, d_in, roots, n, h_split, cap_q, sm_count, min_ply, st, launches);
+        case 5: return ab_run_queue<5>(R, w, d_in, roots, n, h_split, cap_q, sm_count, min_ply, st, launches);
+        case 6: return ab_run_queue<6>(R, w, d_in, roots, n, h_split, cap_q, sm_count, min_ply, st, launches);
+        default: return ab_run_queue<3>(R, w, d_in, roots, n, h_split, cap_q, sm_count, min_ply, st, launches);
+        }
+    }
     const long long capacity = std::min(ceiling, std::max(std::max(needed + 16, kAbPoolStart), ab_hint().load()));
     switch (dialect) {
     case 1: return ab_run_chunk<1>(R, w, d_in, roots, n, h_split, capacity, ceiling, grid_cap, min_ply, st, launches);

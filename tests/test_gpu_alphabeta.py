@@ -129,6 +129,38 @@ def test_schedule_does_not_change_values(dev, oracle, budget, pool):
     assert int(v3[0]) == oracle.ab_subtree(3, 1 << 12, 1 << 6, 6, 2, 1, 0, 6, oracle.tables()["scores_opening"])[0]
 
 
+@pytest.mark.parametrize("env", [{"SQ_AB_MIN_BUDGET": "1"}, {"SQ_AB_MIN_BUDGET": "5", "SQ_AB_NO_YBW": "1"}, {"SQ_AB_MIN_BUDGET": "100000"},
+                                 {"SQ_AB_POOL_NODES": "6000"}, {"SQ_AB_MIN_BUDGET": "3", "SQ_AB_NO_FAST_HORIZON": "1"}, {"SQ_AB_PASSES": "1"},
+                                 {"SQ_AB_PASSES": "1", "SQ_AB_YBW": "1"}])
+def test_queue_schedule_does_not_change_values(dev, oracle, env):
+    """the queue-driven search (one persistent kernel): how eagerly units are split for hungry lanes, whether the
+    brothers wait, a node pool too small to split in, the bit-parallel horizon evaluation on or off -- and the
+    pass-driven search instead -- are scheduling only: no value may move"""
+    from squava_b200 import positions
+    sc = oracle.tables()["scores_ab"]
+    boards, _ = positions.midgame_batch(24, marks=(10, 12, 14), seed=83)
+    so = oracle.tables()["scores_opening"]
+    rows = [(1 << 12, 1 << 6, 6, 2, 1, so[12]), (1 << 0, 1 << 24, 24, 2, 1, so[0]), (1 << 7, 0, 7, 1, -1, 0)]
+    for k, v in env.items():
+        os.environ[k] = v
+    try:
+        values, bv, bm, _ = dev.alphabeta_root(boards, 1, 10, sc)
+        v2, _, _, _ = dev.alphabeta_root(boards[:8], 2, 9, sc)
+        v3, _ = dev.alphabeta_subtrees(subtree_array(dev, rows[:2]), 3, 7, so)
+        v4, _ = dev.alphabeta_subtrees(subtree_array(dev, rows[2:]), 4, 7, so)
+    finally:
+        for k in env:
+            os.environ.pop(k, None)
+    for i in range(boards.shape[0]):
+        ov, obm, obv, _ = oracle.ab1_root(int(boards[i]["x"]), int(boards[i]["o"]), 10, sc)
+        assert values[i].tolist() == ov and (int(bm[i]), int(bv[i])) == (obm, obv), (env, i)
+    for i in range(8):
+        assert v2[i].tolist() == oracle.ab2_root(int(boards[i]["x"]), int(boards[i]["o"]), 9, sc)[0], (env, i)
+    for i, (x, o, last, ply, side, carried) in enumerate(rows):
+        want = oracle.ab_subtree(3 if i < 2 else 4, x, o, last, ply, side, carried, 7, so)[0]
+        assert int((v3 if i < 2 else v4)[i if i < 2 else 0]) == want, (env, i)
+
+
 def test_ab5_avoid_evaluator_live_oracle(dev, oracle):
     """src/alphabeta after SetAvoid(): deltaValue2 (alphabeta.go:382-454)"""
     from squava_b200 import positions
