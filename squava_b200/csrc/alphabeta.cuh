@@ -200,6 +200,24 @@ __device__ __forceinline__ void load_tables(AbTables& dst) {
 // ---- node bookkeeping ---------------------------------------------------------------
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
+// Node data is written by one lane and read by lanes on OTHER multiprocessors while the same kernel runs (queue-driven
+// search), and a node shares its 32-byte sector with its neighbours: a plain load could be served from a line this
+// multiprocessor's L1 fetched before the node was written.  Everything that is written during the search is therefore
+// read from L2 (ld.global.cg).
+__device__ __forceinline__ AbNode ab_ld_node(const AbNode* p) {
+    const uint2* q = reinterpret_cast<const uint2*>(p);
+    const uint2 a = __ldcg(q), b = __ldcg(q + 1), c = __ldcg(q + 2);
+    AbNode n;
+    n.x = a.x; n.o = a.y; n.carried = (int32_t)b.x;
+    n.cell = (int8_t)(b.y & 0xffu); n.ply = (int8_t)((b.y >> 8) & 0xffu); n.side = (int8_t)((b.y >> 16) & 0xffu); n.split = (int8_t)(b.y >> 24);
+    n.parent = (int32_t)c.x; n.group = (int32_t)c.y;
+    return n;
+}
+static_assert(sizeof(AbNode) == 24, "AbNode is read as three 8-byte words");
+__device__ __forceinline__ int ab_node_parent(const AbRun& R, int i) { return __ldcg(reinterpret_cast<const int*>(&R.nodes[i]) + 4); }
+__device__ __forceinline__ int ab_node_side(const AbRun& R, int i) { return (int)(int8_t)((__ldcg(reinterpret_cast<const unsigned*>(&R.nodes[i]) + 3) >> 16) & 0xffu); }
+__device__ __forceinline__ int ab_node_ply(const AbRun& R, int i) { return (int)(int8_t)((__ldcg(reinterpret_cast<const unsigned*>(&R.nodes[i]) + 3) >> 8) & 0xffu); }
+
 // A node becomes a unit: of the next pass (pass-driven search) or of the running kernel (queue-driven: the slot
 // write is what a lane holding that ticket is polling for, so everything about the node is fenced before it).
 __device__ __forceinline__ void ab_enqueue(const AbRun& R, int idx, int ply) {
@@ -213,16 +231,16 @@ __device__ __forceinline__ void ab_enqueue(const AbRun& R, int idx, int ply) {
 // A finished node hands its value to its parent; the last child to finish carries on upward.
 __device__ void ab_complete(const AbRun& R, int node, int value) {
     for (;;) {
-        int parent = R.nodes[node].parent;
+        int parent = ab_node_parent(R, node);
         if (parent < 0) { R.out[-1 - parent] = value; return; }
-        if (R.nodes[parent].side > 0) atomicMax(&R.value[parent], value);
+        if (ab_node_side(R, parent) > 0) atomicMax(&R.value[parent], value);
         else atomicMin(&R.value[parent], value);
         __threadfence();
         // Young brothers wait: the eldest child of a split node has finished, so its value now bounds the parent's
         // slot -- the younger children become units of the next pass and start with that bound (only the thread
         // that completes the eldest gets here: no race on held[]).
-        if (R.kids[parent] == node) {
-            const int nh = R.held[parent];
+        if (__ldcg(&R.kids[parent]) == node) {
+            const int nh = __ldcg(&R.held[parent]);
             if (nh > 0) {
                 R.held[parent] = 0;
                 if (R.queued) {
@@ -230,7 +248,7 @@ __device__ void ab_complete(const AbRun& R, int node, int value) {
                 } else {
                     const unsigned at = atomicAdd(&R.counters[5], (unsigned)nh);
                     for (int k = 0; k < nh; k++) R.released[at + k] = node + 1 + k;
-                    atomicMin(&R.counters[6], (unsigned)R.nodes[node].ply);
+                    atomicMin(&R.counters[6], (unsigned)ab_node_ply(R, node));
                 }
             }
         }
@@ -244,11 +262,11 @@ __device__ void ab_complete(const AbRun& R, int node, int value) {
 
 // alpha from the MAX ancestors' slots, beta from the MIN ancestors' slots
 __device__ __forceinline__ void ab_bounds(const AbRun& R, int node, int& alpha, int& beta) {
-    int p = R.nodes[node].parent;
+    int p = ab_node_parent(R, node);
     while (p >= 0) {
         int v = ld_volatile(&R.value[p]);
-        if (R.nodes[p].side > 0) alpha = max(alpha, v); else beta = min(beta, v);
-        p = R.nodes[p].parent;
+        if (ab_node_side(R, p) > 0) alpha = max(alpha, v); else beta = min(beta, v);
+        p = ab_node_parent(R, p);
     }
 }
 
@@ -386,7 +404,7 @@ ab_expand_kernel(AbRun R, const int* __restrict__ list, int lo, int count) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
     const int idx = list ? list[t] : lo + t;
-    AbNode n = R.nodes[idx];
+    AbNode n = ab_ld_node(&R.nodes[idx]);
     if (list) n.split = 1;
     else if (n.split <= 0) return;
     int value = 0, carried_down = 0;
@@ -474,16 +492,26 @@ ab_expand_kernel(AbRun R, const int* __restrict__ list, int lo, int count) {
 template <int DIALECT>
 __device__ __noinline__ bool ab_split_unit(const AbTables& T, const AbRun& R, int unit, uint32_t cells, int seed_value,
                                            bool have_seed, int carried_down, unsigned long long* evals) {
-    const AbNode n = R.nodes[unit];
+    const AbNode n = ab_ld_node(&R.nodes[unit]);
     const int nch = __popc(cells);
+    const bool hold = R.ybw && !have_seed && nch >= 2;
+    // The queue slots of the children that start now are reserved FIRST: the tail jumps at once, so the other lanes
+    // stop seeing hungry tickets while this one is still building the nodes (no stampede of splits for one idle lane).
+    const int npush = hold ? 1 : nch;
+    atomicAdd(&R.counters[7], (unsigned)npush);
+    const unsigned slot0 = atomicAdd(&R.counters[1], (unsigned)npush);
     unsigned base = *reinterpret_cast<volatile unsigned*>(&R.counters[0]);
-    for (;;) {                                                   // reserve nch contiguous slots, or none
-        if (base + (unsigned)nch > (unsigned)R.node_capacity) return false;
+    for (;;) {                                                   // reserve nch contiguous node slots, or none
+        if (base + (unsigned)nch > (unsigned)R.node_capacity) {
+            // no room: the reserved queue slots are handed to their ticket holders as "nothing here, draw again"
+            for (int q = 0; q < npush; q++) *reinterpret_cast<volatile int*>(&R.units[slot0 + q]) = -2;
+            atomicSub(&R.counters[7], (unsigned)npush);
+            return false;
+        }
         const unsigned seen = atomicCAS(&R.counters[0], base, base + (unsigned)nch);
         if (seen == base) break;
         base = seen;
     }
-    const bool hold = R.ybw && !have_seed && nch >= 2;
     R.kids[unit] = (int)base;
     R.held[unit] = hold ? nch - 1 : 0;
     if (have_seed) { if (n.side > 0) atomicMax(&R.value[unit], seed_value); else atomicMin(&R.value[unit], seed_value); }
@@ -519,7 +547,10 @@ __device__ __noinline__ bool ab_split_unit(const AbTables& T, const AbRun& R, in
         R.pending[ci] = 0;
         R.kids[ci] = -1;
         R.held[ci] = 0;
-        if (!hold || j == 0) ab_enqueue(R, ci, c.ply);
+        if (!hold || j == 0) {                   // publish into the slot reserved above
+            __threadfence();
+            *reinterpret_cast<volatile int*>(&R.units[slot0 + (unsigned)j]) = ci;
+        }
         j++;
     }
     return true;
@@ -639,6 +670,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                 if (ticket != 0xffffffffu && (iter & 7u) != 0) continue;
                 if (ticket == 0xffffffffu) ticket = atomicAdd(&R.counters[2], 1u);
                 const int got = ticket < (unsigned)R.node_capacity ? *reinterpret_cast<const volatile int*>(&R.units[ticket]) : -1;
+                if (got == -2) { ticket = 0xffffffffu; continue; }       // a split that found no room gave its slots back
                 if (got < 0) {
                     // nothing in my slot yet: done if no unit is alive anywhere; else wait (other lanes of the warp step on)
                     if (ld_volatile(reinterpret_cast<const int*>(&R.counters[7])) <= 0 || ld_volatile(reinterpret_cast<const int*>(&R.counters[8])) != 0) break;
@@ -658,7 +690,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                 if (u >= (unsigned)n_units) break;
                 unit = R.units[u];
             }
-            const AbNode n = R.nodes[unit];
+            const AbNode n = ab_ld_node(&R.nodes[unit]);
             int a0 = R.win_lo, b0 = R.win_hi;
             ab_bounds(R, unit, a0, b0);
             if (a0 >= b0) {
@@ -701,8 +733,16 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
             if ((iter & 255u) == 0) *reinterpret_cast<volatile unsigned*>(&R.counters[9]) = (unsigned)clock64();   // heartbeat of the working lanes
             if (ld_volatile(reinterpret_cast<const int*>(&R.counters[8])) != 0) break;            // the watchdog fired somewhere
             // hungry lanes (tickets drawn beyond the tail) and this unit has had its minimum: split it
+            // The node pool cannot grow while the kernel runs and nodes are not recycled: the fuller it gets, the more a
+            // unit must have cost before it may be split (x4 above one half, x32 above three quarters, x256 above 7/8).
+            bool split_now = false;
             if (!no_split && !fresh && evals >= R.min_budget &&
                 (unsigned)ld_volatile(reinterpret_cast<const int*>(&R.counters[2])) > (unsigned)ld_volatile(reinterpret_cast<const int*>(&R.counters[1]))) {
+                const unsigned used = (unsigned)ld_volatile(reinterpret_cast<const int*>(&R.counters[0])), cap = (unsigned)R.node_capacity;
+                const int shift = used > cap / 2 ? (used > cap / 4 * 3 ? (used > cap / 8 * 7 ? 8 : 5) : 2) : 0;
+                split_now = evals >= ((unsigned long long)R.min_budget << shift);
+            }
+            if (split_now) {
                 uint32_t rmoves; int rvalue, rcarried;
                 if (sp == 0) { rmoves = moves; rvalue = value; rcarried = carried; }
                 else {
@@ -1097,7 +1137,7 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
 // the flags afterwards.  The node pool cannot grow while the kernel runs: it is sized from the request and from what
 // the last search of this process needed; if it does fill up, units simply stop being split (correct, less parallel)
 // and the next search starts with a bigger pool.
-constexpr long long kAbQueuePoolStart = 4ll << 20;
+constexpr long long kAbQueuePoolStart = 8ll << 20;
 
 template <int DIALECT>
 cudaError_t ab_run_queue(AbRun R, AbWork& w, const void* d_in, bool roots, int n, const int8_t* h_split,
@@ -1131,9 +1171,12 @@ cudaError_t ab_run_queue(AbRun R, AbWork& w, const void* d_in, bool roots, int n
     int per_sm = 1;
     SQ_AB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ab_dfs_kernel<DIALECT, true>, kAbThreads, smem));
     if (per_sm < 1) per_sm = 1;
-    long long blocks = (long long)sm_count * per_sm;             // every block resident: nobody polls for a block that has not started
-    const long long most = ((long long)n * 25 * 4 + kAbThreads - 1) / kAbThreads;   // a small request does not need the whole machine polling
-    if (blocks > most) blocks = most < 1 ? 1 : most;
+    long long blocks = (long long)sm_count * per_sm;             // the whole machine, every block resident: lanes that find no unit
+                                                                 // wait for the ones the working lanes split off
+    if (R.max_depth - min_ply <= 3) {                            // shallow searches have no work to spread
+        const long long most = ((long long)n * 25 + kAbThreads - 1) / kAbThreads;
+        if (blocks > most) blocks = most < 1 ? 1 : most;
+    }
     const bool trace = getenv("SQ_AB_TRACE") != nullptr;
     auto t0 = std::chrono::steady_clock::now();
     ab_dfs_kernel<DIALECT, true><<<(unsigned)blocks, kAbThreads, smem, st>>>(R, 0, 0ull, n_frames);

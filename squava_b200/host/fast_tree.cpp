@@ -350,8 +350,8 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
     constexpr int kPathLen = 27;
     // walks a thread keeps in flight / paths it prefetches ahead while updating: memory-level parallelism knobs
     auto env_int = [](const char* name, int dflt, int lo, int hi) { const char* e = std::getenv(name); int v = e && *e ? std::atoi(e) : dflt; return v < lo ? lo : v > hi ? hi : v; };
-    const int group = (hk && hk->intn) ? 1 : env_int("SQUAVA_FAST_GROUP", 16, 1, 64);
-    const long long kAhead = env_int("SQUAVA_FAST_AHEAD", 8, 1, 64);
+    const int group = (hk && hk->intn) ? 1 : env_int("SQUAVA_FAST_GROUP", 8, 1, 64);
+    const long long kAhead = env_int("SQUAVA_FAST_AHEAD", 4, 1, 64);
 
     FastResult res;
     std::memset(&res, 0, sizeof res);
