@@ -119,6 +119,7 @@ struct AbRun {
     int* out;                        // final values
     unsigned long long* node_count;  // evaluator calls per group
     int node_capacity;
+    int queue_capacity;              // slots of units[] (queue-driven: nodes + room for the rare slots handed back empty)
     int max_depth;
     int sentinel;        // |value| of a node with no legal move: 20000, or 10000 (opening2)
     int win_lo, win_hi;  // the dialect's root window
@@ -224,7 +225,8 @@ __device__ __forceinline__ void ab_enqueue(const AbRun& R, int idx, int ply) {
     if (R.queued) atomicAdd(&R.counters[7], 1u);
     const unsigned slot = atomicAdd(&R.counters[1], 1u);
     __threadfence();
-    *reinterpret_cast<volatile int*>(&R.units[slot]) = idx;
+    if (slot < (unsigned)R.queue_capacity) *reinterpret_cast<volatile int*>(&R.units[slot]) = idx;
+    else atomicExch(&R.counters[4], 1u);             // cannot happen by sizing; never write past the queue
     if (!R.queued) atomicMin(&R.counters[6], (unsigned)ply);
 }
 
@@ -498,12 +500,15 @@ __device__ __noinline__ bool ab_split_unit(const AbTables& T, const AbRun& R, in
     // The queue slots of the children that start now are reserved FIRST: the tail jumps at once, so the other lanes
     // stop seeing hungry tickets while this one is still building the nodes (no stampede of splits for one idle lane).
     const int npush = hold ? 1 : nch;
+    unsigned base = *reinterpret_cast<volatile unsigned*>(&R.counters[0]);
+    if (base + (unsigned)nch > (unsigned)R.node_capacity) return false;       // clearly no room: nothing reserved, nothing to undo
+    if (*reinterpret_cast<volatile unsigned*>(&R.counters[1]) + 64u > (unsigned)R.queue_capacity) return false;
     atomicAdd(&R.counters[7], (unsigned)npush);
     const unsigned slot0 = atomicAdd(&R.counters[1], (unsigned)npush);
-    unsigned base = *reinterpret_cast<volatile unsigned*>(&R.counters[0]);
     for (;;) {                                                   // reserve nch contiguous node slots, or none
         if (base + (unsigned)nch > (unsigned)R.node_capacity) {
-            // no room: the reserved queue slots are handed to their ticket holders as "nothing here, draw again"
+            // no room after all (lost a race for the last slots): the reserved queue slots are handed to their ticket
+            // holders as "nothing here, draw again".  Rare: the check above keeps a full pool from burning queue slots.
             for (int q = 0; q < npush; q++) *reinterpret_cast<volatile int*>(&R.units[slot0 + q]) = -2;
             atomicSub(&R.counters[7], (unsigned)npush);
             return false;
@@ -530,7 +535,7 @@ __device__ __noinline__ bool ab_split_unit(const AbTables& T, const AbRun& R, in
         c.cell = (int8_t)cell;
         c.ply = n.ply + 1;
         c.side = -n.side;
-        c.split = 0;
+        c.split = (int8_t)(n.split < 100 ? n.split + 1 : n.split);   // queue-driven: how many splits above this node
         c.parent = unit;
         c.group = n.group;
         if (AbTraits<DIALECT>::delayed) {   // the unit's pending move re-evaluated with this child's mark on
@@ -547,12 +552,12 @@ __device__ __noinline__ bool ab_split_unit(const AbTables& T, const AbRun& R, in
         R.pending[ci] = 0;
         R.kids[ci] = -1;
         R.held[ci] = 0;
-        if (!hold || j == 0) {                   // publish into the slot reserved above
-            __threadfence();
-            *reinterpret_cast<volatile int*>(&R.units[slot0 + (unsigned)j]) = ci;
-        }
         j++;
     }
+    // EVERY child is written before ANY is published: the eldest may finish at once and set its brothers free, and
+    // whoever draws them must find their nodes complete
+    __threadfence();
+    for (int q = 0; q < npush; q++) *reinterpret_cast<volatile int*>(&R.units[slot0 + (unsigned)q]) = (int)base + q;
     return true;
 }
 
@@ -649,6 +654,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
     // queue-driven search
     unsigned ticket = 0xffffffffu;             // the queue slot this lane is waiting on
     bool no_split = false;                     // the node pool had no room: finish the unit alone
+    int gen = 0;                               // splits above the unit: each one doubles what it must cost before it is split again
     unsigned iter = 0;
     unsigned beat_seen = 0; long long beat_at = 0;
 
@@ -669,7 +675,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                 // a waiting lane shares its warp with working ones: it looks at its slot on every eighth turn only
                 if (ticket != 0xffffffffu && (iter & 7u) != 0) continue;
                 if (ticket == 0xffffffffu) ticket = atomicAdd(&R.counters[2], 1u);
-                const int got = ticket < (unsigned)R.node_capacity ? *reinterpret_cast<const volatile int*>(&R.units[ticket]) : -1;
+                const int got = ticket < (unsigned)R.queue_capacity ? *reinterpret_cast<const volatile int*>(&R.units[ticket]) : -1;
                 if (got == -2) { ticket = 0xffffffffu; continue; }       // a split that found no room gave its slots back
                 if (got < 0) {
                     // nothing in my slot yet: done if no unit is alive anywhere; else wait (other lanes of the warp step on)
@@ -710,6 +716,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                 continue;
             }
             x = n.x; o = n.o; base_ply = n.ply; base_side = n.side;
+            if (QUEUED) gen = n.split > 8 ? 8 : n.split;
             emp = order_mask(kFull25 & ~(x | o));
             sp = 0;
             moves = emp;
@@ -736,10 +743,10 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
             // The node pool cannot grow while the kernel runs and nodes are not recycled: the fuller it gets, the more a
             // unit must have cost before it may be split (x4 above one half, x32 above three quarters, x256 above 7/8).
             bool split_now = false;
-            if (!no_split && !fresh && evals >= R.min_budget &&
+            if (!no_split && !fresh && evals >= ((unsigned long long)R.min_budget << gen) &&
                 (unsigned)ld_volatile(reinterpret_cast<const int*>(&R.counters[2])) > (unsigned)ld_volatile(reinterpret_cast<const int*>(&R.counters[1]))) {
                 const unsigned used = (unsigned)ld_volatile(reinterpret_cast<const int*>(&R.counters[0])), cap = (unsigned)R.node_capacity;
-                const int shift = used > cap / 2 ? (used > cap / 4 * 3 ? (used > cap / 8 * 7 ? 8 : 5) : 2) : 0;
+                const int shift = gen + (used > cap / 2 ? (used > cap / 4 * 3 ? (used > cap / 8 * 7 ? 8 : 5) : 2) : 0);
                 split_now = evals >= ((unsigned long long)R.min_budget << shift);
             }
             if (split_now) {
@@ -976,7 +983,7 @@ inline cudaError_t ab_alloc(AbWork& w, long long capacity, cudaStream_t st) {
     if ((e = cudaMallocAsync(&w.nodes, sizeof(AbNode) * capacity, st)) != cudaSuccess) return e;
     if ((e = cudaMallocAsync(&w.value, sizeof(int) * capacity, st)) != cudaSuccess) return e;
     if ((e = cudaMallocAsync(&w.pending, sizeof(int) * capacity, st)) != cudaSuccess) return e;
-    if ((e = cudaMallocAsync(&w.units, sizeof(int) * capacity, st)) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(&w.units, sizeof(int) * capacity * 2, st)) != cudaSuccess) return e;
     if ((e = cudaMallocAsync(&w.aborted, sizeof(int) * capacity, st)) != cudaSuccess) return e;
     if ((e = cudaMallocAsync(&w.kids, sizeof(int) * capacity, st)) != cudaSuccess) return e;
     if ((e = cudaMallocAsync(&w.held, sizeof(int) * capacity, st)) != cudaSuccess) return e;
@@ -1023,7 +1030,7 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
     auto bind = [&] {
         R.nodes = w.nodes; R.value = w.value; R.pending = w.pending; R.units = w.units; R.aborted = w.aborted;
         R.kids = w.kids; R.held = w.held; R.released = w.released;
-        R.counters = w.counters; R.node_capacity = (int)capacity;
+        R.counters = w.counters; R.node_capacity = (int)capacity; R.queue_capacity = (int)(2 * capacity);
     };
     bind();
     if (roots) {
@@ -1148,10 +1155,10 @@ cudaError_t ab_run_queue(AbRun R, AbWork& w, const void* d_in, bool roots, int n
     SQ_AB_CK(cudaMallocAsync(&w.split, n, st));
     SQ_AB_CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned int) * 16, st));
     SQ_AB_CK(cudaMemsetAsync(w.split, 0, n, st));
-    SQ_AB_CK(cudaMemsetAsync(w.units, 0xff, sizeof(int) * capacity, st));          // every queue slot: empty
+    SQ_AB_CK(cudaMemsetAsync(w.units, 0xff, sizeof(int) * capacity * 2, st));      // every queue slot: empty
     R.nodes = w.nodes; R.value = w.value; R.pending = w.pending; R.units = w.units; R.aborted = w.aborted;
     R.kids = w.kids; R.held = w.held; R.released = w.released;
-    R.counters = w.counters; R.node_capacity = (int)capacity;
+    R.counters = w.counters; R.node_capacity = (int)capacity; R.queue_capacity = (int)(2 * capacity);
     R.queued = 1;
     R.ybw = getenv("SQ_AB_NO_YBW") == nullptr;
     { const char* e = getenv("SQ_AB_MIN_BUDGET"); R.min_budget = e && *e ? (unsigned)atoi(e) : 96u; }
