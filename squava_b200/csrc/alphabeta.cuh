@@ -657,6 +657,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
     int gen = 0;                               // splits above the unit: each one doubles what it must cost before it is split again
     unsigned iter = 0;
     unsigned beat_seen = 0; long long beat_at = 0;
+    unsigned idle_polls = 0;
 
     auto order_mask = [&](uint32_t cells) -> uint32_t {   // API layout -> child-order space
         if (!kOrdered) return cells;
@@ -672,8 +673,8 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
         iter++;
         if (sp < 0) {
             if (QUEUED) {
-                // a waiting lane shares its warp with working ones: it looks at its slot on every eighth turn only
-                if (ticket != 0xffffffffu && (iter & 7u) != 0) continue;
+                // a waiting lane shares its warp with working ones: it looks at its slot on every 32nd turn only
+                if (ticket != 0xffffffffu && (iter & 31u) != 0) continue;
                 if (ticket == 0xffffffffu) ticket = atomicAdd(&R.counters[2], 1u);
                 const int got = ticket < (unsigned)R.queue_capacity ? *reinterpret_cast<const volatile int*>(&R.units[ticket]) : -1;
                 if (got == -2) { ticket = 0xffffffffu; continue; }       // a split that found no room gave its slots back
@@ -685,11 +686,14 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                     const long long now = clock64();
                     if (beat != beat_seen || beat_at == 0) { beat_seen = beat; beat_at = now; }
                     else if (now - beat_at > R.stall_cycles) { atomicExch(&R.counters[8], 1u); break; }
-                    __nanosleep(200);
+                    // A warp in which EVERY lane is waiting sleeps between looks, longer each time (up to 16 us): a hundred
+                    // thousand lanes polling flat out would take the L2 away from the lanes that work.  A lane that waits
+                    // beside working lanes must not sleep -- the warp moves at the pace of its slowest branch.
+                    if (__activemask() == 0xffffffffu) { __nanosleep(250u << (idle_polls < 6 ? idle_polls : 6)); idle_polls++; }
                     continue;
                 }
                 __threadfence();
-                ticket = 0xffffffffu; no_split = false; beat_at = 0;
+                ticket = 0xffffffffu; no_split = false; beat_at = 0; idle_polls = 0;
                 unit = got;
             } else {
                 unsigned int u = atomicAdd(&R.counters[2], 1u);
