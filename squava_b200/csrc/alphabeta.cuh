@@ -125,6 +125,7 @@ struct AbRun {
     int win_lo, win_hi;  // the dialect's root window
     int shortcuts;       // exact shortcuts allowed (see ab_move_classes); off when |heuristic sums| could reach a win score
     int queued;          // queue-driven search: ONE persistent kernel, units flow through a device-side queue (see ab_dfs_kernel)
+    int gen_scaling;           // queue-driven: every split above a unit doubles what it must cost before it is split again
     unsigned int min_budget;   // queue-driven: evaluator calls a unit spends before it may be split for hungry lanes
     long long stall_cycles;    // queue-driven watchdog: idle lanes give up when the heartbeat stands still this long
     int ybw;             // young brothers wait: a split node's younger children start only when the eldest has finished
@@ -659,6 +660,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
     unsigned beat_seen = 0; long long beat_at = 0;
     unsigned idle_polls = 0;
 
+    auto gen_shift = [&](int g) -> int { return R.gen_scaling ? g : 0; };
     auto order_mask = [&](uint32_t cells) -> uint32_t {   // API layout -> child-order space
         if (!kOrdered) return cells;
         uint32_t m = 0;
@@ -747,10 +749,10 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
             // The node pool cannot grow while the kernel runs and nodes are not recycled: the fuller it gets, the more a
             // unit must have cost before it may be split (x4 above one half, x32 above three quarters, x256 above 7/8).
             bool split_now = false;
-            if (!no_split && !fresh && evals >= ((unsigned long long)R.min_budget << gen) &&
+            if (!no_split && !fresh && evals >= ((unsigned long long)R.min_budget << gen_shift(gen)) &&
                 (unsigned)ld_volatile(reinterpret_cast<const int*>(&R.counters[2])) > (unsigned)ld_volatile(reinterpret_cast<const int*>(&R.counters[1]))) {
                 const unsigned used = (unsigned)ld_volatile(reinterpret_cast<const int*>(&R.counters[0])), cap = (unsigned)R.node_capacity;
-                const int shift = gen + (used > cap / 2 ? (used > cap / 4 * 3 ? (used > cap / 8 * 7 ? 8 : 5) : 2) : 0);
+                const int shift = gen_shift(gen) + (used > cap / 2 ? (used > cap / 4 * 3 ? (used > cap / 8 * 7 ? 8 : 5) : 2) : 0);
                 split_now = evals >= ((unsigned long long)R.min_budget << shift);
             }
             if (split_now) {
@@ -1165,7 +1167,8 @@ cudaError_t ab_run_queue(AbRun R, AbWork& w, const void* d_in, bool roots, int n
     R.counters = w.counters; R.node_capacity = (int)capacity; R.queue_capacity = (int)(2 * capacity);
     R.queued = 1;
     R.ybw = getenv("SQ_AB_NO_YBW") == nullptr;
-    { const char* e = getenv("SQ_AB_MIN_BUDGET"); R.min_budget = e && *e ? (unsigned)atoi(e) : 96u; }
+    { const char* e = getenv("SQ_AB_MIN_BUDGET"); R.min_budget = e && *e ? (unsigned)atoi(e) : 384u; }
+    R.gen_scaling = getenv("SQ_AB_GEN_SCALING") != nullptr;
     R.stall_cycles = 8000000000ll;                  // ~4 s without any working lane's heartbeat: a stuck queue, not a long search
     if (roots) {
         int threads = n * 25;
@@ -1223,7 +1226,8 @@ inline cudaError_t ab_dispatch(int dialect, AbRun R, AbWork& w, const void* d_in
     const long long ceiling = std::max(needed + 16, ab_pool_nodes());
     if (!getenv("SQ_AB_PASSES") && !getenv("SQ_AB_BUDGET") && !getenv("SQ_AB_SPLIT")) {
         // queue-driven search (default).  SQ_AB_PASSES / SQ_AB_BUDGET / SQ_AB_SPLIT select the pass-driven one.
-        const long long cap_q = std::min(ceiling, std::max(std::max(2 * needed + 16, kAbQueuePoolStart), ab_hint().load()));
+        const long long start_q = R.max_depth - min_ply >= 9 ? 4 * kAbQueuePoolStart : kAbQueuePoolStart;     // deep searches split a lot
+        const long long cap_q = std::min(ceiling, std::max(std::max(2 * needed + 16, start_q), ab_hint().load()));
         int dev_id = 0, sm_count = 148;
         if (cudaGetDevice(&dev_id) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev_id) != cudaSuccess) return cudaGetLastError();
         switch (dialect) {
