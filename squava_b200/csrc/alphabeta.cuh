@@ -118,6 +118,9 @@ struct AbRun {
                                      // queue-driven search: [7] units alive (queued or being searched) [8] watchdog fired [9] heartbeat
     int* out;                        // final values
     unsigned long long* node_count;  // evaluator calls per group
+    int cstride;                     // counter k lives at counters[k * cstride]: 1 (pass-driven, the host reads them as one block) or
+                                     // 32 (queue-driven: every counter on its own 128-byte line, so that the lanes polling one
+                                     // do not hold up the atomics on another)
     int node_capacity;
     int queue_capacity;              // slots of units[] (queue-driven: nodes + room for the rare slots handed back empty)
     int max_depth;
@@ -133,6 +136,8 @@ struct AbRun {
     int8_t scores[25];
     HorizonTables hz;
 };
+
+__host__ __device__ __forceinline__ unsigned int* ab_cnt(const AbRun& R, int k) { return R.counters + k * R.cstride; }
 
 // ---- evaluators -----------------------------------------------------------------
 struct Eval { bool terminal; int value; };
@@ -223,12 +228,12 @@ __device__ __forceinline__ int ab_node_ply(const AbRun& R, int i) { return (int)
 // A node becomes a unit: of the next pass (pass-driven search) or of the running kernel (queue-driven: the slot
 // write is what a lane holding that ticket is polling for, so everything about the node is fenced before it).
 __device__ __forceinline__ void ab_enqueue(const AbRun& R, int idx, int ply) {
-    if (R.queued) atomicAdd(&R.counters[7], 1u);
-    const unsigned slot = atomicAdd(&R.counters[1], 1u);
+    if (R.queued) atomicAdd(ab_cnt(R, 7), 1u);
+    const unsigned slot = atomicAdd(ab_cnt(R, 1), 1u);
     __threadfence();
     if (slot < (unsigned)R.queue_capacity) *reinterpret_cast<volatile int*>(&R.units[slot]) = idx;
-    else atomicExch(&R.counters[4], 1u);             // cannot happen by sizing; never write past the queue
-    if (!R.queued) atomicMin(&R.counters[6], (unsigned)ply);
+    else atomicExch(ab_cnt(R, 4), 1u);             // cannot happen by sizing; never write past the queue
+    if (!R.queued) atomicMin(ab_cnt(R, 6), (unsigned)ply);
 }
 
 // A finished node hands its value to its parent; the last child to finish carries on upward.
@@ -249,9 +254,9 @@ __device__ void ab_complete(const AbRun& R, int node, int value) {
                 if (R.queued) {
                     for (int k = 0; k < nh; k++) ab_enqueue(R, node + 1 + k, 0);
                 } else {
-                    const unsigned at = atomicAdd(&R.counters[5], (unsigned)nh);
+                    const unsigned at = atomicAdd(ab_cnt(R, 5), (unsigned)nh);
                     for (int k = 0; k < nh; k++) R.released[at + k] = node + 1 + k;
-                    atomicMin(&R.counters[6], (unsigned)ab_node_ply(R, node));
+                    atomicMin(ab_cnt(R, 6), (unsigned)ab_node_ply(R, node));
                 }
             }
         }
@@ -274,9 +279,9 @@ __device__ __forceinline__ void ab_bounds(const AbRun& R, int node, int& alpha, 
 }
 
 __device__ __forceinline__ int ab_new_node(const AbRun& R, const AbNode& n) {
-    unsigned int idx = atomicAdd(&R.counters[0], 1u);
+    unsigned int idx = atomicAdd(ab_cnt(R, 0), 1u);
     if (idx >= (unsigned)R.node_capacity) {           // the host checks the room before every expansion; if its sizing is
-        atomicExch(&R.counters[4], 1u);               // ever wrong the run is failed (SQ_ERR_NOMEM), never silently short
+        atomicExch(ab_cnt(R, 4), 1u);               // ever wrong the run is failed (SQ_ERR_NOMEM), never silently short
         return -1;
     }
     R.nodes[idx] = n;
@@ -440,9 +445,9 @@ ab_expand_kernel(AbRun R, const int* __restrict__ list, int lo, int count) {
     }
     // the children take one contiguous run of slots, eldest (first in the dialect's visiting order) first
     const int nch = __popc(empties);
-    const unsigned base = atomicAdd(&R.counters[0], (unsigned)nch);
+    const unsigned base = atomicAdd(ab_cnt(R, 0), (unsigned)nch);
     if (base + (unsigned)nch > (unsigned)R.node_capacity) {   // the host checks the room before every expansion; if its
-        atomicExch(&R.counters[4], 1u);                       // sizing is ever wrong the run is failed, never silently short
+        atomicExch(ab_cnt(R, 4), 1u);                       // sizing is ever wrong the run is failed, never silently short
         return;
     }
     // adaptive split of a unit that proved too big: only the eldest child starts now, the others when it is done
@@ -501,20 +506,20 @@ __device__ __noinline__ bool ab_split_unit(const AbTables& T, const AbRun& R, in
     // The queue slots of the children that start now are reserved FIRST: the tail jumps at once, so the other lanes
     // stop seeing hungry tickets while this one is still building the nodes (no stampede of splits for one idle lane).
     const int npush = hold ? 1 : nch;
-    unsigned base = *reinterpret_cast<volatile unsigned*>(&R.counters[0]);
+    unsigned base = *reinterpret_cast<volatile unsigned*>(ab_cnt(R, 0));
     if (base + (unsigned)nch > (unsigned)R.node_capacity) return false;       // clearly no room: nothing reserved, nothing to undo
-    if (*reinterpret_cast<volatile unsigned*>(&R.counters[1]) + 64u > (unsigned)R.queue_capacity) return false;
-    atomicAdd(&R.counters[7], (unsigned)npush);
-    const unsigned slot0 = atomicAdd(&R.counters[1], (unsigned)npush);
+    if (*reinterpret_cast<volatile unsigned*>(ab_cnt(R, 1)) + 64u > (unsigned)R.queue_capacity) return false;
+    atomicAdd(ab_cnt(R, 7), (unsigned)npush);
+    const unsigned slot0 = atomicAdd(ab_cnt(R, 1), (unsigned)npush);
     for (;;) {                                                   // reserve nch contiguous node slots, or none
         if (base + (unsigned)nch > (unsigned)R.node_capacity) {
             // no room after all (lost a race for the last slots): the reserved queue slots are handed to their ticket
             // holders as "nothing here, draw again".  Rare: the check above keeps a full pool from burning queue slots.
             for (int q = 0; q < npush; q++) *reinterpret_cast<volatile int*>(&R.units[slot0 + q]) = -2;
-            atomicSub(&R.counters[7], (unsigned)npush);
+            atomicSub(ab_cnt(R, 7), (unsigned)npush);
             return false;
         }
-        const unsigned seen = atomicCAS(&R.counters[0], base, base + (unsigned)nch);
+        const unsigned seen = atomicCAS(ab_cnt(R, 0), base, base + (unsigned)nch);
         if (seen == base) break;
         base = seen;
     }
@@ -658,7 +663,8 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
     int gen = 0;                               // splits above the unit: each one doubles what it must cost before it is split again
     unsigned iter = 0;
     unsigned beat_seen = 0; long long beat_at = 0;
-    unsigned idle_polls = 0;
+    unsigned idle_polls = 0, looks = 0;
+    unsigned long long busy_turns = 0, idle_turns = 0;   // statistics (SQ_AB_TRACE): loop turns with / without a unit
 
     auto gen_shift = [&](int g) -> int { return R.gen_scaling ? g : 0; };
     auto order_mask = [&](uint32_t cells) -> uint32_t {   // API layout -> child-order space
@@ -673,21 +679,25 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
         bool returning = false;   // `ret` is to be handed to frame sp ...
         bool restore = false;     // ... which is in shared memory (a pushed child came back)
         iter++;
+        if (QUEUED) { if (sp < 0) idle_turns++; else busy_turns++; }
         if (sp < 0) {
             if (QUEUED) {
                 // a waiting lane shares its warp with working ones: it looks at its slot on every 32nd turn only
                 if (ticket != 0xffffffffu && (iter & 31u) != 0) continue;
-                if (ticket == 0xffffffffu) ticket = atomicAdd(&R.counters[2], 1u);
+                if (ticket == 0xffffffffu) ticket = atomicAdd(ab_cnt(R, 2), 1u);
                 const int got = ticket < (unsigned)R.queue_capacity ? *reinterpret_cast<const volatile int*>(&R.units[ticket]) : -1;
                 if (got == -2) { ticket = 0xffffffffu; continue; }       // a split that found no room gave its slots back
                 if (got < 0) {
-                    // nothing in my slot yet: done if no unit is alive anywhere; else wait (other lanes of the warp step on)
-                    if (ld_volatile(reinterpret_cast<const int*>(&R.counters[7])) <= 0 || ld_volatile(reinterpret_cast<const int*>(&R.counters[8])) != 0) break;
-                    // watchdog: working lanes advance the heartbeat; if it stands still for stall_cycles, give up
-                    const unsigned beat = (unsigned)ld_volatile(reinterpret_cast<const int*>(&R.counters[9]));
-                    const long long now = clock64();
-                    if (beat != beat_seen || beat_at == 0) { beat_seen = beat; beat_at = now; }
-                    else if (now - beat_at > R.stall_cycles) { atomicExch(&R.counters[8], 1u); break; }
+                    // nothing in my slot yet.  Every eighth look (the slot itself is the lane's own line; these are shared
+                    // ones): done if no unit is alive anywhere, and the watchdog -- working lanes advance the heartbeat; if
+                    // it stands still for stall_cycles, give up
+                    if ((looks++ & 7u) == 0) {
+                        if (ld_volatile(reinterpret_cast<const int*>(ab_cnt(R, 7))) <= 0 || ld_volatile(reinterpret_cast<const int*>(ab_cnt(R, 8))) != 0) break;
+                        const unsigned beat = (unsigned)ld_volatile(reinterpret_cast<const int*>(ab_cnt(R, 9)));
+                        const long long now = clock64();
+                        if (beat != beat_seen || beat_at == 0) { beat_seen = beat; beat_at = now; }
+                        else if (now - beat_at > R.stall_cycles) { atomicExch(ab_cnt(R, 8), 1u); break; }
+                    }
                     // A warp in which EVERY lane is waiting sleeps between looks, longer each time (up to 16 us): a hundred
                     // thousand lanes polling flat out would take the L2 away from the lanes that work.  A lane that waits
                     // beside working lanes must not sleep -- the warp moves at the pace of its slowest branch.
@@ -695,10 +705,10 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                     continue;
                 }
                 __threadfence();
-                ticket = 0xffffffffu; no_split = false; beat_at = 0; idle_polls = 0;
+                ticket = 0xffffffffu; no_split = false; beat_at = 0; idle_polls = 0; looks = 0;
                 unit = got;
             } else {
-                unsigned int u = atomicAdd(&R.counters[2], 1u);
+                unsigned int u = atomicAdd(ab_cnt(R, 2), 1u);
                 if (u >= (unsigned)n_units) break;
                 unit = R.units[u];
             }
@@ -710,7 +720,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                 // It hands up a value its parent's atomicMin/Max ignores -- the parent is the other kind of
                 // node -- so the unit contributes nothing, as if the sequential search had never reached it.
                 ab_complete(R, unit, n.side > 0 ? 30000 : -30000);
-                if (QUEUED) atomicSub(&R.counters[7], 1u);
+                if (QUEUED) atomicSub(ab_cnt(R, 7), 1u);
                 continue;
             }
             int v0 = 0, carried_down = 0;
@@ -718,7 +728,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
             if (ab_enter<DIALECT>(T, R, n, v0, carried_down)) {
                 atomicAdd(&R.node_count[group], evals);
                 ab_complete(R, unit, v0);
-                if (QUEUED) atomicSub(&R.counters[7], 1u);
+                if (QUEUED) atomicSub(ab_cnt(R, 7), 1u);
                 continue;
             }
             x = n.x; o = n.o; base_ply = n.ply; base_side = n.side;
@@ -738,20 +748,20 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
         }
         if (!QUEUED && evals > budget) {   // too big for one lane: hand the unit back to be split one ply deeper
             atomicAdd(&R.node_count[group], evals);
-            R.aborted[atomicAdd(&R.counters[3], 1u)] = unit;
+            R.aborted[atomicAdd(ab_cnt(R, 3), 1u)] = unit;
             sp = -1;
             continue;
         }
         if (QUEUED && (iter & 31u) == 0) {
-            if ((iter & 255u) == 0) *reinterpret_cast<volatile unsigned*>(&R.counters[9]) = (unsigned)clock64();   // heartbeat of the working lanes
-            if (ld_volatile(reinterpret_cast<const int*>(&R.counters[8])) != 0) break;            // the watchdog fired somewhere
+            if ((iter & 255u) == 0) *reinterpret_cast<volatile unsigned*>(ab_cnt(R, 9)) = (unsigned)clock64();   // heartbeat of the working lanes
+            if (ld_volatile(reinterpret_cast<const int*>(ab_cnt(R, 8))) != 0) break;            // the watchdog fired somewhere
             // hungry lanes (tickets drawn beyond the tail) and this unit has had its minimum: split it
             // The node pool cannot grow while the kernel runs and nodes are not recycled: the fuller it gets, the more a
             // unit must have cost before it may be split (x4 above one half, x32 above three quarters, x256 above 7/8).
             bool split_now = false;
             if (!no_split && !fresh && evals >= ((unsigned long long)R.min_budget << gen_shift(gen)) &&
-                (unsigned)ld_volatile(reinterpret_cast<const int*>(&R.counters[2])) > (unsigned)ld_volatile(reinterpret_cast<const int*>(&R.counters[1]))) {
-                const unsigned used = (unsigned)ld_volatile(reinterpret_cast<const int*>(&R.counters[0])), cap = (unsigned)R.node_capacity;
+                (unsigned)ld_volatile(reinterpret_cast<const int*>(ab_cnt(R, 2))) > (unsigned)ld_volatile(reinterpret_cast<const int*>(ab_cnt(R, 1)))) {
+                const unsigned used = (unsigned)ld_volatile(reinterpret_cast<const int*>(ab_cnt(R, 0))), cap = (unsigned)R.node_capacity;
                 const int shift = gen_shift(gen) + (used > cap / 2 ? (used > cap / 4 * 3 ? (used > cap / 8 * 7 ? 8 : 5) : 2) : 0);
                 split_now = evals >= ((unsigned long long)R.min_budget << shift);
             }
@@ -767,9 +777,10 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                 uint32_t cells = rmoves;
                 if (kOrdered) { cells = 0; for (uint32_t m = rmoves; m; m &= m - 1) cells |= 1u << T.order[__ffs(m) - 1]; }
                 const bool have_seed = rvalue != (base_side > 0 ? -R.sentinel : R.sentinel);
+                atomicAdd(ab_cnt(R, 12), 1u);
                 if (cells && ab_split_unit<DIALECT>(T, R, unit, cells, rvalue, have_seed, rcarried, &evals)) {
                     atomicAdd(&R.node_count[group], evals);
-                    atomicSub(&R.counters[7], 1u);          // after its children were counted in
+                    atomicSub(ab_cnt(R, 7), 1u);          // after its children were counted in
                     sp = -1;
                     continue;
                 }
@@ -890,7 +901,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
             if (sp < 0) {
                 atomicAdd(&R.node_count[group], evals);
                 ab_complete(R, unit, ret);
-                if (QUEUED) atomicSub(&R.counters[7], 1u);
+                if (QUEUED) atomicSub(ab_cnt(R, 7), 1u);
                 break;
             }
             const int s = (sp & 1) ? -base_side : base_side;
@@ -915,6 +926,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
             if (beta <= alpha) { ret = value; sp--; restore = true; } else returning = false;
         }
     }
+    if (QUEUED) { atomicAdd(ab_cnt(R, 10), (unsigned)(busy_turns >> 10)); atomicAdd(ab_cnt(R, 11), (unsigned)(idle_turns >> 10)); }
 #undef SQ_FR
 }
 
@@ -1036,7 +1048,7 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
     auto bind = [&] {
         R.nodes = w.nodes; R.value = w.value; R.pending = w.pending; R.units = w.units; R.aborted = w.aborted;
         R.kids = w.kids; R.held = w.held; R.released = w.released;
-        R.counters = w.counters; R.node_capacity = (int)capacity; R.queue_capacity = (int)(2 * capacity);
+        R.counters = w.counters; R.cstride = 1; R.node_capacity = (int)capacity; R.queue_capacity = (int)(2 * capacity);
     };
     bind();
     if (roots) {
@@ -1157,14 +1169,14 @@ cudaError_t ab_run_queue(AbRun R, AbWork& w, const void* d_in, bool roots, int n
                          long long capacity, int sm_count, int min_ply, cudaStream_t st, uint64_t* launches) {
     (void)h_split;
     SQ_AB_CK(ab_alloc(w, capacity, st));
-    SQ_AB_CK(cudaMallocAsync(&w.counters, sizeof(unsigned int) * 16, st));
+    SQ_AB_CK(cudaMallocAsync(&w.counters, sizeof(unsigned int) * 16 * 32, st));
     SQ_AB_CK(cudaMallocAsync(&w.split, n, st));
-    SQ_AB_CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned int) * 16, st));
+    SQ_AB_CK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned int) * 16 * 32, st));
     SQ_AB_CK(cudaMemsetAsync(w.split, 0, n, st));
     SQ_AB_CK(cudaMemsetAsync(w.units, 0xff, sizeof(int) * capacity * 2, st));      // every queue slot: empty
     R.nodes = w.nodes; R.value = w.value; R.pending = w.pending; R.units = w.units; R.aborted = w.aborted;
     R.kids = w.kids; R.held = w.held; R.released = w.released;
-    R.counters = w.counters; R.node_capacity = (int)capacity; R.queue_capacity = (int)(2 * capacity);
+    R.counters = w.counters; R.cstride = 32; R.node_capacity = (int)capacity; R.queue_capacity = (int)(2 * capacity);
     R.queued = 1;
     R.ybw = getenv("SQ_AB_NO_YBW") == nullptr;
     { const char* e = getenv("SQ_AB_MIN_BUDGET"); R.min_budget = e && *e ? (unsigned)atoi(e) : 384u; }
@@ -1196,13 +1208,16 @@ cudaError_t ab_run_queue(AbRun R, AbWork& w, const void* d_in, bool roots, int n
     ab_dfs_kernel<DIALECT, true><<<(unsigned)blocks, kAbThreads, smem, st>>>(R, 0, 0ull, n_frames);
     (*launches)++;
     SQ_AB_CK(cudaGetLastError());
-    unsigned int h_counters[16];
-    SQ_AB_CK(cudaMemcpyAsync(h_counters, w.counters, sizeof h_counters, cudaMemcpyDeviceToHost, st));
+    unsigned int h_padded[16 * 32], h_counters[16];
+    SQ_AB_CK(cudaMemcpyAsync(h_padded, w.counters, sizeof h_padded, cudaMemcpyDeviceToHost, st));
     SQ_AB_CK(cudaStreamSynchronize(st));
+    for (int k = 0; k < 16; k++) h_counters[k] = h_padded[k * 32];
     if (trace)
-        fprintf(stderr, "[ab] queue: %d level-0 inputs, %u nodes of %lld, %u units queued, %u tickets drawn, %u alive at the end, %u blocks, %.3f ms\n",
+        fprintf(stderr, "[ab] queue: %d level-0 inputs, %u nodes of %lld, %u units queued, %u tickets drawn, %u alive at the end, %u blocks, %.3f ms; "
+                "%u split attempts, lane turns busy %.3g idle %.3g\n",
                 n, h_counters[0], capacity, h_counters[1], h_counters[2], h_counters[7], (unsigned)blocks,
-                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), h_counters[12],
+                1024.0 * h_counters[10], 1024.0 * h_counters[11]);
     ab_free(w, st);
     if (h_counters[8] || h_counters[7]) return cudaErrorLaunchTimeout;   // the watchdog fired / units left over: never a silent wrong answer
     // remember what this search needed: twice the nodes it used, so that the next one has room to split freely
