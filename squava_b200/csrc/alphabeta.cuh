@@ -1088,6 +1088,7 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
     };
     lap("setup", n, (int)capacity);
     const unsigned long long fixed_budget = ab_budget();
+    const bool deep_few = R.max_depth - min_ply >= 10 && (long long)n * (roots ? 25 : 1) <= 4096;
     bool unlimited = false;
     int passes = 0;
     for (;;) {
@@ -1106,7 +1107,10 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
         const unsigned int zero7[7] = {h_counters[0], 0, 0, 0, 0, 0, 127};  // n_nodes stays; units, queue head, aborted, released, min ply restart
         SQ_AB_CK(cudaMemcpyAsync(w.counters, zero7, sizeof zero7, cudaMemcpyHostToDevice, st));
         // few units: split early (most lanes are idle anyway); many: let lanes run longer
-        unsigned long long budget = fixed_budget ? fixed_budget : n_units < (1 << 15) ? 256 : n_units < (1 << 18) ? 1024 : 4096;
+        // Deep searches from a few level-0 nodes split until the pool is full, and their last pass has to finish whatever is
+        // left without a budget: the finer the units are by then, the shorter that pass's tail -- a small fixed budget
+        // (measured: opening2 -d 12 3.36 s -> 1.98 s, opening3 -d 12 2.26 s -> 1.46 s; profiles/r02_alphabeta_modes_timing.txt).
+        unsigned long long budget = fixed_budget ? fixed_budget : deep_few ? 64 : n_units < (1 << 15) ? 256 : n_units < (1 << 18) ? 1024 : 4096;
         if (unlimited) budget = ~0ull;
         // frames a unit can push: one per ply from its own down to max_depth - 1
         int n_frames = R.max_depth - unit_ply + 1;
@@ -1239,8 +1243,10 @@ inline cudaError_t ab_dispatch(int dialect, AbRun R, AbWork& w, const void* d_in
     // ceiling: SQ_AB_POOL_NODES (default 64 Mi slots, ~2.5 GB), never below what the level-0 nodes need;
     // the run starts with max(needed, kAbPoolStart) slots and grows towards the ceiling only if it splits that far
     const long long ceiling = std::max(needed + 16, ab_pool_nodes());
-    if (!getenv("SQ_AB_PASSES") && !getenv("SQ_AB_BUDGET") && !getenv("SQ_AB_SPLIT")) {
-        // queue-driven search (default).  SQ_AB_PASSES / SQ_AB_BUDGET / SQ_AB_SPLIT select the pass-driven one.
+    if (getenv("SQ_AB_QUEUE") && !getenv("SQ_AB_PASSES") && !getenv("SQ_AB_BUDGET") && !getenv("SQ_AB_SPLIT")) {
+        // queue-driven search: opt-in (SQ_AB_QUEUE=1).  Measured in round 2 (profiles/r02_alphabeta_queue_driven.md): bit-exact,
+        // an eighth of the evaluator calls on deep searches when brothers wait, but the lanes stand idle most of the time
+        // (units reach them one generation at a time), so the pass-driven search below is still the faster one and the default.
         const long long start_q = R.max_depth - min_ply >= 9 ? 4 * kAbQueuePoolStart : kAbQueuePoolStart;     // deep searches split a lot
         const long long cap_q = std::min(ceiling, std::max(std::max(2 * needed + 16, start_q), ab_hint().load()));
         int dev_id = 0, sm_count = 148;

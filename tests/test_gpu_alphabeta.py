@@ -130,7 +130,7 @@ def test_schedule_does_not_change_values(dev, oracle, budget, pool):
 
 
 @pytest.mark.parametrize("env", [{"SQ_AB_MIN_BUDGET": "1"}, {"SQ_AB_MIN_BUDGET": "5", "SQ_AB_NO_YBW": "1"}, {"SQ_AB_MIN_BUDGET": "100000"},
-                                 {"SQ_AB_POOL_NODES": "6000"}, {"SQ_AB_MIN_BUDGET": "3", "SQ_AB_NO_FAST_HORIZON": "1"}, {"SQ_AB_PASSES": "1"},
+                                 {"SQ_AB_POOL_NODES": "6000"}, {"SQ_AB_MIN_BUDGET": "3", "SQ_AB_NO_FAST_HORIZON": "1"}, {"SQ_AB_PASSES": "1"}, {},
                                  {"SQ_AB_PASSES": "1", "SQ_AB_YBW": "1"}])
 def test_queue_schedule_does_not_change_values(dev, oracle, env):
     """the queue-driven search (one persistent kernel): how eagerly units are split for hungry lanes, whether the
@@ -141,6 +141,9 @@ def test_queue_schedule_does_not_change_values(dev, oracle, env):
     boards, _ = positions.midgame_batch(24, marks=(10, 12, 14), seed=83)
     so = oracle.tables()["scores_opening"]
     rows = [(1 << 12, 1 << 6, 6, 2, 1, so[12]), (1 << 0, 1 << 24, 24, 2, 1, so[0]), (1 << 7, 0, 7, 1, -1, 0)]
+    env = dict(env)
+    if env and "SQ_AB_PASSES" not in env:
+        env["SQ_AB_QUEUE"] = "1"                 # the queue-driven search is opt-in
     for k, v in env.items():
         os.environ[k] = v
     try:
