@@ -356,45 +356,52 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
     FastResult res;
     std::memset(&res, 0, sizeof res);
     Pool pool(T);
-    std::vector<Leaf> leaves;
-    std::vector<uint32_t> paths;
-    std::vector<sq_board> boards;
-    std::vector<int8_t> to_move;
-    std::vector<uint64_t> out;
-    std::vector<uint8_t> packed;
-    long long done = 0;
+    // One batch: its leaves, the paths that led to them, and the playout results.  Two of them alternate so that the GPU
+    // call of batch k overlaps the selection of batch k+1 (double-buffered leaf batches).
+    struct Batch {
+        long long B = 0; int p = 1;
+        std::vector<Leaf> leaves; std::vector<uint32_t> paths; std::vector<sq_board> boards; std::vector<int8_t> to_move;
+        std::vector<uint64_t> out; std::vector<uint8_t> packed;
+    };
+    Batch bufs[2];
+    long long done = 0, planned = 0;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
-    while (done < itermax && !overflow.load()) {
-        long long remaining = itermax - done;
-        int p = P;
-        if (p > remaining) p = (int)remaining;
-        long long B = B0;
-        if (B * p > remaining) B = remaining / p;
-        if (B < 1) B = 1;
-        leaves.resize((size_t)B); boards.resize((size_t)B); to_move.resize((size_t)B); out.assign((size_t)B * 4, 0);
-        paths.resize((size_t)B * kPathLen);
-        auto t0 = now();
+    // sizes of the next batch; false when the budget is used up
+    auto plan = [&](Batch& bt) -> bool {
+        const long long remaining = itermax - planned;
+        if (remaining <= 0) return false;
+        bt.p = P;
+        if (bt.p > remaining) bt.p = (int)remaining;
+        bt.B = B0;
+        if (bt.B * bt.p > remaining) bt.B = remaining / bt.p;
+        if (bt.B < 1) bt.B = 1;
+        planned += bt.B * bt.p;
+        bt.leaves.resize((size_t)bt.B); bt.boards.resize((size_t)bt.B); bt.to_move.resize((size_t)bt.B); bt.out.assign((size_t)bt.B * 4, 0);
+        bt.paths.resize((size_t)bt.B * kPathLen);
+        return true;
+    };
+    auto select_phase = [&](Batch& bt) {
         pool.run([&](int t) {
-            const long long lo = B * t / T, hi = B * (t + 1) / T;
+            const long long lo = bt.B * t / T, hi = bt.B * (t + 1) / T;
             Walk walks[64];
             long long slot_of[64];
             Chunk& ck = chunks[(size_t)t];
             Shard* sh = exact ? nullptr : &shards[(size_t)t];
             long long next = lo;
             int active = 0;
-            for (; active < group && next < hi; active++, next++) { slot_of[active] = next; start_walk(walks[active], &paths[(size_t)next * kPathLen]); }
+            for (; active < group && next < hi; active++, next++) { slot_of[active] = next; start_walk(walks[active], &bt.paths[(size_t)next * kPathLen]); }
             if (!exact && hi > lo) nodes[root].visits.fetch_add((uint32_t)((hi - lo) * P), std::memory_order_release);
             while (active > 0) {
                 for (int g = 0; g < active; g++) {
                     Walk& w = walks[g];
                     const long long k = slot_of[g];
-                    if (!step(rngs[(size_t)t], ck, sh, w, &paths[(size_t)k * kPathLen])) continue;
-                    Leaf& lf = leaves[(size_t)k];
+                    if (!step(rngs[(size_t)t], ck, sh, w, &bt.paths[(size_t)k * kPathLen])) continue;
+                    Leaf& lf = bt.leaves[(size_t)k];
                     lf.node = w.idx; lf.x = w.x; lf.o = w.o; lf.to_move = (int8_t)-w.pjm; lf.fresh = w.fresh; lf.depth = (uint8_t)w.depth;
-                    boards[(size_t)k] = sq_board{w.x, w.o};
-                    to_move[(size_t)k] = lf.to_move;
-                    if (next < hi) { slot_of[g] = next; start_walk(w, &paths[(size_t)next * kPathLen]); next++; }
+                    bt.boards[(size_t)k] = sq_board{w.x, w.o};
+                    bt.to_move[(size_t)k] = lf.to_move;
+                    if (next < hi) { slot_of[g] = next; start_walk(w, &bt.paths[(size_t)next * kPathLen]); next++; }
                     else { walks[g] = walks[active - 1]; slot_of[g] = slot_of[active - 1]; active--; g--; }
                 }
             }
@@ -408,39 +415,41 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
                 }
             }
         });
-        auto t1 = now();
+    };
+    auto gpu_phase = [&](Batch& bt) {
         const uint64_t sid = next_stream();
-        if (hk && hk->playouts) hk->playouts(boards.data(), to_move.data(), B, (uint64_t)p, sid, (uint64_t(*)[4])out.data());
-        else if (p == 1) {
-            // one playout per leaf: one outcome byte per leaf comes back (1 B instead of 32 B), unpacked below
-            packed.resize((size_t)B);
-            if (opt.device_slot >= 0) must(sq_playouts_packed_on(opt.device_slot, boards.data(), to_move.data(), B, sid, packed.data()), "sq_playouts_packed_on");
-            else must(sq_playouts_packed(boards.data(), to_move.data(), B, sid, packed.data()), "sq_playouts_packed");
-            for (long long k = 0; k < B; k++) {
-                const uint8_t c = packed[(size_t)k];
-                uint64_t* r = &out[(size_t)k * 4];
+        if (hk && hk->playouts) hk->playouts(bt.boards.data(), bt.to_move.data(), bt.B, (uint64_t)bt.p, sid, (uint64_t(*)[4])bt.out.data());
+        else if (bt.p == 1) {
+            // one playout per leaf: one outcome byte per leaf comes back (1 byte instead of 32), unpacked below
+            bt.packed.resize((size_t)bt.B);
+            if (opt.device_slot >= 0) must(sq_playouts_packed_on(opt.device_slot, bt.boards.data(), bt.to_move.data(), bt.B, sid, bt.packed.data()), "sq_playouts_packed_on");
+            else must(sq_playouts_packed(bt.boards.data(), bt.to_move.data(), bt.B, sid, bt.packed.data()), "sq_playouts_packed");
+            for (long long k = 0; k < bt.B; k++) {
+                const uint8_t c = bt.packed[(size_t)k];
+                uint64_t* r = &bt.out[(size_t)k * 4];
                 r[0] = (c & 3) == 1; r[1] = (c & 3) == 2; r[2] = (c & 3) == 3; r[3] = c >> 2;
             }
         }
-        else if (opt.device_slot >= 0) must(sq_playouts_on(opt.device_slot, boards.data(), to_move.data(), B, (uint64_t)p, sid, (uint64_t(*)[4])out.data()), "sq_playouts_on");
-        else must(sq_playouts(boards.data(), to_move.data(), B, (uint64_t)p, sid, (uint64_t(*)[4])out.data()), "sq_playouts");
-        auto t2 = now();
+        else if (opt.device_slot >= 0) must(sq_playouts_on(opt.device_slot, bt.boards.data(), bt.to_move.data(), bt.B, (uint64_t)bt.p, sid, (uint64_t(*)[4])bt.out.data()), "sq_playouts_on");
+        else must(sq_playouts(bt.boards.data(), bt.to_move.data(), bt.B, (uint64_t)bt.p, sid, (uint64_t(*)[4])bt.out.data()), "sq_playouts");
+    };
+    auto update_phase = [&](Batch& bt) {
         pool.run([&](int t) {
-            const long long lo = B * t / T, hi = B * (t + 1) / T;
+            const long long lo = bt.B * t / T, hi = bt.B * (t + 1) / T;
             // the paths are known: their nodes are pulled in kAhead paths early
             uint64_t root_wins = 0;
             Shard* sh = exact ? nullptr : &shards[(size_t)t];
             const uint32_t fc1 = nodes[root].first_child.load(std::memory_order_acquire);
             for (long long k = lo; k < hi; k++) {
                 if (k + kAhead < hi) {
-                    const uint32_t* pp = &paths[(size_t)(k + kAhead) * kPathLen];
-                    const int d = leaves[(size_t)(k + kAhead)].depth;
+                    const uint32_t* pp = &bt.paths[(size_t)(k + kAhead) * kPathLen];
+                    const int d = bt.leaves[(size_t)(k + kAhead)].depth;
                     for (int i = 0; i < d; i++) __builtin_prefetch(&nodes[pp[i]], 1, 1);
                 }
-                const Leaf& lf = leaves[(size_t)k];
-                const uint64_t* r = &out[(size_t)k * 4];
+                const Leaf& lf = bt.leaves[(size_t)k];
+                const uint64_t* r = &bt.out[(size_t)k * 4];
                 if (lf.fresh) nodes[lf.node].untried.store(r[3] != 0 ? (kFull & ~(lf.x | lf.o)) : 0u, std::memory_order_release);
-                const uint32_t* pp = &paths[(size_t)k * kPathLen];
+                const uint32_t* pp = &bt.paths[(size_t)k * kPathLen];
                 root_wins += (nodes[root].info & 32u) ? r[0] : r[1];              // pp[0] is the root: one add per thread
                 int from = 1;
                 if (sh && lf.depth > 1) {                                          // first and second level: into the shard
@@ -468,10 +477,43 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
                         if (sh->w2[a][b]) { nodes[fc2 + (uint32_t)b].wins.fetch_add((uint32_t)sh->w2[a][b], std::memory_order_relaxed); sh->w2[a][b] = 0; }
                 }
         });
-        auto t3 = now();
-        res.select_seconds += secs(t0, t1); res.gpu_seconds += secs(t1, t2); res.update_seconds += secs(t2, t3);
+    };
+    // Pipelined (throughput mode): while the GPU plays batch k the host threads already select batch k+1 -- they see the
+    // tree with batch k's visits on it (virtual loss) but not yet its wins.  The exact mode (reference tie rule, caller-
+    // supplied rand.Intn) keeps the strict select / play / update sequence the golden trees were grown with.
+    const bool pipelined = !exact && (!(hk && hk->playouts) || std::getenv("SQUAVA_FAST_PIPELINE") != nullptr) &&
+                           std::getenv("SQUAVA_FAST_NO_PIPELINE") == nullptr;
+    int cur = 0;
+    bool have = plan(bufs[cur]);
+    if (have) { auto t0 = now(); select_phase(bufs[cur]); res.select_seconds += secs(t0, now()); }
+    while (have && !overflow.load()) {
+        Batch& bt = bufs[cur];
+        bool have_next = false;
+        auto t1 = now();
+        if (pipelined) {
+            std::thread gpu_thread([&] { gpu_phase(bt); });
+            have_next = plan(bufs[cur ^ 1]);
+            auto s0 = now();
+            if (have_next) select_phase(bufs[cur ^ 1]);
+            auto s1 = now();
+            gpu_thread.join();
+            res.select_seconds += secs(s0, s1);
+            res.gpu_seconds += secs(s1, now());          // what the GPU call still took after the selection was done
+        } else {
+            gpu_phase(bt);
+            res.gpu_seconds += secs(t1, now());
+        }
+        auto t2 = now();
+        update_phase(bt);
+        res.update_seconds += secs(t2, now());
         res.batches++;
-        done += B * p;
+        done += bt.B * bt.p;
+        if (!pipelined) {
+            have_next = plan(bufs[cur ^ 1]);
+            if (have_next) { auto t0 = now(); select_phase(bufs[cur ^ 1]); res.select_seconds += secs(t0, now()); }
+        }
+        cur ^= 1;
+        have = have_next;
     }
     if (overflow.load()) { std::fprintf(stderr, "fast_uct: node arena exhausted (%llu slots)\n", (unsigned long long)cap); std::exit(2); }
     res.iterations = done;

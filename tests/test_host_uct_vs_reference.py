@@ -190,6 +190,16 @@ def test_fast_arena_tree_many_threads_keeps_its_books(host_lib):
         assert best.value in range(25) and nodes.value > iters // ppl
 
 
+def test_fast_arena_tree_pipelined_batches_keep_their_books(host_lib, monkeypatch):
+    """double-buffered batches: the rollouts of batch k run on a second thread while the host threads select batch k+1
+    (they see batch k's visits but not yet its wins); every iteration must still be counted exactly once everywhere"""
+    monkeypatch.setenv("SQUAVA_FAST_PIPELINE", "1")
+    test_fast_arena_tree_many_threads_keeps_its_books(host_lib)
+    monkeypatch.delenv("SQUAVA_FAST_PIPELINE")
+    monkeypatch.setenv("SQUAVA_FAST_NO_PIPELINE", "1")
+    test_fast_arena_tree_many_threads_keeps_its_books(host_lib)
+
+
 def test_fast_arena_tree_throughput_mode_searches_like_the_exact_mode(host_lib):
     """same synthetic game (the chance that X wins a rollout depends on who holds the inner ring), same budget:
     the 4-thread / batched / single-precision / sharded search must spend its visits on the same first
