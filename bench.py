@@ -242,8 +242,13 @@ def secondary_c4(sq, rank, world, dev, dist, torch, peak_ops):
     pairs, st = opening3_subtrees(sq)
     sq.alphabeta_subtrees(st[:4], 3, 5, SCORES_OPENING)                          # warm-up
     t0 = time.perf_counter()
-    _, pilot = sq.alphabeta_subtrees(st, 3, 7, SCORES_OPENING)                   # every rank: the same weights
-    mine = lpt_assign([float(v) for v in pilot], world)[rank]
+    _, pilot = sq.alphabeta_subtrees(st, 3, 7, SCORES_OPENING)
+    # evaluator counts depend on how the GPU happened to schedule the search: ONE rank's counts are the weights for
+    # everybody (a broadcast of 85 integers), so that all ranks derive the same partition
+    weights = torch.from_numpy(pilot.astype(np.int64)).to(dev)
+    if world > 1:
+        dist.broadcast(weights, src=0)
+    mine = lpt_assign([float(v) for v in weights.cpu().numpy()], world)[rank]
     vals = torch.zeros(len(pairs), dtype=torch.int64, device=dev)
     nodes = torch.zeros(len(pairs), dtype=torch.int64, device=dev)
     if mine:

@@ -140,10 +140,12 @@ SQ_UNROLL
 //   that led to it (alphabeta.go:173-177), so a quad whose hole is j0 does not count, and the pending move of THIS
 //   node -- walk masks pe1 / pe2, API layout -- loses one (two) counted quads when the child stands on a pe1
 //   (pe2) cell; both are folded into the per-cell count.  first_cnt: the three-of-four count of the child on the
-//   FIRST empty cell (its j0 is the second empty cell), which the caller gets from one table walk.
+//   FIRST empty cell (its j0 is the second empty cell), which the caller gets from one table walk; first_score:
+//   scores[] of that cell.
 template <bool DELAYED>
 __host__ __device__ __forceinline__ int horizon_node_value(uint32_t own, uint32_t opp, uint32_t emp, int term, int konst,
-                                                           uint32_t pe1, uint32_t pe2, int first_cnt, const HorizonTables& H) {
+                                                           uint32_t pe1, uint32_t pe2, int first_cnt, int first_score,
+                                                           const HorizonTables& H) {
     (void)opp;
     const uint32_t m = pad(own), e = pad(emp);
     uint32_t win, sui;
@@ -156,9 +158,7 @@ __host__ __device__ __forceinline__ int horizon_node_value(uint32_t own, uint32_
         const uint32_t f1p = pad(pe1), f2p = pad(pe2);
         if (cand & f0) {
             const int t0 = first_cnt + ((f1p & f0) ? 1 : 0) + ((f2p & f0) ? 1 : 0);
-            int v0 = 30 * t0 + H.score_min;
-            for (int k = 0; k < H.n_planes; k++) if (H.score_plane[k] & f0) v0 += 1 << k;
-            v0 += konst;
+            const int v0 = 30 * t0 + first_score + konst;
             best = v0 > best ? v0 : best;
         }
         cand &= ~f0;

@@ -861,7 +861,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                         const int first_cnt = __popc(w0.e1 & ~f1) + __popc(w0.e2 & ~f1);
                         int konst = -30 * (__popc(w.e1) + __popc(w.e2)) - R.scores[cell];
                         if (AbTraits<DIALECT>::delayed_sum) konst -= side * d;
-                        const int rel = horizon_node_value<true>(own2, opp2, emp_after, kWin - (cply + 1), konst, w.e1, w.e2, first_cnt, R.hz);
+                        const int rel = horizon_node_value<true>(own2, opp2, emp_after, kWin - (cply + 1), konst, w.e1, w.e2, first_cnt, R.scores[__ffs(f0) - 1], R.hz);
                         ret = -side * rel;
                         evals += 3;          // about three table walks of instructions
                         returning = true;
@@ -873,7 +873,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                     else if (emp_after == 0) { ret = side > 0 ? R.sentinel : -R.sentinel; returning = true; }
                     else if (!kPenalties && R.fast_horizon && cply == R.max_depth - 1 && (emp_after & (emp_after - 1u))) {
                         const uint32_t own2 = side > 0 ? os : xs, opp2 = side > 0 ? xs : os;
-                        const int rel = horizon_node_value<false>(own2, opp2, kFull25 & ~(xs | os), kWin - (cply + 1), -side * (dv + carried), 0u, 0u, 0, R.hz);
+                        const int rel = horizon_node_value<false>(own2, opp2, kFull25 & ~(xs | os), kWin - (cply + 1), -side * (dv + carried), 0u, 0u, 0, 0, R.hz);
                         ret = -side * rel;
                         evals += 2;
                         returning = true;

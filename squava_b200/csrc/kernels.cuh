@@ -196,8 +196,10 @@ __device__ __forceinline__ void ply_block(PlyState& S, const uint32_t (&w)[4], u
             const uint32_t m = a + bit;          // bit is an empty cell: + is |
 #if SQ_PL_LINE3
             // r_d = m & m<<d & m<<2d: bit at the END of every run of >= 3 in direction d; a run of >= 4 also has m<<3d
-            const uint32_t h1 = m << 1, h2 = m << 2, h3 = m << 3, v1 = m << 6, v2 = m << 12, v3 = m << 18;
-            const uint32_t d1 = m << 7, d2 = m << 14, d3 = m << 21, a1 = m << 5, a2 = m << 10, a3 = m << 15;
+#define SQ_SHL(x, k, i) (SQ_PL_SHF > (i) ? shl_alu((x), (k)) : ((x) << (k)))      /* the first SQ_PL_SHF of these go to the ALU pipe */
+            const uint32_t h1 = m << 1, h2 = m << 2, h3 = SQ_SHL(m, 3, 3), v1 = SQ_SHL(m, 6, 0), v2 = m << 12, v3 = SQ_SHL(m, 18, 4);
+            const uint32_t d1 = SQ_SHL(m, 7, 1), d2 = m << 14, d3 = SQ_SHL(m, 21, 5), a1 = SQ_SHL(m, 5, 2), a2 = m << 10, a3 = m << 15;
+#undef SQ_SHL
             const uint32_t rh = m & h1 & h2, rv = m & v1 & v2, rd = m & d1 & d2, ra = m & a1 & a2;
             const uint32_t t3 = rh | rv | rd | ra;
             const uint32_t t4 = (rh & h3) | (rv & v3) | (rd & d3) | (ra & a3);

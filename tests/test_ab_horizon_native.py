@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.skipif(shutil.which("nvcc") is None, reason="needs nvcc (host-only compile)")
 def test_horizon_node_value_equals_per_child_walk(tmp_path):
     exe = str(tmp_path / "ab_horizon_check")
-    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe,
+    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe,
                            os.path.join(ROOT, "tests", "native", "ab_horizon_check.cu")])
     for seed in (1, 2):
         out = subprocess.run([exe, "150000", str(seed)], capture_output=True, text=True, timeout=300)

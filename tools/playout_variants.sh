@@ -7,11 +7,12 @@ cd "$(dirname "$0")/.."
 mkdir -p variants
 declare -A V
 V[base]=""
-V[line3_off]="-DSQ_PL_LINE3=0"
-V[ctas5]="-DSQ_PLAYOUT_CTAS_PER_SM=5"
-V[ctas5_line3_off]="-DSQ_PLAYOUT_CTAS_PER_SM=5 -DSQ_PL_LINE3=0"
-V[ctas6_line3_off]="-DSQ_PLAYOUT_CTAS_PER_SM=6 -DSQ_PL_LINE3=0"
-V[acc_alu_line3_off]="-DSQ_PL_ACC_ALU=1 -DSQ_PL_LINE3=0"
+V[shf1]="-DSQ_PL_SHF=1"
+V[shf2]="-DSQ_PL_SHF=2"
+V[shf4]="-DSQ_PL_SHF=4"
+V[acc_alu]="-DSQ_PL_ACC_ALU=1"
+V[acc_alu_shf2]="-DSQ_PL_ACC_ALU=1 -DSQ_PL_SHF=2"
+V[ctas6]="-DSQ_PLAYOUT_CTAS_PER_SM=6"
 if [ "$1" = "run" ]; then
     for k in "${!V[@]}"; do
         export SQUAVA_B200_LIB="$PWD/variants/libsquava_b200_$k.so"
