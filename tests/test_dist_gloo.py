@@ -46,6 +46,17 @@ def worker(rank, ws, port, q):
     v, w = mcts.root_statistics(root)
     mv, mw = sqd.merge_root_statistics(v, w)
     best, _ = mcts.choose_from_statistics(mv, mw, 1.0)
+    # 3. size-sharded subtrees (bench.py secondary_c4): every rank measures DIFFERENT pilot weights (evaluator counts
+    #    depend on GPU scheduling); after the broadcast of rank 0's they must derive the same partition, and the
+    #    zero-padded all-reduce must then hold every subtree's value exactly once
+    import bench
+    local_w = torch.tensor(np.random.Generator(np.random.PCG64(7 + rank)).integers(1, 1000, size=85), dtype=torch.int64)
+    dist.broadcast(local_w, src=0)
+    mine = bench.lpt_assign([float(x) for x in local_w.numpy()], ws)[rank]
+    vals = torch.zeros(85, dtype=torch.int64)
+    vals[mine] = torch.tensor([1000 + i for i in mine], dtype=torch.int64)
+    dist.all_reduce(vals)
+    ok_merge = ok_merge and vals.tolist() == [1000 + i for i in range(85)]
     q.put((rank, ok_merge, float(v.sum()), float(mv.sum()), mv.tolist(), best))
     dist.barrier()
     dist.destroy_process_group()
