@@ -200,6 +200,12 @@ uint64_t sq_launch_count(void);
 /* Duration in ms of the most recent playout kernel on device slot, measured
  * with CUDA events on the stream it ran on (synchronises that stream).       */
 int sq_last_playout_kernel_ms(int slot, float *ms);
+/* 1 if this library was built with -DSQ_CHECKED=1 (`make -C squava_b200/csrc checked`): the kernels then carry bounds
+ * checks of their own (compute-sanitizer is closed on the development pool, profiles/r02_sanitizer.md).
+ * sq_debug_check_failures: out = {failed checks since the last call, code of the first, its two arguments}, all
+ * zero in an unchecked build.                                                                              */
+int sq_abi_checked(void);
+int sq_debug_check_failures(uint32_t out[4]);
 /* Philox4x32-10 block on the device (known-answer tests of the RNG).         */
 int sq_debug_philox(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
 

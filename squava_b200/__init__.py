@@ -38,7 +38,7 @@ EXPORTS = [
     "sq_init", "sq_shutdown", "sq_strerror", "sq_last_error", "sq_abi_version", "sq_device_count",
     "sq_sm_count", "sq_classify", "sq_playouts", "sq_alphabeta_root", "sq_alphabeta_subtrees", "sq_negascout_root",
     "sq_classify_dev", "sq_playouts_dev", "sq_int32_peak", "sq_launch_count",
-    "sq_last_playout_kernel_ms", "sq_debug_philox", "sq_playouts_packed", "sq_last_error_copy", "sq_playouts_on", "sq_playouts_packed_on",
+    "sq_last_playout_kernel_ms", "sq_debug_philox", "sq_playouts_packed", "sq_last_error_copy", "sq_playouts_on", "sq_playouts_packed_on", "sq_abi_checked", "sq_debug_check_failures",
 ]
 
 
@@ -76,6 +76,7 @@ def lib():
         L.sq_playouts.argtypes = [vp, vp, i64, u64, u64, vp]
         L.sq_playouts_packed.argtypes = [vp, vp, i64, u64, vp]
         L.sq_last_error_copy.argtypes = [C.c_char_p, i32]
+        L.sq_debug_check_failures.argtypes = [vp]
         L.sq_playouts_on.argtypes = [i32, vp, vp, i64, u64, u64, vp]
         L.sq_playouts_packed_on.argtypes = [i32, vp, vp, i64, u64, vp]
         L.sq_alphabeta_root.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, vp]
@@ -231,6 +232,13 @@ def alphabeta_subtrees(subtrees, dialect, max_depth, scores):
     _ck(lib().sq_alphabeta_subtrees(t.ctypes.data, n, dialect, max_depth, s.ctypes.data,
                                     value.ctypes.data, nodes.ctypes.data), "sq_alphabeta_subtrees")
     return value, nodes
+
+
+def check_failures():
+    """Checked build: (failed in-kernel checks since the last call, code of the first, its two arguments)."""
+    out = np.zeros(4, np.uint32)
+    _ck(lib().sq_debug_check_failures(out.ctypes.data), "sq_debug_check_failures")
+    return tuple(int(v) for v in out)
 
 
 def int32_peak(kind=2, reps=5, slot=0):

@@ -825,6 +825,29 @@ int sq_last_playout_kernel_ms(int slot, float* ms) {
     return SQ_OK;
 }
 
+int sq_abi_checked(void) { return SQ_CHECKED; }
+
+// Checked build only: {failures, code of the first, its two arguments} summed / taken over the devices, then reset.
+int sq_debug_check_failures(uint32_t out[4]) {
+    std::shared_lock<std::shared_mutex> sl(g_state);
+    int rc = check_ready();
+    if (rc) return rc;
+    if (!out) return SQ_ERR_INVALID;
+    out[0] = out[1] = out[2] = out[3] = 0;
+#if SQ_CHECKED
+    for (auto& d : g_dev) {
+        CK(cudaSetDevice(d->id));
+        CK(cudaDeviceSynchronize());
+        unsigned int h[4] = {0, 0, 0, 0}, zero[4] = {0, 0, 0, 0};
+        CK(cudaMemcpyFromSymbol(h, sq::g_sq_check_fail, sizeof h));
+        CK(cudaMemcpyToSymbol(sq::g_sq_check_fail, zero, sizeof zero));
+        if (h[0] && !out[0]) { out[1] = h[1]; out[2] = h[2]; out[3] = h[3]; }
+        out[0] += h[0];
+    }
+#endif
+    return SQ_OK;
+}
+
 int sq_debug_philox(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]) {
     std::shared_lock<std::shared_mutex> sl(g_state);
     int rc = check_ready();

@@ -231,6 +231,7 @@ __device__ __forceinline__ void ab_enqueue(const AbRun& R, int idx, int ply) {
     if (R.queued) atomicAdd(ab_cnt(R, 7), 1u);
     const unsigned slot = atomicAdd(ab_cnt(R, 1), 1u);
     __threadfence();
+    SQ_CHECK(slot < (unsigned)R.queue_capacity && idx >= 0 && idx < R.node_capacity, 13, slot, idx);
     if (slot < (unsigned)R.queue_capacity) *reinterpret_cast<volatile int*>(&R.units[slot]) = idx;
     else atomicExch(ab_cnt(R, 4), 1u);             // cannot happen by sizing; never write past the queue
     if (!R.queued) atomicMin(ab_cnt(R, 6), (unsigned)ply);
@@ -240,6 +241,7 @@ __device__ __forceinline__ void ab_enqueue(const AbRun& R, int idx, int ply) {
 __device__ void ab_complete(const AbRun& R, int node, int value) {
     for (;;) {
         int parent = ab_node_parent(R, node);
+        SQ_CHECK(node >= 0 && node < R.node_capacity && parent < R.node_capacity, 10, node, parent);
         if (parent < 0) { R.out[-1 - parent] = value; return; }
         if (ab_node_side(R, parent) > 0) atomicMax(&R.value[parent], value);
         else atomicMin(&R.value[parent], value);
@@ -272,6 +274,7 @@ __device__ void ab_complete(const AbRun& R, int node, int value) {
 __device__ __forceinline__ void ab_bounds(const AbRun& R, int node, int& alpha, int& beta) {
     int p = ab_node_parent(R, node);
     while (p >= 0) {
+        SQ_CHECK(p < R.node_capacity, 11, node, p);
         int v = ld_volatile(&R.value[p]);
         if (ab_node_side(R, p) > 0) alpha = max(alpha, v); else beta = min(beta, v);
         p = ab_node_parent(R, p);
@@ -712,7 +715,9 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                 if (u >= (unsigned)n_units) break;
                 unit = R.units[u];
             }
+            SQ_CHECK(unit >= 0 && unit < R.node_capacity, 12, unit, R.node_capacity);
             const AbNode n = ab_ld_node(&R.nodes[unit]);
+            SQ_CHECK((n.side == 1 || n.side == -1) && n.cell >= 0 && n.cell < 25 && !(n.x & n.o) && (((n.x | n.o) >> n.cell) & 1u), 14, unit, n.x | n.o);
             int a0 = R.win_lo, b0 = R.win_hi;
             ab_bounds(R, unit, a0, b0);
             if (a0 >= b0) {
@@ -882,6 +887,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                 }
                 if (!returning) {
                     // push: the register frame goes to shared memory, the child becomes the register frame
+                    SQ_CHECK(sp >= 0 && sp < n_frames, 15, sp, n_frames);
                     SQ_FR(sp, 0) = moves | ((uint32_t)kidx << 25);
                     SQ_FR(sp, 1) = ((uint32_t)value & 0xffffu) | ((uint32_t)alpha << 16);
                     SQ_FR(sp, 2) = ((uint32_t)beta & 0xffffu) | ((uint32_t)carried << 16);

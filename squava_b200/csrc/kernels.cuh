@@ -193,6 +193,8 @@ __device__ __forceinline__ void ply_block(PlyState& S, const uint32_t (&w)[4], u
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(last) : "r"(al));
             asm volatile("st.shared.u32 [%0], %1;" :: "r"(ai), "r"(last));
             asm volatile("st.shared.u32 [%0], %1;" :: "r"(al), "r"(bit));
+            SQ_CHECK(idx < n && n >= 1u && n <= 25u, 1, idx, n);                          // the draw stays inside the lane's array
+            SQ_CHECK((bit & (bit - 1u)) == 0u && ((a | b) & bit) == 0u, 2, bit, a | b);    // one cell, and an empty one
             const uint32_t m = a + bit;          // bit is an empty cell: + is |
 #if SQ_PL_LINE3
             // r_d = m & m<<d & m<<2d: bit at the END of every run of >= 3 in direction d; a run of >= 4 also has m<<3d

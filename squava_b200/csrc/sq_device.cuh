@@ -14,6 +14,22 @@
 
 namespace sq {
 
+// Checked build (-DSQ_CHECKED=1, `make checked`): compute-sanitizer is closed on the pool this was developed on
+// (profiles/r02_sanitizer.md), so the kernels carry their own bounds checks -- node indices, queue slots, search-stack
+// frames, Fisher-Yates slots -- compiled in only here and reported through sq_debug_check_failures().
+#ifndef SQ_CHECKED
+#define SQ_CHECKED 0
+#endif
+#if SQ_CHECKED
+__device__ unsigned int g_sq_check_fail[4];   // [0] failures, [1] code of the first, [2] [3] its two arguments
+__device__ __forceinline__ void sq_check_fail(unsigned code, unsigned a, unsigned b) {
+    if (atomicAdd(&g_sq_check_fail[0], 1u) == 0) { g_sq_check_fail[1] = code; g_sq_check_fail[2] = a; g_sq_check_fail[3] = b; }
+}
+#define SQ_CHECK(cond, code, a, b) do { if (!(cond)) ::sq::sq_check_fail((code), (unsigned)(a), (unsigned)(b)); } while (0)
+#else
+#define SQ_CHECK(cond, code, a, b) do { } while (0)
+#endif
+
 constexpr uint32_t kFull25 = 0x1FFFFFFu;
 constexpr uint32_t kFullPadded = 0x1F7DF7DFu;  // 5 cells in each of 5 six-bit rows
 
