@@ -132,6 +132,7 @@ struct AbRun {
     unsigned int min_budget;   // queue-driven: evaluator calls a unit spends before it may be split for hungry lanes
     long long stall_cycles;    // queue-driven watchdog: idle lanes give up when the heartbeat stands still this long
     int ybw;             // young brothers wait: a split node's younger children start only when the eldest has finished
+    int killers;         // killer-move ordering inside the per-lane search (SQ_AB_NO_KILLERS switches it off)
     int fast_horizon;    // horizon-1 nodes are valued in one bit-parallel shot (ab_horizon.cuh): needs the shortcuts and a bias table spanning < 30
     int8_t scores[25];
     HorizonTables hz;
@@ -623,7 +624,10 @@ __device__ __forceinline__ AbWalk ab_walk(const AbWalkTables& W, uint32_t own, u
     return r;
 }
 
-template <int DIALECT> struct AbFrameWords { static constexpr int n = AbTraits<DIALECT>::delayed ? 5 : 3; };
+// words of a frame in shared memory: the saved register frame (5 or 3) + the KILLER of that depth: the child that
+// last cut a node off there is tried first at the next node of the same depth.  Any visiting order gives the same
+// root values; the reference's own order (row-major in src/alphabeta) prunes poorly.
+template <int DIALECT> struct AbFrameWords { static constexpr int saved = AbTraits<DIALECT>::delayed ? 5 : 3; static constexpr int n = saved + 1; };
 
 //
 // QUEUED = false: pass-driven.  The host launches one pass per generation of units; a unit that exceeds `budget`
@@ -679,6 +683,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
 
     for (;;) {
         int ret = 0;
+        uint32_t cur_kbit = 0;    // the child (child-order space) whose value is being handed to frame sp
         bool returning = false;   // `ret` is to be handed to frame sp ...
         bool restore = false;     // ... which is in shared memory (a pushed child came back)
         iter++;
@@ -825,7 +830,11 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
             ret = value; returning = true;            // node done (also: a node with no legal move)
             sp--; restore = true;
         } else {
-            const uint32_t kbit = moves & (0u - moves);
+            // the killer of this depth first (stale or never-set words are harmless: only legal moves pass the mask)
+            const uint32_t pref = R.killers ? (moves & SQ_FR(sp, AbFrameWords<DIALECT>::saved)) : 0u;
+            const uint32_t from = pref ? pref : moves;
+            const uint32_t kbit = from & (0u - from);
+            cur_kbit = kbit;
             moves ^= kbit;
             const int kidx = __ffs(kbit) - 1;
             const int cell = kOrdered ? T.order[kidx] : kidx;
@@ -925,11 +934,15 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                 const uint32_t bit = 1u << (kOrdered ? T.order[kidx] : kidx);
                 if (s > 0) x &= ~bit; else o &= ~bit;
                 emp |= 1u << kidx;
+                cur_kbit = 1u << kidx;
             }
             if (s > 0) { value = max(value, ret); alpha = max(alpha, value); }
             else { value = min(value, ret); beta = min(beta, value); }
             if (sp == 0) ab_bounds(R, unit, alpha, beta);        // siblings may have tightened the window
-            if (beta <= alpha) { ret = value; sp--; restore = true; } else returning = false;
+            if (beta <= alpha) {
+                if (R.killers && cur_kbit) SQ_FR(sp, AbFrameWords<DIALECT>::saved) = cur_kbit;     // this child cut the node off
+                ret = value; sp--; restore = true; cur_kbit = 0;
+            } else returning = false;
         }
     }
     if (QUEUED) { atomicAdd(ab_cnt(R, 10), (unsigned)(busy_turns >> 10)); atomicAdd(ab_cnt(R, 11), (unsigned)(idle_turns >> 10)); }
@@ -946,14 +959,14 @@ inline cudaError_t ab_configure_dialect(int max_smem) {
 
 inline cudaError_t ab_configure(int* blocks_per_sm) {
     int b1 = 0;
-    const int max_smem = (kAbMaxDepth + 2) * 5 * kAbThreads * 4;
+    const int max_smem = (kAbMaxDepth + 2) * 6 * kAbThreads * 4;      // 5 saved words + the killer word
     cudaError_t e;
     if ((e = ab_configure_dialect<1>(max_smem)) != cudaSuccess) return e;
     if ((e = ab_configure_dialect<2>(max_smem)) != cudaSuccess) return e;
     if ((e = ab_configure_dialect<3>(max_smem)) != cudaSuccess) return e;
     if ((e = ab_configure_dialect<5>(max_smem)) != cudaSuccess) return e;
     if ((e = ab_configure_dialect<6>(max_smem)) != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, ab_dfs_kernel<1, false>, kAbThreads, 10 * 5 * kAbThreads * 4);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, ab_dfs_kernel<1, false>, kAbThreads, 10 * 6 * kAbThreads * 4);
     if (e != cudaSuccess) return e;
     *blocks_per_sm = b1 < 1 ? 1 : b1;
     return cudaSuccess;
@@ -1298,6 +1311,7 @@ inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t score
     // measured (profiles/r02_alphabeta_ybw_passes.md): with a barrier between passes the brothers' wait costs more
     // time than the pruning it buys except in very deep searches, so it is opt-in for the pass-driven search
     R.ybw = getenv("SQ_AB_YBW") != nullptr;
+    R.killers = getenv("SQ_AB_NO_KILLERS") == nullptr;
 }
 
 // worst-case node count below one level-0 node with e empties and `split` expanded plies
