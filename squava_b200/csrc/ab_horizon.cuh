@@ -92,6 +92,41 @@ SQ_UNROLL
     return r;
 }
 
+// The same for src/alphabeta's DELAYED evaluation: a child marks its own first empty cell j0 before it evaluates, so a
+// window whose other empty cell is j0 does not count.  For every child but the one ON the first empty cell f0, j0 = f0:
+// windows through f0 are dropped.  For the child on f0, j0 is the second empty cell f1: its count is the number of good
+// windows through f0 that do not hold f1 (first_cnt).
+__host__ __device__ __forceinline__ CountPlanes window_counts_delayed(uint32_t m, uint32_t u, uint32_t f0, uint32_t f1, int& first_cnt) {
+    uint32_t lo[4], hi[4];
+    int fc = 0;
+SQ_UNROLL
+    for (int k = 0; k < 4; k++) {
+        const int d = k == 0 ? 1 : k == 1 ? 6 : k == 2 ? 7 : 5;
+        uint32_t g = good_windows(m, u, d);
+        const uint32_t w0 = f0 | (f0 >> d) | (f0 >> (2 * d)) | (f0 >> (3 * d));     // starts of the windows that hold f0
+        const uint32_t w1 = f1 | (f1 >> d) | (f1 >> (2 * d)) | (f1 >> (3 * d));
+        fc += SQ_POPC(g & w0 & ~w1);
+        g &= ~w0;
+        const uint32_t s0 = g, s1 = g << d, s2 = g << (2 * d), s3 = g << (3 * d);
+        const uint32_t x = s0 ^ s1 ^ s2, c = (s0 & s1) | (s2 & (s0 | s1));
+        lo[k] = x ^ s3;
+        hi[k] = c | (x & s3);
+    }
+    first_cnt = fc;
+    const uint32_t p0 = lo[0] ^ lo[1], pc = lo[0] & lo[1];
+    const uint32_t p1 = hi[0] ^ hi[1] ^ pc, p2 = (hi[0] & hi[1]) | (pc & (hi[0] | hi[1]));
+    const uint32_t q0 = lo[2] ^ lo[3], qc = lo[2] & lo[3];
+    const uint32_t q1 = hi[2] ^ hi[3] ^ qc, q2 = (hi[2] & hi[3]) | (qc & (hi[2] | hi[3]));
+    CountPlanes r;
+    r.b0 = p0 ^ q0;
+    const uint32_t c0 = p0 & q0;
+    r.b1 = p1 ^ q1 ^ c0;
+    const uint32_t c1 = (p1 & q1) | (c0 & (p1 | q1));
+    r.b2 = p2 ^ q2 ^ c1;
+    r.b3 = (p2 & q2) | (c1 & (p2 | q2));
+    return r;
+}
+
 // planes += f1 + f2 (two more one-bit inputs per cell; the sum stays below 16)
 __host__ __device__ __forceinline__ void add_two_bits(CountPlanes& p, uint32_t f1, uint32_t f2) {
     const uint32_t s0 = p.b0 ^ f1 ^ f2, c0 = (p.b0 & f1) | (f2 & (p.b0 | f1));
@@ -139,13 +174,11 @@ SQ_UNROLL
 //   DELAYED (src/alphabeta, src/abbook): the child marks its own first empty cell j0 before it evaluates the move
 //   that led to it (alphabeta.go:173-177), so a quad whose hole is j0 does not count, and the pending move of THIS
 //   node -- walk masks pe1 / pe2, API layout -- loses one (two) counted quads when the child stands on a pe1
-//   (pe2) cell; both are folded into the per-cell count.  first_cnt: the three-of-four count of the child on the
-//   FIRST empty cell (its j0 is the second empty cell), which the caller gets from one table walk; first_score:
-//   scores[] of that cell.
+//   (pe2) cell; both are folded into the per-cell count.  first_score: scores[] of the FIRST empty cell (the one child
+//   whose j0 is the second empty cell; its count comes out of window_counts_delayed).
 template <bool DELAYED>
 __host__ __device__ __forceinline__ int horizon_node_value(uint32_t own, uint32_t opp, uint32_t emp, int term, int konst,
-                                                           uint32_t pe1, uint32_t pe2, int first_cnt, int first_score,
-                                                           const HorizonTables& H) {
+                                                           uint32_t pe1, uint32_t pe2, int first_score, const HorizonTables& H) {
     (void)opp;
     const uint32_t m = pad(own), e = pad(emp);
     uint32_t win, sui;
@@ -154,8 +187,10 @@ __host__ __device__ __forceinline__ int horizon_node_value(uint32_t own, uint32_
     int best = sui ? -term : -0x40000000;
     uint32_t cand = e & ~sui;
     if (DELAYED) {
-        const uint32_t f0 = e & (0u - e);
+        const uint32_t f0 = e & (0u - e), rest = e ^ f0, f1 = rest & (0u - rest);
         const uint32_t f1p = pad(pe1), f2p = pad(pe2);
+        int first_cnt;
+        CountPlanes p = window_counts_delayed(m, m | e, f0, f1, first_cnt);
         if (cand & f0) {
             const int t0 = first_cnt + ((f1p & f0) ? 1 : 0) + ((f2p & f0) ? 1 : 0);
             const int v0 = 30 * t0 + first_score + konst;
@@ -163,7 +198,6 @@ __host__ __device__ __forceinline__ int horizon_node_value(uint32_t own, uint32_
         }
         cand &= ~f0;
         if (cand) {
-            CountPlanes p = window_counts(m, m | (e & ~f0));      // a window through the first empty cell never counts
             add_two_bits(p, f1p, f2p);
             const int v = best_of(p, cand, H) + konst;
             best = v > best ? v : best;

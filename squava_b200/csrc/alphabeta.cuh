@@ -132,6 +132,7 @@ struct AbRun {
     unsigned int min_budget;   // queue-driven: evaluator calls a unit spends before it may be split for hungry lanes
     long long stall_cycles;    // queue-driven watchdog: idle lanes give up when the heartbeat stands still this long
     int ybw;             // young brothers wait: a split node's younger children start only when the eldest has finished
+    int defer_min;       // > 0: horizon evaluations are deferred until this many lanes of the warp need one (SQ_AB_DEFER)
     int killers;         // killer-move ordering inside the per-lane search (SQ_AB_NO_KILLERS switches it off)
     int fast_horizon;    // horizon-1 nodes are valued in one bit-parallel shot (ab_horizon.cuh): needs the shortcuts and a bias table spanning < 30
     int8_t scores[25];
@@ -664,6 +665,12 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
     unsigned long long evals = 0;
     bool fresh = false;                        // the register frame was just entered
     (void)n_frames;
+    // deferred horizon evaluations (pass-driven search, R.defer_min > 0): a lane that needs one waits until enough lanes
+    // of its warp need one too, so that the most expensive phase of the loop runs with a fuller warp
+    bool pend_h = false, done = false;
+    uint32_t d_bit = 0, d_kbit = 0, d_e1 = 0, d_e2 = 0;
+    int d_konst = 0, stall = 0;
+    const bool kDefer = !QUEUED && R.defer_min > 0;
     // queue-driven search
     unsigned ticket = 0xffffffffu;             // the queue slot this lane is waiting on
     bool no_split = false;                     // the node pool had no room: finish the unit alone
@@ -686,6 +693,35 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
         uint32_t cur_kbit = 0;    // the child (child-order space) whose value is being handed to frame sp
         bool returning = false;   // `ret` is to be handed to frame sp ...
         bool restore = false;     // ... which is in shared memory (a pushed child came back)
+        bool served = false;
+        if (kDefer) {
+            const unsigned hm = __ballot_sync(0xffffffffu, pend_h), dm = __ballot_sync(0xffffffffu, done);
+            if (dm == 0xffffffffu) break;
+            if (hm) {
+                // serve when enough lanes wait, when nobody else can make progress, or when someone has waited two turns
+                const bool go = __popc(hm) >= R.defer_min || (hm | dm) == 0xffffffffu || __any_sync(0xffffffffu, pend_h && stall >= 2);
+                if (pend_h) {
+                    if (!go) { stall++; continue; }
+                    const int s_side = (sp & 1) ? -base_side : base_side;
+                    const int s_cply = base_ply + sp + 1;
+                    const uint32_t xs = x | (s_side > 0 ? d_bit : 0u), os = o | (s_side > 0 ? 0u : d_bit);
+                    const uint32_t own2 = s_side > 0 ? os : xs, opp2 = s_side > 0 ? xs : os;
+                    int rel;
+                    if (kDelayed) {
+                        const uint32_t emp_after = emp & ~d_kbit;                 // child-order space == cell space here
+                        const uint32_t f0 = emp_after & (0u - emp_after);
+                        rel = horizon_node_value<true>(own2, opp2, emp_after, kWin - (s_cply + 1), d_konst, d_e1, d_e2, R.scores[__ffs(f0) - 1], R.hz);
+                    } else {
+                        rel = horizon_node_value<false>(own2, opp2, kFull25 & ~(xs | os), kWin - (s_cply + 1), d_konst, 0u, 0u, 0, R.hz);
+                    }
+                    ret = -s_side * rel;
+                    cur_kbit = d_kbit;
+                    returning = true; served = true; pend_h = false; stall = 0;
+                }
+            }
+            if (done) continue;
+        }
+        if (!served) {
         iter++;
         if (QUEUED) { if (sp < 0) idle_turns++; else busy_turns++; }
         if (sp < 0) {
@@ -717,7 +753,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                 unit = got;
             } else {
                 unsigned int u = atomicAdd(ab_cnt(R, 2), 1u);
-                if (u >= (unsigned)n_units) break;
+                if (u >= (unsigned)n_units) { if (kDefer) { done = true; continue; } break; }
                 unit = R.units[u];
             }
             SQ_CHECK(unit >= 0 && unit < R.node_capacity, 12, unit, R.node_capacity);
@@ -870,15 +906,16 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                     } else if (!kPenalties && R.fast_horizon && cply == R.max_depth - 1 && (emp_after & (emp_after - 1u))) {
                         // the child is a horizon-1 node that cannot run out of cells: its value in one shot
                         const uint32_t own2 = side > 0 ? os : xs, opp2 = side > 0 ? xs : os;      // the child's mover is the other side
-                        const uint32_t f0 = emp_after & (0u - emp_after), rest = emp_after ^ f0, f1 = rest & (0u - rest);
-                        const AbWalk w0 = ab_walk(W, own2 | f0, opp2, __ffs(f0) - 1);
-                        const int first_cnt = __popc(w0.e1 & ~f1) + __popc(w0.e2 & ~f1);
+                        const uint32_t f0 = emp_after & (0u - emp_after);
                         int konst = -30 * (__popc(w.e1) + __popc(w.e2)) - R.scores[cell];
                         if (AbTraits<DIALECT>::delayed_sum) konst -= side * d;
-                        const int rel = horizon_node_value<true>(own2, opp2, emp_after, kWin - (cply + 1), konst, w.e1, w.e2, first_cnt, R.scores[__ffs(f0) - 1], R.hz);
-                        ret = -side * rel;
                         evals += 3;          // about three table walks of instructions
-                        returning = true;
+                        if (kDefer) { d_bit = bit; d_kbit = kbit; d_e1 = w.e1; d_e2 = w.e2; d_konst = konst; pend_h = true; }
+                        else {
+                            const int rel = horizon_node_value<true>(own2, opp2, emp_after, kWin - (cply + 1), konst, w.e1, w.e2, R.scores[__ffs(f0) - 1], R.hz);
+                            ret = -side * rel;
+                            returning = true;
+                        }
                     }
                 } else {
                     int dv = side * (30 * (__popc(w.e1) + __popc(w.e2)) + R.scores[cell]);
@@ -887,14 +924,17 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                     else if (emp_after == 0) { ret = side > 0 ? R.sentinel : -R.sentinel; returning = true; }
                     else if (!kPenalties && R.fast_horizon && cply == R.max_depth - 1 && (emp_after & (emp_after - 1u))) {
                         const uint32_t own2 = side > 0 ? os : xs, opp2 = side > 0 ? xs : os;
-                        const int rel = horizon_node_value<false>(own2, opp2, kFull25 & ~(xs | os), kWin - (cply + 1), -side * (dv + carried), 0u, 0u, 0, 0, R.hz);
-                        ret = -side * rel;
                         evals += 2;
-                        returning = true;
+                        if (kDefer) { d_bit = bit; d_kbit = kbit; d_konst = -side * (dv + carried); pend_h = true; }
+                        else {
+                            const int rel = horizon_node_value<false>(own2, opp2, kFull25 & ~(xs | os), kWin - (cply + 1), -side * (dv + carried), 0u, 0u, 0, R.hz);
+                            ret = -side * rel;
+                            returning = true;
+                        }
                     }
                     else d = dv + carried;
                 }
-                if (!returning) {
+                if (!returning && !pend_h) {
                     // push: the register frame goes to shared memory, the child becomes the register frame
                     SQ_CHECK(sp >= 0 && sp < n_frames, 15, sp, n_frames);
                     SQ_FR(sp, 0) = moves | ((uint32_t)kidx << 25);
@@ -911,6 +951,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
                 }
             }
         }
+        }   // !served
         // hand `ret` to frame sp; a cutoff there hands that frame's value further up
         while (returning) {
             if (sp < 0) {
@@ -1312,6 +1353,7 @@ inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t score
     // time than the pruning it buys except in very deep searches, so it is opt-in for the pass-driven search
     R.ybw = getenv("SQ_AB_YBW") != nullptr;
     R.killers = getenv("SQ_AB_NO_KILLERS") == nullptr;
+    { const char* e = getenv("SQ_AB_DEFER"); R.defer_min = e && *e ? atoi(e) : 0; }
 }
 
 // worst-case node count below one level-0 node with e empties and `split` expanded plies

@@ -67,9 +67,8 @@ int main(int argc, char** argv) {
         }
         terminal += any_win;
         const int cf0 = __builtin_ctz(f0);
-        const int first_cnt = count_three_of_four(own | f0, opp, cf0, f1);
-        const int got_d = horizon_node_value<true>(own, opp, emp, term, konst_d, pe1, pe2, first_cnt, scores[cf0], H);
-        const int got_n = horizon_node_value<false>(own, opp, emp, term, konst_n, 0, 0, 0, 0, H);
+        const int got_d = horizon_node_value<true>(own, opp, emp, term, konst_d, pe1, pe2, scores[cf0], H);
+        const int got_n = horizon_node_value<false>(own, opp, emp, term, konst_n, 0, 0, 0, H);
         if (got_d != ref_d || got_n != ref_n) {
             printf("MISMATCH own %07x opp %07x pe1 %07x pe2 %07x term %d: delayed %d vs %d, entry %d vs %d (mode %d)\n", own, opp, pe1, pe2, term, got_d, ref_d, got_n, ref_n, mode);
             return 1;

@@ -140,6 +140,21 @@ def test_packed_outcomes_equal_the_counted_form(dev):
     assert ((pk >> 2) == full[:, 3]).all() and ((pk & 3 == 1) == (full[:, 0] == 1)).all()
 
 
+def test_playouts_on_one_slot_equal_the_sharded_call(dev):
+    """sq_playouts_on / sq_playouts_packed_on (root-parallel hosts: one tree, one device) give the counts the
+    sharded call gives: the stream depends on (seed, stream_id, leaf index) only"""
+    from squava_b200 import positions
+    import ctypes as C
+    boards, tm = positions.midgame_batch(700, seed=71)
+    want = dev.playouts(boards, tm, 3000, 5)
+    assert (dev.playouts(boards, tm, 3000, 5, slot=0) == want).all()
+    pk = np.empty(700, np.uint8)
+    rc = dev.lib().sq_playouts_packed_on(0, boards.ctypes.data, tm.ctypes.data, 700, 9, pk.ctypes.data)
+    assert rc == 0 and (pk == dev.playouts_packed(boards, tm, 9)).all()
+    with pytest.raises(dev.SquavaError):
+        dev.playouts(boards, tm, 10, 5, slot=99)
+
+
 def test_concurrent_host_threads_on_one_device(dev, oracle):
     """calls arriving on several OS threads (cgo's situation) each take their own call context: results must be
     exactly those of the same calls made one after the other"""

@@ -284,3 +284,15 @@ def test_squavam_fast_arena_tree_decision():
     s = re.search(r"fast tree: (\d+) iterations, (\d+) batches, (\d+) node slots, (\d+) threads", out)
     assert m and s and int(s.group(1)) == 300000 and int(s.group(2)) == 37 and int(s.group(3)) > 300000
     assert 0 <= int(m.group(1)) <= 4 and 0 <= int(m.group(2)) <= 4
+
+
+def test_squavam_root_parallel_decision():
+    """squavam -fast -root-parallel: independent arena trees (one per device named by -gpus; here one), statistics
+    merged by move, every iteration counted once"""
+    rc, out, err = run("squavam", "-C", "-i", "4000000", "-u", "1.0", "-batch", "1024", "-ppl", "64", "-fast", "-root-parallel",
+                       "-stats", "-seed", "4")
+    assert rc == 0, err
+    m = re.search(r"My move: (\d) (\d) (\S+)", out)
+    s = re.search(r"fast tree: (\d+) iterations, (\d+) batches", out)
+    assert m and s and int(s.group(1)) == 4000000
+    assert len(re.findall(r"^searcher \d+: \d+ iterations", out, flags=re.M)) >= 1

@@ -7,4 +7,5 @@ tail -4 gpurun_out/r02m_pytest_ab.log
 OUT=gpurun_out/r02m_ab.txt; : > $OUT
 echo "== killers on" >> $OUT;  AB_DEEP=1 timeout 300 python tools/ab_time.py >> $OUT 2>&1
 echo "== killers off" >> $OUT; SQ_AB_NO_KILLERS=1 timeout 300 python tools/ab_time.py >> $OUT 2>&1
+for dm in 12 16 20 24; do echo "== defer $dm" >> $OUT; SQ_AB_DEFER=$dm timeout 300 python tools/ab_time.py >> $OUT 2>&1; done
 cat $OUT
