@@ -867,7 +867,10 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
             sp--; restore = true;
         } else {
             // the killer of this depth first (stale or never-set words are harmless: only legal moves pass the mask)
-            const uint32_t pref = R.killers ? (moves & SQ_FR(sp, AbFrameWords<DIALECT>::saved)) : 0u;
+            uint32_t pref = R.killers ? (moves & SQ_FR(sp, AbFrameWords<DIALECT>::saved)) : 0u;
+            // then (delayed dialects, where the walk of the pending move is at hand) the holes of the opponent's
+            // three-of-four quads: a move there blocks a four
+            if (kDelayed && R.killers >= 2) { const uint32_t blk = moves & fe1; if (R.killers == 2) { if (!pref) pref = blk; } else if (blk) pref = blk; }
             const uint32_t from = pref ? pref : moves;
             const uint32_t kbit = from & (0u - from);
             cur_kbit = kbit;
@@ -1353,6 +1356,7 @@ inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t score
     // time than the pruning it buys except in very deep searches, so it is opt-in for the pass-driven search
     R.ybw = getenv("SQ_AB_YBW") != nullptr;
     R.killers = getenv("SQ_AB_NO_KILLERS") == nullptr;
+    { const char* e = getenv("SQ_AB_ORDER"); if (R.killers && e && *e) R.killers = 1 + atoi(e); }   // 1: + blocking moves after the killer, 2: before it
     { const char* e = getenv("SQ_AB_DEFER"); R.defer_min = e && *e ? atoi(e) : 0; }
 }
 
