@@ -133,6 +133,7 @@ struct AbRun {
     long long stall_cycles;    // queue-driven watchdog: idle lanes give up when the heartbeat stands still this long
     int ybw;             // young brothers wait: a split node's younger children start only when the eldest has finished
     int defer_min;       // > 0: horizon evaluations are deferred until this many lanes of the warp need one (SQ_AB_DEFER)
+    int two_killers;     // a second killer per depth (the previous one)
     int killers;         // killer-move ordering inside the per-lane search (SQ_AB_NO_KILLERS switches it off)
     int fast_horizon;    // horizon-1 nodes are valued in one bit-parallel shot (ab_horizon.cuh): needs the shortcuts and a bias table spanning < 30
     int8_t scores[25];
@@ -628,7 +629,7 @@ __device__ __forceinline__ AbWalk ab_walk(const AbWalkTables& W, uint32_t own, u
 // words of a frame in shared memory: the saved register frame (5 or 3) + the KILLER of that depth: the child that
 // last cut a node off there is tried first at the next node of the same depth.  Any visiting order gives the same
 // root values; the reference's own order (row-major in src/alphabeta) prunes poorly.
-template <int DIALECT> struct AbFrameWords { static constexpr int saved = AbTraits<DIALECT>::delayed ? 5 : 3; static constexpr int n = saved + 1; };
+template <int DIALECT> struct AbFrameWords { static constexpr int saved = AbTraits<DIALECT>::delayed ? 5 : 3; static constexpr int n = saved + 2; };
 
 //
 // QUEUED = false: pass-driven.  The host launches one pass per generation of units; a unit that exceeds `budget`
@@ -868,6 +869,7 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
         } else {
             // the killer of this depth first (stale or never-set words are harmless: only legal moves pass the mask)
             uint32_t pref = R.killers ? (moves & SQ_FR(sp, AbFrameWords<DIALECT>::saved)) : 0u;
+            if (R.killers && R.two_killers && !pref) pref = moves & SQ_FR(sp, AbFrameWords<DIALECT>::saved + 1);   // the one before
             // then (delayed dialects, where the walk of the pending move is at hand) the holes of the opponent's
             // three-of-four quads: a move there blocks a four
             if (kDelayed && R.killers >= 2) { const uint32_t blk = moves & fe1; if (R.killers == 2) { if (!pref) pref = blk; } else if (blk) pref = blk; }
@@ -984,7 +986,10 @@ ab_dfs_kernel(AbRun R, int n_units, unsigned long long budget, int n_frames) {
             else { value = min(value, ret); beta = min(beta, value); }
             if (sp == 0) ab_bounds(R, unit, alpha, beta);        // siblings may have tightened the window
             if (beta <= alpha) {
-                if (R.killers && cur_kbit) SQ_FR(sp, AbFrameWords<DIALECT>::saved) = cur_kbit;     // this child cut the node off
+                if (R.killers && cur_kbit) {                                                     // this child cut the node off
+                    const uint32_t k1 = SQ_FR(sp, AbFrameWords<DIALECT>::saved);
+                    if (k1 != cur_kbit) { SQ_FR(sp, AbFrameWords<DIALECT>::saved + 1) = k1; SQ_FR(sp, AbFrameWords<DIALECT>::saved) = cur_kbit; }
+                }
                 ret = value; sp--; restore = true; cur_kbit = 0;
             } else returning = false;
         }
@@ -1003,14 +1008,14 @@ inline cudaError_t ab_configure_dialect(int max_smem) {
 
 inline cudaError_t ab_configure(int* blocks_per_sm) {
     int b1 = 0;
-    const int max_smem = (kAbMaxDepth + 2) * 6 * kAbThreads * 4;      // 5 saved words + the killer word
+    const int max_smem = (kAbMaxDepth + 2) * 7 * kAbThreads * 4;      // 5 saved words + two killer words
     cudaError_t e;
     if ((e = ab_configure_dialect<1>(max_smem)) != cudaSuccess) return e;
     if ((e = ab_configure_dialect<2>(max_smem)) != cudaSuccess) return e;
     if ((e = ab_configure_dialect<3>(max_smem)) != cudaSuccess) return e;
     if ((e = ab_configure_dialect<5>(max_smem)) != cudaSuccess) return e;
     if ((e = ab_configure_dialect<6>(max_smem)) != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, ab_dfs_kernel<1, false>, kAbThreads, 10 * 6 * kAbThreads * 4);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, ab_dfs_kernel<1, false>, kAbThreads, 10 * 7 * kAbThreads * 4);
     if (e != cudaSuccess) return e;
     *blocks_per_sm = b1 < 1 ? 1 : b1;
     return cudaSuccess;
@@ -1356,6 +1361,7 @@ inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t score
     // time than the pruning it buys except in very deep searches, so it is opt-in for the pass-driven search
     R.ybw = getenv("SQ_AB_YBW") != nullptr;
     R.killers = getenv("SQ_AB_NO_KILLERS") == nullptr;
+    R.two_killers = getenv("SQ_AB_ONE_KILLER") == nullptr;
     { const char* e = getenv("SQ_AB_ORDER"); if (R.killers && e && *e) R.killers = 1 + atoi(e); }   // 1: + blocking moves after the killer, 2: before it
     { const char* e = getenv("SQ_AB_DEFER"); R.defer_min = e && *e ? atoi(e) : 0; }
 }
