@@ -133,6 +133,7 @@ struct AbRun {
     long long stall_cycles;    // queue-driven watchdog: idle lanes give up when the heartbeat stands still this long
     int ybw;             // young brothers wait: a split node's younger children start only when the eldest has finished
     int defer_min;       // > 0: horizon evaluations are deferred until this many lanes of the warp need one (SQ_AB_DEFER)
+    int ybw_below_ply;   // brothers wait only under split nodes above this ply (SQ_AB_YBW = number of plies below the level-0 nodes)
     int two_killers;     // a second killer per depth (the previous one)
     int killers;         // killer-move ordering inside the per-lane search (SQ_AB_NO_KILLERS switches it off)
     int fast_horizon;    // horizon-1 nodes are valued in one bit-parallel shot (ab_horizon.cuh): needs the shortcuts and a bias table spanning < 30
@@ -457,7 +458,7 @@ ab_expand_kernel(AbRun R, const int* __restrict__ list, int lo, int count) {
         return;
     }
     // adaptive split of a unit that proved too big: only the eldest child starts now, the others when it is done
-    const bool hold = list != nullptr && R.ybw && nch >= 2;
+    const bool hold = list != nullptr && R.ybw && nch >= 2 && n.ply < R.ybw_below_ply;
     R.kids[idx] = (int)base;
     R.held[idx] = hold ? nch - 1 : 0;
     R.pending[idx] = nch;
@@ -1155,6 +1156,7 @@ cudaError_t ab_run_chunk(AbRun R, AbWork& w, const void* d_in, bool roots, int n
         t_prev = now;
     };
     lap("setup", n, (int)capacity);
+    { const char* e = getenv("SQ_AB_YBW"); const int k = e && *e ? atoi(e) : 0; if (k >= 1) R.ybw_below_ply = min_ply + k; }   // SQ_AB_YBW=all: everywhere; =k: the top k plies
     const unsigned long long fixed_budget = ab_budget();
     const bool deep_few = R.max_depth - min_ply >= 10 && (long long)n * (roots ? 25 : 1) <= 4096;
     bool unlimited = false;
@@ -1360,6 +1362,7 @@ inline void ab_fill_run(AbRun& R, int dialect, int max_depth, const int8_t score
     // measured (profiles/r02_alphabeta_ybw_passes.md): with a barrier between passes the brothers' wait costs more
     // time than the pruning it buys except in very deep searches, so it is opt-in for the pass-driven search
     R.ybw = getenv("SQ_AB_YBW") != nullptr;
+    R.ybw_below_ply = 127;
     R.killers = getenv("SQ_AB_NO_KILLERS") == nullptr;
     R.two_killers = getenv("SQ_AB_ONE_KILLER") == nullptr;
     { const char* e = getenv("SQ_AB_ORDER"); if (R.killers && e && *e) R.killers = 1 + atoi(e); }   // 1: + blocking moves after the killer, 2: before it

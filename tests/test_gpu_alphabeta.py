@@ -131,7 +131,7 @@ def test_schedule_does_not_change_values(dev, oracle, budget, pool):
 
 @pytest.mark.parametrize("env", [{"SQ_AB_MIN_BUDGET": "1"}, {"SQ_AB_MIN_BUDGET": "5", "SQ_AB_NO_YBW": "1"}, {"SQ_AB_MIN_BUDGET": "100000"},
                                  {"SQ_AB_POOL_NODES": "6000"}, {"SQ_AB_MIN_BUDGET": "3", "SQ_AB_NO_FAST_HORIZON": "1"}, {"SQ_AB_PASSES": "1"}, {},
-                                 {"SQ_AB_PASSES": "1", "SQ_AB_YBW": "1"}, {"SQ_AB_PASSES": "1", "SQ_AB_NO_KILLERS": "1"}, {"SQ_AB_PASSES": "1", "SQ_AB_DEFER": "16"},
+                                 {"SQ_AB_PASSES": "1", "SQ_AB_YBW": "all"}, {"SQ_AB_PASSES": "1", "SQ_AB_YBW": "2"}, {"SQ_AB_PASSES": "1", "SQ_AB_NO_KILLERS": "1"}, {"SQ_AB_PASSES": "1", "SQ_AB_DEFER": "16"},
                                  {"SQ_AB_PASSES": "1", "SQ_AB_DEFER": "32", "SQ_AB_BUDGET": "40"}])
 def test_queue_schedule_does_not_change_values(dev, oracle, env):
     """the queue-driven search (one persistent kernel): how eagerly units are split for hungry lanes, whether the
