@@ -6,7 +6,8 @@
 // batched-mode conventions (visits counted at selection time = virtual loss, wins when the batch
 // returns, a node created inside a batch learns whether it is terminal from its own rollout).
 // What differs is the data structure, built for 10^9 nodes and many selecting threads:
-//   * nodes are 24-byte records in one lazily committed arena, addressed by 32-bit index;
+//   * nodes are 16-byte records in one lazily committed arena, addressed by 32-bit index (a node's move is its slot in
+//     the parent's child block, its side the parity of its depth: neither is stored);
 //   * the children of a node live in ONE contiguous block (slot = rank of the move among the
 //     node's empty cells), allocated when the first child is made: a UCB1 scan is a linear read;
 //   * counts are 32-bit atomics; a thread claims an untried move with one fetch_and, so any
@@ -35,17 +36,17 @@ namespace {
 
 constexpr uint32_t kFull = 0x1FFFFFFu;
 constexpr uint32_t kPending = 1u << 31;      // untried: the node's first rollout has not come back yet
+constexpr int kRankShift = 26;               // untried bits 26..30: creation rank among the parent's children
+constexpr uint32_t kRankMask = 31u << kRankShift;
 const double kEps = std::numeric_limits<double>::denorm_min();
 
 struct FNode {
     std::atomic<uint32_t> visits;        // includes selections still in flight
     std::atomic<uint32_t> wins;          // of the player who moved INTO this node (Update, mcts.go:268-271)
     std::atomic<uint32_t> first_child;   // arena index of the child block, 0 = none yet
-    std::atomic<uint32_t> untried;       // moves nobody has claimed (25 bits) | kPending
-    uint32_t parent;
-    uint32_t info;                       // move (5 bits) | playerJustMoved == MAXIMIZER (bit 5) | creation rank (bits 6..10)
+    std::atomic<uint32_t> untried;       // moves nobody has claimed (25 bits) | creation rank (bits 26..30) | kPending
 };
-static_assert(sizeof(FNode) == 24, "node record");
+static_assert(sizeof(FNode) == 16, "node record");
 
 struct Rng {                              // xoshiro256**, one per selecting thread
     uint64_t s[4];
@@ -71,6 +72,20 @@ struct Rng {                              // xoshiro256**, one per selecting thr
 inline int nth_set_bit(uint32_t m, int n) {
     for (int i = 0; i < n; i++) m &= m - 1;
     return __builtin_ctz(m);
+}
+
+// ln(n) for n >= 1 in single precision without libm: exponent + a cubic on the mantissa (|error| < 7e-4), for the
+// throughput mode's exploration term (the exact mode keeps std::log in double)
+inline float fast_logf(uint32_t n) {
+    float x = (float)n;
+    uint32_t b;
+    std::memcpy(&b, &x, 4);
+    const int e = (int)(b >> 23) - 127;
+    b = (b & 0x7fffffu) | 0x3f800000u;
+    float m;
+    std::memcpy(&m, &b, 4);                                  // mantissa in [1, 2)
+    const float l2 = ((0.44717955f * m - 1.4699568f) * m + 2.8212026f) * m - 1.7417939f;
+    return ((float)e + l2) * 0.69314718f;
 }
 
 // run fn(t) for t in [0, T) on T threads; the pool lives as long as the search
@@ -136,20 +151,26 @@ int best_child_scalar(const FNode* blk, int slots, float k_sqrt_lg, const uint32
 
 __attribute__((target("avx2,fma")))
 int best_child_avx2(const FNode* blk, int slots, float k_sqrt_lg, const uint32_t* dv) {
+    // Records are 4 dwords {visits, wins, first_child, untried}: two per 256-bit load.  Four loads and four in-lane
+    // shuffles give the visits and the wins of 8 children, in slot order (0,2,4,6,1,3,5,7) -- no gathers.
     alignas(32) float sc[32];
     alignas(32) static const uint32_t zero[32] = {0};
+    alignas(32) static const int kSlotOfLane[8] = {0, 2, 4, 6, 1, 3, 5, 7};
     if (!dv) dv = zero;
     const __m256 c = _mm256_set1_ps(k_sqrt_lg), half = _mm256_set1_ps(0.5f), three = _mm256_set1_ps(3.0f);
-    const __m256i stride = _mm256_setr_epi32(0, 6, 12, 18, 24, 30, 36, 42);      // records are 6 dwords: visits, wins, ...
+    const __m256i lane_slot = _mm256_load_si256((const __m256i*)kSlotOfLane);
     __m256 top = _mm256_set1_ps(-1.f);
-    const int* base = reinterpret_cast<const int*>(blk);
     for (int k = 0; k < slots; k += 8) {
         // lanes past the block read the next records of the arena (mapped, possibly foreign): masked out below
-        const __m256i live = _mm256_cmpgt_epi32(_mm256_set1_epi32(slots - k), _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7));
-        const __m256i gv = _mm256_mask_i32gather_epi32(_mm256_setzero_si256(), base + 6 * k, stride, live, 4);
-        const __m256i gw = _mm256_mask_i32gather_epi32(_mm256_setzero_si256(), base + 6 * k + 1, stride, live, 4);
+        const float* p = reinterpret_cast<const float*>(blk + k);
+        const __m256 l0 = _mm256_loadu_ps(p), l1 = _mm256_loadu_ps(p + 8), l2 = _mm256_loadu_ps(p + 16), l3 = _mm256_loadu_ps(p + 24);
+        const __m256 a = _mm256_shuffle_ps(l0, l1, 0x44), b = _mm256_shuffle_ps(l2, l3, 0x44);     // v w v w | v w v w
+        const __m256i gv = _mm256_castps_si256(_mm256_shuffle_ps(a, b, 0x88));                       // visits
+        const __m256i gw = _mm256_castps_si256(_mm256_shuffle_ps(a, b, 0xDD));                       // wins
+        const __m256i live = _mm256_cmpgt_epi32(_mm256_set1_epi32(slots - k), lane_slot);
         const __m256i some = _mm256_andnot_si256(_mm256_cmpeq_epi32(gv, _mm256_setzero_si256()), live);   // visits != 0: the child is set up
-        const __m256 vv = _mm256_cvtepi32_ps(_mm256_add_epi32(gv, _mm256_loadu_si256((const __m256i*)(dv + k))));
+        const __m256i dvv = _mm256_permutevar8x32_epi32(_mm256_loadu_si256((const __m256i*)(dv + k)), lane_slot);
+        const __m256 vv = _mm256_cvtepi32_ps(_mm256_add_epi32(gv, dvv));
         const __m256 ww = _mm256_cvtepi32_ps(gw);
         __m256 rs = _mm256_rsqrt_ps(vv);                                   // 1/sqrt(v), 12 bits ...
         rs = _mm256_mul_ps(_mm256_mul_ps(half, rs), _mm256_fnmadd_ps(_mm256_mul_ps(vv, rs), rs, three));   // ... one Newton step
@@ -158,14 +179,18 @@ int best_child_avx2(const FNode* blk, int slots, float k_sqrt_lg, const uint32_t
         _mm256_store_ps(sc + k, m);
         top = _mm256_max_ps(top, m);
     }
-    // first lane holding the maximum, without a data-dependent branch per child
+    // first SLOT holding the maximum (ties: the lowest slot, as the scalar scan)
     __m256 t = _mm256_max_ps(top, _mm256_permute2f128_ps(top, top, 1));
     t = _mm256_max_ps(t, _mm256_shuffle_ps(t, t, 0x4E));
     t = _mm256_max_ps(t, _mm256_shuffle_ps(t, t, 0xB1));
     if (!(_mm_cvtss_f32(_mm256_castps256_ps128(t)) > 0.f)) return -1;
     for (int k = 0; k < slots; k += 8) {
         const int hit = _mm256_movemask_ps(_mm256_cmp_ps(_mm256_load_ps(sc + k), t, _CMP_EQ_OQ));
-        if (hit) return k + __builtin_ctz((unsigned)hit);
+        if (hit) {
+            int best = 99;
+            for (int j = 0; j < 8; j++) if ((hit >> j & 1) && kSlotOfLane[j] < best) best = kSlotOfLane[j];
+            return k + best;
+        }
     }
     return -1;
 }
@@ -224,8 +249,6 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
             terminal = flags != 0;
         }
         nodes[root].untried.store(terminal ? 0u : rootstate.board.empty());
-        nodes[root].info = 31u | (rootstate.playerJustMoved == MAXIMIZER ? 32u : 0u);
-        nodes[root].parent = 0;
     }
     const double factor = opt.ucb_factor2 ? 2. : 1.;
     const bool exact = opt.exact_ucb || (hk && hk->intn);
@@ -281,9 +304,7 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
             w.pjm = -w.pjm;
             if (w.pjm == MAXIMIZER) w.x |= bit; else w.o |= bit;
             FNode& c = nodes[child];
-            c.parent = w.idx;
-            c.info = (uint32_t)m | (w.pjm == MAXIMIZER ? 32u : 0u) | ((uint32_t)(slots - cnt) << 6);
-            c.untried.store(kPending, std::memory_order_relaxed);
+            c.untried.store(kPending | ((uint32_t)(slots - cnt) << kRankShift), std::memory_order_relaxed);
             c.visits.store((uint32_t)P, std::memory_order_release);   // nobody touches a child before its visits are non-zero: a plain store, no locked RMW on a cold line
             if (w.depth == 1) w.slot1 = (int)(child - fc); else if (w.depth == 2) w.slot2 = (int)(child - fc);
             w.idx = child;
@@ -314,11 +335,11 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
                 const uint32_t v = c.visits.load(std::memory_order_acquire);
                 if (!v) continue;                                // claimed, still being set up
                 const double sc = (double)c.wins.load(std::memory_order_relaxed) / ((double)v + kEps) + UCTK * std::sqrt(lg / ((double)v + kEps));
-                const uint32_t rank = (c.info >> 6) & 31u;
+                const uint32_t rank = (c.untried.load(std::memory_order_relaxed) & kRankMask) >> kRankShift;
                 if (sc > bestscore || (best >= 0 && sc == bestscore && rank < best_rank)) { bestscore = sc; best = k; best_rank = rank; }
             }
         } else {
-            best = best_child_float(&nodes[fc], slots, (float)(UCTK * std::sqrt(factor * (double)std::log((float)seen))), dv);
+            best = best_child_float(&nodes[fc], slots, (float)UCTK * __builtin_sqrtf((float)factor * fast_logf(seen)), dv);
         }
         if (best < 0 && !exact) {
             // no child scored above zero: take any child that is set up rather than wait (a walk that waits keeps
@@ -335,11 +356,11 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
         w.idx = fc + (uint32_t)best;
         FNode& c = nodes[w.idx];
         // the scan saw this child's visits non-zero through plain (vector) loads; this load pairs with the
-        // creator's release store, so the child's parent / info fields are visible before they are read
+        // creator's release store, so the child's other fields are visible before they are read
         (void)c.visits.load(std::memory_order_acquire);
         if (dv) { dv[best] += (uint32_t)P; if (w.depth == 1) w.slot1 = best; else w.slot2 = best; }
         else c.visits.fetch_add((uint32_t)P, std::memory_order_release);
-        const uint32_t bit = 1u << (c.info & 31u);
+        const uint32_t bit = 1u << nth_set_bit(emp, best);          // the child's move is its slot among the empty cells
         w.pjm = -w.pjm;
         if (w.pjm == MAXIMIZER) w.x |= bit; else w.o |= bit;
         path[w.depth++] = w.idx;
@@ -433,6 +454,9 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
         else if (opt.device_slot >= 0) must(sq_playouts_on(opt.device_slot, bt.boards.data(), bt.to_move.data(), bt.B, (uint64_t)bt.p, sid, (uint64_t(*)[4])bt.out.data()), "sq_playouts_on");
         else must(sq_playouts(bt.boards.data(), bt.to_move.data(), bt.B, (uint64_t)bt.p, sid, (uint64_t(*)[4])bt.out.data()), "sq_playouts");
     };
+    // the player who moved INTO the node at depth i of a path (the root is depth 0): sides alternate from the root's
+    const bool root_max = rootstate.playerJustMoved == MAXIMIZER;
+    auto is_max = [root_max](int i) { return (i & 1) ? !root_max : root_max; };
     auto update_phase = [&](Batch& bt) {
         pool.run([&](int t) {
             const long long lo = bt.B * t / T, hi = bt.B * (t + 1) / T;
@@ -448,23 +472,26 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
                 }
                 const Leaf& lf = bt.leaves[(size_t)k];
                 const uint64_t* r = &bt.out[(size_t)k * 4];
-                if (lf.fresh) nodes[lf.node].untried.store(r[3] != 0 ? (kFull & ~(lf.x | lf.o)) : 0u, std::memory_order_release);
+                if (lf.fresh) {
+                    const uint32_t rank = nodes[lf.node].untried.load(std::memory_order_relaxed) & kRankMask;
+                    nodes[lf.node].untried.store(rank | (r[3] != 0 ? (kFull & ~(lf.x | lf.o)) : 0u), std::memory_order_release);
+                }
                 const uint32_t* pp = &bt.paths[(size_t)k * kPathLen];
-                root_wins += (nodes[root].info & 32u) ? r[0] : r[1];              // pp[0] is the root: one add per thread
+                root_wins += is_max(0) ? r[0] : r[1];                             // pp[0] is the root: one add per thread
                 int from = 1;
                 if (sh && lf.depth > 1) {                                          // first and second level: into the shard
                     const int a = (int)(pp[1] - fc1);
-                    sh->w1[a] += (nodes[pp[1]].info & 32u) ? r[0] : r[1];
+                    sh->w1[a] += is_max(1) ? r[0] : r[1];
                     from = 2;
                     if (lf.depth > 2) {
                         const int b = (int)(pp[2] - nodes[pp[1]].first_child.load(std::memory_order_relaxed));
-                        sh->w2[a][b] += (nodes[pp[2]].info & 32u) ? r[0] : r[1];
+                        sh->w2[a][b] += is_max(2) ? r[0] : r[1];
                         from = 3;
                     }
                 }
                 for (int i = from; i < lf.depth; i++) {                            // Update, mcts.go:190-192,268-271
                     FNode& nd = nodes[pp[i]];
-                    const uint32_t add = (uint32_t)((nd.info & 32u) ? r[0] : r[1]);
+                    const uint32_t add = (uint32_t)(is_max(i) ? r[0] : r[1]);
                     if (add) nd.wins.fetch_add(add, std::memory_order_relaxed);
                 }
             }
@@ -524,14 +551,15 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
     const int slots = __builtin_popcount(rootstate.board.empty());
     int order[25], n = 0;
     for (int k = 0; k < slots && fc; k++) if (nodes[fc + (uint32_t)k].visits.load()) order[n++] = k;
-    std::sort(order, order + n, [&](int a, int b) { return ((nodes[fc + (uint32_t)a].info >> 6) & 31u) < ((nodes[fc + (uint32_t)b].info >> 6) & 31u); });
+    auto rank_of = [&](int k) { return (nodes[fc + (uint32_t)k].untried.load() & kRankMask) >> kRankShift; };
+    std::sort(order, order + n, [&](int a, int b) { return rank_of(a) < rank_of(b); });
     const double lg = factor * std::log((double)nodes[root].visits.load());
     double bestscore = kEps;
     res.best_move = -1;
     for (int i = 0; i < n; i++) {
         const FNode& c = nodes[fc + (uint32_t)order[i]];
         const double v = (double)c.visits.load(), w = (double)c.wins.load();
-        res.child_move[i] = (int)(c.info & 31u); res.child_visits[i] = v; res.child_wins[i] = w;
+        res.child_move[i] = nth_set_bit(rootstate.board.empty(), order[i]); res.child_visits[i] = v; res.child_wins[i] = w;
         const double s = w / (v + kEps) + UCTK * std::sqrt(lg / (v + kEps));
         if (s > bestscore) { bestscore = s; res.best_move = res.child_move[i]; res.value = (int)(1000. * s); }
     }
