@@ -195,9 +195,47 @@ int best_child_avx2(const FNode* blk, int slots, float k_sqrt_lg, const uint32_t
     return -1;
 }
 
+// the same scan with two gathers per 8 children (stride 4 dwords) instead of loads + shuffles: measured on the GPU box's
+// host (profiles/r02_host_tree_layout.txt) and selectable with SQUAVA_FAST_SCAN=gather / scalar
+__attribute__((target("avx2,fma")))
+int best_child_avx2_gather(const FNode* blk, int slots, float k_sqrt_lg, const uint32_t* dv) {
+    alignas(32) float sc[32];
+    alignas(32) static const uint32_t zero[32] = {0};
+    if (!dv) dv = zero;
+    const __m256 c = _mm256_set1_ps(k_sqrt_lg), half = _mm256_set1_ps(0.5f), three = _mm256_set1_ps(3.0f);
+    const __m256i stride = _mm256_setr_epi32(0, 4, 8, 12, 16, 20, 24, 28);
+    __m256 top = _mm256_set1_ps(-1.f);
+    const int* base = reinterpret_cast<const int*>(blk);
+    for (int k = 0; k < slots; k += 8) {
+        const __m256i live = _mm256_cmpgt_epi32(_mm256_set1_epi32(slots - k), _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7));
+        const __m256i gv = _mm256_mask_i32gather_epi32(_mm256_setzero_si256(), base + 4 * k, stride, live, 4);
+        const __m256i gw = _mm256_mask_i32gather_epi32(_mm256_setzero_si256(), base + 4 * k + 1, stride, live, 4);
+        const __m256i some = _mm256_andnot_si256(_mm256_cmpeq_epi32(gv, _mm256_setzero_si256()), live);
+        const __m256 vv = _mm256_cvtepi32_ps(_mm256_add_epi32(gv, _mm256_loadu_si256((const __m256i*)(dv + k))));
+        const __m256 ww = _mm256_cvtepi32_ps(gw);
+        __m256 rs = _mm256_rsqrt_ps(vv);
+        rs = _mm256_mul_ps(_mm256_mul_ps(half, rs), _mm256_fnmadd_ps(_mm256_mul_ps(vv, rs), rs, three));
+        const __m256 s = _mm256_fmadd_ps(_mm256_mul_ps(ww, rs), rs, _mm256_mul_ps(c, rs));
+        const __m256 m = _mm256_blendv_ps(_mm256_set1_ps(-1.f), s, _mm256_castsi256_ps(some));
+        _mm256_store_ps(sc + k, m);
+        top = _mm256_max_ps(top, m);
+    }
+    __m256 t = _mm256_max_ps(top, _mm256_permute2f128_ps(top, top, 1));
+    t = _mm256_max_ps(t, _mm256_shuffle_ps(t, t, 0x4E));
+    t = _mm256_max_ps(t, _mm256_shuffle_ps(t, t, 0xB1));
+    if (!(_mm_cvtss_f32(_mm256_castps256_ps128(t)) > 0.f)) return -1;
+    for (int k = 0; k < slots; k += 8) {
+        const int hit = _mm256_movemask_ps(_mm256_cmp_ps(_mm256_load_ps(sc + k), t, _CMP_EQ_OQ));
+        if (hit) return k + __builtin_ctz((unsigned)hit);
+    }
+    return -1;
+}
+
 int best_child_float(const FNode* blk, int slots, float k_sqrt_lg, const uint32_t* dv) {
     static const bool avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma");
-    return avx2 ? best_child_avx2(blk, slots, k_sqrt_lg, dv) : best_child_scalar(blk, slots, k_sqrt_lg, dv);
+    static const int mode = [] { const char* e = std::getenv("SQUAVA_FAST_SCAN"); return !e ? 0 : e[0] == 'g' ? 1 : e[0] == 's' ? 2 : 0; }();
+    if (!avx2 || mode == 2) return best_child_scalar(blk, slots, k_sqrt_lg, dv);
+    return mode == 1 ? best_child_avx2_gather(blk, slots, k_sqrt_lg, dv) : best_child_avx2(blk, slots, k_sqrt_lg, dv);
 }
 
 struct Chunk { uint64_t at = 0, end = 0; };            // a thread's private piece of the arena
