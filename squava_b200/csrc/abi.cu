@@ -9,7 +9,9 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <shared_mutex>
@@ -268,6 +270,270 @@ int init_device(Device& d, const sq::ScanTables& tables, const sq::AbTables& ab_
 }
 
 bool bad_board(const sq_board& b) { return (b.x & b.o) || ((b.x | b.o) >> 25); }
+
+// NegaScout, one position over many warps (negascout.cuh: NsItem).  negaScout's recursion (negascout.go:232-266) and
+// ChooseMove's loop over it (:92-113) are replayed HERE down to a split ply; every call below that is an item searched on the
+// device.  A loop makes its first call alone (its window is the loop's own); after that ALL remaining children are
+// searched at once with the null window (-alpha-1, -alpha) they get if alpha does not move.  Results are consumed in the
+// reference's order, and only if alpha is still the one they were searched with: a null-window result above the score
+// needs the re-search (-beta, -cur); if that raises alpha, the unconsumed calls are dropped and the rest is searched again
+// under the new alpha; a cut-off drops the rest.  Every value, the visiting order, movekeeper's set and the leaf counter
+// are exactly the sequential recursion's; what is speculative is only WHICH calls are in flight.
+struct NsCall {
+    int32_t parent = -1;            // the loop waiting for this call (-1: ChooseMove's, the loop IS the position)
+    uint32_t gen = 0;               // bumped when the slot is released: results of dropped calls are recognised by it
+    int32_t pos = 0;                // index in the list of positions
+    uint8_t state = 0;              // 0 free, 1 item (waiting for the device), 2 loop, 3 done
+    uint8_t ply = 0;                // of the node
+    uint8_t path[7];
+    int32_t a = 0, b = 0;           // the window the node is called with
+    int32_t ret = 0;
+    uint64_t nodes = 0;             // staticValue calls below, its own included
+    // the loop (state 2), negascout.go:240-262
+    uint32_t x = 0, o = 0;
+    int32_t alpha = 0, beta = 0, score = 0, n = 0, i = 0, n_kids = 0, spec_alpha = 0;
+    int32_t again = -1;             // the re-search of child i
+    int32_t first[25];              // the calls (-n, -alpha) of the children, -1: none
+    uint8_t cell[25];
+};
+
+struct NsRootOut {                  // what ChooseMove leaves behind, movekeeper.go:26-44
+    int keeper_max = -30000, first_best = -1, n_visited = 0;
+    uint32_t keeper_mask = 0;
+};
+
+class NsSplit {
+public:
+    NsSplit(Device& d, Ctx& c, const sq_board* h_pos, const sq_board* d_pos, const int* list, int64_t n_list, int max_depth,
+            const sq::NsScores& sc, unsigned int* d_counter, int32_t (*values)[25], int8_t (*visit_order)[25])
+        : d_(d), c_(c), h_pos_(h_pos), d_pos_(d_pos), list_(list), n_list_(n_list), max_depth_(max_depth), sc_(sc),
+          d_counter_(d_counter), values_(values), visit_order_(visit_order) {
+        const char* e = getenv("SQ_NS_SPLIT_PLY");
+        // loops at ply < split_ply run here: deep enough for the items to be small next to the whole search, and never a
+        // loop at the horizon or just above it (those are scans inside the kernel)
+        int wide = e ? atoi(e) : 3;
+        const char* e2 = getenv("SQ_NS_SPLIT_PLY_NULL");
+        int null_w = e2 ? atoi(e2) : 2;
+        const int most = max_depth - 3 < 6 ? max_depth - 3 : 6;
+        split_wide_ = wide < 1 ? 1 : wide; if (split_wide_ > most) split_wide_ = most; if (split_wide_ < 1) split_wide_ = 1;
+        split_null_ = null_w < 1 ? 1 : null_w; if (split_null_ > split_wide_) split_null_ = split_wide_;
+        // an item that turns out long gives up and becomes a loop here, its children items: no round waits for one search
+        const char* e3 = getenv("SQ_NS_ITEM_BUDGET");
+        item_budget_ = e3 ? (uint32_t)strtoul(e3, nullptr, 10) : 16384u;
+        deepest_loop_ = most < 1 ? 0 : most;
+    }
+
+    int run(int32_t* best_value, uint32_t* best_mask, int8_t* first_best, uint64_t* nodes) {
+        order_max_.resize((size_t)n_list_ * 25); order_min_.resize((size_t)n_list_ * 25);
+        roots_.resize((size_t)n_list_);
+        root_call_.resize((size_t)n_list_);
+        for (int64_t q = 0; q < n_list_; q++) {
+            const sq_board& bd = h_pos_[list_[q]];
+            const uint32_t x = bd.x & sq::kFull25, o = bd.o & sq::kFull25;
+            sq::ns_reorder_host(g_ns_tables, x, o, &order_max_[(size_t)q * 25], &order_min_[(size_t)q * 25]);
+            for (int k = 0; k < 25; k++) { values_[list_[q]][k] = SQ_NO_MOVE; if (visit_order_) visit_order_[list_[q]][k] = -1; }
+            const int ci = alloc();
+            NsCall& c = calls_[(size_t)ci];
+            c.parent = -1; c.pos = (int32_t)q; c.ply = 0; c.a = -20000; c.b = 20000;
+            start_loop(c, x, o);
+            root_call_[(size_t)q] = ci;
+            ready_.push_back(ci);
+        }
+        pump();
+        std::vector<sq::NsItem> items;
+        std::vector<std::pair<int32_t, uint32_t>> sent;
+        std::vector<sq::NsItemOut> outs;
+        const sq::NsOut none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        const int64_t cap = (int64_t)d_.sm_count * 6;
+        while (!outbox_.empty()) {
+            // wide windows first: they are the long searches
+            items.clear(); sent.clear();
+            for (int pass = 0; pass < 2; pass++)
+                for (const auto& w : outbox_) {
+                    const NsCall& k = calls_[(size_t)w.first];
+                    if (k.gen != w.second || k.state != 1 || (k.b - k.a > 1) != (pass == 0)) continue;
+                    sq::NsItem it;
+                    it.pos = list_[k.pos]; it.a = k.a; it.b = k.b; it.n_path = k.ply;
+                    it.budget = k.ply <= deepest_loop_ ? item_budget_ : 0u;
+                    memcpy(it.path, k.path, 7);
+                    items.push_back(it); sent.push_back(w);
+                }
+            outbox_.clear();
+            if (items.empty()) break;
+            int r;
+            if ((r = reserve(c_, 1, items.size() * sizeof(sq::NsItem)))) return r;
+            if ((r = reserve(c_, 2, items.size() * sizeof(sq::NsItemOut)))) return r;
+            CK(cudaMemcpyAsync(c_.buf[1], items.data(), items.size() * sizeof(sq::NsItem), cudaMemcpyHostToDevice, c_.stream));
+            CK(cudaMemsetAsync(d_counter_, 0, sizeof(unsigned int), c_.stream));
+            const int64_t want = ((int64_t)items.size() + sq::kNsWarps - 1) / sq::kNsWarps;
+            sq::negascout_fast_kernel<true><<<(int)(want < cap ? want : cap), sq::kNsWarps * 32, 0, c_.stream>>>(
+                d_pos_, nullptr, (int)items.size(), max_depth_, sc_, none, d_counter_, (const sq::NsItem*)c_.buf[1],
+                (sq::NsItemOut*)c_.buf[2], 0ull);
+            g_launches += 1;
+            CK(cudaGetLastError());
+            outs.resize(items.size());
+            CK(cudaMemcpyAsync(outs.data(), c_.buf[2], items.size() * sizeof(sq::NsItemOut), cudaMemcpyDeviceToHost, c_.stream));
+            CK(cudaStreamSynchronize(c_.stream));
+            rounds_++; items_ += items.size();
+            for (size_t t = 0; t < sent.size(); t++) {
+                NsCall& k = calls_[(size_t)sent[t].first];
+                if (k.gen != sent[t].second || k.state != 1) { dropped_++; continue; }      // dropped while in flight
+                if (outs[t].nodes == sq::kNsAborted) {                                      // too long for one warp: its loop runs here
+                    uint32_t x = h_pos_[list_[k.pos]].x & sq::kFull25, o = h_pos_[list_[k.pos]].o & sq::kFull25;
+                    for (int j = 0; j < k.ply; j++) { if (j & 1) o |= 1u << k.path[j]; else x |= 1u << k.path[j]; }
+                    start_loop(k, x, o);
+                    ready_.push_back(sent[t].first);
+                    expanded_++;
+                    continue;
+                }
+                k.state = 3; k.ret = outs[t].ret; k.nodes = outs[t].nodes;
+                ready_.push_back(k.parent);
+            }
+            pump();
+        }
+        for (int64_t q = 0; q < n_list_; q++) {
+            const NsCall& c = calls_[(size_t)root_call_[(size_t)q]];
+            if (c.state != 3) { snprintf(t_err, sizeof t_err, "NegaScout split driver: a position did not finish"); return SQ_ERR_CUDA; }
+            const NsRootOut& ro = roots_[(size_t)q];
+            const int p = list_[q];
+            if (best_value) best_value[p] = ro.keeper_mask ? ro.keeper_max : 0;
+            if (best_mask) best_mask[p] = ro.keeper_mask;
+            if (first_best) first_best[p] = (int8_t)ro.first_best;
+            if (nodes) nodes[p] = c.nodes;
+        }
+        if (getenv("SQ_NS_TRACE"))
+            fprintf(stderr, "ns split: %lld positions, split ply %d/%d, item budget %u, %llu rounds, %llu items (%llu dropped in flight, %llu given up), %zu call slots\n",
+                    (long long)n_list_, split_wide_, split_null_, item_budget_, (unsigned long long)rounds_, (unsigned long long)items_,
+                    (unsigned long long)dropped_, (unsigned long long)expanded_, calls_.size());
+        return SQ_OK;
+    }
+
+private:
+    int alloc() {
+        if (!free_.empty()) { const int ci = free_.back(); free_.pop_back(); return ci; }
+        calls_.emplace_back();
+        return (int)calls_.size() - 1;
+    }
+    void release(int ci) {
+        NsCall& c = calls_[(size_t)ci];
+        c.state = 0; c.gen++;
+        free_.push_back(ci);
+    }
+    // a call that is no longer wanted, with everything below it
+    void drop(int ci) {
+        stack_.clear(); stack_.push_back(ci);
+        while (!stack_.empty()) {
+            const int k = stack_.back(); stack_.pop_back();
+            NsCall& c = calls_[(size_t)k];
+            if (c.state == 2) {
+                if (c.again >= 0) stack_.push_back(c.again);
+                for (int j = 0; j < c.n_kids; j++) if (c.first[j] >= 0) stack_.push_back(c.first[j]);
+            }
+            release(k);
+        }
+    }
+    void start_loop(NsCall& c, uint32_t x, uint32_t o) {
+        c.state = 2; c.x = x; c.o = o; c.nodes = 0;
+        c.alpha = c.a; c.beta = c.b; c.score = -30000; c.n = c.b; c.i = 0; c.spec_alpha = c.a; c.again = -1;
+        const uint8_t* ord = (c.ply & 1) ? &order_min_[(size_t)c.pos * 25] : &order_max_[(size_t)c.pos * 25];
+        const int n_root = 25 - __builtin_popcount(h_pos_[list_[c.pos]].x | h_pos_[list_[c.pos]].o);
+        c.n_kids = 0;
+        for (int k = 0; k < n_root; k++) if (!(((x | o) >> ord[k]) & 1u)) { c.first[c.n_kids] = -1; c.cell[c.n_kids++] = ord[k]; }
+    }
+    // the call negaScout(child j of loop `pi`, window (a, b)): a loop of its own above the split ply, an item below
+    int spawn(int pi, int j, int a, int b) {
+        const int ci = alloc();
+        NsCall& p = calls_[(size_t)pi];
+        NsCall& c = calls_[(size_t)ci];
+        const int cell = p.cell[j];
+        const bool x_moves = !(p.ply & 1);
+        c.parent = pi; c.pos = p.pos; c.ply = (uint8_t)(p.ply + 1); c.a = a; c.b = b;
+        memcpy(c.path, p.path, 7);
+        c.path[p.ply] = (uint8_t)cell;
+        const bool ends = sq::ns_move_ends_game(g_ns_tables, x_moves ? p.x : p.o, cell);
+        if (!ends && c.ply < (b - a > 1 ? split_wide_ : split_null_)) {
+            start_loop(c, p.x | (x_moves ? 1u << cell : 0u), p.o | (x_moves ? 0u : 1u << cell));
+            ready_.push_back(ci);
+        } else {
+            c.state = 1;
+            outbox_.emplace_back(ci, c.gen);
+        }
+        return ci;
+    }
+    void pump() {
+        while (!ready_.empty()) { const int ci = ready_.back(); ready_.pop_back(); if (ci >= 0) advance(ci); }
+    }
+    // run the loop of call `ci` as far as the results at hand reach
+    void advance(int ci) {
+        if (calls_[(size_t)ci].state != 2) return;
+        for (;;) {
+            NsCall& c = calls_[(size_t)ci];                          // (a deque: spawn() does not move it, but keep it local)
+            if (c.again >= 0) {
+                NsCall& r = calls_[(size_t)c.again];
+                if (r.state != 3) return;
+                c.score = -r.ret; c.nodes += r.nodes;                // score = -negaScout(.., -beta, -cur)
+                release(c.again); c.again = -1;
+            } else {
+                if (c.i == c.n_kids) { finish(ci); return; }         // (a node without children)
+                if (c.i == 0) {
+                    if (c.first[0] < 0) { const int k = spawn(ci, 0, -c.n, -c.alpha); calls_[(size_t)ci].first[0] = k; }
+                } else {
+                    if (c.spec_alpha != c.alpha) {
+                        for (int j = c.i; j < c.n_kids; j++) if (c.first[j] >= 0) { drop(c.first[j]); c.first[j] = -1; }
+                        c.spec_alpha = c.alpha;
+                    }
+                    for (int j = c.i; j < c.n_kids; j++)
+                        if (calls_[(size_t)ci].first[j] < 0) { const int k = spawn(ci, j, -c.alpha - 1, -c.alpha); calls_[(size_t)ci].first[j] = k; }
+                }
+                NsCall& r = calls_[(size_t)c.first[c.i]];
+                if (r.state != 3) return;
+                const int cur = -r.ret;
+                c.nodes += r.nodes;
+                release(c.first[c.i]); c.first[c.i] = -1;
+                if (cur > c.score) {
+                    if (c.n == c.beta || (c.ply > 0 && c.ply == max_depth_ - 2)) c.score = cur;
+                    else { const int k = spawn(ci, c.i, -c.beta, -cur); calls_[(size_t)ci].again = k; continue; }
+                }
+            }
+            if (c.score > c.alpha) c.alpha = c.score;
+            if (c.ply == 0) {                                        // moves.SetMove(i, j, alpha), movekeeper.go:26-36
+                NsRootOut& ro = roots_[(size_t)c.pos];
+                const int p = list_[c.pos], cell = c.cell[c.i];
+                values_[p][cell] = c.alpha;
+                if (visit_order_) visit_order_[p][ro.n_visited] = (int8_t)cell;
+                ro.n_visited++;
+                if (c.alpha >= ro.keeper_max) {
+                    if (c.alpha > ro.keeper_max) { ro.keeper_max = c.alpha; ro.keeper_mask = 0; ro.first_best = cell; }
+                    ro.keeper_mask |= 1u << cell;
+                }
+            }
+            c.i++;
+            if (c.alpha >= c.beta || c.i == c.n_kids) { finish(ci); return; }
+            c.n = c.alpha + 1;
+        }
+    }
+    void finish(int ci) {
+        NsCall& c = calls_[(size_t)ci];
+        for (int j = 0; j < c.n_kids; j++) if (c.first[j] >= 0) { drop(c.first[j]); c.first[j] = -1; }
+        c.state = 3; c.ret = c.score;
+        if (c.ply > 0) c.nodes += 1;                                 // the call itself (its parent's loop counts it)
+        if (c.parent >= 0) ready_.push_back(c.parent);
+    }
+
+    Device& d_; Ctx& c_;
+    const sq_board* h_pos_; const sq_board* d_pos_; const int* list_; int64_t n_list_; int max_depth_;
+    sq::NsScores sc_;
+    unsigned int* d_counter_;
+    int32_t (*values_)[25]; int8_t (*visit_order_)[25];
+    int split_wide_ = 1, split_null_ = 1, deepest_loop_ = 0;
+    uint32_t item_budget_ = 0;
+    std::deque<NsCall> calls_;
+    std::vector<int> free_, ready_, stack_, root_call_;
+    std::vector<std::pair<int32_t, uint32_t>> outbox_;
+    std::vector<uint8_t> order_max_, order_min_;
+    std::vector<NsRootOut> roots_;
+    uint64_t rounds_ = 0, items_ = 0, dropped_ = 0, expanded_ = 0;
+};
 
 }  // namespace
 
@@ -660,9 +926,19 @@ int sq_negascout_root(const sq_board* positions, int64_t n, int max_depth, const
         CK(cudaMemcpyAsync(c->buf[5], order.data(), cnt * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         const int64_t cap = (int64_t)d.sm_count * 6;
         auto grid = [&](int64_t units) { int64_t want = (units + sq::kNsWarps - 1) / sq::kNsWarps; return (int)(want < cap ? want : cap); };
-        if (n_fast) {
-            sq::negascout_fast_kernel<<<grid(n_fast), sq::kNsWarps * 32, 0, c->stream>>>(
-                (const sq_board*)c->buf[0], (const int*)c->buf[5], (int)n_fast, max_depth, sc, out, (unsigned int*)blk);
+        // One warp replays the whole ChooseMove of a position -- up to `budget` staticValue calls; a position that needs more
+        // is given up by its warp and finished by NsSplit over many warps, so that a batch does not end on a few long
+        // searches.  Short lists go to NsSplit at once (the latency case: one position per call).  SQ_NS_SPLIT=0: no budget.
+        const char* e_split = getenv("SQ_NS_SPLIT");
+        const bool split = n_fast > 0 && max_depth >= 4 && !(e_split && e_split[0] == '0');
+        const char* e_budget = getenv("SQ_NS_BUDGET");
+        const unsigned long long budget = !split ? ~0ull : e_budget ? strtoull(e_budget, nullptr, 10) : (1ull << 17);
+        const char* e_direct = getenv("SQ_NS_DIRECT");
+        const bool direct = split && n_fast <= (e_direct ? atoi(e_direct) : 16);
+        if (n_fast && !direct) {
+            sq::negascout_fast_kernel<false><<<grid(n_fast), sq::kNsWarps * 32, 0, c->stream>>>(
+                (const sq_board*)c->buf[0], (const int*)c->buf[5], (int)n_fast, max_depth, sc, out, (unsigned int*)blk, nullptr, nullptr,
+                budget);
             g_launches += 1;
             CK(cudaGetLastError());
         }
@@ -681,6 +957,17 @@ int sq_negascout_root(const sq_board* positions, int64_t n, int max_depth, const
         if (best_mask) memcpy(best_mask + lo, h.data() + o_bm, 4 * cnt);
         if (visit_order) memcpy(visit_order + lo, h.data() + o_visit, 25 * cnt);
         if (first_best) memcpy(first_best + lo, h.data() + o_first, cnt);
+        if (split) {
+            std::vector<int> hard;
+            const unsigned long long* got = (const unsigned long long*)(h.data() + o_nodes);
+            for (int64_t q = 0; q < n_fast; q++) if (direct || got[order[(size_t)q]] == sq::kNsAborted) hard.push_back(order[(size_t)q]);
+            if (!hard.empty()) {
+                NsSplit driver(d, *c, positions + lo, (const sq_board*)c->buf[0], hard.data(), (int64_t)hard.size(), max_depth, sc,
+                               (unsigned int*)blk + 2, values + lo, visit_order ? visit_order + lo : nullptr);
+                return driver.run(best_value ? best_value + lo : nullptr, best_mask ? best_mask + lo : nullptr,
+                                  first_best ? first_best + lo : nullptr, nodes ? nodes + lo : nullptr);
+            }
+        }
         return SQ_OK;
     });
 }

@@ -358,9 +358,65 @@ __device__ __forceinline__ NsChild ns_child(const NsCellTables& C, uint32_t x, u
 
 struct NsFastFrame { int alpha, beta, score, n, k, at_phase; uint32_t active, term; };
 
+// CALL ITEMS.  Every call of negaScout (negascout.go:232-266) is a function of the node and its window (alpha, beta) alone.
+// One item = one such call on the node reached from a position by `path` (the root's mover first): the kernel searches
+// it exactly as the whole-position kernel would (same order, same windows, same node count) and hands back the value
+// and the number of staticValue calls below it (its own included).  The host replays the loops ABOVE the items
+// (abi.cu: NsSplit): the first child of a loop alone, then ALL remaining children at once under the alpha they would get
+// if nothing improves; a result is used only if the loop really makes that call, so values, visiting order,
+// movekeeper set and leaf counter stay bit-identical while the searches of one position spread over many warps.
+struct NsItem {
+    int32_t pos;        // position index
+    int32_t a, b;       // the window the node is called with
+    uint8_t n_path;     // >= 1: the node's ply
+    uint8_t path[7];    // cells played from the position, the position's mover (X) first; no node before the last is terminal
+    uint32_t budget;    // give up after this many staticValue calls (0: never): the host then runs this node's loop itself
+};
+struct NsItemOut { int32_t ret; uint32_t pad; unsigned long long nodes; };
+constexpr unsigned long long kNsAborted = ~0ull;      // NsOut.nodes of a position that ran out of its node budget
+
+// reorderMoves on the host: the driver needs the children of a node in the mover's order
+inline int ns_reorder_host(const NsTables& t, uint32_t x, uint32_t o, uint8_t order_max[25], uint8_t order_min[25]) {
+    uint8_t good[25], dull[25], bad[25];
+    int ng = 0, nd = 0, nb = 0;
+    for (int i = 0; i < 25; i++) {
+        const int c = t.initial_order[i];
+        if (((x | o) >> c) & 1u) continue;
+        int kind = 0;
+        for (int k = 0; k < t.n_cell_quads[c] && kind == 0; k++) {
+            const uint32_t m = t.cell_quads[c][k];
+            const int sum = __builtin_popcount(m & x) - __builtin_popcount(m & o);
+            if (sum == 3 || sum == 2) kind = 1; else if (sum == -3 || sum == -2) kind = -1;
+        }
+        for (int k = 0; k < t.n_cell_trips[c] && kind == 0; k++) {
+            const uint32_t m = t.cell_trips[c][k];
+            const int sum = __builtin_popcount(m & x) - __builtin_popcount(m & o);
+            if (sum == -2) kind = 1; else if (sum == 2) kind = -1;
+        }
+        if (kind > 0) good[ng++] = (uint8_t)c; else if (kind < 0) bad[nb++] = (uint8_t)c; else dull[nd++] = (uint8_t)c;
+    }
+    int n = 0, m = 0;
+    for (int i = 0; i < ng; i++) order_max[n++] = good[i];
+    for (int i = 0; i < nd; i++) order_max[n++] = dull[i];
+    for (int i = 0; i < nb; i++) order_max[n++] = bad[i];
+    for (int i = 0; i < nb; i++) order_min[m++] = bad[i];
+    for (int i = 0; i < nd; i++) order_min[m++] = dull[i];
+    for (int i = 0; i < ng; i++) order_min[m++] = good[i];
+    return n;
+}
+
+// does the mover's mark on `cell` end the game (a four or a three of the mover's through the cell)?  own: the mover's marks before
+inline bool ns_move_ends_game(const NsTables& t, uint32_t own, int cell) {
+    for (int k = 0; k < t.n_cell_quads[cell]; k++) if (__builtin_popcount(t.cell_quads[cell][k] & own) == 3) return true;
+    for (int k = 0; k < t.n_cell_trips[cell]; k++) if (__builtin_popcount(t.cell_trips[cell][k] & own) == 2) return true;
+    return false;
+}
+
+template <bool ITEMS>
 __global__ void __launch_bounds__(kNsWarps * 32)
 negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ idx, int n_pos, int max_depth, NsScores sc,
-                      NsOut out, unsigned int* __restrict__ queue) {
+                      NsOut out, unsigned int* __restrict__ queue, const NsItem* __restrict__ items, NsItemOut* __restrict__ item_out,
+                      unsigned long long budget) {
     __shared__ NsCellTables C;
     __shared__ NsFastFrame s_frames[kNsWarps][kNsMaxDepth + 2];
     __shared__ int s_cur[kNsWarps][kNsMaxDepth + 2][32], s_sum[kNsWarps][kNsMaxDepth + 2][32];
@@ -385,13 +441,18 @@ negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ 
         if (lane == 0) p = atomicAdd(queue, 1u);
         p = __shfl_sync(full, p, 0);
         if (p >= (unsigned)n_pos) break;
-        p = idx[p];
+        const unsigned item_index = p;
+        NsItem item;
+        int base = 0;                                  // ply of the loop this warp starts in
+        if (ITEMS) { item = items[p]; p = (unsigned)item.pos; base = item.n_path - 1; } else p = idx[p];
         uint32_t x = pos[p].x & kFull25, o = pos[p].o & kFull25;
         unsigned long long nodes = 0;
         ns_reorder(x, o, lane, s_order[warp]);
         const int n_moves = __popc(kFull25 & ~(x | o));
+        if (ITEMS)
+            for (int j = 0; j < base; j++) { if (j & 1) o |= 1u << item.path[j]; else x |= 1u << item.path[j]; }
         int bias = __reduce_add_sync(full, lane < 25 ? (int)((x >> lane) & 1u) * my_score - (int)((o >> lane) & 1u) * my_score : 0);
-        // the root's raw sum (no complete line on it: the host checked)
+        // the starting node's raw sum (no complete line on it: the host checked)
         int vsum;
         {
             const int cx = __popc(my_quad & x), co = __popc(my_quad & o);
@@ -400,12 +461,13 @@ negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ 
             vsum = __reduce_add_sync(full, contrib);
         }
 
-        int ply = 0;
+        int ply = base;
         int alpha = -2 * 10000, beta = 2 * 10000, score = -3 * 10000, n = beta, k = 0, at = 0, phase = 0;
         uint32_t active = 0, term = 0;
         int keeper_max = -3 * 10000, first_best = -1, n_visited = 0;
         uint32_t keeper_mask = 0;
-        if (lane < 25) { out.values[p][lane] = SQ_NO_MOVE; out.visit_order[p][lane] = -1; }
+        bool aborted = false;
+        if (!ITEMS && lane < 25) { out.values[p][lane] = SQ_NO_MOVE; out.visit_order[p][lane] = -1; }
 
         // one pass over the children of the node that starts its loop at `ply` (mover pl)
         auto children = [&](int at_ply, int raw_sum) {
@@ -418,12 +480,20 @@ negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ 
             return ch;
         };
         {
-            const NsChild ch = children(0, vsum);
-            s_cur[warp][0][lane] = ch.cur; s_sum[warp][0][lane] = ch.sum;
+            const NsChild ch = children(base, vsum);
+            s_cur[warp][base][lane] = ch.cur; s_sum[warp][base][lane] = ch.sum;
             __syncwarp();
         }
         int ret = 0, rs_cur = 0;
         bool returned = false, enter = false;
+        if (ITEMS) {
+            // the loop at `base` is about to call negaScout on its child path[base] with the window (a, b)
+            const int cell = item.path[base], pl = (base & 1) ? -1 : 1;
+            at = __ffs(__ballot_sync(full, lane < n_moves && s_order[warp][pl > 0 ? 1 : 0][lane] == cell)) - 1;
+            alpha = -item.b; n = -item.a; phase = 1; k = at + 1; enter = true;
+            if (pl > 0) x |= 1u << cell; else o |= 1u << cell;
+            bias += pl * __shfl_sync(full, my_score, cell);
+        }
         for (;;) {
             const int player = (ply & 1) ? -1 : 1;
             if (!returned && !enter) {
@@ -451,6 +521,7 @@ negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ 
                 const int cply = ply + 1;
                 enter = false;
                 nodes++;
+                if (ITEMS ? (item.budget != 0 && nodes > item.budget) : nodes > budget) { aborted = true; break; }   // the host takes over (NsSplit)
                 if ((term >> at) & 1u) {               // the child is a finished game
                     ret = -s_cur[warp][ply][at];
                     returned = true;
@@ -491,6 +562,10 @@ negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ 
                 }
             }
             // `ret` came back to the running loop (:243-262)
+            if (ITEMS && ply == base) {                  // ... which, for an item, is the host's
+                if (lane == 0) { item_out[item_index].ret = ret; item_out[item_index].nodes = nodes; }
+                break;
+            }
             returned = false;
             if (phase == 1) {
                 const int cur = -ret;
@@ -525,11 +600,12 @@ negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ 
             }
             n = alpha + 1;
         }
-        if (lane == 0) {
+        if (ITEMS && aborted && lane == 0) item_out[item_index].nodes = kNsAborted;
+        if (!ITEMS && lane == 0) {
             out.best_value[p] = keeper_mask ? keeper_max : 0;
             out.best_mask[p] = keeper_mask;
             out.first_best[p] = (int8_t)first_best;
-            out.nodes[p] = nodes;
+            out.nodes[p] = aborted ? kNsAborted : nodes;
         }
         __syncwarp();
     }

@@ -195,8 +195,8 @@ int best_child_avx2(const FNode* blk, int slots, float k_sqrt_lg, const uint32_t
     return -1;
 }
 
-// the same scan with two gathers per 8 children (stride 4 dwords) instead of loads + shuffles: measured on the GPU box's
-// host (profiles/r02_host_tree_layout.txt) and selectable with SQUAVA_FAST_SCAN=gather / scalar
+// the same scan with two gathers per 8 children (stride 4 dwords) instead of loads + shuffles: the default, the fastest of
+// the three on the GPU box's host (profiles/r02_host_tree_layout.txt); SQUAVA_FAST_SCAN=shuffle / scalar select the others
 __attribute__((target("avx2,fma")))
 int best_child_avx2_gather(const FNode* blk, int slots, float k_sqrt_lg, const uint32_t* dv) {
     alignas(32) float sc[32];
@@ -233,7 +233,7 @@ int best_child_avx2_gather(const FNode* blk, int slots, float k_sqrt_lg, const u
 
 int best_child_float(const FNode* blk, int slots, float k_sqrt_lg, const uint32_t* dv) {
     static const bool avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma");
-    static const int mode = [] { const char* e = std::getenv("SQUAVA_FAST_SCAN"); return !e ? 0 : e[0] == 'g' ? 1 : e[0] == 's' ? 2 : 0; }();
+    static const int mode = [] { const char* e = std::getenv("SQUAVA_FAST_SCAN"); return !e ? 1 : e[0] == 'g' ? 1 : e[0] == 's' ? (e[1] == 'h' ? 0 : 2) : 1; }();
     if (!avx2 || mode == 2) return best_child_scalar(blk, slots, k_sqrt_lg, dv);
     return mode == 1 ? best_child_avx2_gather(blk, slots, k_sqrt_lg, dv) : best_child_avx2(blk, slots, k_sqrt_lg, dv);
 }
@@ -584,6 +584,12 @@ FastResult fast_uct(const GameState& rootstate, long long itermax, double UCTK, 
     res.iterations = done;
     res.nodes = next_free.load();
     res.threads = T;
+    res.huge_page_kb = -1;
+    if (FILE* f = std::fopen("/proc/self/smaps_rollup", "r")) {
+        char line[256];
+        while (std::fgets(line, sizeof line, f)) if (std::sscanf(line, "AnonHugePages: %lld kB", &res.huge_page_kb) == 1) break;
+        std::fclose(f);
+    }
     // children of the root in creation order; the move returned is argmax UCB1 (mcts.go:196-198)
     const uint32_t fc = nodes[root].first_child.load();
     const int slots = __builtin_popcount(rootstate.board.empty());

@@ -152,6 +152,7 @@ struct FastOptions {
 struct FastResult {
     int best_move, value;            // argmax UCB1 over the root's children, int(1000*UCB1) (mcts.go:196-198)
     long long iterations, batches;
+    long long huge_page_kb;           // AnonHugePages of the process when the search ended (-1: not readable): did the arena get 2 MB pages?
     int n_children, child_move[25];  // root children in creation order
     double child_visits[25], child_wins[25], root_visits;
     double select_seconds, gpu_seconds, update_seconds;

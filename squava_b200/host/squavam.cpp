@@ -77,9 +77,10 @@ int main(int argc, char** argv) {
                 double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
                 std::printf("My move: %d %d %s\n", m / 5, m % 5, go_duration(el).c_str());
                 if (stats)
-                    std::printf("fast tree: %lld iterations, %lld batches, %llu node slots, %d threads; select %.3fs (%.3g/s) gpu %.3fs update %.3fs\n",
+                    std::printf("fast tree: %lld iterations, %lld batches, %llu node slots, %d threads; select %.3fs (%.3g/s) gpu %.3fs update %.3fs; %lld MB in 2 MB pages\n",
                                 r.iterations, r.batches, (unsigned long long)r.nodes, r.threads, r.select_seconds,
-                                (double)r.iterations / ppl / (r.select_seconds > 0 ? r.select_seconds : 1e-9), r.gpu_seconds, r.update_seconds);
+                                (double)r.iterations / ppl / (r.select_seconds > 0 ? r.select_seconds : 1e-9), r.gpu_seconds, r.update_seconds,
+                                r.huge_page_kb / 1024);
                 state.DoMove(m);
                 movesNode.reset();
                 continue;

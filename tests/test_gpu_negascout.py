@@ -80,3 +80,40 @@ def test_batch_order_and_size_do_not_matter(dev, oracle):
     assert (one["values"][0] == a["values"][123]).all() and int(one["nodes"][0]) == int(a["nodes"][123])
     empty = dev.negascout_root(boards[:0], 6, sc)
     assert empty["values"].shape == (0, 25)
+
+
+def same(a, b):
+    return all((a[k] == b[k]).all() for k in ("values", "visit_order", "best_mask", "best_value", "first_best", "nodes"))
+
+
+def test_split_over_many_warps_changes_nothing(dev, oracle, monkeypatch):
+    """NsSplit (abi.cu): positions over their node budget, and short lists, are searched as items under loops replayed on
+    the host; an item over ITS budget becomes such a loop.  Whatever the split plies, the budgets and the list length: every output equals the one-warp replay's
+    (SQ_NS_SPLIT=0), which the tests above pin to the oracle."""
+    from squava_b200 import positions
+    sc = oracle.tables()["scores_ab"]
+    cases = [(positions.midgame_batch(40, marks=(8, 10, 12, 14), seed=31)[0], 6),
+             (positions.midgame_batch(24, marks=(10, 12), seed=32)[0], 8),
+             (positions.midgame_batch(6, marks=(4, 6), seed=33)[0], 5),
+             (positions.midgame_batch(30, marks=(16, 18, 20, 21), seed=34)[0], 10),
+             (positions.midgame_batch(12, marks=(12,), seed=35)[0], 4)]
+    for boards, depth in cases:
+        monkeypatch.setenv("SQ_NS_SPLIT", "0")
+        plain = dev.negascout_root(boards, depth, sc)
+        monkeypatch.delenv("SQ_NS_SPLIT")
+        for env in [{}, {"SQ_NS_DIRECT": "1000"}, {"SQ_NS_DIRECT": "0", "SQ_NS_BUDGET": "200"},
+                    {"SQ_NS_DIRECT": "0", "SQ_NS_BUDGET": "5000", "SQ_NS_SPLIT_PLY": "1"},
+                    {"SQ_NS_DIRECT": "1000", "SQ_NS_SPLIT_PLY": "2", "SQ_NS_SPLIT_PLY_NULL": "1"},
+                    {"SQ_NS_DIRECT": "1000", "SQ_NS_SPLIT_PLY": "6", "SQ_NS_SPLIT_PLY_NULL": "6"},
+                    {"SQ_NS_DIRECT": "1000", "SQ_NS_SPLIT_PLY": "4", "SQ_NS_SPLIT_PLY_NULL": "3", "SQ_NS_ITEM_BUDGET": "0"},
+                    {"SQ_NS_DIRECT": "1000", "SQ_NS_SPLIT_PLY": "1", "SQ_NS_ITEM_BUDGET": "40"},
+                    {"SQ_NS_DIRECT": "0", "SQ_NS_BUDGET": "1000", "SQ_NS_ITEM_BUDGET": "300"}]:
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            got = dev.negascout_root(boards, depth, sc)
+            for k in env:
+                monkeypatch.delenv(k)
+            assert same(plain, got), (depth, env)
+    # and straight against the oracle, split on
+    boards, _ = positions.midgame_batch(6, marks=(10,), seed=36)
+    check(dev, oracle, boards, 7, sc)
