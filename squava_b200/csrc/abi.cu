@@ -32,6 +32,19 @@ namespace {
 // buffers, pinned block, timing events and scheduling counters.  A device carries kCtx of them, so
 // calls arriving on different host threads overlap on the SAME device (and calls on different
 // devices never meet at all); a context is held for the duration of one call.
+// NegaScout call items in flight (NsSplit): a stream of its own and pinned, mapped memory the kernel reads the items from
+// and writes the results to in place -- a flight costs one launch and one event, no copies
+struct NsFlight {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    sq::NsItem* items = nullptr;
+    sq::NsItemOut* out = nullptr;
+    size_t cap = 0, n = 0;
+    bool busy = false;
+    std::vector<std::pair<int32_t, uint32_t>> sent;      // (call, generation) of every item
+};
+constexpr int kNsFlights = 16;
+
 struct Ctx {
     std::mutex mu;
     cudaStream_t stream = nullptr;
@@ -46,6 +59,7 @@ struct Ctx {
     // [counter | out | boards | to_move], so a call is memcpy-in, H2D, memset, kernel, D2H
     uint8_t* pin = nullptr;
     uint8_t* small = nullptr;
+    NsFlight flight[kNsFlights];                // made on first use
 };
 
 constexpr int kCtx = 4;
@@ -215,6 +229,13 @@ void destroy_device(Device& d) {
         if (c.counters) cudaFree(c.counters);
         if (c.small) cudaFree(c.small);
         if (c.pin) cudaFreeHost(c.pin);
+        for (auto& f : c.flight) {
+            if (f.stream) { cudaStreamSynchronize(f.stream); cudaStreamDestroy(f.stream); }
+            if (f.done) cudaEventDestroy(f.done);
+            if (f.items) cudaFreeHost(f.items);
+            if (f.out) cudaFreeHost(f.out);
+            f = NsFlight();
+        }
         if (c.ev0) cudaEventDestroy(c.ev0);
         if (c.ev1) cudaEventDestroy(c.ev1);
         if (c.stream) cudaStreamDestroy(c.stream);
@@ -283,7 +304,7 @@ struct NsCall {
     int32_t parent = -1;            // the loop waiting for this call (-1: ChooseMove's, the loop IS the position)
     uint32_t gen = 0;               // bumped when the slot is released: results of dropped calls are recognised by it
     int32_t pos = 0;                // index in the list of positions
-    uint8_t state = 0;              // 0 free, 1 item (waiting for the device), 2 loop, 3 done
+    uint8_t state = 0;              // 0 free, 1 item waiting for a flight, 4 item in flight, 2 loop, 3 done
     uint8_t ply = 0;                // of the node
     uint8_t path[7];
     int32_t a = 0, b = 0;           // the window the node is called with
@@ -321,9 +342,14 @@ public:
         const char* e3 = getenv("SQ_NS_ITEM_BUDGET");
         item_budget_ = e3 ? (uint32_t)strtoul(e3, nullptr, 10) : 16384u;
         deepest_loop_ = most < 1 ? 0 : most;
+        const char* e4 = getenv("SQ_NS_FLIGHTS");
+        n_flights_ = e4 ? atoi(e4) : 8;
+        if (n_flights_ < 1) n_flights_ = 1;
+        if (n_flights_ > kNsFlights) n_flights_ = kNsFlights;
     }
 
     int run(int32_t* best_value, uint32_t* best_mask, int8_t* first_best, uint64_t* nodes) {
+        for (auto& f : c_.flight) if (f.busy) { CK(cudaStreamSynchronize(f.stream)); f.busy = false; }      // left by a call that failed
         order_max_.resize((size_t)n_list_ * 25); order_min_.resize((size_t)n_list_ * 25);
         roots_.resize((size_t)n_list_);
         root_call_.resize((size_t)n_list_);
@@ -340,54 +366,74 @@ public:
             ready_.push_back(ci);
         }
         pump();
-        std::vector<sq::NsItem> items;
-        std::vector<std::pair<int32_t, uint32_t>> sent;
-        std::vector<sq::NsItemOut> outs;
+        // Items go out in FLIGHTS, several at a time, and come back whenever they are done: a long search holds up the
+        // loops that wait for it and nothing else.  Wide windows (the long searches) and null windows fly apart.
+        int busy = 0;
+        std::vector<std::pair<int32_t, uint32_t>> later;
         const sq::NsOut none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
         const int64_t cap = (int64_t)d_.sm_count * 6;
-        while (!outbox_.empty()) {
-            // wide windows first: they are the long searches
-            items.clear(); sent.clear();
-            for (int pass = 0; pass < 2; pass++)
+        for (;;) {
+            for (int kind = 0; kind < 2 && !outbox_.empty(); kind++) {
+                size_t n = 0;
+                for (const auto& w : outbox_) n += wanted(w) && wide(w) == (kind == 0);
+                if (!n) continue;
+                NsFlight* f = nullptr;
+                for (int k = 0; k < n_flights_ && !f; k++) if (!c_.flight[k].busy) f = &c_.flight[k];
+                if (!f) break;                                     // all in the air: these wait for the next landing
+                int r;
+                if ((r = ready_flight(*f, n))) return r;
+                f->n = 0; f->sent.clear();
                 for (const auto& w : outbox_) {
+                    if (!wanted(w) || wide(w) != (kind == 0)) continue;
                     const NsCall& k = calls_[(size_t)w.first];
-                    if (k.gen != w.second || k.state != 1 || (k.b - k.a > 1) != (pass == 0)) continue;
-                    sq::NsItem it;
+                    sq::NsItem& it = f->items[f->n++];
                     it.pos = list_[k.pos]; it.a = k.a; it.b = k.b; it.n_path = k.ply;
                     it.budget = k.ply <= deepest_loop_ ? item_budget_ : 0u;
                     memcpy(it.path, k.path, 7);
-                    items.push_back(it); sent.push_back(w);
+                    f->sent.push_back(w);
+                    calls_[(size_t)w.first].state = 4;             // in the air
                 }
-            outbox_.clear();
-            if (items.empty()) break;
-            int r;
-            if ((r = reserve(c_, 1, items.size() * sizeof(sq::NsItem)))) return r;
-            if ((r = reserve(c_, 2, items.size() * sizeof(sq::NsItemOut)))) return r;
-            CK(cudaMemcpyAsync(c_.buf[1], items.data(), items.size() * sizeof(sq::NsItem), cudaMemcpyHostToDevice, c_.stream));
-            CK(cudaMemsetAsync(d_counter_, 0, sizeof(unsigned int), c_.stream));
-            const int64_t want = ((int64_t)items.size() + sq::kNsWarps - 1) / sq::kNsWarps;
-            sq::negascout_fast_kernel<true><<<(int)(want < cap ? want : cap), sq::kNsWarps * 32, 0, c_.stream>>>(
-                d_pos_, nullptr, (int)items.size(), max_depth_, sc_, none, d_counter_, (const sq::NsItem*)c_.buf[1],
-                (sq::NsItemOut*)c_.buf[2], 0ull);
-            g_launches += 1;
-            CK(cudaGetLastError());
-            outs.resize(items.size());
-            CK(cudaMemcpyAsync(outs.data(), c_.buf[2], items.size() * sizeof(sq::NsItemOut), cudaMemcpyDeviceToHost, c_.stream));
-            CK(cudaStreamSynchronize(c_.stream));
-            rounds_++; items_ += items.size();
-            for (size_t t = 0; t < sent.size(); t++) {
-                NsCall& k = calls_[(size_t)sent[t].first];
-                if (k.gen != sent[t].second || k.state != 1) { dropped_++; continue; }      // dropped while in flight
-                if (outs[t].nodes == sq::kNsAborted) {                                      // too long for one warp: its loop runs here
-                    uint32_t x = h_pos_[list_[k.pos]].x & sq::kFull25, o = h_pos_[list_[k.pos]].o & sq::kFull25;
-                    for (int j = 0; j < k.ply; j++) { if (j & 1) o |= 1u << k.path[j]; else x |= 1u << k.path[j]; }
-                    start_loop(k, x, o);
-                    ready_.push_back(sent[t].first);
-                    expanded_++;
-                    continue;
+                const int64_t want = ((int64_t)f->n + sq::kNsWarps - 1) / sq::kNsWarps;
+                sq::negascout_fast_kernel<true><<<(int)(want < cap ? want : cap), sq::kNsWarps * 32, 0, f->stream>>>(
+                    d_pos_, nullptr, (int)f->n, max_depth_, sc_, none, nullptr, f->items, f->out, 0ull);
+                g_launches += 1;
+                CK(cudaGetLastError());
+                CK(cudaEventRecord(f->done, f->stream));
+                f->busy = true; busy++;
+                rounds_++; items_ += f->n;
+            }
+            // what did not get a flight stays in the outbox
+            later.clear();
+            for (const auto& w : outbox_) if (wanted(w)) later.push_back(w);
+            outbox_.swap(later);
+            if (busy == 0) {
+                if (outbox_.empty()) break;
+                snprintf(t_err, sizeof t_err, "NegaScout split driver: items left and nothing in flight"); return SQ_ERR_CUDA;
+            }
+            // wait for a landing; take every flight that is back
+            for (bool any = false; !any;) {
+                for (int k = 0; k < n_flights_; k++) {
+                    NsFlight& f = c_.flight[k];
+                    if (!f.busy) continue;
+                    const cudaError_t e = cudaEventQuery(f.done);
+                    if (e == cudaErrorNotReady) continue;
+                    if (e != cudaSuccess) return fail_cuda(e, "cudaEventQuery(flight)");
+                    f.busy = false; busy--; any = true;
+                    for (size_t t = 0; t < f.n; t++) {
+                        NsCall& k2 = calls_[(size_t)f.sent[t].first];
+                        if (k2.gen != f.sent[t].second || k2.state != 4) { dropped_++; continue; }   // dropped while in flight
+                        if (f.out[t].nodes == sq::kNsAborted) {                            // too long for one warp: its loop runs here
+                            uint32_t x = h_pos_[list_[k2.pos]].x & sq::kFull25, o = h_pos_[list_[k2.pos]].o & sq::kFull25;
+                            for (int j = 0; j < k2.ply; j++) { if (j & 1) o |= 1u << k2.path[j]; else x |= 1u << k2.path[j]; }
+                            start_loop(k2, x, o);
+                            ready_.push_back(f.sent[t].first);
+                            expanded_++;
+                            continue;
+                        }
+                        k2.state = 3; k2.ret = f.out[t].ret; k2.nodes = f.out[t].nodes;
+                        ready_.push_back(k2.parent);
+                    }
                 }
-                k.state = 3; k.ret = outs[t].ret; k.nodes = outs[t].nodes;
-                ready_.push_back(k.parent);
             }
             pump();
         }
@@ -402,13 +448,31 @@ public:
             if (nodes) nodes[p] = c.nodes;
         }
         if (getenv("SQ_NS_TRACE"))
-            fprintf(stderr, "ns split: %lld positions, split ply %d/%d, item budget %u, %llu rounds, %llu items (%llu dropped in flight, %llu given up), %zu call slots\n",
+            fprintf(stderr, "ns split: %lld positions, split ply %d/%d, item budget %u, %llu flights, %llu items (%llu dropped in flight, %llu given up), %zu call slots\n",
                     (long long)n_list_, split_wide_, split_null_, item_budget_, (unsigned long long)rounds_, (unsigned long long)items_,
                     (unsigned long long)dropped_, (unsigned long long)expanded_, calls_.size());
         return SQ_OK;
     }
 
 private:
+    bool wanted(const std::pair<int32_t, uint32_t>& w) const { const NsCall& k = calls_[(size_t)w.first]; return k.gen == w.second && k.state == 1; }
+    bool wide(const std::pair<int32_t, uint32_t>& w) const { const NsCall& k = calls_[(size_t)w.first]; return k.b - k.a > 1; }
+    int ready_flight(NsFlight& f, size_t n) {
+        CK(cudaSetDevice(d_.id));
+        if (!f.stream) CK(cudaStreamCreateWithFlags(&f.stream, cudaStreamNonBlocking));
+        if (!f.done) CK(cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+        if (f.cap < n) {
+            if (f.items) CK(cudaFreeHost(f.items));
+            if (f.out) CK(cudaFreeHost(f.out));
+            f.items = nullptr; f.out = nullptr; f.cap = 0;
+            size_t cap = 4096;
+            while (cap < n) cap *= 2;
+            CK(cudaHostAlloc((void**)&f.items, cap * sizeof(sq::NsItem), cudaHostAllocMapped));
+            CK(cudaHostAlloc((void**)&f.out, cap * sizeof(sq::NsItemOut), cudaHostAllocMapped));
+            f.cap = cap;
+        }
+        return SQ_OK;
+    }
     int alloc() {
         if (!free_.empty()) { const int ci = free_.back(); free_.pop_back(); return ci; }
         calls_.emplace_back();
@@ -525,7 +589,7 @@ private:
     sq::NsScores sc_;
     unsigned int* d_counter_;
     int32_t (*values_)[25]; int8_t (*visit_order_)[25];
-    int split_wide_ = 1, split_null_ = 1, deepest_loop_ = 0;
+    int split_wide_ = 1, split_null_ = 1, deepest_loop_ = 0, n_flights_ = 8;
     uint32_t item_budget_ = 0;
     std::deque<NsCall> calls_;
     std::vector<int> free_, ready_, stack_, root_call_;

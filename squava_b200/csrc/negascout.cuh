@@ -436,10 +436,13 @@ negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ 
 #pragma unroll
     for (int c = 0; c < 25; c++) if (lane == c) my_score = sc.s[c];
 
-    for (;;) {
+    for (unsigned turn = 0;; turn++) {
         unsigned int p = 0;
-        if (lane == 0) p = atomicAdd(queue, 1u);
-        p = __shfl_sync(full, p, 0);
+        if (ITEMS) p = (turn * gridDim.x + blockIdx.x) * kNsWarps + warp;       // items: no queue (nothing to reset between flights)
+        else {
+            if (lane == 0) p = atomicAdd(queue, 1u);
+            p = __shfl_sync(full, p, 0);
+        }
         if (p >= (unsigned)n_pos) break;
         const unsigned item_index = p;
         NsItem item;
