@@ -326,9 +326,9 @@ struct NsRootOut {                  // what ChooseMove leaves behind, movekeeper
 class NsSplit {
 public:
     NsSplit(Device& d, Ctx& c, const sq_board* h_pos, const sq_board* d_pos, const int* list, int64_t n_list, int max_depth,
-            const sq::NsScores& sc, unsigned int* d_counter, int32_t (*values)[25], int8_t (*visit_order)[25])
+            const sq::NsScores& sc, int32_t (*values)[25], int8_t (*visit_order)[25])
         : d_(d), c_(c), h_pos_(h_pos), d_pos_(d_pos), list_(list), n_list_(n_list), max_depth_(max_depth), sc_(sc),
-          d_counter_(d_counter), values_(values), visit_order_(visit_order) {
+          values_(values), visit_order_(visit_order) {
         const char* e = getenv("SQ_NS_SPLIT_PLY");
         // loops at ply < split_ply run here: deep enough for the items to be small next to the whole search, and never a
         // loop at the horizon or just above it (those are scans inside the kernel)
@@ -340,10 +340,10 @@ public:
         split_null_ = null_w < 1 ? 1 : null_w; if (split_null_ > split_wide_) split_null_ = split_wide_;
         // an item that turns out long gives up and becomes a loop here, its children items: no round waits for one search
         const char* e3 = getenv("SQ_NS_ITEM_BUDGET");
-        item_budget_ = e3 ? (uint32_t)strtoul(e3, nullptr, 10) : 16384u;
+        item_budget_ = e3 ? (uint32_t)strtoul(e3, nullptr, 10) : 8192u;
         deepest_loop_ = most < 1 ? 0 : most;
         const char* e4 = getenv("SQ_NS_FLIGHTS");
-        n_flights_ = e4 ? atoi(e4) : 8;
+        n_flights_ = e4 ? atoi(e4) : kNsFlights;
         if (n_flights_ < 1) n_flights_ = 1;
         if (n_flights_ > kNsFlights) n_flights_ = kNsFlights;
     }
@@ -389,6 +389,7 @@ public:
                     sq::NsItem& it = f->items[f->n++];
                     it.pos = list_[k.pos]; it.a = k.a; it.b = k.b; it.n_path = k.ply;
                     it.budget = k.ply <= deepest_loop_ ? item_budget_ : 0u;
+                    it.deepest = (uint8_t)deepest_loop_;
                     memcpy(it.path, k.path, 7);
                     f->sent.push_back(w);
                     calls_[(size_t)w.first].state = 4;             // in the air
@@ -423,10 +424,7 @@ public:
                         NsCall& k2 = calls_[(size_t)f.sent[t].first];
                         if (k2.gen != f.sent[t].second || k2.state != 4) { dropped_++; continue; }   // dropped while in flight
                         if (f.out[t].nodes == sq::kNsAborted) {                            // too long for one warp: its loop runs here
-                            uint32_t x = h_pos_[list_[k2.pos]].x & sq::kFull25, o = h_pos_[list_[k2.pos]].o & sq::kFull25;
-                            for (int j = 0; j < k2.ply; j++) { if (j & 1) o |= 1u << k2.path[j]; else x |= 1u << k2.path[j]; }
-                            start_loop(k2, x, o);
-                            ready_.push_back(f.sent[t].first);
+                            resume(f.sent[t].first, f.out[t]);
                             expanded_++;
                             continue;
                         }
@@ -504,8 +502,32 @@ private:
         c.n_kids = 0;
         for (int k = 0; k < n_root; k++) if (!(((x | o) >> ord[k]) & 1u)) { c.first[c.n_kids] = -1; c.cell[c.n_kids++] = ord[k]; }
     }
+    // An item gave up (negascout.cuh: NsItemOut).  Its node's loop runs here now, and so do the loops of the first children it
+    // had followed; the deepest of them continues where the item stood, minus the child it was in.
+    void resume(int ci, const sq::NsItemOut& got) {
+        {
+            NsCall& k = calls_[(size_t)ci];
+            uint32_t x = h_pos_[list_[k.pos]].x & sq::kFull25, o = h_pos_[list_[k.pos]].o & sq::kFull25;
+            for (int j = 0; j < k.ply; j++) { if (j & 1) o |= 1u << k.path[j]; else x |= 1u << k.path[j]; }
+            start_loop(k, x, o);
+        }
+        bool exact = true;                                           // the whole chain could be rebuilt
+        for (int j = 0; j < got.n_chain; j++) {
+            NsCall& k = calls_[(size_t)ci];
+            if (k.n_kids == 0 || k.cell[0] != got.cells[j] || k.ply >= deepest_loop_) { exact = false; break; }
+            const int child = spawn(ci, 0, -k.beta, -k.alpha, true);
+            calls_[(size_t)ci].first[0] = child;
+            ci = child;
+        }
+        NsCall& k = calls_[(size_t)ci];
+        if (exact && got.i_done > 0 && got.i_done < k.n_kids) {
+            k.i = got.i_done; k.alpha = got.alpha; k.score = got.score; k.n = got.alpha + 1; k.spec_alpha = got.alpha;
+            k.nodes = got.nodes_done;
+        }
+        ready_.push_back(ci);
+    }
     // the call negaScout(child j of loop `pi`, window (a, b)): a loop of its own above the split ply, an item below
-    int spawn(int pi, int j, int a, int b) {
+    int spawn(int pi, int j, int a, int b, bool as_loop = false) {
         const int ci = alloc();
         NsCall& p = calls_[(size_t)pi];
         NsCall& c = calls_[(size_t)ci];
@@ -515,7 +537,7 @@ private:
         memcpy(c.path, p.path, 7);
         c.path[p.ply] = (uint8_t)cell;
         const bool ends = sq::ns_move_ends_game(g_ns_tables, x_moves ? p.x : p.o, cell);
-        if (!ends && c.ply < (b - a > 1 ? split_wide_ : split_null_)) {
+        if (as_loop || (!ends && c.ply < (b - a > 1 ? split_wide_ : split_null_))) {
             start_loop(c, p.x | (x_moves ? 1u << cell : 0u), p.o | (x_moves ? 0u : 1u << cell));
             ready_.push_back(ci);
         } else {
@@ -587,7 +609,6 @@ private:
     Device& d_; Ctx& c_;
     const sq_board* h_pos_; const sq_board* d_pos_; const int* list_; int64_t n_list_; int max_depth_;
     sq::NsScores sc_;
-    unsigned int* d_counter_;
     int32_t (*values_)[25]; int8_t (*visit_order_)[25];
     int split_wide_ = 1, split_null_ = 1, deepest_loop_ = 0, n_flights_ = 8;
     uint32_t item_budget_ = 0;
@@ -1027,7 +1048,7 @@ int sq_negascout_root(const sq_board* positions, int64_t n, int max_depth, const
             for (int64_t q = 0; q < n_fast; q++) if (direct || got[order[(size_t)q]] == sq::kNsAborted) hard.push_back(order[(size_t)q]);
             if (!hard.empty()) {
                 NsSplit driver(d, *c, positions + lo, (const sq_board*)c->buf[0], hard.data(), (int64_t)hard.size(), max_depth, sc,
-                               (unsigned int*)blk + 2, values + lo, visit_order ? visit_order + lo : nullptr);
+                               values + lo, visit_order ? visit_order + lo : nullptr);
                 return driver.run(best_value ? best_value + lo : nullptr, best_mask ? best_mask + lo : nullptr,
                                   first_best ? first_best + lo : nullptr, nodes ? nodes + lo : nullptr);
             }

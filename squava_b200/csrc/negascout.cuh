@@ -370,9 +370,20 @@ struct NsItem {
     int32_t a, b;       // the window the node is called with
     uint8_t n_path;     // >= 1: the node's ply
     uint8_t path[7];    // cells played from the position, the position's mover (X) first; no node before the last is terminal
-    uint32_t budget;    // give up after this many staticValue calls (0: never): the host then runs this node's loop itself
+    uint32_t budget;    // give up after this many staticValue calls (0: never): the host then runs the loop itself
+    uint8_t deepest;    // ... at a node of at most this ply
+    uint8_t pad[3];
 };
-struct NsItemOut { int32_t ret; uint32_t pad; unsigned long long nodes; };
+// An item that gives up says how far it got: below its node it followed `n_chain` FIRST children (no loop on that way had
+// finished a child yet) to a loop that had finished `i_done` children -- that loop's alpha, score and the staticValue calls
+// under its finished children come back, so the host resumes exactly there and only the child in progress is searched again.
+struct NsItemOut {
+    int32_t ret, score;
+    unsigned long long nodes;       // kNsAborted: gave up
+    int32_t alpha;
+    uint32_t nodes_done;
+    uint8_t n_chain, i_done, cells[6];
+};
 constexpr unsigned long long kNsAborted = ~0ull;      // NsOut.nodes of a position that ran out of its node budget
 
 // reorderMoves on the host: the driver needs the children of a node in the mover's order
@@ -421,6 +432,7 @@ negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ 
     __shared__ NsFastFrame s_frames[kNsWarps][kNsMaxDepth + 2];
     __shared__ int s_cur[kNsWarps][kNsMaxDepth + 2][32], s_sum[kNsWarps][kNsMaxDepth + 2][32];
     __shared__ uint8_t s_order[kNsWarps][2][32];
+    __shared__ uint32_t s_start[ITEMS ? kNsWarps : 1][kNsMaxDepth + 2], s_mark[ITEMS ? kNsWarps : 1][kNsMaxDepth + 2];   // see the give-up block
     for (int i = threadIdx.x; i < (int)(sizeof(NsCellTables) / 4); i += blockDim.x) ((uint32_t*)&C)[i] = ((const uint32_t*)&c_ns_cell)[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -523,8 +535,33 @@ negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ 
                 const int ca = phase == 1 ? -n : -beta, cb = phase == 1 ? -alpha : -rs_cur;
                 const int cply = ply + 1;
                 enter = false;
+                if (ITEMS && phase == 1 && lane == 0) s_mark[warp][ply] = (uint32_t)nodes;     // calls so far when this child's first search starts
                 nodes++;
-                if (ITEMS ? (item.budget != 0 && nodes > item.budget) : nodes > budget) { aborted = true; break; }   // the host takes over (NsSplit)
+                if (ITEMS ? (item.budget != 0 && nodes > item.budget) : nodes > budget) {     // the host takes over (NsSplit)
+                    aborted = true;
+                    if (ITEMS) {
+                        // the loop to resume at: the shallowest one that has finished a child (all above it are at their first)
+                        NsItemOut r;
+                        r.ret = 0; r.score = -3 * 10000; r.nodes = kNsAborted; r.alpha = item.a; r.nodes_done = 0; r.n_chain = 0; r.i_done = 0;
+                        __syncwarp();
+                        for (int L = base + 1; L <= ply; L++) {
+                            const uint32_t act = L == ply ? active : frames[L].active;
+                            const int l_at = L == ply ? at : (frames[L].at_phase & 31);
+                            const int fin = __popc(act & ((1u << l_at) - 1u));
+                            if (fin > 0 || L == ply || L >= (int)item.deepest) {
+                                r.i_done = (uint8_t)fin;
+                                r.alpha = L == ply ? alpha : frames[L].alpha;
+                                r.score = L == ply ? score : frames[L].score;
+                                r.nodes_done = s_mark[warp][L] - s_start[warp][L];
+                                break;
+                            }
+                            if (r.n_chain < 6) r.cells[r.n_chain] = s_order[warp][(L & 1) ? 0 : 1][l_at];
+                            r.n_chain++;
+                        }
+                        if (lane == 0) item_out[item_index] = r;
+                    }
+                    break;
+                }
                 if ((term >> at) & 1u) {               // the child is a finished game
                     ret = -s_cur[warp][ply][at];
                     returned = true;
@@ -560,6 +597,7 @@ negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ 
                     s_cur[warp][cply][lane] = ch.cur; s_sum[warp][cply][lane] = ch.sum;
                     __syncwarp();
                     ply = cply;
+                    if (ITEMS && lane == 0) s_start[warp][cply] = (uint32_t)nodes;
                     alpha = ca; beta = cb; score = -3 * 10000; n = cb; k = 0;
                     continue;
                 }
@@ -603,7 +641,6 @@ negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ 
             }
             n = alpha + 1;
         }
-        if (ITEMS && aborted && lane == 0) item_out[item_index].nodes = kNsAborted;
         if (!ITEMS && lane == 0) {
             out.best_value[p] = keeper_mask ? keeper_max : 0;
             out.best_mask[p] = keeper_mask;
