@@ -215,6 +215,41 @@ def secondary_c3(sq, peak_ops):
     return rec
 
 
+def secondary_negascout(sq):
+    """playoff5's N engine (src/negascout) as a batch and as a single decision: sq_negascout_root with host buffers, split
+    over many warps (the default) beside one warp per position (SQ_NS_SPLIT=0, round 1's schedule).  The search is
+    order-dependent, so parity is everything: values, visiting order, movekeeper set and leaf counter of the two
+    schedules must be identical here, and a sample is compared with the CPU oracle."""
+    from squava_b200 import positions
+    rec = {}
+    o = oracle_handle()
+    for name, count, marks, depth, sample in [("batch", 1024, 8, 8, 2), ("one_position", 1, 2, 6, 0)]:
+        boards, _ = positions.midgame_batch(count, marks=(marks,), seed=4000 + marks)
+        sq.negascout_root(boards[:1], 4, SCORES_AB)                              # warm-up
+        l0 = sq.launch_count()
+        t0 = time.perf_counter(); split = sq.negascout_root(boards, depth, SCORES_AB); split_s = time.perf_counter() - t0
+        launches = sq.launch_count() - l0
+        os.environ["SQ_NS_SPLIT"] = "0"
+        try:
+            t0 = time.perf_counter(); plain = sq.negascout_root(boards, depth, SCORES_AB); plain_s = time.perf_counter() - t0
+        finally:
+            del os.environ["SQ_NS_SPLIT"]
+        same = all((split[k] == plain[k]).all() for k in ("values", "visit_order", "best_mask", "best_value", "first_best", "nodes"))
+        mism = 0
+        order = sorted(range(count), key=lambda i: int(split["nodes"][i]))[:sample]
+        for i in order:
+            vals, vis, bm, bv, fb, leaves = o.negascout_root(int(boards[i]["x"]), int(boards[i]["o"]), depth, SCORES_AB)
+            ok = (split["values"][i].tolist() == vals and [int(c) for c in split["visit_order"][i] if c >= 0] == vis
+                  and (int(split["best_mask"][i]), int(split["best_value"][i]), int(split["first_best"][i])) == (bm, bv, fb)
+                  and int(split["nodes"][i]) == leaves)
+            mism += 0 if ok else 1
+        rec[name] = {"workload": "%d position(s), %d marks, negascout depth %d, sq_negascout_root (host buffers)" % (count, marks, depth),
+                     "seconds": split_s, "seconds_one_warp_per_position": plain_s, "static_value_calls": int(split["nodes"].sum()),
+                     "calls_per_s": int(split["nodes"].sum()) / split_s, "gpu_launches": launches,
+                     "schedules_identical": bool(same), "oracle_sample": len(order), "oracle_mismatches": mism}
+    return rec
+
+
 def opening3_subtrees(sq):
     """opening3.go:66-128: the (first move, reply) pairs not equivalent under the program's 8 symmetries
     (opening3.go:379-451) to a pair computed earlier: 85 = 14 + 24 + 14 + 14 + 14 + 5."""
@@ -645,6 +680,7 @@ def main():
         sec["c4"]["mcts"] = secondary_c4_mcts(sq, rank, world, dev, dist, torch, 2 ** 30)
         if rank == 0 and world == 1:
             sec["c3"] = secondary_c3(sq, peak_mixed)
+            sec["negascout"] = secondary_negascout(sq)
             sec.update(secondary_c0_c2(sq, int(args.c2_iterations)))
         line["secondary"] = sec
 

@@ -147,7 +147,9 @@ int sq_alphabeta_root(const sq_board *positions, int64_t n, int dialect, int max
  * MAXIMIZER to move; max_depth = p.maxDepth as SetDepth leaves it (:69-79).  This search is
  * not a plain minimax (null-window results are accepted two plies above the horizon, the
  * root hands its running alpha to movekeeper), so the GPU replays the reference's recursion
- * step for step, one warp per position, and every output is bit-exact including nodes[]:
+ * step for step -- one warp per position, and a search that runs long spread over many warps
+ * as calls of negaScout whose results are consumed in the reference's order -- and every
+ * output is bit-exact including nodes[]:
  * values[i][c] = the alpha recorded by moves.SetMove for root move c (SQ_NO_MOVE if not
  * visited); visit_order[i][k] = k-th root cell searched, -1 padded (may be NULL);
  * best_value / best_mask = movekeeper's max and the cells it holds; first_best[i] = the cell
