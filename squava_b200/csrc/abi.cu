@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -306,6 +307,7 @@ struct NsCall {
     int32_t pos = 0;                // index in the list of positions
     uint8_t state = 0;              // 0 free, 1 item waiting for a flight, 4 item in flight, 2 loop, 3 done
     uint8_t ply = 0;                // of the node
+    uint8_t eager = 0;              // a null-window loop known to be big: all children go out with the first
     uint8_t path[7];
     int32_t a = 0, b = 0;           // the window the node is called with
     int32_t ret = 0;
@@ -342,6 +344,10 @@ public:
         const char* e3 = getenv("SQ_NS_ITEM_BUDGET");
         item_budget_ = e3 ? (uint32_t)strtoul(e3, nullptr, 10) : 8192u;
         deepest_loop_ = most < 1 ? 0 : most;
+        const char* e6 = getenv("SQ_NS_ITEM_BUDGET_WIDE");
+        item_budget_wide_ = e6 ? (uint32_t)strtoul(e6, nullptr, 10) : item_budget_;
+        const char* e5 = getenv("SQ_NS_EAGER");
+        eager_ = e5 ? (uint8_t)(atoi(e5) != 0) : (uint8_t)(n_list <= 8);
         const char* e4 = getenv("SQ_NS_FLIGHTS");
         n_flights_ = e4 ? atoi(e4) : kNsFlights;
         if (n_flights_ < 1) n_flights_ = 1;
@@ -349,6 +355,7 @@ public:
     }
 
     int run(int32_t* best_value, uint32_t* best_mask, int8_t* first_best, uint64_t* nodes) {
+        t_run_ = std::chrono::steady_clock::now();
         for (auto& f : c_.flight) if (f.busy) { CK(cudaStreamSynchronize(f.stream)); f.busy = false; }      // left by a call that failed
         order_max_.resize((size_t)n_list_ * 25); order_min_.resize((size_t)n_list_ * 25);
         roots_.resize((size_t)n_list_);
@@ -388,7 +395,7 @@ public:
                     const NsCall& k = calls_[(size_t)w.first];
                     sq::NsItem& it = f->items[f->n++];
                     it.pos = list_[k.pos]; it.a = k.a; it.b = k.b; it.n_path = k.ply;
-                    it.budget = k.ply <= deepest_loop_ ? item_budget_ : 0u;
+                    it.budget = k.ply > deepest_loop_ ? 0u : kind == 0 ? item_budget_wide_ : item_budget_;
                     it.deepest = (uint8_t)deepest_loop_;
                     memcpy(it.path, k.path, 7);
                     f->sent.push_back(w);
@@ -446,8 +453,8 @@ public:
             if (nodes) nodes[p] = c.nodes;
         }
         if (getenv("SQ_NS_TRACE"))
-            fprintf(stderr, "ns split: %lld positions, split ply %d/%d, item budget %u, %llu flights, %llu items (%llu dropped in flight, %llu given up), %zu call slots\n",
-                    (long long)n_list_, split_wide_, split_null_, item_budget_, (unsigned long long)rounds_, (unsigned long long)items_,
+            fprintf(stderr, "ns split: %.4f s, %lld positions, split ply %d/%d, item budget %u, %llu flights, %llu items (%llu dropped in flight, %llu given up), %zu call slots\n",
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - t_run_).count(), (long long)n_list_, split_wide_, split_null_, item_budget_, (unsigned long long)rounds_, (unsigned long long)items_,
                     (unsigned long long)dropped_, (unsigned long long)expanded_, calls_.size());
         return SQ_OK;
     }
@@ -495,7 +502,7 @@ private:
         }
     }
     void start_loop(NsCall& c, uint32_t x, uint32_t o) {
-        c.state = 2; c.x = x; c.o = o; c.nodes = 0;
+        c.state = 2; c.x = x; c.o = o; c.nodes = 0; c.eager = 0;
         c.alpha = c.a; c.beta = c.b; c.score = -30000; c.n = c.b; c.i = 0; c.spec_alpha = c.a; c.again = -1;
         const uint8_t* ord = (c.ply & 1) ? &order_min_[(size_t)c.pos * 25] : &order_max_[(size_t)c.pos * 25];
         const int n_root = 25 - __builtin_popcount(h_pos_[list_[c.pos]].x | h_pos_[list_[c.pos]].o);
@@ -517,9 +524,11 @@ private:
             if (k.n_kids == 0 || k.cell[0] != got.cells[j] || k.ply >= deepest_loop_) { exact = false; break; }
             const int child = spawn(ci, 0, -k.beta, -k.alpha, true);
             calls_[(size_t)ci].first[0] = child;
+            calls_[(size_t)ci].eager = eager_;
             ci = child;
         }
         NsCall& k = calls_[(size_t)ci];
+        k.eager = eager_;
         if (exact && got.i_done > 0 && got.i_done < k.n_kids) {
             k.i = got.i_done; k.alpha = got.alpha; k.score = got.score; k.n = got.alpha + 1; k.spec_alpha = got.alpha;
             k.nodes = got.nodes_done;
@@ -563,6 +572,12 @@ private:
                 if (c.i == c.n_kids) { finish(ci); return; }         // (a node without children)
                 if (c.i == 0) {
                     if (c.first[0] < 0) { const int k = spawn(ci, 0, -c.n, -c.alpha); calls_[(size_t)ci].first[0] = k; }
+                    // In a null-window loop the first child either cuts off or leaves alpha where it is: the window of
+                    // the other children is known before it returns.  Sending them along is pure speculation on "no
+                    // cut-off" -- done for loops that are known to be long while the device has room.
+                    if (c.eager && c.beta - c.alpha == 1)
+                        for (int j = 1; j < c.n_kids; j++)
+                            if (calls_[(size_t)ci].first[j] < 0) { const int k = spawn(ci, j, -c.alpha - 1, -c.alpha); calls_[(size_t)ci].first[j] = k; }
                 } else {
                     if (c.spec_alpha != c.alpha) {
                         for (int j = c.i; j < c.n_kids; j++) if (c.first[j] >= 0) { drop(c.first[j]); c.first[j] = -1; }
@@ -611,7 +626,9 @@ private:
     sq::NsScores sc_;
     int32_t (*values_)[25]; int8_t (*visit_order_)[25];
     int split_wide_ = 1, split_null_ = 1, deepest_loop_ = 0, n_flights_ = 8;
-    uint32_t item_budget_ = 0;
+    uint32_t item_budget_ = 0, item_budget_wide_ = 0;
+    uint8_t eager_ = 0;
+    std::chrono::steady_clock::time_point t_run_;
     std::deque<NsCall> calls_;
     std::vector<int> free_, ready_, stack_, root_call_;
     std::vector<std::pair<int32_t, uint32_t>> outbox_;
@@ -1034,8 +1051,12 @@ int sq_negascout_root(const sq_board* positions, int64_t n, int max_depth, const
             CK(cudaGetLastError());
         }
         std::vector<uint8_t> h(total);
+        const auto t_pass = std::chrono::steady_clock::now();
         CK(cudaMemcpyAsync(h.data(), blk, total, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
+        if (getenv("SQ_NS_TRACE") && n_fast && !direct)
+            fprintf(stderr, "ns one warp per position: %lld positions, budget %llu, %.4f s\n", (long long)n_fast, budget,
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - t_pass).count());
         memcpy(values + lo, h.data() + o_values, 100 * cnt);
         if (nodes) memcpy(nodes + lo, h.data() + o_nodes, 8 * cnt);
         if (best_value) memcpy(best_value + lo, h.data() + o_bv, 4 * cnt);

@@ -107,7 +107,9 @@ def test_split_over_many_warps_changes_nothing(dev, oracle, monkeypatch):
                     {"SQ_NS_DIRECT": "1000", "SQ_NS_SPLIT_PLY": "6", "SQ_NS_SPLIT_PLY_NULL": "6"},
                     {"SQ_NS_DIRECT": "1000", "SQ_NS_SPLIT_PLY": "4", "SQ_NS_SPLIT_PLY_NULL": "3", "SQ_NS_ITEM_BUDGET": "0"},
                     {"SQ_NS_DIRECT": "1000", "SQ_NS_SPLIT_PLY": "1", "SQ_NS_ITEM_BUDGET": "40"},
-                    {"SQ_NS_DIRECT": "0", "SQ_NS_BUDGET": "1000", "SQ_NS_ITEM_BUDGET": "300"}]:
+                    {"SQ_NS_DIRECT": "0", "SQ_NS_BUDGET": "1000", "SQ_NS_ITEM_BUDGET": "300"},
+                    {"SQ_NS_DIRECT": "1000", "SQ_NS_ITEM_BUDGET": "200", "SQ_NS_EAGER": "1", "SQ_NS_ITEM_BUDGET_WIDE": "50"},
+                    {"SQ_NS_DIRECT": "1000", "SQ_NS_ITEM_BUDGET": "2000", "SQ_NS_EAGER": "0", "SQ_NS_FLIGHTS": "2"}]:
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             got = dev.negascout_root(boards, depth, sc)
@@ -117,3 +119,28 @@ def test_split_over_many_warps_changes_nothing(dev, oracle, monkeypatch):
     # and straight against the oracle, split on
     boards, _ = positions.midgame_batch(6, marks=(10,), seed=36)
     check(dev, oracle, boards, 7, sc)
+
+
+def test_split_searches_from_several_host_threads(dev, oracle):
+    """every call context carries its own flights: searches arriving on several OS threads at once (split and one-warp
+    passes mixed) return what the same calls return one after the other"""
+    import threading
+    from squava_b200 import positions
+    sc = oracle.tables()["scores_ab"]
+    jobs = [(positions.midgame_batch(3, marks=(6,), seed=41)[0], 7), (positions.midgame_batch(80, marks=(10, 12), seed=42)[0], 8),
+            (positions.midgame_batch(1, marks=(4,), seed=43)[0], 6), (positions.midgame_batch(40, marks=(14,), seed=44)[0], 10),
+            (positions.midgame_batch(2, marks=(8,), seed=45)[0], 7), (positions.midgame_batch(200, marks=(12, 16), seed=46)[0], 6)]
+    want = [dev.negascout_root(b, d, sc) for b, d in jobs]
+    got, errs = [None] * len(jobs), []
+
+    def worker(k):
+        try:
+            for _ in range(2):
+                got[k] = dev.negascout_root(jobs[k][0], jobs[k][1], sc)
+        except Exception as e:        # pragma: no cover
+            errs.append(e)
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(len(jobs))]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert not errs, errs
+    for k in range(len(jobs)):
+        assert same(want[k], got[k]), k
