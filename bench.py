@@ -277,13 +277,15 @@ def secondary_c4(sq, rank, world, dev, dist, torch, peak_ops):
     pairs, st = opening3_subtrees(sq)
     sq.alphabeta_subtrees(st[:4], 3, 5, SCORES_OPENING)                          # warm-up
     t0 = time.perf_counter()
-    _, pilot = sq.alphabeta_subtrees(st, 3, 7, SCORES_OPENING)
-    # evaluator counts depend on how the GPU happened to schedule the search: ONE rank's counts are the weights for
-    # everybody (a broadcast of 85 integers), so that all ranks derive the same partition
-    weights = torch.from_numpy(pilot.astype(np.int64)).to(dev)
     if world > 1:
+        _, pilot = sq.alphabeta_subtrees(st, 3, 7, SCORES_OPENING)
+        # evaluator counts depend on how the GPU happened to schedule the search: ONE rank's counts are the weights for
+        # everybody (a broadcast of 85 integers), so that all ranks derive the same partition
+        weights = torch.from_numpy(pilot.astype(np.int64)).to(dev)
         dist.broadcast(weights, src=0)
-    mine = lpt_assign([float(v) for v in weights.cpu().numpy()], world)[rank]
+        mine = lpt_assign([float(v) for v in weights.cpu().numpy()], world)[rank]
+    else:
+        mine = list(range(len(pairs)))                                           # one rank: nothing to partition, no pilot search
     vals = torch.zeros(len(pairs), dtype=torch.int64, device=dev)
     nodes = torch.zeros(len(pairs), dtype=torch.int64, device=dev)
     if mine:
@@ -298,7 +300,7 @@ def secondary_c4(sq, rank, world, dev, dist, torch, peak_ops):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     secs = float(t.item())
     got = vals.cpu().numpy().tolist()
-    rec = {"workload": "configs[4] alpha-beta: opening3's 85 subtrees, AB-3 depth 10, sharded over %d rank(s) by pilot-search size, NCCL merge" % world,
+    rec = {"workload": "configs[4] alpha-beta: opening3's 85 subtrees, AB-3 depth 10, sharded over %d rank(s) by pilot-search size (pilot inside the timed region when there is more than one rank), NCCL merge" % world,
            "seconds": secs, "gpu_evaluator_calls": int(nodes.sum().item()), "subtrees_on_rank0": len(mine) if rank == 0 else None}
     gp = os.path.join(ROOT, "tests", "golden", "c4_opening3_depth10.json")
     if os.path.exists(gp):
