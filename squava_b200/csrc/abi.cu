@@ -307,10 +307,6 @@ struct NsCall {
     int32_t pos = 0;                // index in the list of positions
     uint8_t state = 0;              // 0 free, 1 item waiting for a flight, 4 item in flight, 2 loop, 3 done
     uint8_t ply = 0;                // of the node
-    uint8_t eager = 0;              // a null-window loop known to be big: all children go out with the first
-    int8_t big_kid = -1;            // a child known to be long (an item was in it when it gave up): its call starts as a loop
-    int8_t kid = 0;                 // which child of the parent's loop this call is
-    uint32_t kid_big = 0;           // children whose call has given up once: their next call (new alpha, re-search) starts as a loop
     uint8_t path[7];
     int32_t a = 0, b = 0;           // the window the node is called with
     int32_t ret = 0;
@@ -349,10 +345,6 @@ public:
         deepest_loop_ = most < 1 ? 0 : most;
         const char* e6 = getenv("SQ_NS_ITEM_BUDGET_WIDE");
         item_budget_wide_ = e6 ? (uint32_t)strtoul(e6, nullptr, 10) : item_budget_ / 4;
-        const char* e7 = getenv("SQ_NS_BIG_HINT");
-        big_hint_ = e7 ? (uint8_t)(atoi(e7) != 0) : 1;
-        const char* e5 = getenv("SQ_NS_EAGER");
-        eager_ = e5 ? (uint8_t)(atoi(e5) != 0) : (uint8_t)(n_list <= 8);
         const char* e4 = getenv("SQ_NS_FLIGHTS");
         n_flights_ = e4 ? atoi(e4) : kNsFlights;
         if (n_flights_ < 1) n_flights_ = 1;
@@ -507,7 +499,7 @@ private:
         }
     }
     void start_loop(NsCall& c, uint32_t x, uint32_t o) {
-        c.state = 2; c.x = x; c.o = o; c.nodes = 0; c.eager = 0; c.big_kid = -1; c.kid_big = 0;
+        c.state = 2; c.x = x; c.o = o; c.nodes = 0;
         c.alpha = c.a; c.beta = c.b; c.score = -30000; c.n = c.b; c.i = 0; c.spec_alpha = c.a; c.again = -1;
         const uint8_t* ord = (c.ply & 1) ? &order_min_[(size_t)c.pos * 25] : &order_max_[(size_t)c.pos * 25];
         const int n_root = 25 - __builtin_popcount(h_pos_[list_[c.pos]].x | h_pos_[list_[c.pos]].o);
@@ -519,7 +511,6 @@ private:
     void resume(int ci, const sq::NsItemOut& got) {
         {
             NsCall& k = calls_[(size_t)ci];
-            if (k.parent >= 0) calls_[(size_t)k.parent].kid_big |= 1u << k.kid;
             uint32_t x = h_pos_[list_[k.pos]].x & sq::kFull25, o = h_pos_[list_[k.pos]].o & sq::kFull25;
             for (int j = 0; j < k.ply; j++) { if (j & 1) o |= 1u << k.path[j]; else x |= 1u << k.path[j]; }
             start_loop(k, x, o);
@@ -530,12 +521,9 @@ private:
             if (k.n_kids == 0 || k.cell[0] != got.cells[j] || k.ply >= deepest_loop_) { exact = false; break; }
             const int child = spawn(ci, 0, -k.beta, -k.alpha, true);
             calls_[(size_t)ci].first[0] = child;
-            calls_[(size_t)ci].eager = eager_;
             ci = child;
         }
         NsCall& k = calls_[(size_t)ci];
-        k.eager = eager_;
-        if (exact && big_hint_ && (uint32_t)got.ret >= item_budget_ / 2 && got.i_done < k.n_kids) k.big_kid = (int8_t)got.i_done;
         if (exact && got.i_done > 0 && got.i_done < k.n_kids) {
             k.i = got.i_done; k.alpha = got.alpha; k.score = got.score; k.n = got.alpha + 1; k.spec_alpha = got.alpha;
             k.nodes = got.nodes_done;
@@ -549,8 +537,7 @@ private:
         NsCall& c = calls_[(size_t)ci];
         const int cell = p.cell[j];
         const bool x_moves = !(p.ply & 1);
-        c.parent = pi; c.pos = p.pos; c.ply = (uint8_t)(p.ply + 1); c.a = a; c.b = b; c.kid = (int8_t)j;
-        if (big_hint_ && (p.kid_big >> j & 1u)) as_loop = true;
+        c.parent = pi; c.pos = p.pos; c.ply = (uint8_t)(p.ply + 1); c.a = a; c.b = b;
         memcpy(c.path, p.path, 7);
         c.path[p.ply] = (uint8_t)cell;
         const bool ends = sq::ns_move_ends_game(g_ns_tables, x_moves ? p.x : p.o, cell);
@@ -579,20 +566,14 @@ private:
             } else {
                 if (c.i == c.n_kids) { finish(ci); return; }         // (a node without children)
                 if (c.i == 0) {
-                    if (c.first[0] < 0) { const int k = spawn(ci, 0, -c.n, -c.alpha, c.big_kid == 0); calls_[(size_t)ci].first[0] = k; }
-                    // In a null-window loop the first child either cuts off or leaves alpha where it is: the window of
-                    // the other children is known before it returns.  Sending them along is pure speculation on "no
-                    // cut-off" -- done for loops that are known to be long while the device has room.
-                    if (c.eager && c.beta - c.alpha == 1)
-                        for (int j = 1; j < c.n_kids; j++)
-                            if (calls_[(size_t)ci].first[j] < 0) { const int k = spawn(ci, j, -c.alpha - 1, -c.alpha); calls_[(size_t)ci].first[j] = k; }
+                    if (c.first[0] < 0) { const int k = spawn(ci, 0, -c.n, -c.alpha); calls_[(size_t)ci].first[0] = k; }
                 } else {
                     if (c.spec_alpha != c.alpha) {
                         for (int j = c.i; j < c.n_kids; j++) if (c.first[j] >= 0) { drop(c.first[j]); c.first[j] = -1; }
                         c.spec_alpha = c.alpha;
                     }
                     for (int j = c.i; j < c.n_kids; j++)
-                        if (calls_[(size_t)ci].first[j] < 0) { const int k = spawn(ci, j, -c.alpha - 1, -c.alpha, c.big_kid == j); calls_[(size_t)ci].first[j] = k; }
+                        if (calls_[(size_t)ci].first[j] < 0) { const int k = spawn(ci, j, -c.alpha - 1, -c.alpha); calls_[(size_t)ci].first[j] = k; }
                 }
                 NsCall& r = calls_[(size_t)c.first[c.i]];
                 if (r.state != 3) return;
@@ -635,7 +616,6 @@ private:
     int32_t (*values_)[25]; int8_t (*visit_order_)[25];
     int split_wide_ = 1, split_null_ = 1, deepest_loop_ = 0, n_flights_ = 8;
     uint32_t item_budget_ = 0, item_budget_wide_ = 0;
-    uint8_t eager_ = 0, big_hint_ = 1;
     std::chrono::steady_clock::time_point t_run_;
     std::deque<NsCall> calls_;
     std::vector<int> free_, ready_, stack_, root_call_;

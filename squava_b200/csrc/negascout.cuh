@@ -378,7 +378,7 @@ struct NsItem {
 // finished a child yet) to a loop that had finished `i_done` children -- that loop's alpha, score and the staticValue calls
 // under its finished children come back, so the host resumes exactly there and only the child in progress is searched again.
 struct NsItemOut {
-    int32_t ret, score;             // (gave up: ret = the calls spent in the child that was in progress)
+    int32_t ret, score;
     unsigned long long nodes;       // kNsAborted: gave up
     int32_t alpha;
     uint32_t nodes_done;
@@ -553,7 +553,6 @@ negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ 
                                 r.alpha = L == ply ? alpha : frames[L].alpha;
                                 r.score = L == ply ? score : frames[L].score;
                                 r.nodes_done = s_mark[warp][L] - s_start[warp][L];
-                                r.ret = (int32_t)((uint32_t)nodes - s_mark[warp][L]);      // calls spent in the child in progress
                                 break;
                             }
                             if (r.n_chain < 6) r.cells[r.n_chain] = s_order[warp][(L & 1) ? 0 : 1][l_at];

@@ -108,8 +108,8 @@ def test_split_over_many_warps_changes_nothing(dev, oracle, monkeypatch):
                     {"SQ_NS_DIRECT": "1000", "SQ_NS_SPLIT_PLY": "4", "SQ_NS_SPLIT_PLY_NULL": "3", "SQ_NS_ITEM_BUDGET": "0"},
                     {"SQ_NS_DIRECT": "1000", "SQ_NS_SPLIT_PLY": "1", "SQ_NS_ITEM_BUDGET": "40"},
                     {"SQ_NS_DIRECT": "0", "SQ_NS_BUDGET": "1000", "SQ_NS_ITEM_BUDGET": "300"},
-                    {"SQ_NS_DIRECT": "1000", "SQ_NS_ITEM_BUDGET": "200", "SQ_NS_EAGER": "1", "SQ_NS_ITEM_BUDGET_WIDE": "50"},
-                    {"SQ_NS_DIRECT": "1000", "SQ_NS_ITEM_BUDGET": "2000", "SQ_NS_EAGER": "0", "SQ_NS_FLIGHTS": "2", "SQ_NS_BIG_HINT": "0"}]:
+                    {"SQ_NS_DIRECT": "1000", "SQ_NS_ITEM_BUDGET": "200", "SQ_NS_ITEM_BUDGET_WIDE": "50"},
+                    {"SQ_NS_DIRECT": "1000", "SQ_NS_ITEM_BUDGET": "2000", "SQ_NS_FLIGHTS": "2"}]:
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             got = dev.negascout_root(boards, depth, sc)
