@@ -318,9 +318,14 @@ inline void build_ns_cell_tables(const NsTables& t, NsCellTables& c) {
     }
 }
 
+// No popcounts below: POPC issues at a quarter of the ALU rate on its own pipe (8 cycles per warp instruction), and one pass
+// over a node's children used to need ~60 of them.  Every count that matters here is "all of these two / three cells", which
+// is a mask compare.
 __device__ __forceinline__ int ns_deadly_term(uint32_t in, uint32_t out, uint32_t x, uint32_t o) {
-    const int inner = __popc(in & x) - __popc(in & o), outer = __popc(out & x) - __popc(out & o);
-    return (outer == 0 && (inner == 2 || inner == -2)) ? -(inner / 2) * 5 : 0;
+    // inner cells both one player's, outer cells balanced (both empty or one each): -5 for X's pair, +5 for O's
+    const bool ix = in != 0u && (in & x) == in, io = in != 0u && (in & o) == in;
+    const bool balanced = ((out & x) == 0u) == ((out & o) == 0u);
+    return balanced ? (ix ? -5 : io ? 5 : 0) : 0;
 }
 
 struct NsChild { bool term; int cur; int sum; };   // cur: the child's value as the parent's loop sees it (-ret)
@@ -329,18 +334,22 @@ struct NsChild { bool term; int cur; int sum; };   // cur: the child's value as 
 __device__ __forceinline__ NsChild ns_child(const NsCellTables& C, uint32_t x, uint32_t o, int pl, int cell, int vsum,
                                             int bias_child, int cply) {
     const uint32_t own = pl > 0 ? x : o, opp = pl > 0 ? o : x;
+    const uint32_t bit = 1u << cell;
     bool four = false, three = false;
     int gain = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         const uint32_t q = C.quads[k][cell];
-        const int oc = __popc(q & own), pc = __popc(q & opp);
-        four |= (oc == 3) & (pc == 0);
-        if ((oc == 2 && pc == 0) || (oc == 0 && pc == 3)) gain += C.quad_w[k][cell];   // a new own three, or an opposing one blocked
+        const uint32_t m = q & ~own;               // cells of the quad the mover does not hold: the new one among them
+        four |= m == bit;                          // ... and nothing else: four in a row
+        const uint32_t r = m & ~bit;               // the others
+        // a new own three: exactly one other cell missing and it is empty; or an opposing three blocked: the other three are all opposing
+        const bool own_three = r != 0u && (r & ((r - 1u) | opp)) == 0u;
+        const bool blocked = (q & ~opp) == bit;
+        gain += (own_three || blocked) ? C.quad_w[k][cell] : 0;
     }
 #pragma unroll
-    for (int k = 0; k < 12; k++) three |= __popc(C.trips[k][cell] & own) == 2;
-    const uint32_t bit = 1u << cell;
+    for (int k = 0; k < 12; k++) three |= (C.trips[k][cell] & ~own) == bit;
     const uint32_t x2 = x | (pl > 0 ? bit : 0u), o2 = o | (pl > 0 ? 0u : bit);
     int dd = 0;
 #pragma unroll
