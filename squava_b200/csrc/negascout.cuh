@@ -468,7 +468,10 @@ negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ 
         const unsigned item_index = p;
         NsItem item;
         int base = 0;                                  // ply of the loop this warp starts in
-        if (ITEMS) { item = items[p]; p = (unsigned)item.pos; base = item.n_path - 1; } else p = idx[p];
+        if (ITEMS) {
+            item = items[p]; p = (unsigned)item.pos; base = item.n_path - 1;
+            SQ_CHECK(item.n_path >= 1 && item.n_path <= 7 && item.n_path <= max_depth && item.a < item.b, 20, item.n_path, item_index);
+        } else p = idx[p];
         uint32_t x = pos[p].x & kFull25, o = pos[p].o & kFull25;
         unsigned long long nodes = 0;
         ns_reorder(x, o, lane, s_order[warp]);
@@ -514,6 +517,7 @@ negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ 
             // the loop at `base` is about to call negaScout on its child path[base] with the window (a, b)
             const int cell = item.path[base], pl = (base & 1) ? -1 : 1;
             at = __ffs(__ballot_sync(full, lane < n_moves && s_order[warp][pl > 0 ? 1 : 0][lane] == cell)) - 1;
+            SQ_CHECK(at >= 0 && !(((x | o) >> cell) & 1u), 21, cell, x | o);        // the path's last cell is one of the node's moves
             alpha = -item.b; n = -item.a; phase = 1; k = at + 1; enter = true;
             if (pl > 0) x |= 1u << cell; else o |= 1u << cell;
             bias += pl * __shfl_sync(full, my_score, cell);
@@ -562,6 +566,7 @@ negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ 
                                 r.alpha = L == ply ? alpha : frames[L].alpha;
                                 r.score = L == ply ? score : frames[L].score;
                                 r.nodes_done = s_mark[warp][L] - s_start[warp][L];
+                                SQ_CHECK(s_mark[warp][L] >= s_start[warp][L] && r.n_chain <= 5 && L <= kNsMaxDepth, 22, s_mark[warp][L], s_start[warp][L]);
                                 break;
                             }
                             if (r.n_chain < 6) r.cells[r.n_chain] = s_order[warp][(L & 1) ? 0 : 1][l_at];
@@ -602,6 +607,7 @@ negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ 
                     f.alpha = alpha; f.beta = beta; f.score = score; f.n = n; f.k = k; f.at_phase = at | (phase << 5);
                     f.active = active; f.term = term;
                     if (lane == 0) frames[ply] = f;
+                    SQ_CHECK(cply <= kNsMaxDepth + 1, 23, cply, max_depth);                         // frames and child arrays hold kNsMaxDepth + 2 plies
                     const NsChild ch = children(cply, s_sum[warp][ply][at]);
                     s_cur[warp][cply][lane] = ch.cur; s_sum[warp][cply][lane] = ch.sum;
                     __syncwarp();

@@ -1,5 +1,5 @@
 """The CHECKED build of the library (-DSQ_CHECKED=1: the kernels' own bounds checks on node indices, queue slots,
-search-stack frames and Fisher-Yates slots) on a small mixed workload and on BASELINE-shaped batches: no check may fire.
+search-stack frames, Fisher-Yates slots and NegaScout call items) on a small mixed workload and on BASELINE-shaped batches: no check may fire.
 This is what stands in for compute-sanitizer, which is closed on the development pool (profiles/r02_sanitizer.md)."""
 import os
 import subprocess
@@ -38,6 +38,11 @@ for env in ({}, {"SQ_AB_BUDGET": "16"}, {"SQ_AB_QUEUE": "1", "SQ_AB_MIN_BUDGET":
     for k in env:
         os.environ.pop(k)
 sq.negascout_root(ab[:8], 6, sc)
+for env in ({"SQ_NS_SPLIT": "0"}, {"SQ_NS_DIRECT": "0", "SQ_NS_BUDGET": "500", "SQ_NS_ITEM_BUDGET": "100"}, {"SQ_NS_DIRECT": "1000", "SQ_NS_ITEM_BUDGET": "60", "SQ_NS_SPLIT_PLY": "1"}):
+    os.environ.update(env)
+    sq.negascout_root(ab, 7, sc)
+    for k in env:
+        os.environ.pop(k)
 print("CHECKS", sq.check_failures())
 sq.shutdown()
 """
