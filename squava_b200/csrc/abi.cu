@@ -40,11 +40,13 @@ struct NsFlight {
     cudaEvent_t done = nullptr;
     sq::NsItem* items = nullptr;
     sq::NsItemOut* out = nullptr;
-    size_t cap = 0, n = 0;
+    int32_t* landed = nullptr;                           // item indices in the order they finish (-1: not yet), mapped too
+    unsigned int* n_landed = nullptr;                    // device memory: next slot of `landed`
+    size_t cap = 0, n = 0, seen = 0;
     bool busy = false;
     std::vector<std::pair<int32_t, uint32_t>> sent;      // (call, generation) of every item
 };
-constexpr int kNsFlights = 16;
+constexpr int kNsFlights = 32;
 
 struct Ctx {
     std::mutex mu;
@@ -235,6 +237,8 @@ void destroy_device(Device& d) {
             if (f.done) cudaEventDestroy(f.done);
             if (f.items) cudaFreeHost(f.items);
             if (f.out) cudaFreeHost(f.out);
+            if (f.landed) cudaFreeHost(f.landed);
+            if (f.n_landed) cudaFree(f.n_landed);
             f = NsFlight();
         }
         if (c.ev0) cudaEventDestroy(c.ev0);
@@ -346,7 +350,7 @@ public:
         const char* e6 = getenv("SQ_NS_ITEM_BUDGET_WIDE");
         item_budget_wide_ = e6 ? (uint32_t)strtoul(e6, nullptr, 10) : item_budget_ / 4;
         const char* e4 = getenv("SQ_NS_FLIGHTS");
-        n_flights_ = e4 ? atoi(e4) : kNsFlights;
+        n_flights_ = e4 ? atoi(e4) : 16;
         if (n_flights_ < 1) n_flights_ = 1;
         if (n_flights_ > kNsFlights) n_flights_ = kNsFlights;
     }
@@ -370,74 +374,96 @@ public:
             ready_.push_back(ci);
         }
         pump();
-        // Items go out in FLIGHTS, several at a time, and come back whenever they are done: a long search holds up the
-        // loops that wait for it and nothing else.  Wide windows (the long searches) and null windows fly apart.
+        // Items go out in FLIGHTS -- concurrent launches on their own streams -- and every item lands by itself: the kernel
+        // appends its index to the flight's landing list in mapped memory when its result is written, and the host reads the
+        // lists while the kernels run.  A long search holds up the loops that wait for it and nothing else.  Wide windows
+        // (the long searches) and null windows fly apart.  New items are sent when nothing more is landing (or a few hundred
+        // have piled up): results that arrive together make ONE next flight.
         int busy = 0;
         std::vector<std::pair<int32_t, uint32_t>> later;
         const sq::NsOut none = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
         const int64_t cap = (int64_t)d_.sm_count * 6;
-        for (;;) {
-            for (int kind = 0; kind < 2 && !outbox_.empty(); kind++) {
-                size_t n = 0;
-                for (const auto& w : outbox_) n += wanted(w) && wide(w) == (kind == 0);
-                if (!n) continue;
-                NsFlight* f = nullptr;
-                for (int k = 0; k < n_flights_ && !f; k++) if (!c_.flight[k].busy) f = &c_.flight[k];
-                if (!f) break;                                     // all in the air: these wait for the next landing
-                int r;
-                if ((r = ready_flight(*f, n))) return r;
-                f->n = 0; f->sent.clear();
-                for (const auto& w : outbox_) {
-                    if (!wanted(w) || wide(w) != (kind == 0)) continue;
-                    const NsCall& k = calls_[(size_t)w.first];
-                    sq::NsItem& it = f->items[f->n++];
-                    it.pos = list_[k.pos]; it.a = k.a; it.b = k.b; it.n_path = k.ply;
-                    it.budget = k.ply > deepest_loop_ ? 0u : kind == 0 ? item_budget_wide_ : item_budget_;
-                    it.deepest = (uint8_t)deepest_loop_;
-                    memcpy(it.path, k.path, 7);
-                    f->sent.push_back(w);
-                    calls_[(size_t)w.first].state = 4;             // in the air
+        auto last_progress = std::chrono::steady_clock::now();
+        bool progressed = true;
+        for (unsigned long long spin = 0;; spin++) {
+            if (!outbox_.empty() && (!progressed || busy == 0 || outbox_.size() >= 256)) {
+                for (int kind = 0; kind < 2; kind++) {
+                    size_t n = 0;
+                    for (const auto& w : outbox_) n += wanted(w) && wide(w) == (kind == 0);
+                    if (!n) continue;
+                    NsFlight* f = nullptr;
+                    for (int k = 0; k < n_flights_ && !f; k++) if (!c_.flight[k].busy) f = &c_.flight[k];
+                    if (!f) break;                                 // all in the air: these wait for a flight to empty
+                    int r;
+                    if ((r = ready_flight(*f, n))) return r;
+                    f->n = 0; f->seen = 0; f->sent.clear();
+                    for (const auto& w : outbox_) {
+                        if (!wanted(w) || wide(w) != (kind == 0)) continue;
+                        const NsCall& k = calls_[(size_t)w.first];
+                        sq::NsItem& it = f->items[f->n];
+                        it.pos = list_[k.pos]; it.a = k.a; it.b = k.b; it.n_path = k.ply;
+                        it.budget = k.ply > deepest_loop_ ? 0u : kind == 0 ? item_budget_wide_ : item_budget_;
+                        it.deepest = (uint8_t)deepest_loop_;
+                        memcpy(it.path, k.path, 7);
+                        f->landed[f->n] = -1;
+                        f->n++;
+                        f->sent.push_back(w);
+                        calls_[(size_t)w.first].state = 4;         // in the air
+                    }
+                    const int64_t want = ((int64_t)f->n + sq::kNsWarps - 1) / sq::kNsWarps;
+                    CK(cudaMemsetAsync(f->n_landed, 0, sizeof(unsigned int), f->stream));
+                    sq::negascout_fast_kernel<true><<<(int)(want < cap ? want : cap), sq::kNsWarps * 32, 0, f->stream>>>(
+                        d_pos_, nullptr, (int)f->n, max_depth_, sc_, none, nullptr, f->items, f->out, 0ull, f->landed, f->n_landed);
+                    g_launches += 1;
+                    CK(cudaGetLastError());
+                    CK(cudaEventRecord(f->done, f->stream));
+                    f->busy = true; busy++;
+                    rounds_++; items_ += f->n;
                 }
-                const int64_t want = ((int64_t)f->n + sq::kNsWarps - 1) / sq::kNsWarps;
-                sq::negascout_fast_kernel<true><<<(int)(want < cap ? want : cap), sq::kNsWarps * 32, 0, f->stream>>>(
-                    d_pos_, nullptr, (int)f->n, max_depth_, sc_, none, nullptr, f->items, f->out, 0ull);
-                g_launches += 1;
-                CK(cudaGetLastError());
-                CK(cudaEventRecord(f->done, f->stream));
-                f->busy = true; busy++;
-                rounds_++; items_ += f->n;
+                // what did not get a flight stays in the outbox
+                later.clear();
+                for (const auto& w : outbox_) if (wanted(w)) later.push_back(w);
+                outbox_.swap(later);
             }
-            // what did not get a flight stays in the outbox
-            later.clear();
-            for (const auto& w : outbox_) if (wanted(w)) later.push_back(w);
-            outbox_.swap(later);
             if (busy == 0) {
                 if (outbox_.empty()) break;
                 snprintf(t_err, sizeof t_err, "NegaScout split driver: items left and nothing in flight"); return SQ_ERR_CUDA;
             }
-            // wait for a landing; take every flight that is back
-            for (bool any = false; !any;) {
-                for (int k = 0; k < n_flights_; k++) {
-                    NsFlight& f = c_.flight[k];
-                    if (!f.busy) continue;
+            // take what has landed
+            progressed = false;
+            for (int k = 0; k < n_flights_; k++) {
+                NsFlight& f = c_.flight[k];
+                if (!f.busy) continue;
+                bool finished = false;
+                if ((spin & 1023u) == 1023u) {                      // a kernel that died would never fill its list
                     const cudaError_t e = cudaEventQuery(f.done);
-                    if (e == cudaErrorNotReady) continue;
-                    if (e != cudaSuccess) return fail_cuda(e, "cudaEventQuery(flight)");
-                    f.busy = false; busy--; any = true;
-                    for (size_t t = 0; t < f.n; t++) {
-                        NsCall& k2 = calls_[(size_t)f.sent[t].first];
-                        if (k2.gen != f.sent[t].second || k2.state != 4) { dropped_++; continue; }   // dropped while in flight
-                        if (f.out[t].nodes == sq::kNsAborted) {                            // too long for one warp: its loop runs here
-                            resume(f.sent[t].first, f.out[t]);
+                    if (e == cudaSuccess) finished = true;
+                    else if (e != cudaErrorNotReady) return fail_cuda(e, "cudaEventQuery(flight)");
+                }
+                for (int pass = 0; pass < (finished ? 2 : 1); pass++)
+                    while (f.seen < f.n) {
+                        const int t = *((volatile int32_t*)f.landed + f.seen);
+                        if (t < 0) break;
+                        std::atomic_thread_fence(std::memory_order_acquire);
+                        f.seen++;
+                        progressed = true;
+                        NsCall& k2 = calls_[(size_t)f.sent[(size_t)t].first];
+                        if (k2.gen != f.sent[(size_t)t].second || k2.state != 4) { dropped_++; continue; }   // dropped while in flight
+                        if (f.out[t].nodes == sq::kNsAborted) {                              // too long for one warp: its loop runs here
+                            resume(f.sent[(size_t)t].first, f.out[t]);
                             expanded_++;
                             continue;
                         }
                         k2.state = 3; k2.ret = f.out[t].ret; k2.nodes = f.out[t].nodes;
                         ready_.push_back(k2.parent);
                     }
-                }
+                if (f.seen == f.n) { f.busy = false; busy--; }
+                else if (finished) { snprintf(t_err, sizeof t_err, "NegaScout split driver: a flight ended with %zu of %zu items landed", f.seen, f.n); return SQ_ERR_CUDA; }
             }
-            pump();
+            if (progressed) { pump(); last_progress = std::chrono::steady_clock::now(); }
+            else if ((spin & 0xfffffu) == 0xfffffu && std::chrono::duration<double>(std::chrono::steady_clock::now() - last_progress).count() > 60.) {
+                snprintf(t_err, sizeof t_err, "NegaScout split driver: nothing landed for 60 s"); return SQ_ERR_CUDA;
+            }
         }
         for (int64_t q = 0; q < n_list_; q++) {
             const NsCall& c = calls_[(size_t)root_call_[(size_t)q]];
@@ -463,14 +489,18 @@ private:
         CK(cudaSetDevice(d_.id));
         if (!f.stream) CK(cudaStreamCreateWithFlags(&f.stream, cudaStreamNonBlocking));
         if (!f.done) CK(cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+        if (!f.n_landed) CK(cudaMalloc((void**)&f.n_landed, sizeof(unsigned int)));
         if (f.cap < n) {
+            CK(cudaStreamSynchronize(f.stream));                 // the last kernel that used the old buffers has left
             if (f.items) CK(cudaFreeHost(f.items));
             if (f.out) CK(cudaFreeHost(f.out));
-            f.items = nullptr; f.out = nullptr; f.cap = 0;
-            size_t cap = 4096;
+            if (f.landed) CK(cudaFreeHost(f.landed));
+            f.items = nullptr; f.out = nullptr; f.landed = nullptr; f.cap = 0;
+            size_t cap = 1024;
             while (cap < n) cap *= 2;
             CK(cudaHostAlloc((void**)&f.items, cap * sizeof(sq::NsItem), cudaHostAllocMapped));
             CK(cudaHostAlloc((void**)&f.out, cap * sizeof(sq::NsItemOut), cudaHostAllocMapped));
+            CK(cudaHostAlloc((void**)&f.landed, cap * sizeof(int32_t), cudaHostAllocMapped));
             f.cap = cap;
         }
         return SQ_OK;
@@ -1028,7 +1058,7 @@ int sq_negascout_root(const sq_board* positions, int64_t n, int max_depth, const
         if (n_fast && !direct) {
             sq::negascout_fast_kernel<false><<<grid(n_fast), sq::kNsWarps * 32, 0, c->stream>>>(
                 (const sq_board*)c->buf[0], (const int*)c->buf[5], (int)n_fast, max_depth, sc, out, (unsigned int*)blk, nullptr, nullptr,
-                budget);
+                budget, nullptr, nullptr);
             g_launches += 1;
             CK(cudaGetLastError());
         }

@@ -432,11 +432,21 @@ inline bool ns_move_ends_game(const NsTables& t, uint32_t own, int cell) {
     return false;
 }
 
+// An item's result is in host memory (mapped); now its index goes into the flight's landing list, which the host reads
+// WHILE the kernel runs: results are consumed one by one, the slow items of a flight hold up nobody else.  The fence orders
+// the result before the index for an observer on the host; the list slot comes from a counter in device memory.
+__device__ __forceinline__ void ns_land(int* landed, unsigned int* n_landed, unsigned item_index) {
+    __threadfence_system();
+    const unsigned slot = atomicAdd(n_landed, 1u);
+    *((volatile int*)landed + slot) = (int)item_index;
+    __threadfence_system();
+}
+
 template <bool ITEMS>
 __global__ void __launch_bounds__(kNsWarps * 32)
 negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ idx, int n_pos, int max_depth, NsScores sc,
                       NsOut out, unsigned int* __restrict__ queue, const NsItem* __restrict__ items, NsItemOut* __restrict__ item_out,
-                      unsigned long long budget) {
+                      unsigned long long budget, int* landed, unsigned int* n_landed) {
     __shared__ NsCellTables C;
     __shared__ NsFastFrame s_frames[kNsWarps][kNsMaxDepth + 2];
     __shared__ int s_cur[kNsWarps][kNsMaxDepth + 2][32], s_sum[kNsWarps][kNsMaxDepth + 2][32];
@@ -470,7 +480,8 @@ negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ 
         int base = 0;                                  // ply of the loop this warp starts in
         if (ITEMS) {
             item = items[p]; p = (unsigned)item.pos; base = item.n_path - 1;
-            SQ_CHECK(item.n_path >= 1 && item.n_path <= 7 && item.n_path <= max_depth && item.a < item.b, 20, item.n_path, item_index);
+            // (a >= b happens: the reference re-searches (-beta, -cur) even when cur >= beta, negascout.go:251)
+            SQ_CHECK(item.n_path >= 1 && item.n_path <= 7 && item.n_path <= max_depth, 20, item.n_path, item_index);
         } else p = idx[p];
         uint32_t x = pos[p].x & kFull25, o = pos[p].o & kFull25;
         unsigned long long nodes = 0;
@@ -572,7 +583,7 @@ negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ 
                             if (r.n_chain < 6) r.cells[r.n_chain] = s_order[warp][(L & 1) ? 0 : 1][l_at];
                             r.n_chain++;
                         }
-                        if (lane == 0) item_out[item_index] = r;
+                        if (lane == 0) { item_out[item_index] = r; ns_land(landed, n_landed, item_index); }
                     }
                     break;
                 }
@@ -619,7 +630,7 @@ negascout_fast_kernel(const sq_board* __restrict__ pos, const int* __restrict__ 
             }
             // `ret` came back to the running loop (:243-262)
             if (ITEMS && ply == base) {                  // ... which, for an item, is the host's
-                if (lane == 0) { item_out[item_index].ret = ret; item_out[item_index].nodes = nodes; }
+                if (lane == 0) { item_out[item_index].ret = ret; item_out[item_index].nodes = nodes; ns_land(landed, n_landed, item_index); }
                 break;
             }
             returned = false;
