@@ -343,7 +343,7 @@ public:
         const int most = max_depth - 3 < 6 ? max_depth - 3 : 6;
         split_wide_ = wide < 1 ? 1 : wide; if (split_wide_ > most) split_wide_ = most; if (split_wide_ < 1) split_wide_ = 1;
         split_null_ = null_w < 1 ? 1 : null_w; if (split_null_ > split_wide_) split_null_ = split_wide_;
-        // an item that turns out long gives up and becomes a loop here, its children items: no round waits for one search
+        // an item that turns out long gives up and becomes a loop here, its children items
         const char* e3 = getenv("SQ_NS_ITEM_BUDGET");
         item_budget_ = e3 ? (uint32_t)strtoul(e3, nullptr, 10) : 8192u;
         deepest_loop_ = most < 1 ? 0 : most;
