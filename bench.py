@@ -279,32 +279,38 @@ def secondary_c4(sq, rank, world, dev, dist, torch, peak_ops):
     oracle's depth-10 vectors (tests/golden/c4_opening3_depth10.json)."""
     pairs, st = opening3_subtrees(sq)
     sq.alphabeta_subtrees(st[:4], 3, 5, SCORES_OPENING)                          # warm-up
-    t0 = time.perf_counter()
-    if world > 1:
-        _, pilot = sq.alphabeta_subtrees(st, 3, 7, SCORES_OPENING)
-        # evaluator counts depend on how the GPU happened to schedule the search: ONE rank's counts are the weights for
-        # everybody (a broadcast of 85 integers), so that all ranks derive the same partition
-        weights = torch.from_numpy(pilot.astype(np.int64)).to(dev)
-        dist.broadcast(weights, src=0)
-        mine = lpt_assign([float(v) for v in weights.cpu().numpy()], world)[rank]
-    else:
-        mine = list(range(len(pairs)))                                           # one rank: nothing to partition, no pilot search
-    vals = torch.zeros(len(pairs), dtype=torch.int64, device=dev)
-    nodes = torch.zeros(len(pairs), dtype=torch.int64, device=dev)
-    if mine:
-        v, n = sq.alphabeta_subtrees(st[mine], 3, 10, SCORES_OPENING)
-        vals[mine] = torch.from_numpy(v.astype(np.int64)).to(dev)
-        nodes[mine] = torch.from_numpy(n.astype(np.int64)).to(dev)
-    if world > 1:
-        dist.all_reduce(vals); dist.all_reduce(nodes)
-    torch.cuda.synchronize()
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    runs = []
+    for rep in range(2):                                                         # the first run also grows the node pool; both are reported
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        if world > 1:
+            _, pilot = sq.alphabeta_subtrees(st, 3, 7, SCORES_OPENING)
+            # evaluator counts depend on how the GPU happened to schedule the search: ONE rank's counts are the weights for
+            # everybody (a broadcast of 85 integers), so that all ranks derive the same partition
+            weights = torch.from_numpy(pilot.astype(np.int64)).to(dev)
+            dist.broadcast(weights, src=0)
+            mine = lpt_assign([float(v) for v in weights.cpu().numpy()], world)[rank]
+        else:
+            mine = list(range(len(pairs)))                                           # one rank: nothing to partition, no pilot search
+        vals = torch.zeros(len(pairs), dtype=torch.int64, device=dev)
+        nodes = torch.zeros(len(pairs), dtype=torch.int64, device=dev)
+        if mine:
+            v, n = sq.alphabeta_subtrees(st[mine], 3, 10, SCORES_OPENING)
+            vals[mine] = torch.from_numpy(v.astype(np.int64)).to(dev)
+            nodes[mine] = torch.from_numpy(n.astype(np.int64)).to(dev)
+        if world > 1:
+            dist.all_reduce(vals); dist.all_reduce(nodes)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        runs.append(float(t.item()))
+    t = torch.tensor([min(runs)], dtype=torch.float64, device=dev)
     secs = float(t.item())
     got = vals.cpu().numpy().tolist()
     rec = {"workload": "configs[4] alpha-beta: opening3's 85 subtrees, AB-3 depth 10, sharded over %d rank(s) by pilot-search size (pilot inside the timed region when there is more than one rank), NCCL merge" % world,
-           "seconds": secs, "gpu_evaluator_calls": int(nodes.sum().item()), "subtrees_on_rank0": len(mine) if rank == 0 else None}
+           "seconds": secs, "seconds_runs": runs, "gpu_evaluator_calls": int(nodes.sum().item()), "subtrees_on_rank0": len(mine) if rank == 0 else None}
     gp = os.path.join(ROOT, "tests", "golden", "c4_opening3_depth10.json")
     if os.path.exists(gp):
         g = json.load(open(gp))
