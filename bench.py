@@ -419,6 +419,21 @@ def secondary_c0_c2(sq, iters_c2):
                      "seconds": dt, "iterations_per_s": iters_c2 / dt, "host_threads": host_threads(),
                      "select_seconds": secs[0], "gpu_seconds": secs[1], "update_seconds": secs[2], "tree_node_slots": int(nodes.value),
                      "best_move": best.value}
+    # configs[2] with the tree in HBM (sq_mcts_decide): the same decision, select / playout / update all on the device.
+    # 1e8 first; the full 1e9 of BASELINE.json when that took a few seconds.  Checked inside the run: the books.
+    for iters in (iters_c2, 10 * iters_c2):
+        t0 = time.perf_counter()
+        r = sq.mcts_decide(0, 0, 1, iters, uctk=1.0, ucb_factor2=False, batch=65536, playouts_per_leaf=1, seed=iters)
+        dt = time.perf_counter() - t0
+        assert r["iterations"] == iters and r["root_visits"] == iters and iters - 64 <= r["visits"].sum() <= iters
+        assert (r["wins"] <= r["visits"]).all()
+        out["c2_gpu_tree_%.0e" % iters] = {
+            "workload": "configs[2] at %.0e iterations: one tree in HBM (sq_mcts_decide), one playout per leaf, batches of 65536 walks" % iters,
+            "seconds": dt, "device_seconds": r["device_ms"] * 1e-3, "iterations_per_s": iters / dt, "batches": int(r["batches"]),
+            "tree_node_slots": int(r["nodes"]), "arena_slots": int(r["arena_slots"]), "arena_full": r["arena_full"],
+            "best_move": r["best_move"], "root_children_visits_max_share": float(r["visits"].max() / r["visits"].sum())}
+        if dt > 12.0:
+            break
     return out
 
 

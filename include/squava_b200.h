@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SQ_ABI_VERSION 2
+#define SQ_ABI_VERSION 3
 
 typedef enum sq_status {
     SQ_OK = 0,
@@ -81,6 +81,7 @@ int sq_last_error_copy(char *buf, int len);
 int sq_abi_version(void);
 int sq_device_count(void);          /* devices this library was initialised on */
 int sq_sm_count(int slot);          /* multiprocessors of device slot (0 <= slot < sq_device_count()) */
+int sq_device_id(int slot);         /* CUDA device ordinal of device slot, or a negative status             */
 
 /* ---- terminal-position test ------------------------------------------- */
 /* Replaces (*MCTS).FindWinner src/mcts/mcts.go:92-121 (winner_mcts_order) and
@@ -177,6 +178,31 @@ typedef struct sq_subtree {
 } sq_subtree;
 int sq_alphabeta_subtrees(const sq_subtree *subtrees, int64_t n, int dialect, int max_depth,
                           const int8_t scores[25], int32_t *value, uint64_t *nodes);
+
+/* ---- one UCT decision, tree in HBM ---------------------------------------
+ * Replaces UCT(rootstate, itermax, UCTK) of src/mcts/mcts.go:140-200 as squavam.go:60-78 calls it, for throughput
+ * runs (BASELINE configs[2]: 10^9 one-playout iterations through ONE tree).  The tree lives in device memory of
+ * device slot `slot`; an iteration batch is three launches on one stream -- select (`walkers` threads, each taking
+ * its share of the batch's walks one after the other: visits are added on the way down, so later walks see earlier
+ * ones), the playout kernel on the leaves (random stream ids stream_base + batch number), update -- and only the
+ * root's children come back.  Select is UCB1 = w/v + uctk*sqrt(f*ln(N)/v), f = 2 if ucb_factor2 else 1, first
+ * maximum in cell order; expansion takes a random untried move (mcts.go:166-171).  player_just_moved: +1 X, -1 O
+ * (GameState.playerJustMoved).  max_nodes 0: the arena is sized from the iteration count and the free memory.
+ * The caller picks the move: argmax of UCB1 over the children (mcts.go:196-198).                               */
+typedef struct {
+    int32_t n_children;
+    int32_t child_move[25];          /* cell of every root child that was visited, ascending           */
+    double child_visits[25], child_wins[25];
+    double root_visits;
+    int64_t iterations, batches;
+    uint64_t nodes, arena_slots;     /* tree slots handed out / reserved                               */
+    int32_t arena_full;              /* 1: the arena ran out and the search went on without growing    */
+    double device_ms;                /* first select to last update, CUDA events                       */
+} sq_mcts_result;
+int sq_mcts_decide(int slot, const sq_board *root, int player_just_moved, int64_t iterations, double uctk,
+                   int ucb_factor2, int64_t batch, int playouts_per_leaf, int walkers, uint64_t max_nodes,
+                   uint64_t stream_base, uint64_t seed, sq_mcts_result *out);
+const char *sq_mcts_last_error(void);   /* message of the last failed sq_mcts_decide on this thread    */
 
 /* ---- device-resident forms ---------------------------------------------
  * Same semantics, but every data pointer is DEVICE memory on device slot

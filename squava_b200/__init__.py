@@ -39,7 +39,15 @@ EXPORTS = [
     "sq_sm_count", "sq_classify", "sq_playouts", "sq_alphabeta_root", "sq_alphabeta_subtrees", "sq_negascout_root",
     "sq_classify_dev", "sq_playouts_dev", "sq_int32_peak", "sq_launch_count",
     "sq_last_playout_kernel_ms", "sq_debug_philox", "sq_playouts_packed", "sq_last_error_copy", "sq_playouts_on", "sq_playouts_packed_on", "sq_abi_checked", "sq_debug_check_failures",
+    "sq_device_id", "sq_mcts_decide", "sq_mcts_last_error",
 ]
+
+
+class MctsResult(C.Structure):
+    """sq_mcts_result, include/squava_b200.h"""
+    _fields_ = [("n_children", C.c_int32), ("child_move", C.c_int32 * 25), ("child_visits", C.c_double * 25),
+                ("child_wins", C.c_double * 25), ("root_visits", C.c_double), ("iterations", C.c_int64), ("batches", C.c_int64),
+                ("nodes", C.c_uint64), ("arena_slots", C.c_uint64), ("arena_full", C.c_int32), ("device_ms", C.c_double)]
 
 
 class SquavaError(RuntimeError):
@@ -88,6 +96,9 @@ def lib():
         L.sq_launch_count.restype = u64
         L.sq_last_playout_kernel_ms.argtypes = [i32, C.POINTER(C.c_float)]
         L.sq_debug_philox.argtypes = [vp, vp, vp]
+        L.sq_device_id.argtypes = [i32]
+        L.sq_mcts_decide.argtypes = [i32, vp, i32, i64, C.c_double, i32, i64, i32, i32, u64, u64, u64, C.POINTER(MctsResult)]
+        L.sq_mcts_last_error.restype = C.c_char_p
         _lib = L
     return _lib
 
@@ -221,6 +232,28 @@ def negascout_root(positions, max_depth, scores):
                                 r["visit_order"].ctypes.data, r["best_value"].ctypes.data, r["best_mask"].ctypes.data,
                                 r["first_best"].ctypes.data, r["nodes"].ctypes.data), "sq_negascout_root")
     return r
+
+
+def mcts_decide(x, o, player_just_moved, iterations, uctk=1.0, ucb_factor2=True, batch=65536, playouts_per_leaf=1, walkers=0,
+                max_nodes=0, stream_base=0, seed=1, slot=0):
+    """sq_mcts_decide: one UCT decision with the tree in HBM -> dict(moves, visits, wins, root_visits, best_move, ...).
+    best_move is argmax UCB1 over the root's children (mcts.go:196-198)."""
+    b = np.array([(x, o)], dtype=BOARD)
+    r = MctsResult()
+    st = lib().sq_mcts_decide(slot, b.ctypes.data, player_just_moved, iterations, uctk, 1 if ucb_factor2 else 0, batch, playouts_per_leaf,
+                              walkers, max_nodes, stream_base, seed, C.byref(r))
+    if st != 0:
+        raise RuntimeError("sq_mcts_decide: %d %s" % (st, lib().sq_mcts_last_error().decode()))
+    n = r.n_children
+    moves = [r.child_move[i] for i in range(n)]
+    visits = np.array([r.child_visits[i] for i in range(n)]); wins = np.array([r.child_wins[i] for i in range(n)])
+    best = None
+    if n:
+        lg = (2.0 if ucb_factor2 else 1.0) * np.log(max(r.root_visits, 1.0))
+        score = wins / (visits + 1e-6) + uctk * np.sqrt(lg / (visits + 1e-6))
+        best = moves[int(np.argmax(score))]
+    return dict(moves=moves, visits=visits, wins=wins, root_visits=r.root_visits, best_move=best, iterations=r.iterations,
+                batches=r.batches, nodes=r.nodes, arena_slots=r.arena_slots, arena_full=bool(r.arena_full), device_ms=r.device_ms)
 
 
 def alphabeta_subtrees(subtrees, dialect, max_depth, scores):

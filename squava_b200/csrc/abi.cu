@@ -733,6 +733,12 @@ int sq_sm_count(int slot) {
     if (check_slot(slot)) return 0;
     return g_dev[slot]->sm_count;
 }
+int sq_device_id(int slot) {
+    std::shared_lock<std::shared_mutex> sl(g_state);
+    const int rc = check_slot(slot);
+    if (rc) return rc;
+    return g_dev[slot]->id;
+}
 uint64_t sq_launch_count(void) { return g_launches.load(); }
 
 // ---- device-resident forms -------------------------------------------------

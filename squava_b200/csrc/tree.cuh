@@ -1,0 +1,239 @@
+// tree.cuh -- the MCTS tree of squavam's UCT (src/mcts/mcts.go:140-200) kept in HBM.
+//
+// configs[2] of BASELINE.json is 10^9 one-playout iterations through ONE tree.  On the host that is a chain of
+// dependent DRAM misses per walk (squava_b200/host/fast_tree.cpp: 6*10^6 walks/s on 16 cores); here the tree never
+// leaves the device: a batch is three launches on one stream -- select (thousands of walks at once, every level a
+// handful of L2/HBM reads), the playout kernel on the leaves the walks wrote, update -- and nothing crosses PCIe
+// until the decision is read back.  Semantics are the host arena tree's throughput mode (fast_tree.cpp):
+//   * a walk adds its visits on the way down (virtual loss, seen by every later step of every walk), its wins when the
+//     batch's playouts are back;
+//   * select: first maximum of UCB1 = w/v + UCTK*sqrt(f*ln(N)/v) over the children that are set up (mcts.go:218-238);
+//     expand: one random untried move, claimed by an atomic AND (mcts.go:166-171); a node waiting for its first rollout
+//     is a leaf for everybody who reaches it;
+//   * a child block (one slot per empty cell of the parent, the child's move is its slot's rank among the empty cells)
+//     is taken from a bump pointer by the first expansion of the parent; a block that lost the race is not used.
+// The functions below are __host__ __device__: tests/native/tree_check.cu runs the same code sequentially on the
+// host against a CPU rollout.
+#pragma once
+#include <cstdint>
+#include "../../include/squava_b200.h"
+
+#if defined(__CUDA_ARCH__)
+#define SQT_DEVICE 1
+#else
+#define SQT_DEVICE 0
+#endif
+
+namespace sqt {
+
+constexpr uint32_t kFull = 0x1ffffffu;
+constexpr uint32_t kPending = 1u << 31;        // in `untried`: the node waits for its first rollout
+constexpr int kPathLen = 27;                   // root + 25 moves + 1
+
+struct Tree {
+    uint32_t* visits;
+    uint32_t* wins;
+    uint32_t* first_child;                     // 0: no child block yet
+    uint32_t* untried;                         // mask of the moves not expanded yet | kPending
+    unsigned long long* next_free;             // bump pointer (slot 0 is never handed out: it means "none")
+    unsigned long long cap;
+    uint32_t* overflow;                        // set when the arena ran out: the search goes on without growing
+};
+
+struct Walks {                                 // what the select step leaves for the playout and update steps
+    sq_board* boards;
+    int8_t* to_move;
+    uint32_t* leaf;
+    uint8_t* fresh;                            // the leaf was made by this walk
+    uint8_t* depth;                            // nodes on the path
+    uint32_t* paths;                           // [walk][kPathLen]
+};
+
+// ---- memory operations: L2-coherent on the device, plain on the host (sequential emulation) ----
+__host__ __device__ inline uint32_t t_load(const uint32_t* p) {
+#if SQT_DEVICE
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+__host__ __device__ inline void t_store(uint32_t* p, uint32_t v) {
+#if SQT_DEVICE
+    __stcg(p, v);
+#else
+    *p = v;
+#endif
+}
+__host__ __device__ inline uint32_t t_add(uint32_t* p, uint32_t v) {
+#if SQT_DEVICE
+    return atomicAdd(p, v);
+#else
+    const uint32_t old = *p; *p = old + v; return old;
+#endif
+}
+__host__ __device__ inline uint32_t t_and(uint32_t* p, uint32_t v) {
+#if SQT_DEVICE
+    return atomicAnd(p, v);
+#else
+    const uint32_t old = *p; *p = old & v; return old;
+#endif
+}
+__host__ __device__ inline uint32_t t_or(uint32_t* p, uint32_t v) {
+#if SQT_DEVICE
+    return atomicOr(p, v);
+#else
+    const uint32_t old = *p; *p = old | v; return old;
+#endif
+}
+__host__ __device__ inline uint32_t t_cas(uint32_t* p, uint32_t expect, uint32_t v) {
+#if SQT_DEVICE
+    return atomicCAS(p, expect, v);
+#else
+    const uint32_t old = *p; if (old == expect) *p = v; return old;
+#endif
+}
+__host__ __device__ inline unsigned long long t_add64(unsigned long long* p, unsigned long long v) {
+#if SQT_DEVICE
+    return atomicAdd(p, v);
+#else
+    const unsigned long long old = *p; *p = old + v; return old;
+#endif
+}
+__host__ __device__ inline void t_fence() {
+#if SQT_DEVICE
+    __threadfence();
+#endif
+}
+__host__ __device__ inline int t_popc(uint32_t v) {
+#if SQT_DEVICE
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+__host__ __device__ inline int t_nth_set_bit(uint32_t m, int n) {
+    for (int i = 0; i < n; i++) m &= m - 1u;
+#if SQT_DEVICE
+    return __ffs(m) - 1;
+#else
+    return __builtin_ctz(m);
+#endif
+}
+__host__ __device__ inline uint64_t t_mix(uint64_t z) {           // splitmix64: which untried move a walk expands
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+// One walk from the root to a leaf (mcts.go:153-171).  pjm: the player who just moved at the root (+1 X, -1 O).
+// c2 = UCTK^2 * f (the exploration term is sqrt(c2 * ln N / v)).
+__host__ __device__ inline void tree_walk(const Tree& T, uint32_t root, uint32_t rx, uint32_t ro, int root_pjm, uint32_t P, float c2,
+                                          uint64_t key, long long k, const Walks& W, bool add_root_visit) {
+    uint32_t idx = root, x = rx, o = ro;
+    int pjm = root_pjm, depth = 0;
+    bool fresh = false;
+    uint32_t* path = W.paths + (size_t)k * kPathLen;
+    if (add_root_visit) t_add(&T.visits[root], P);
+    path[depth++] = root;
+    int waited = 0;
+    for (;;) {
+        const uint32_t u = t_load(&T.untried[idx]);
+        if (u & kPending) break;                                 // waits for its first rollout: a leaf
+        const uint32_t um = u & kFull;
+        const uint32_t emp = kFull & ~(x | o);
+        if (um) {                                                // expand
+            const int cnt = t_popc(um);
+            const int m = t_nth_set_bit(um, (int)(t_mix(key ^ ((uint64_t)k << 8) ^ (uint64_t)depth) % (uint64_t)cnt));
+            const uint32_t bit = 1u << m;
+            if (!(t_and(&T.untried[idx], ~bit) & bit)) continue; // another walk took it: look again (at most 25 times)
+            const int slots = t_popc(emp);
+            uint32_t fc = t_load(&T.first_child[idx]);
+            if (!fc) {
+                const unsigned long long base = t_add64(T.next_free, (unsigned long long)slots);
+                if (base + (unsigned long long)slots >= T.cap) {  // arena full: hand the move back, roll out from here
+                    t_store(T.overflow, 1u);
+                    t_or(&T.untried[idx], bit);
+                    break;
+                }
+                const uint32_t old = t_cas(&T.first_child[idx], 0u, (uint32_t)base);
+                fc = old ? old : (uint32_t)base;                 // lost the race: that block is simply not used
+            }
+            const uint32_t child = fc + (uint32_t)t_popc(emp & (bit - 1u));
+            pjm = -pjm;
+            if (pjm > 0) x |= bit; else o |= bit;
+            t_store(&T.untried[child], kPending);
+            t_fence();
+            t_store(&T.visits[child], P);                        // nobody looks at a child before its visits are non-zero
+            idx = child;
+            path[depth++] = child;
+            fresh = true;
+            break;
+        }
+        const uint32_t fc = t_load(&T.first_child[idx]);
+        if (!fc) break;                                          // a finished game: no moves
+        const int slots = t_popc(emp);
+        uint32_t seen = t_load(&T.visits[idx]);
+        if (seen < (uint32_t)slots * P + 1u) seen = (uint32_t)slots * P + 1u;    // every child was made by a walk through the node
+#if SQT_DEVICE
+        const float lg = c2 * __logf((float)seen);
+#else
+        const float lg = c2 * __builtin_logf((float)seen);
+#endif
+        int best = -1;
+        float best_score = -1.f;
+        for (int j = 0; j < slots; j++) {
+            const uint32_t v = t_load(&T.visits[fc + (uint32_t)j]);
+            if (!v) continue;                                    // claimed, still being set up
+            const float w = (float)t_load(&T.wins[fc + (uint32_t)j]);
+            const float inv = 1.f / (float)v;
+#if SQT_DEVICE
+            const float s = w * inv + sqrtf(lg * inv);
+#else
+            const float s = w * inv + __builtin_sqrtf(lg * inv);
+#endif
+            if (s > best_score) { best_score = s; best = j; }
+        }
+        if (best < 0) {                                          // every child is being set up by another walk right now
+            if (++waited < 64) {
+#if SQT_DEVICE
+                __nanosleep(100);
+#endif
+                continue;
+            }
+            break;                                               // roll out from here rather than wait
+        }
+        idx = fc + (uint32_t)best;
+        t_add(&T.visits[idx], P);
+        const uint32_t bit = 1u << t_nth_set_bit(emp, best);
+        pjm = -pjm;
+        if (pjm > 0) x |= bit; else o |= bit;
+        path[depth++] = idx;
+    }
+    W.boards[k].x = x; W.boards[k].o = o;
+    W.to_move[k] = (int8_t)-pjm;
+    W.leaf[k] = idx;
+    W.fresh[k] = fresh ? 1 : 0;
+    W.depth[k] = (uint8_t)depth;
+}
+
+// Update (mcts.go:190-192, 268-271) of one walk.  counts: {X wins, O wins, draws, plies} of the leaf's playouts.
+// The node at depth i of a path was moved INTO by the root's player-just-moved when i is even.  Returns what the root
+// gets (the caller adds it: one atomic per warp instead of one per walk).
+__host__ __device__ inline uint32_t tree_update(const Tree& T, int root_pjm, const unsigned long long* counts, long long k, const Walks& W) {
+    const uint32_t* path = W.paths + (size_t)k * kPathLen;
+    const int depth = W.depth[k];
+    const uint32_t xw = (uint32_t)counts[0], ow = (uint32_t)counts[1];
+    if (W.fresh[k]) {
+        const uint32_t emp = kFull & ~(W.boards[k].x | W.boards[k].o);
+        t_store(&T.untried[W.leaf[k]], counts[3] != 0 ? emp : 0u);          // no ply played: the game was over at the leaf
+    }
+    for (int i = 1; i < depth; i++) {
+        const bool x_moved_in = (i & 1) ? root_pjm < 0 : root_pjm > 0;
+        const uint32_t add = x_moved_in ? xw : ow;
+        if (add) t_add(&T.wins[path[i]], add);
+    }
+    return root_pjm > 0 ? xw : ow;
+}
+
+}  // namespace sqt

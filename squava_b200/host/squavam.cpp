@@ -3,6 +3,7 @@
 // The UCT loop's rollout block (squavam.go:128-147) runs on the GPU in leaf-parallel
 // batches; extra flags: -batch, -ppl, -gpus, -seed.
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 
 #include "squava_host.hpp"
@@ -32,7 +33,8 @@ static int readMove(const Board& bd) {             // squavam.go:345-372
 
 int main(int argc, char** argv) {
     int iterMax = 10000, batch = 256, ppl = 1, gpus = 0, seed = -1, threads = 0;
-    bool fast = false, stats = false, rootParallel = false;
+    bool fast = false, stats = false, rootParallel = false, gpuTree = false;
+    int walkers = 0;
     double uctk = 1.00;
     bool computerFirst = false;
     Flags fl;
@@ -45,6 +47,8 @@ int main(int argc, char** argv) {
     fl.Int("threads", &threads, "with -fast: host threads (default: all)");
     fl.Bool("stats", &stats, "with -fast: print iterations, nodes and the time spent selecting / on the GPU / updating");
     fl.Bool("root-parallel", &rootParallel, "with -fast -gpus N: N independent trees, one per GPU, root statistics merged once per decision (squavam2.go's N searchers without the shared tree)");
+    fl.Bool("gpu-tree", &gpuTree, "the whole tree in GPU memory (sq_mcts_decide): select, playouts and update are device kernels, nothing but the decision comes back; for 10^8..10^9 iterations; no tree reuse");
+    fl.Int("walkers", &walkers, "with -gpu-tree: walks of a batch in flight at once (default 8192)");
     fl.Int("gpus", &gpus, "number of GPUs (default 1)");
     fl.Int("seed", &seed, "seed for reproducible play (default: clock, as the reference)");
     fl.Parse(argc, argv);
@@ -61,6 +65,31 @@ int main(int argc, char** argv) {
         std::printf("%s\n", state.board.str().c_str());
         if (state.playerJustMoved == MAXIMIZER) {
             auto start = std::chrono::steady_clock::now();
+            if (gpuTree) {
+                sq_board rb{state.board.x, state.board.o};
+                sq_mcts_result r;
+                const int rc = sq_mcts_decide(0, &rb, state.playerJustMoved, iterMax, uctk, 0, batch < 1024 ? 65536 : batch, ppl, walkers, 0,
+                                              (uint64_t)host_rng()() << 20, (uint64_t)host_rng()(), &r);
+                if (rc != SQ_OK) { std::fprintf(stderr, "sq_mcts_decide: %s\n", sq_mcts_last_error()); std::exit(2); }
+                // the move returned is argmax UCB1 over the root's children (mcts.go:196-198)
+                const double lg = std::log(r.root_visits > 1. ? r.root_visits : 1.);
+                double bestscore = 1e-6;
+                m = -1;
+                for (int i = 0; i < r.n_children; i++) {
+                    const double sc = r.child_wins[i] / (r.child_visits[i] + 1e-6) + uctk * std::sqrt(lg / (r.child_visits[i] + 1e-6));
+                    if (sc > bestscore) { bestscore = sc; m = r.child_move[i]; }
+                }
+                if (m < 0) { std::fprintf(stderr, "Node has %d children\n", r.n_children); std::exit(2); }
+                double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+                std::printf("My move: %d %d %s\n", m / 5, m % 5, go_duration(el).c_str());
+                if (stats)
+                    std::printf("gpu tree: %lld iterations, %lld batches, %llu node slots of %llu%s; device %.3fs (%.3g iterations/s)\n",
+                                (long long)r.iterations, (long long)r.batches, (unsigned long long)r.nodes, (unsigned long long)r.arena_slots,
+                                r.arena_full ? " (FULL)" : "", r.device_ms * 1e-3, (double)r.iterations / (r.device_ms * 1e-3 + 1e-12));
+                state.DoMove(m);
+                movesNode.reset();
+                continue;
+            }
             if (fast) {
                 FastOptions fo; fo.batch = batch; fo.playouts_per_leaf = ppl; fo.ucb_factor2 = false; fo.threads = threads;
                 FastResult r;

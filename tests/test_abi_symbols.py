@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(sq):
     L = sq.lib()
     for name in declared_symbols():
         assert hasattr(L, name), name
-    assert L.sq_abi_version() == 2
+    assert L.sq_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_init(sq):

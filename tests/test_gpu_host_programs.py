@@ -296,3 +296,12 @@ def test_squavam_root_parallel_decision():
     s = re.search(r"fast tree: (\d+) iterations, (\d+) batches", out)
     assert m and s and int(s.group(1)) == 4000000
     assert len(re.findall(r"^searcher \d+: \d+ iterations", out, flags=re.M)) >= 1
+
+
+def test_squavam_gpu_tree_decision():
+    """squavam -gpu-tree: one decision with the whole tree in GPU memory (sq_mcts_decide)"""
+    rc, out, err = run("squavam", "-C", "-i", "3000000", "-u", "1.0", "-gpu-tree", "-stats", "-seed", "4")
+    assert rc == 0, err
+    assert re.search(r"My move: [0-4] [0-4] ", out)
+    s = re.search(r"gpu tree: (\d+) iterations, (\d+) batches, (\d+) node slots of (\d+);", out)
+    assert s and int(s.group(1)) == 3000000 and int(s.group(2)) == 46 and int(s.group(3)) > 3000000
