@@ -425,7 +425,7 @@ def secondary_c0_c2(sq, iters_c2):
         t0 = time.perf_counter()
         r = sq.mcts_decide(0, 0, 1, iters, uctk=1.0, ucb_factor2=False, batch=65536, playouts_per_leaf=1, seed=iters)
         dt = time.perf_counter() - t0
-        assert r["iterations"] == iters and r["root_visits"] == iters and iters - 64 <= r["visits"].sum() <= iters
+        assert r["iterations"] == iters and r["root_visits"] == iters and iters - 4096 <= r["visits"].sum() <= iters
         assert (r["wins"] <= r["visits"]).all()
         out["c2_gpu_tree_%.0e" % iters] = {
             "workload": "configs[2] at %.0e iterations: one tree in HBM (sq_mcts_decide), one playout per leaf, batches of 65536 walks" % iters,

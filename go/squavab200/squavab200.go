@@ -194,6 +194,43 @@ func NegaScoutRoot(positions []Board, maxDepth int, scores *[25]int8) []NegaScou
 	return out
 }
 
+// MctsResult is what UCT() leaves at the root (mcts.go:196-198): the visited children of the root and their counts.
+type MctsResult struct {
+	ChildMove                []int // cells, ascending
+	ChildVisits, ChildWins   []float64
+	RootVisits               float64
+	Iterations, Batches      int64
+	Nodes                    uint64
+	ArenaFull                bool
+	DeviceSeconds            float64
+}
+
+// MctsDecide replaces UCT(rootstate, itermax, UCTK) (mcts.go:140-200) for searches that keep no tree between moves:
+// the whole tree lives in GPU memory, select / playouts / update are device kernels (DESIGN 3.5).
+// playerJustMoved: +1 X, -1 O (GameState.playerJustMoved).  The caller picks argmax UCB1 as bestMove() does.
+func MctsDecide(slot int, root Board, playerJustMoved int, iterations int64, uctk float64, ucbFactor2 bool, batch int64,
+	playoutsPerLeaf int, streamBase, seed uint64) MctsResult {
+	var r C.sq_mcts_result
+	f2 := C.int(0)
+	if ucbFactor2 {
+		f2 = 1
+	}
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	if rc := C.sq_mcts_decide(C.int(slot), (*C.sq_board)(unsafe.Pointer(&root)), C.int(playerJustMoved), C.int64_t(iterations),
+		C.double(uctk), f2, C.int64_t(batch), C.int(playoutsPerLeaf), 0, -1, 0, C.uint64_t(streamBase), C.uint64_t(seed), &r); rc != C.SQ_OK {
+		panic(fmt.Sprintf("sq_mcts_decide: %s (%s)", C.GoString(C.sq_strerror(rc)), C.GoString(C.sq_mcts_last_error())))
+	}
+	out := MctsResult{RootVisits: float64(r.root_visits), Iterations: int64(r.iterations), Batches: int64(r.batches),
+		Nodes: uint64(r.nodes), ArenaFull: r.arena_full != 0, DeviceSeconds: float64(r.device_ms) * 1e-3}
+	for i := 0; i < int(r.n_children); i++ {
+		out.ChildMove = append(out.ChildMove, int(r.child_move[i]))
+		out.ChildVisits = append(out.ChildVisits, float64(r.child_visits[i]))
+		out.ChildWins = append(out.ChildWins, float64(r.child_wins[i]))
+	}
+	return out
+}
+
 // Subtree is one unit of squavathr's toDo channel / one top-level call of opening2/3.
 type Subtree struct {
 	B          Board

@@ -187,7 +187,10 @@ int sq_alphabeta_subtrees(const sq_subtree *subtrees, int64_t n, int dialect, in
  * ones), the playout kernel on the leaves (random stream ids stream_base + batch number), update -- and only the
  * root's children come back.  Select is UCB1 = w/v + uctk*sqrt(f*ln(N)/v), f = 2 if ucb_factor2 else 1, first
  * maximum in cell order; expansion takes a random untried move (mcts.go:166-171).  player_just_moved: +1 X, -1 O
- * (GameState.playerJustMoved).  max_nodes 0: the arena is sized from the iteration count and the free memory.
+ * (GameState.playerJustMoved).  sync_levels (-1: default 4): on that many levels below the root the walks of a batch
+ * move level by level, and the K walks that stand on one node share out its children as K sequential selections
+ * with virtual loss would (0: every walk on its own from the root -- thousands that arrive together then take the
+ * same child).  max_nodes 0: the arena is sized from the iteration count and the free memory.
  * The caller picks the move: argmax of UCB1 over the children (mcts.go:196-198).                               */
 typedef struct {
     int32_t n_children;
@@ -200,8 +203,8 @@ typedef struct {
     double device_ms;                /* first select to last update, CUDA events                       */
 } sq_mcts_result;
 int sq_mcts_decide(int slot, const sq_board *root, int player_just_moved, int64_t iterations, double uctk,
-                   int ucb_factor2, int64_t batch, int playouts_per_leaf, int walkers, uint64_t max_nodes,
-                   uint64_t stream_base, uint64_t seed, sq_mcts_result *out);
+                   int ucb_factor2, int64_t batch, int playouts_per_leaf, int walkers, int sync_levels,
+                   uint64_t max_nodes, uint64_t stream_base, uint64_t seed, sq_mcts_result *out);
 const char *sq_mcts_last_error(void);   /* message of the last failed sq_mcts_decide on this thread    */
 
 /* ---- device-resident forms ---------------------------------------------

@@ -97,7 +97,7 @@ def lib():
         L.sq_last_playout_kernel_ms.argtypes = [i32, C.POINTER(C.c_float)]
         L.sq_debug_philox.argtypes = [vp, vp, vp]
         L.sq_device_id.argtypes = [i32]
-        L.sq_mcts_decide.argtypes = [i32, vp, i32, i64, C.c_double, i32, i64, i32, i32, u64, u64, u64, C.POINTER(MctsResult)]
+        L.sq_mcts_decide.argtypes = [i32, vp, i32, i64, C.c_double, i32, i64, i32, i32, i32, u64, u64, u64, C.POINTER(MctsResult)]
         L.sq_mcts_last_error.restype = C.c_char_p
         _lib = L
     return _lib
@@ -235,13 +235,13 @@ def negascout_root(positions, max_depth, scores):
 
 
 def mcts_decide(x, o, player_just_moved, iterations, uctk=1.0, ucb_factor2=True, batch=65536, playouts_per_leaf=1, walkers=0,
-                max_nodes=0, stream_base=0, seed=1, slot=0):
+                sync_levels=-1, max_nodes=0, stream_base=0, seed=1, slot=0):
     """sq_mcts_decide: one UCT decision with the tree in HBM -> dict(moves, visits, wins, root_visits, best_move, ...).
     best_move is argmax UCB1 over the root's children (mcts.go:196-198)."""
     b = np.array([(x, o)], dtype=BOARD)
     r = MctsResult()
     st = lib().sq_mcts_decide(slot, b.ctypes.data, player_just_moved, iterations, uctk, 1 if ucb_factor2 else 0, batch, playouts_per_leaf,
-                              walkers, max_nodes, stream_base, seed, C.byref(r))
+                              walkers, sync_levels, max_nodes, stream_base, seed, C.byref(r))
     if st != 0:
         raise RuntimeError("sq_mcts_decide: %d %s" % (st, lib().sq_mcts_last_error().decode()))
     n = r.n_children

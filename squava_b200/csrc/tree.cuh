@@ -38,6 +38,7 @@ struct Tree {
     unsigned long long* next_free;             // bump pointer (slot 0 is never handed out: it means "none")
     unsigned long long cap;
     uint32_t* overflow;                        // set when the arena ran out: the search goes on without growing
+    uint32_t* arrivals;                        // per node: walks of the current batch that stand on it (synchronised levels only)
 };
 
 struct Walks {                                 // what the select step leaves for the playout and update steps
@@ -47,7 +48,14 @@ struct Walks {                                 // what the select step leaves fo
     uint8_t* fresh;                            // the leaf was made by this walk
     uint8_t* depth;                            // nodes on the path
     uint32_t* paths;                           // [walk][kPathLen]
+    // synchronised levels: the walk's place among the walks on its node, and what it decided to do next
+    uint32_t* rank;                            // kNoRank: holds no place
+    uint8_t* act;                              // kActNone / kActDescend / kActExpand / kActDone
+    uint8_t* arg;                              // child slot / cell
+    int8_t* pjm;                               // player who just moved at the walk's node
 };
+constexpr uint32_t kNoRank = 0xffffffffu;
+constexpr uint8_t kActNone = 0, kActDescend = 1, kActExpand = 2, kActDone = 3;
 
 // ---- memory operations: L2-coherent on the device, plain on the host (sequential emulation) ----
 __host__ __device__ inline uint32_t t_load(const uint32_t* p) {
@@ -126,18 +134,34 @@ __host__ __device__ inline uint64_t t_mix(uint64_t z) {           // splitmix64:
     return z ^ (z >> 31);
 }
 
-// One walk from the root to a leaf (mcts.go:153-171).  pjm: the player who just moved at the root (+1 X, -1 O).
-// c2 = UCTK^2 * f (the exploration term is sqrt(c2 * ln N / v)).
-__host__ __device__ inline void tree_walk(const Tree& T, uint32_t root, uint32_t rx, uint32_t ro, int root_pjm, uint32_t P, float c2,
-                                          uint64_t key, long long k, const Walks& W, bool add_root_visit) {
-    uint32_t idx = root, x = rx, o = ro;
-    int pjm = root_pjm, depth = 0;
-    bool fresh = false;
+// Expand move `bit` of node idx (its claim already made): the child's slot, set up and counted.  0: the arena is full.
+__host__ __device__ inline uint32_t tree_make_child(const Tree& T, uint32_t idx, uint32_t emp, uint32_t bit, uint32_t P) {
+    const int slots = t_popc(emp);
+    uint32_t fc = t_load(&T.first_child[idx]);
+    if (!fc) {
+        const unsigned long long base = t_add64(T.next_free, (unsigned long long)slots);
+        if (base + (unsigned long long)slots >= T.cap) {      // arena full: hand the move back
+            t_store(T.overflow, 1u);
+            t_or(&T.untried[idx], bit);
+            return 0u;
+        }
+        const uint32_t old = t_cas(&T.first_child[idx], 0u, (uint32_t)base);
+        fc = old ? old : (uint32_t)base;                     // lost the race: that block is simply not used
+    }
+    const uint32_t child = fc + (uint32_t)t_popc(emp & (bit - 1u));
+    t_store(&T.untried[child], kPending);
+    t_fence();
+    t_store(&T.visits[child], P);                            // nobody looks at a child before its visits are non-zero
+    return child;
+}
+
+// The rest of a walk, from node idx (board x/o, pjm just moved, `depth` nodes on the path so far) to its leaf
+// (mcts.go:153-171): every step sees the tree as it is at that moment.
+__host__ __device__ inline void tree_walk_from(const Tree& T, uint32_t idx, uint32_t x, uint32_t o, int pjm, int depth, bool fresh, uint32_t P,
+                                               float c2, uint64_t key, long long k, const Walks& W) {
     uint32_t* path = W.paths + (size_t)k * kPathLen;
-    if (add_root_visit) t_add(&T.visits[root], P);
-    path[depth++] = root;
     int waited = 0;
-    for (;;) {
+    while (!fresh) {
         const uint32_t u = t_load(&T.untried[idx]);
         if (u & kPending) break;                                 // waits for its first rollout: a leaf
         const uint32_t um = u & kFull;
@@ -147,24 +171,10 @@ __host__ __device__ inline void tree_walk(const Tree& T, uint32_t root, uint32_t
             const int m = t_nth_set_bit(um, (int)(t_mix(key ^ ((uint64_t)k << 8) ^ (uint64_t)depth) % (uint64_t)cnt));
             const uint32_t bit = 1u << m;
             if (!(t_and(&T.untried[idx], ~bit) & bit)) continue; // another walk took it: look again (at most 25 times)
-            const int slots = t_popc(emp);
-            uint32_t fc = t_load(&T.first_child[idx]);
-            if (!fc) {
-                const unsigned long long base = t_add64(T.next_free, (unsigned long long)slots);
-                if (base + (unsigned long long)slots >= T.cap) {  // arena full: hand the move back, roll out from here
-                    t_store(T.overflow, 1u);
-                    t_or(&T.untried[idx], bit);
-                    break;
-                }
-                const uint32_t old = t_cas(&T.first_child[idx], 0u, (uint32_t)base);
-                fc = old ? old : (uint32_t)base;                 // lost the race: that block is simply not used
-            }
-            const uint32_t child = fc + (uint32_t)t_popc(emp & (bit - 1u));
+            const uint32_t child = tree_make_child(T, idx, emp, bit, P);
+            if (!child) break;                                   // arena full: roll out from here
             pjm = -pjm;
             if (pjm > 0) x |= bit; else o |= bit;
-            t_store(&T.untried[child], kPending);
-            t_fence();
-            t_store(&T.visits[child], P);                        // nobody looks at a child before its visits are non-zero
             idx = child;
             path[depth++] = child;
             fresh = true;
@@ -215,6 +225,171 @@ __host__ __device__ inline void tree_walk(const Tree& T, uint32_t root, uint32_t
     W.leaf[k] = idx;
     W.fresh[k] = fresh ? 1 : 0;
     W.depth[k] = (uint8_t)depth;
+}
+
+// One walk from the root to a leaf.  pjm: the player who just moved at the root (+1 X, -1 O).
+// c2 = UCTK^2 * f (the exploration term is sqrt(c2 * ln N / v)).
+__host__ __device__ inline void tree_walk(const Tree& T, uint32_t root, uint32_t rx, uint32_t ro, int root_pjm, uint32_t P, float c2,
+                                          uint64_t key, long long k, const Walks& W, bool add_root_visit) {
+    if (add_root_visit) t_add(&T.visits[root], P);
+    W.paths[(size_t)k * kPathLen] = root;
+    tree_walk_from(T, root, rx, ro, root_pjm, 1, false, P, c2, key, k, W);
+}
+
+// ---- synchronised levels ---------------------------------------------------------------------------------------------------
+// Thousands of walks that reach a node in the same instant see the same statistics and would all take the same child: the
+// virtual loss of the others is not there yet.  For the first levels of the tree -- where a batch's walks still travel
+// together -- the descent therefore goes level by level, two steps per level over all walks of the batch:
+//   arrive:  every walk carries out what it decided (descend: add its visits to the child; expand: make the child), then
+//            takes a place (rank) among the walks standing on its node;
+//   decide:  nothing in the tree changes during this step.  The K walks on a node read the same numbers and split
+//            themselves among the children exactly as K sequential selections with virtual loss would: the first
+//            popc(untried) ranks expand one untried move each; the others share out the ready children so that all
+//            children that get walks end at the same UCB1 ("water level", found by bisection; the number of visits that
+//            brings a child down to a level is a closed form), and a walk's rank picks its child from the running sums.
+// Below the synchronised levels the walks have spread out and finish with tree_walk_from.
+
+// arrive.  level 0: the walk starts at the root.
+__host__ __device__ inline void tree_arrive(const Tree& T, int level, uint32_t root, uint32_t rx, uint32_t ro, int root_pjm, uint32_t P,
+                                            long long k, const Walks& W, bool take_place) {
+    uint32_t* path = W.paths + (size_t)k * kPathLen;
+    if (level == 0) {
+        W.boards[k].x = rx; W.boards[k].o = ro; W.pjm[k] = (int8_t)root_pjm; W.leaf[k] = root; W.depth[k] = 1; W.fresh[k] = 0;
+        W.act[k] = kActNone; W.rank[k] = kNoRank;
+        path[0] = root;
+    } else {
+        const uint32_t node = W.leaf[k];
+        if (W.rank[k] == 0u) t_store(&T.arrivals[node], 0u);     // the first of the node's walks clears its counter for the next batch
+        W.rank[k] = kNoRank;
+        const uint8_t act = W.act[k];
+        if (act == kActDone) return;
+        uint32_t x = W.boards[k].x, o = W.boards[k].o;
+        const uint32_t emp = kFull & ~(x | o);
+        int pjm = W.pjm[k];
+        if (act == kActDescend) {
+            const uint32_t child = t_load(&T.first_child[node]) + (uint32_t)W.arg[k];
+            t_add(&T.visits[child], P);
+            const uint32_t bit = 1u << t_nth_set_bit(emp, (int)W.arg[k]);
+            pjm = -pjm;
+            if (pjm > 0) x |= bit; else o |= bit;
+            path[W.depth[k]] = child;
+            W.depth[k]++;
+            W.leaf[k] = child;
+        } else if (act == kActExpand) {
+            const uint32_t bit = 1u << W.arg[k];
+            W.act[k] = kActDone;
+            if (!(t_and(&T.untried[node], ~bit) & bit)) return;  // (cannot happen: ranks hold different moves) -- roll out from the node
+            const uint32_t child = tree_make_child(T, node, emp, bit, P);
+            if (!child) return;                                  // arena full: roll out from the node
+            pjm = -pjm;
+            if (pjm > 0) x |= bit; else o |= bit;
+            path[W.depth[k]] = child;
+            W.depth[k]++;
+            W.leaf[k] = child;
+            W.fresh[k] = 1;
+            W.boards[k].x = x; W.boards[k].o = o; W.pjm[k] = (int8_t)pjm;
+            return;
+        }
+        W.boards[k].x = x; W.boards[k].o = o; W.pjm[k] = (int8_t)pjm;
+        W.act[k] = kActNone;
+    }
+    if (take_place) W.rank[k] = t_add(&T.arrivals[W.leaf[k]], 1u);
+}
+
+// visits that bring a child (w wins, v visits) down to UCB1 level lambda; s = sqrt(c2 * ln N)
+__host__ __device__ inline double tree_visits_to_level(double w, double v, double s, double lambda) {
+    // w/v' + s/sqrt(v') = lambda, t = 1/sqrt(v'):  w t^2 + s t - lambda = 0
+    double t;
+    if (w > 0.) {
+#if SQT_DEVICE
+        t = (-s + sqrt(s * s + 4. * w * lambda)) / (2. * w);
+#else
+        t = (-s + __builtin_sqrt(s * s + 4. * w * lambda)) / (2. * w);
+#endif
+    } else t = lambda / s;
+    const double vp = 1. / (t * t);
+    return vp > v ? vp - v : 0.;
+}
+
+// decide.  Nothing in the tree is written here.
+__host__ __device__ inline void tree_decide(const Tree& T, uint32_t P, float c2, uint64_t key, long long k, const Walks& W) {
+    if (W.act[k] == kActDone || W.rank[k] == kNoRank) return;
+    const uint32_t idx = W.leaf[k];
+    const uint32_t rank = W.rank[k], K = t_load(&T.arrivals[idx]);
+    const uint32_t u = t_load(&T.untried[idx]);
+    if (u & kPending) { W.act[k] = kActDone; return; }          // waits for its first rollout: a leaf for all of them
+    const uint32_t um = u & kFull;
+    const uint32_t emp = kFull & ~(W.boards[k].x | W.boards[k].o);
+    const uint32_t cnt = (uint32_t)t_popc(um);
+    if (rank < cnt) {                                            // one untried move each, in an order that changes from batch to batch
+        const uint32_t rot = (uint32_t)(t_mix(key ^ (uint64_t)idx) % (uint64_t)cnt);
+        W.act[k] = kActExpand;
+        W.arg[k] = (uint8_t)t_nth_set_bit(um, (int)((rank + rot) % cnt));
+        return;
+    }
+    const uint32_t fc = t_load(&T.first_child[idx]);
+    if (!fc) { W.act[k] = kActDone; return; }                   // a finished game, or no child is ready yet: roll out from here
+    const int slots = t_popc(emp);
+    double v[25], w[25];
+    int n_ready = 0, best = -1;
+    double top = -1.;
+    uint32_t seen = t_load(&T.visits[idx]);
+    if (seen < (uint32_t)slots * P + 1u) seen = (uint32_t)slots * P + 1u;
+#if SQT_DEVICE
+    const double s = sqrt((double)c2 * log((double)seen));
+#else
+    const double s = __builtin_sqrt((double)c2 * __builtin_log((double)seen));
+#endif
+    for (int j = 0; j < slots; j++) {
+        v[j] = (double)t_load(&T.visits[fc + (uint32_t)j]);
+        w[j] = (double)t_load(&T.wins[fc + (uint32_t)j]);
+        if (v[j] > 0.) {
+            n_ready++;
+#if SQT_DEVICE
+            const double f = w[j] / v[j] + s / sqrt(v[j]);
+#else
+            const double f = w[j] / v[j] + s / __builtin_sqrt(v[j]);
+#endif
+            if (f > top) { top = f; best = j; }
+        }
+    }
+    if (!n_ready) { W.act[k] = kActDone; return; }
+    const uint32_t Kp = K - (cnt < K ? cnt : K);                 // walks that select (this one among them)
+    const uint32_t r = rank - cnt;
+    W.act[k] = kActDescend;
+    if (Kp <= 1u) { W.arg[k] = (uint8_t)best; return; }          // alone: the plain argmax
+    // the level that Kp * P more visits fill the children up to
+    const double want = (double)Kp * (double)P;
+    double lo = 0., hi = top;                                    // total(hi) = 0, total(lo -> 0) -> infinity
+    for (int it = 0; it < 40; it++) {
+        const double mid = 0.5 * (lo + hi);
+        double total = 0.;
+        for (int j = 0; j < slots; j++) if (v[j] > 0.) total += tree_visits_to_level(w[j], v[j], s, mid);
+        if (total > want) lo = mid; else hi = mid;
+    }
+    const double level = 0.5 * (lo + hi);
+    double total = 0.;
+    for (int j = 0; j < slots; j++) if (v[j] > 0.) total += tree_visits_to_level(w[j], v[j], s, level);
+    if (!(total > 0.)) { W.arg[k] = (uint8_t)best; return; }
+    // the walk's rank picks its child from the running sums (scaled so that they end at Kp exactly)
+    const double mine = ((double)r + 0.5) * total / (double)Kp;
+    double run = 0.;
+    int pick = best;
+    for (int j = 0; j < slots; j++) {
+        if (!(v[j] > 0.)) continue;
+        run += tree_visits_to_level(w[j], v[j], s, level);
+        if (mine < run) { pick = j; break; }
+    }
+    W.arg[k] = (uint8_t)pick;
+}
+
+// after the last synchronised level: carry out what was decided, then finish the walk on its own
+__host__ __device__ inline void tree_finish(const Tree& T, int levels, uint32_t root, uint32_t rx, uint32_t ro, int root_pjm, uint32_t P, float c2,
+                                            uint64_t key, long long k, const Walks& W) {
+    if (levels == 0) { tree_walk(T, root, rx, ro, root_pjm, P, c2, key, k, W, false); return; }
+    tree_arrive(T, levels, root, rx, ro, root_pjm, P, k, W, false);
+    if (W.act[k] == kActDone) { W.to_move[k] = (int8_t)-W.pjm[k]; return; }     // its leaf record is what the arrive steps left
+    tree_walk_from(T, W.leaf[k], W.boards[k].x, W.boards[k].o, W.pjm[k], W.depth[k], false, P, c2, key, k, W);
 }
 
 // Update (mcts.go:190-192, 268-271) of one walk.  counts: {X wins, O wins, draws, plies} of the leaf's playouts.

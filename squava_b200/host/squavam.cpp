@@ -34,7 +34,7 @@ static int readMove(const Board& bd) {             // squavam.go:345-372
 int main(int argc, char** argv) {
     int iterMax = 10000, batch = 256, ppl = 1, gpus = 0, seed = -1, threads = 0;
     bool fast = false, stats = false, rootParallel = false, gpuTree = false;
-    int walkers = 0;
+    int walkers = 0, syncLevels = -1;
     double uctk = 1.00;
     bool computerFirst = false;
     Flags fl;
@@ -48,7 +48,8 @@ int main(int argc, char** argv) {
     fl.Bool("stats", &stats, "with -fast: print iterations, nodes and the time spent selecting / on the GPU / updating");
     fl.Bool("root-parallel", &rootParallel, "with -fast -gpus N: N independent trees, one per GPU, root statistics merged once per decision (squavam2.go's N searchers without the shared tree)");
     fl.Bool("gpu-tree", &gpuTree, "the whole tree in GPU memory (sq_mcts_decide): select, playouts and update are device kernels, nothing but the decision comes back; for 10^8..10^9 iterations; no tree reuse");
-    fl.Int("walkers", &walkers, "with -gpu-tree: walks of a batch in flight at once (default 8192)");
+    fl.Int("walkers", &walkers, "with -gpu-tree: walks of a batch in flight at once below the synchronised levels (default 8192)");
+    fl.Int("sync-levels", &syncLevels, "with -gpu-tree: levels below the root on which the walks of a batch share out the children by counts (default 4; 0: none)");
     fl.Int("gpus", &gpus, "number of GPUs (default 1)");
     fl.Int("seed", &seed, "seed for reproducible play (default: clock, as the reference)");
     fl.Parse(argc, argv);
@@ -68,7 +69,7 @@ int main(int argc, char** argv) {
             if (gpuTree) {
                 sq_board rb{state.board.x, state.board.o};
                 sq_mcts_result r;
-                const int rc = sq_mcts_decide(0, &rb, state.playerJustMoved, iterMax, uctk, 0, batch < 1024 ? 65536 : batch, ppl, walkers, 0,
+                const int rc = sq_mcts_decide(0, &rb, state.playerJustMoved, iterMax, uctk, 0, batch < 1024 ? 65536 : batch, ppl, walkers, syncLevels, 0,
                                               (uint64_t)host_rng()() << 20, (uint64_t)host_rng()(), &r);
                 if (rc != SQ_OK) { std::fprintf(stderr, "sq_mcts_decide: %s\n", sq_mcts_last_error()); std::exit(2); }
                 // the move returned is argmax UCB1 over the root's children (mcts.go:196-198)

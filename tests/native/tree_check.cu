@@ -1,7 +1,7 @@
 // The HBM tree's walk and update (squava_b200/csrc/tree.cuh) run sequentially on the host against a CPU rollout
 // (uniform random legal moves; four in a row wins, three loses, four first): the books must balance at every node,
 // and the search must find a move that wins at once.
-// usage: tree_check ITERATIONS BATCH PLAYOUTS_PER_LEAF SEED X O PJM   -> prints what tests/test_tree_native.py reads
+// usage: tree_check ITERATIONS BATCH PLAYOUTS_PER_LEAF SEED X O PJM [SYNC_LEVELS]   -> prints what tests/test_tree_native.py reads
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -43,12 +43,13 @@ int main(int argc, char** argv) {
     rng_state = strtoull(argv[4], nullptr, 10);
     const uint32_t rx = (uint32_t)strtoul(argv[5], nullptr, 0), ro = (uint32_t)strtoul(argv[6], nullptr, 0);
     const int pjm = atoi(argv[7]);
+    const int sync_levels = argc > 8 ? atoi(argv[8]) : 0;
     sq::build_scan_tables(S);
     const unsigned long long cap = (unsigned long long)(26.0 * (double)(iterations / P + 1)) + 1024;
-    std::vector<uint32_t> visits(cap, 0), wins(cap, 0), first_child(cap, 0), untried(cap, 0);
+    std::vector<uint32_t> visits(cap, 0), wins(cap, 0), first_child(cap, 0), untried(cap, 0), arrivals(cap, 0);
     unsigned long long next_free = 2;
     uint32_t overflow = 0;
-    sqt::Tree T{visits.data(), wins.data(), first_child.data(), untried.data(), &next_free, cap, &overflow};
+    sqt::Tree T{visits.data(), wins.data(), first_child.data(), untried.data(), &next_free, cap, &overflow, arrivals.data()};
     const uint32_t root = 1;
     // a root on which the game is already over has no moves
     const bool over = has(rx, S.ab_quads, 28) || has(ro, S.ab_quads, 28) || has(rx, S.ab_triplets, 48) || has(ro, S.ab_triplets, 48);
@@ -57,7 +58,10 @@ int main(int argc, char** argv) {
     std::vector<int8_t> to_move((size_t)batch);
     std::vector<uint32_t> leaf((size_t)batch), paths((size_t)batch * sqt::kPathLen);
     std::vector<uint8_t> fresh((size_t)batch), depth((size_t)batch);
-    sqt::Walks W{boards.data(), to_move.data(), leaf.data(), fresh.data(), depth.data(), paths.data()};
+    std::vector<uint32_t> rank((size_t)batch);
+    std::vector<uint8_t> act((size_t)batch), arg((size_t)batch);
+    std::vector<int8_t> wpjm((size_t)batch);
+    sqt::Walks W{boards.data(), to_move.data(), leaf.data(), fresh.data(), depth.data(), paths.data(), rank.data(), act.data(), arg.data(), wpjm.data()};
     std::vector<unsigned long long> counts((size_t)batch * 4);
     long long done = 0, batches = 0;
     while (done < iterations) {
@@ -65,9 +69,19 @@ int main(int argc, char** argv) {
         uint32_t p = P;
         if ((long long)p > remaining) p = (uint32_t)remaining;
         long long B = batch;
+        if (batches < 16 && (256ll << batches) < B) B = 256ll << batches;       // the first batches grow with the tree: 256, 512, ...
         if (B * (long long)p > remaining) B = remaining / p;
         if (B < 1) B = 1;
-        for (long long k = 0; k < B; k++) sqt::tree_walk(T, root, rx, ro, pjm, p, 2.0f, sqt::t_mix((uint64_t)batches), k, W, true);
+        const uint64_t key = sqt::t_mix((uint64_t)batches);
+        if (sync_levels == 0) for (long long k = 0; k < B; k++) sqt::tree_walk(T, root, rx, ro, pjm, p, 2.0f, key, k, W, true);
+        else {
+            visits[root] += (uint32_t)(B * (long long)p);
+            for (int level = 0; level < sync_levels; level++) {
+                for (long long k = 0; k < B; k++) sqt::tree_arrive(T, level, root, rx, ro, pjm, p, k, W, true);
+                for (long long k = 0; k < B; k++) sqt::tree_decide(T, p, 2.0f, key, k, W);
+            }
+            for (long long k = 0; k < B; k++) sqt::tree_finish(T, sync_levels, root, rx, ro, pjm, p, 2.0f, key, k, W);
+        }
         for (long long k = 0; k < B; k++) {
             unsigned long long* c = &counts[(size_t)k * 4];
             c[0] = c[1] = c[2] = c[3] = 0;
@@ -86,7 +100,8 @@ int main(int argc, char** argv) {
         batches++;
     }
     // the books: every walk is counted once at every node of its path
-    unsigned long long bad = 0, pending = 0, nodes = 0;
+    unsigned long long bad = 0, pending = 0, nodes = 0, root_gap = 0;
+    for (unsigned long long i = 0; i < next_free; i++) if (arrivals[i]) bad++;          // every counter was cleared
     for (unsigned long long i = 1; i < next_free; i++) {
         if (!visits[i]) continue;
         nodes++;
@@ -100,14 +115,15 @@ int main(int argc, char** argv) {
         if (i == root) {
             const int slots = __builtin_popcount(sqt::kFull & ~(rx | ro));
             for (int k = 0; k < slots; k++) sum += visits[fc + (uint32_t)k];
-            if (sum != visits[root]) bad++;
+            if (sum > visits[root]) bad++;
+            root_gap = visits[root] - sum;                 // walks that rolled out from the root itself (no child was ready)
         }
     }
     const uint32_t fc = first_child[root];
     const uint32_t emp = sqt::kFull & ~(rx | ro);
     const int slots = __builtin_popcount(emp);
-    std::printf("root_visits %u iterations %lld batches %lld nodes %llu used %llu bad %llu pending %llu overflow %u\n", visits[root], done,
-                batches, nodes, next_free, bad, pending, overflow);
+    std::printf("root_visits %u iterations %lld batches %lld nodes %llu used %llu bad %llu pending %llu overflow %u root_gap %llu\n", visits[root], done,
+                batches, nodes, next_free, bad, pending, overflow, root_gap);
     uint32_t e = emp;
     for (int k = 0; k < slots && fc; k++, e &= e - 1u) std::printf("child %d %u %u\n", __builtin_ctz(e), visits[fc + (uint32_t)k], wins[fc + (uint32_t)k]);
     return 0;
