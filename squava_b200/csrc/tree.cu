@@ -97,7 +97,7 @@ int sq_mcts_decide(int slot, const sq_board* root_board, int player_just_moved, 
     t_tree_err[0] = 0;
     (void)cudaGetLastError();                                   // whatever an earlier call left behind is not this call's
     if (!root_board || !out || iterations < 1 || batch < 1 || playouts_per_leaf < 1 || (player_just_moved != 1 && player_just_moved != -1) ||
-        (root_board->x & root_board->o) || ((root_board->x | root_board->o) >> 25)) {
+        (root_board->x & root_board->o) || ((root_board->x | root_board->o) >> 25) || iterations > 4000000000ll) {        // 32-bit counts
         snprintf(t_tree_err, sizeof t_tree_err, "sq_mcts_decide: bad argument");
         return SQ_ERR_INVALID;
     }
