@@ -296,19 +296,38 @@ __host__ __device__ inline void tree_arrive(const Tree& T, int level, uint32_t r
     if (take_place) W.rank[k] = t_add(&T.arrivals[W.leaf[k]], 1u);
 }
 
-// visits that bring a child (w wins, v visits) down to UCB1 level lambda; s = sqrt(c2 * ln N)
-__host__ __device__ inline double tree_visits_to_level(double w, double v, double s, double lambda) {
-    // w/v' + s/sqrt(v') = lambda, t = 1/sqrt(v'):  w t^2 + s t - lambda = 0
-    double t;
-    if (w > 0.) {
-#if SQT_DEVICE
-        t = (-s + sqrt(s * s + 4. * w * lambda)) / (2. * w);
-#else
-        t = (-s + __builtin_sqrt(s * s + 4. * w * lambda)) / (2. * w);
+// The decide step's arithmetic.  Single precision: the launch list (profiles/r02_gpu_tree_launches.json) had this step at
+// 2.0 of the 2.6 ms of a batch in double precision (236 registers, FP64 square roots and divisions in a 40-step bisection
+// that every walk on a node repeats).  What single precision costs is a child's share of a batch being off by a few
+// visits in 65536 when the counts reach 10^8..10^9; every walk on a node still computes the SAME numbers, which is what
+// makes the ranks partition the children.  -DSQT_REAL=double brings the old arithmetic back.
+#ifndef SQT_REAL
+#define SQT_REAL float
 #endif
-    } else t = lambda / s;
-    const double vp = 1. / (t * t);
-    return vp > v ? vp - v : 0.;
+typedef SQT_REAL treal;
+__host__ __device__ inline treal t_sqrt(treal a) {
+#if SQT_DEVICE
+    return (treal)sqrt(a);                       // (overload resolution picks sqrtf for float)
+#else
+    return sizeof(treal) == 4 ? (treal)__builtin_sqrtf((float)a) : (treal)__builtin_sqrt((double)a);
+#endif
+}
+__host__ __device__ inline treal t_log(treal a) {
+#if SQT_DEVICE
+    return (treal)log(a);
+#else
+    return sizeof(treal) == 4 ? (treal)__builtin_logf((float)a) : (treal)__builtin_log((double)a);
+#endif
+}
+
+// visits that bring a child (w wins, v visits) down to UCB1 level lambda; s = sqrt(c2 * ln N)
+__host__ __device__ inline treal tree_visits_to_level(treal w, treal v, treal s, treal lambda) {
+    // w/v' + s/sqrt(v') = lambda, t = 1/sqrt(v'):  w t^2 + s t - lambda = 0
+    treal t;
+    if (w > (treal)0) t = (-s + t_sqrt(s * s + (treal)4 * w * lambda)) / ((treal)2 * w);
+    else t = lambda / s;
+    const treal vp = (treal)1 / (t * t);
+    return vp > v ? vp - v : (treal)0;
 }
 
 // decide.  Nothing in the tree is written here.
@@ -330,26 +349,18 @@ __host__ __device__ inline void tree_decide(const Tree& T, uint32_t P, float c2,
     const uint32_t fc = t_load(&T.first_child[idx]);
     if (!fc) { W.act[k] = kActDone; return; }                   // a finished game, or no child is ready yet: roll out from here
     const int slots = t_popc(emp);
-    double v[25], w[25];
+    treal v[25], w[25];
     int n_ready = 0, best = -1;
-    double top = -1.;
+    treal top = (treal)-1;
     uint32_t seen = t_load(&T.visits[idx]);
     if (seen < (uint32_t)slots * P + 1u) seen = (uint32_t)slots * P + 1u;
-#if SQT_DEVICE
-    const double s = sqrt((double)c2 * log((double)seen));
-#else
-    const double s = __builtin_sqrt((double)c2 * __builtin_log((double)seen));
-#endif
+    const treal s = t_sqrt((treal)c2 * t_log((treal)seen));
     for (int j = 0; j < slots; j++) {
-        v[j] = (double)t_load(&T.visits[fc + (uint32_t)j]);
-        w[j] = (double)t_load(&T.wins[fc + (uint32_t)j]);
-        if (v[j] > 0.) {
+        v[j] = (treal)t_load(&T.visits[fc + (uint32_t)j]);
+        w[j] = (treal)t_load(&T.wins[fc + (uint32_t)j]);
+        if (v[j] > (treal)0) {
             n_ready++;
-#if SQT_DEVICE
-            const double f = w[j] / v[j] + s / sqrt(v[j]);
-#else
-            const double f = w[j] / v[j] + s / __builtin_sqrt(v[j]);
-#endif
+            const treal f = w[j] / v[j] + s / t_sqrt(v[j]);
             if (f > top) { top = f; best = j; }
         }
     }
@@ -359,24 +370,25 @@ __host__ __device__ inline void tree_decide(const Tree& T, uint32_t P, float c2,
     W.act[k] = kActDescend;
     if (Kp <= 1u) { W.arg[k] = (uint8_t)best; return; }          // alone: the plain argmax
     // the level that Kp * P more visits fill the children up to
-    const double want = (double)Kp * (double)P;
-    double lo = 0., hi = top;                                    // total(hi) = 0, total(lo -> 0) -> infinity
-    for (int it = 0; it < 40; it++) {
-        const double mid = 0.5 * (lo + hi);
-        double total = 0.;
-        for (int j = 0; j < slots; j++) if (v[j] > 0.) total += tree_visits_to_level(w[j], v[j], s, mid);
+    const treal want = (treal)Kp * (treal)P;
+    treal lo = (treal)0, hi = top;                               // total(hi) = 0, total(lo -> 0) -> infinity
+    const int steps = sizeof(treal) == 4 ? 26 : 40;
+    for (int it = 0; it < steps; it++) {
+        const treal mid = (treal)0.5 * (lo + hi);
+        treal total = (treal)0;
+        for (int j = 0; j < slots; j++) if (v[j] > (treal)0) total += tree_visits_to_level(w[j], v[j], s, mid);
         if (total > want) lo = mid; else hi = mid;
     }
-    const double level = 0.5 * (lo + hi);
-    double total = 0.;
-    for (int j = 0; j < slots; j++) if (v[j] > 0.) total += tree_visits_to_level(w[j], v[j], s, level);
-    if (!(total > 0.)) { W.arg[k] = (uint8_t)best; return; }
+    const treal level = (treal)0.5 * (lo + hi);
+    treal total = (treal)0;
+    for (int j = 0; j < slots; j++) if (v[j] > (treal)0) total += tree_visits_to_level(w[j], v[j], s, level);
+    if (!(total > (treal)0)) { W.arg[k] = (uint8_t)best; return; }
     // the walk's rank picks its child from the running sums (scaled so that they end at Kp exactly)
-    const double mine = ((double)r + 0.5) * total / (double)Kp;
-    double run = 0.;
+    const treal mine = ((treal)r + (treal)0.5) * total / (treal)Kp;
+    treal run = (treal)0;
     int pick = best;
     for (int j = 0; j < slots; j++) {
-        if (!(v[j] > 0.)) continue;
+        if (!(v[j] > (treal)0)) continue;
         run += tree_visits_to_level(w[j], v[j], s, level);
         if (mine < run) { pick = j; break; }
     }
